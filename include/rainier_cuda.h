@@ -1,0 +1,203 @@
+/*
+ * rainier_cuda.h -- the C ABI of librainier_cuda.so: the drop-in boundary for Rainier's HMC hot path.
+ *
+ * Every entry point replaces one seam of the reference (paths relative to the stripe/rainier tree):
+ *
+ *   rn_model_create    <- Compiler.compileTargets(group): ir.DataFunction
+ *                         rainier-compute/src/main/scala/com/stripe/rainier/compute/Compiler.scala:14-20
+ *                         (bytecode emitter ir/CompiledFunction.scala:42-120 replaced by a CUDA source emitter)
+ *   rn_density_batch   <- DensityFunction.update / density / gradient
+ *                         rainier-sampler/src/main/scala/com/stripe/rainier/sampler/DensityFunction.scala:3-8
+ *                         as implemented by Model.density(), rainier-core/.../core/Model.scala:38-50
+ *   rn_sample          <- Model.sample(config, nChains) -> Driver.sample per chain
+ *                         rainier-core/.../core/Model.scala:13-24, rainier-sampler/.../sampler/Driver.scala:7-46
+ *   rn_config          <- SamplerConfig + the built-in Sampler / StepSizeTuner / MassMatrixTuner classes
+ *                         rainier-sampler/.../sampler/Sampler.scala:3-62, HMC.scala:3, EHMC.scala:3-6,
+ *                         DualAvg.scala:3, MassMatrix.scala:120-181
+ *   rn_chain_stats     <- Stats  rainier-sampler/.../sampler/Stats.scala:3-17
+ *   rn_emit_source     <- rainier-decompile (debug dump of the generated code), Decompiler.scala:8-26
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer; a handle owns its device
+ * memory, CUDA module and stream and is freed only by the matching destroy; no C++ exception crosses the
+ * ABI; every function returns RN_OK (0) or a negative RN_E_* code and leaves a message retrievable with
+ * rn_last_error() (thread-local).  NaN/inf are *values* and propagate exactly as in the reference
+ * (LeapFrog.scala:43-46,138-142); only a lookup index outside its table -- a NullPointerException thrown from
+ * generated code in the reference (ir/MethodGenerator.scala:164-167) -- is an error (RN_E_LOOKUP).
+ * A handle is not thread-safe (one stream); distinct handles may be used from distinct threads.
+ *
+ * The CPU oracle (oracle/, test infrastructure only) exports the same symbols with an `rno_` prefix so the
+ * parity tests can diff the two call for call.
+ */
+#ifndef RAINIER_CUDA_H
+#define RAINIER_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------------------------------------ */
+enum {
+  RN_OK = 0,
+  RN_E_INVALID = -1,   /* bad argument / malformed RIR */
+  RN_E_CUDA = -2,      /* CUDA driver / runtime failure (includes "no device": there is no CPU fallback) */
+  RN_E_COMPILE = -3,   /* NVRTC rejected the emitted source (message holds the log) */
+  RN_E_LOOKUP = -4,    /* a LookupIR index fell outside [low, low+len) on some chain */
+  RN_E_UNSUPPORTED = -5,
+  RN_E_NCCL = -6
+};
+
+/* ---- sampler configuration (POD mirror of SamplerConfig and friends) --------------------------------- */
+enum { RN_SAMPLER_HMC = 0, RN_SAMPLER_EHMC = 1 };                  /* HMCSampler / EHMCSampler */
+enum { RN_STEP_DUAL_AVG = 0, RN_STEP_STATIC = 1 };                 /* DualAvgTuner / StaticStepSize */
+enum { RN_MASS_IDENTITY = 0, RN_MASS_DIAGONAL = 1, RN_MASS_DENSE = 2, RN_MASS_STATIC = 3 };
+                                      /* IdentityMassMatrixTuner / DiagonalMassMatrixTuner /
+                                         DenseMassMatrixTuner / StaticMassMatrix */
+enum { RN_MATRIX_IDENTITY = 0, RN_MATRIX_DIAGONAL = 1, RN_MATRIX_DENSE = 2 }; /* MassMatrix ADT, MassMatrix.scala:3-32 */
+enum { RN_ADAPT_PER_CHAIN = 0, RN_ADAPT_POOLED = 1 };
+enum { RN_MATH_PARITY = 0, RN_MATH_FAST = 1 };
+enum { RN_GRAD_AUTO = 0, RN_GRAD_SYMBOLIC = 1, RN_GRAD_ADJOINT = 2 };
+
+/* java.util.Random state (48-bit LCG + cached second Gaussian), so that a chain can continue a stream the
+ * host already drew from (the reference shares one RNG between data synthesis and sampling,
+ * rainier-test/.../core/SBCModel.scala:31-39). */
+typedef struct rn_rng_state {
+  int64_t seed48;           /* scrambled internal state, < 2^48 */
+  double next_gaussian;     /* nextNextGaussian */
+  int32_t have_next;        /* haveNextNextGaussian */
+  int32_t reserved;
+} rn_rng_state;
+
+typedef struct rn_config {
+  int32_t struct_size;      /* sizeof(rn_config), for forward compatibility */
+
+  /* SamplerConfig, Sampler.scala:3-11,17-27 */
+  int32_t iterations;        /* default 1000 */
+  int32_t warmup_iterations; /* default 1000 */
+  int32_t stats_window;      /* default 100 */
+
+  /* sampler(): HMCSampler(nSteps) HMC.scala:3 | EHMCSampler(maxSteps,minSteps,bufSize,pCount) EHMC.scala:3-6 */
+  int32_t sampler;           /* RN_SAMPLER_* */
+  int32_t n_steps;           /* HMC */
+  int32_t max_steps;         /* EHMC, default 1024 (DefaultConfig) */
+  int32_t min_steps;         /* EHMC, default 1 */
+  int32_t buf_size;          /* EHMC, default 100 */
+  int32_t reserved0;
+  double p_count;            /* EHMC, default 0.1 */
+
+  /* stepSizeTuner(): DualAvgTuner(delta) DualAvg.scala:3 | StaticStepSize(stepSize) Sampler.scala:36-40 */
+  int32_t step_size_tuner;   /* RN_STEP_* */
+  int32_t reserved1;
+  double delta;              /* default 0.8 */
+  double static_step_size;
+
+  /* massMatrixTuner(): MassMatrix.scala:120-181, Sampler.scala:47-50 */
+  int32_t mass_tuner;        /* RN_MASS_* */
+  int32_t initial_window_size; /* default 50 */
+  double window_expansion;   /* default 1.5 */
+  int32_t skip_first;        /* default 50 */
+  int32_t skip_last;         /* default 50 */
+  int32_t static_matrix;     /* RN_MATRIX_* when mass_tuner == RN_MASS_STATIC */
+  int32_t reserved2;
+  const double* static_matrix_elements; /* n (diagonal) or n*n (dense) doubles, shared by all chains */
+
+  /* extensions (not in the reference) */
+  int32_t adaptation;        /* RN_ADAPT_PER_CHAIN (parity with the reference, default) or RN_ADAPT_POOLED:
+                                mass-matrix windows pool Welford statistics over all chains (and, when a
+                                communicator is attached, all ranks) */
+  int32_t math_mode;         /* RN_MATH_PARITY: no FMA contraction, the reference's operation order;
+                                RN_MATH_FAST: FMA contraction allowed */
+  int32_t gradient_mode;     /* RN_GRAD_AUTO: use the RIR's symbolic gradient outputs when present, else adjoint */
+  int32_t launch_iterations; /* iterations per kernel launch (0 = library default) */
+  const rn_rng_state* rng_states; /* optional [chains]; overrides seeds when non-NULL */
+  double* stats_rings;       /* optional host buffer [chains][3][stats_window]: the stepSizes, acceptanceRates
+                                and gradsPerIteration ring buffers in RingBuffer slot order (Stats.scala:19-59) */
+} rn_config;
+
+/* Stats.scala:3-17, one per chain, sampling phase (the reference resets stats after warmup, Driver.scala:31) */
+typedef struct rn_chain_stats {
+  int64_t gradient_evaluations; /* the reference's accounting: 2l+1 per takeSteps(l) (LeapFrog.scala:194-200) */
+  int64_t leapfrog_steps;       /* integrator steps taken (l per takeSteps(l)); the throughput numerator */
+  int32_t iterations;
+  int32_t divergences;          /* never written by the reference (Stats.scala:6); always 0 */
+  int32_t accepted;             /* accepted proposals (diagnostic, not in the reference) */
+  int32_t error_flags;          /* bit 0: lookup index out of range */
+  double step_size;             /* stepSizeTuner.stepSize used for sampling (Driver.scala:37) */
+  double energy_mean;           /* energyVariance.mean(0) */
+  double energy_raw;            /* energyVariance.raw(0) */
+  double energy_transitions2;   /* bfmi = energy_transitions2 / energy_raw */
+  int32_t energy_samples;
+  int32_t ring_pos;             /* RingBuffer.i of the three rings (identical for all three) */
+  int32_t ring_full;
+  int32_t reserved;
+  double step_sizes_mean;       /* RingBuffer.mean semantics (Stats.scala:47-58) */
+  double acceptance_rates_mean;
+  double grads_per_iteration_mean;
+  rn_rng_state rng;             /* RNG state after the last iteration */
+} rn_chain_stats;
+
+typedef struct rn_model rn_model;
+typedef struct rn_sampler rn_sampler;
+typedef struct rn_comm rn_comm;
+
+/* fills *cfg with the reference's DefaultConfig (Sampler.scala:17-27) */
+void rn_config_default(rn_config* cfg);
+
+/* ---- model ------------------------------------------------------------------------------------------- */
+/* rir/len: container of rainier_rir.h.  cols[i] (i < n_cols) are the column placeholders' data in input
+ * order (input index n_params + i), col_rows[i] their lengths; copied to the device.  device: CUDA ordinal. */
+int rn_model_create(const void* rir, size_t len, const double* const* cols, const int64_t* col_rows,
+                    int n_cols, int device, rn_model** out);
+int rn_model_nvars(const rn_model* m);
+/* q: host [chains][n];  out: host [chains][n+1] = density then gradient (Model.scala:48-49) */
+int rn_density_batch(rn_model* m, const double* q, int chains, double* out);
+/* debug: emitted CUDA source of the fused kernel for `cfg` (NUL-terminated).  Returns RN_OK and the needed
+ * size (incl. NUL) in *needed; copies at most cap bytes. */
+int rn_emit_source(rn_model* m, const rn_config* cfg, char* buf, size_t cap, size_t* needed);
+/* debug: the compiled cubin of the same kernel (for cuobjdump -sass). */
+int rn_emit_cubin(rn_model* m, const rn_config* cfg, void* buf, size_t cap, size_t* needed);
+void rn_model_destroy(rn_model* m);
+
+/* ---- one-call sampling (the path Model.sample lowers to) ------------------------------------------------ */
+/* seeds[c]: chain c behaves exactly like a single-chain reference run with ScalaRNG(seeds[c]).
+ * samples: host [chains][iterations][n].  mass: host [chains][n] (diagonal/identity: variances, identity = 1)
+ * or [chains][n*n] (dense), may be NULL.  stats: host [chains], may be NULL. */
+int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, double* samples,
+              double* mass, rn_chain_stats* stats);
+
+/* ---- staged / device-resident sampling (what rn_sample is built from) ----------------------------------- */
+int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, rn_sampler** out);
+/* LeapFrog.initialize + Driver.warmup (Driver.scala:22,48-90) for `iterations` more warmup iterations
+ * (first call also initializes); call until cfg->warmup_iterations are consumed or pass -1 for "all". */
+int rn_sampler_warmup(rn_sampler* s, int iterations);
+/* Driver.collectSamples (Driver.scala:92-119): `iterations` sampling iterations.  d_samples: device pointer
+ * to [iterations][n][chains] doubles (chain fastest: coalesced), or NULL to discard samples. */
+int rn_sampler_run(rn_sampler* s, int iterations, double* d_samples);
+/* blocks until all queued work is done */
+int rn_sampler_sync(rn_sampler* s);
+/* current q of every chain -> host [chains][n] */
+int rn_sampler_positions(rn_sampler* s, double* q);
+int rn_sampler_stats(rn_sampler* s, rn_chain_stats* stats, double* mass, double* stats_rings);
+/* the CUstream the sampler launches on (for CUDA-event timing by the caller) */
+void* rn_sampler_stream(rn_sampler* s);
+/* number of kernel launches issued so far on this sampler */
+int64_t rn_sampler_launches(const rn_sampler* s);
+/* attach a communicator: pooled adaptation all-reduces over its ranks */
+int rn_sampler_set_comm(rn_sampler* s, rn_comm* comm);
+void rn_sampler_destroy(rn_sampler* s);
+
+/* ---- multi-GPU plumbing (one process per GPU; chains are sharded by the caller) ------------------------- */
+/* NCCL unique id exchange is the caller's job (e.g. torch.distributed broadcast of the 128 bytes). */
+int rn_comm_unique_id(char id[128]);
+int rn_comm_create(const char id[128], int rank, int world, int device, rn_comm** out);
+void rn_comm_destroy(rn_comm* c);
+
+const char* rn_last_error(void);
+const char* rn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
