@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the HMC hot path (BASELINE.json: leapfrog-steps*chains/sec fp64, Neal's funnel).
+
+One "step" = one pass of the hot path over one batch: ITERS HMC iterations (nSteps=5 leapfrog steps each) for CHAINS
+chains of the 10-dim Neal's funnel, sampling phase, every sample written out.  Metric = leapfrog steps x chains per
+second = CHAINS*ITERS*5 / time.
+
+  value     : device-resident (chain state + sample buffer in HBM), timed with CUDA events on the sampler's stream.
+  e2e       : the same work through the public one-call API (rn_sample over the C ABI) with HOST buffers: seeds
+              host->device and every sample device->host inside the timed region.
+  roofline  : compulsory-traffic HBM accounting of SURVEY.md 8(d) (B_step = [8(2(2n+1)+n)+32]/L bytes per leapfrog
+              step) against MEASURED_PEAKS.json; plus an fp64 view (emitter op counts vs a DFMA peak measured here),
+              because this path is FP64-pipe bound, not HBM bound.
+  cpu_baseline / --impl reference : the CPU oracle (C++ restatement of the reference's LeapFrog + DataFunction
+              interpreter; the JVM reference cannot run here) on the box's host cores, bounded sample.
+
+Multi-GPU (torchrun): chains are sharded over ranks, no data-path collective, weak scaling (CHAINS per GPU fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_DIM = 10
+N_STEPS = 5
+STEP_SIZE = 0.1
+METRIC = "leapfrog_steps_x_chains_per_sec"
+
+
+def bytes_per_leapfrog_step(n, L):
+    """read+write the params array, write one sample, RNG state r/w, per HMC iteration of L steps."""
+    return (8.0 * (2 * (2 * n + 1) + n) + 32.0) / L
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=5)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle (stand-in for the JVM `asm` path, which cannot run here) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.rainier_py.binding import OracleModel, default_config, lib
+    from rainier_b200 import abi
+    rir = open(os.path.join(ROOT, "rainier_b200", "models", "funnel10.rir"), "rb").read()
+    om = OracleModel(rir, [])
+    cores = lib().rno_hardware_threads()
+    cfg = default_config()
+    cfg.sampler, cfg.n_steps = abi.RN_SAMPLER_HMC, N_STEPS
+    cfg.step_size_tuner, cfg.static_step_size = abi.RN_STEP_STATIC, STEP_SIZE
+    cfg.mass_tuner = abi.RN_MASS_IDENTITY
+    cfg.warmup_iterations = 0
+    chains = cores * 4
+    # size the per-step sample so that warmup+steps finish in a few minutes: calibrate on a short run
+    cfg.iterations = 2000
+    t = time.perf_counter()
+    om.sample(cfg, seeds=np.arange(chains) + 1000)
+    dt = time.perf_counter() - t
+    rate0 = chains * cfg.iterations * N_STEPS / dt
+    target_s = 4.0
+    cfg.iterations = max(100, int(rate0 * target_s / (chains * N_STEPS)))
+    for _ in range(args.warmup):
+        om.sample(cfg, seeds=np.arange(chains) + 1000)
+    t = time.perf_counter()
+    for k in range(args.steps):
+        om.sample(cfg, seeds=np.arange(chains) + 1000 + k)
+    dt = time.perf_counter() - t
+    value = args.steps * chains * cfg.iterations * N_STEPS / dt
+    sample = "%d chains x %d HMC iterations x %d leapfrog steps per step, one chain per thread" % (chains, cfg.iterations, N_STEPS)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "leapfrog-steps*chains/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "neals_funnel_10d_hmc_nsteps5", "sampler": "HMC(nSteps=5)", "step_size": STEP_SIZE,
+                   "chains": chains, "iterations_per_step": cfg.iterations},
+        "cpu_baseline": {"value": value, "unit": "leapfrog-steps*chains/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of the reference's LeapFrog/HMC + DataFunction interpreter (oracle/), "
+                                 "stand-in for the JVM asm path which cannot run in this image"},
+        "e2e": {"value": value, "unit": "leapfrog-steps*chains/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg():
+    from oracle.rainier_py.binding import OracleModel, default_config, lib
+    from rainier_b200 import abi
+    rir = open(os.path.join(ROOT, "rainier_b200", "models", "funnel10.rir"), "rb").read()
+    om = OracleModel(rir, [])
+    cores = lib().rno_hardware_threads()
+    cfg = default_config()
+    cfg.sampler, cfg.n_steps = abi.RN_SAMPLER_HMC, N_STEPS
+    cfg.step_size_tuner, cfg.static_step_size = abi.RN_STEP_STATIC, STEP_SIZE
+    cfg.mass_tuner = abi.RN_MASS_IDENTITY
+    cfg.warmup_iterations = 0
+    chains = cores * 4
+    cfg.iterations = 2000
+    t = time.perf_counter()
+    om.sample(cfg, seeds=np.arange(chains) + 1000)
+    dt = time.perf_counter() - t
+    rate0 = chains * cfg.iterations * N_STEPS / dt
+    cfg.iterations = max(100, int(rate0 * 12.0 / (chains * N_STEPS)))
+    t = time.perf_counter()
+    om.sample(cfg, seeds=np.arange(chains) + 1000)
+    dt = time.perf_counter() - t
+    return {"value": chains * cfg.iterations * N_STEPS / dt, "unit": "leapfrog-steps*chains/s", "cores": cores, "kind": "port",
+            "sample": "%d chains x %d HMC iterations x %d leapfrog steps (%.1f s), one chain per host thread" % (
+                chains, cfg.iterations, N_STEPS, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--chains", type=int, default=131072, help="chains per GPU")
+    ap.add_argument("--iters", type=int, default=100, help="HMC iterations per step")
+    ap.add_argument("--math", default="parity", choices=["parity", "fast"])
+    ap.add_argument("--grad", default="auto", choices=["auto", "symbolic", "adjoint"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from rainier_b200 import abi, api
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    C_, I_ = args.chains, args.iters
+    rir = open(os.path.join(ROOT, "rainier_b200", "models", "funnel10.rir"), "rb").read()
+    model = api.CudaModel(rir, [], device=local_rank)
+    cfg = api.make_config(iterations=I_, warmupIterations=0, sampler=api.HMCSampler(N_STEPS),
+                          stepSizeTuner=api.StaticStepSize(STEP_SIZE), massMatrixTuner=api.IdentityMassMatrixTuner(),
+                          mathMode=abi.RN_MATH_FAST if args.math == "fast" else abi.RN_MATH_PARITY,
+                          gradientMode={"auto": 0, "symbolic": 1, "adjoint": 2}[args.grad], launchIterations=I_)
+    seeds = np.arange(C_, dtype=np.int64) + 1000 + rank * C_  # chain c of the job: ScalaRNG(1000 + c)
+
+    # ---------------- device-resident leg ("value") ----------------
+    smp = api.CudaSampler(model, cfg, seeds=seeds)
+    smp.warmup(-1)  # LeapFrog.initialize (no warmup iterations configured)
+    stream = torch.cuda.ExternalStream(smp.stream, device=torch.device("cuda", local_rank))
+    d_samples = torch.empty((I_, N_DIM, C_), dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2
+    for _ in range(args.warmup):
+        smp.run(I_, d_samples.data_ptr())
+    smp.sync()
+    launches0 = smp.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        for k in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()  # L2 flush between timed steps (outside the per-step events)
+                ev[k][0].record(stream)
+            smp.run(I_, d_samples.data_ptr())
+            ev[k][1].record(stream)
+        smp.sync()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = smp.launches - launches0
+    stats, _ = smp.stats()
+    acc = float(np.mean([s.accepted / max(1, s.iterations) for s in stats[:4096]]))
+    t_total = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    ms_max = float(t_total.item())
+    total_steps = float(world) * C_ * I_ * N_STEPS * args.steps
+    value = total_steps / (ms_max * 1e-3)
+    smp.close()
+
+    # ---------------- end-to-end leg: public one-call API, host buffers ----------------
+    e2e_cfg, keep = api.lower_config(cfg)
+    import ctypes as CT
+    samples_host = torch.empty((C_, I_, N_DIM), dtype=torch.float64).pin_memory() if False else np.empty((C_, I_, N_DIM))
+    seeds_host = np.ascontiguousarray(seeds)
+
+    def e2e_step():
+        rc = api.lib().rn_sample(model.h, CT.byref(e2e_cfg), seeds_host.ctypes.data, C_, samples_host.ctypes.data, None, None)
+        if rc != 0:
+            raise RuntimeError(api.lib().rn_last_error().decode())
+
+    e2e_step()  # warm (page-faults the host buffer, loads nothing new on the device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n_e2e = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t_e2e = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = float(world) * C_ * I_ * N_STEPS * n_e2e / float(t_e2e.item())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        bps = bytes_per_leapfrog_step(N_DIM, N_STEPS)
+        per_gpu_rate = value / world
+        achieved = per_gpu_rate * bps / 1e9
+        counts = model.op_counts(cfg)
+        evals_per_step = (N_STEPS + 1) / N_STEPS  # l+1 density evaluations per takeSteps(l)
+        flops_step = counts["flops_invariant"] * evals_per_step + 6.0 * N_DIM  # + integrator updates
+        line = {
+            "metric": METRIC, "value": value, "unit": "leapfrog-steps*chains/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "neals_funnel_10d_hmc_nsteps5", "sampler": "HMC(nSteps=5)", "step_size": STEP_SIZE,
+                       "chains_per_gpu": C_, "iterations_per_step": I_, "math": args.math, "gradient": args.grad,
+                       "parallelism": "chains sharded over %d GPU(s), no data-path collective" % world,
+                       "l2": "state %.0f MB < L2; L2 flushed (256 MB write) between timed steps; sample stream %.0f MB/step" % (
+                           C_ * (3 * N_DIM + 8) * 8 / 1e6, C_ * I_ * N_DIM * 8 / 1e6),
+                       "accept_rate": acc},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "leapfrog-steps*chains/s", "h2d_bytes_per_step": int(C_ * 8),
+                    "d2h_bytes_per_step": int(C_ * I_ * N_DIM * 8), "api": "rn_sample (C ABI) with host buffers",
+                    "steps": n_e2e},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                         "bytes_per_leapfrog_step": bps,
+                         "note": "compulsory-traffic accounting (SURVEY.md 8d); the kernel is FP64-pipe bound, see fp64"},
+            "fp64": {"flops_per_leapfrog_step": flops_step, "special_per_leapfrog_step": counts["special_invariant"] * evals_per_step,
+                     "achieved_tflops": per_gpu_rate * flops_step / 1e12},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

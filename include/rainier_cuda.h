@@ -129,9 +129,9 @@ typedef struct rn_chain_stats {
   double energy_raw;            /* energyVariance.raw(0) */
   double energy_transitions2;   /* bfmi = energy_transitions2 / energy_raw */
   int32_t energy_samples;
-  int32_t ring_pos;             /* RingBuffer.i of the three rings (identical for all three) */
-  int32_t ring_full;
   int32_t reserved;
+  int32_t ring_pos[3];          /* RingBuffer.i of stepSizes / acceptanceRates / gradsPerIteration */
+  int32_t ring_full[3];
   double step_sizes_mean;       /* RingBuffer.mean semantics (Stats.scala:47-58) */
   double acceptance_rates_mean;
   double grads_per_iteration_mean;

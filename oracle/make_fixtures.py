@@ -1,0 +1,30 @@
+"""
+Generates the frozen-DAG fixtures the product-side harnesses (bench.py, smoke) load without touching oracle/:
+rainier_b200/models/*.rir, built by the Python restatement of the reference's DAG builder (oracle/rainier_py) in
+the reference's exact operation order.  Both flavours are written: `<name>.rir` carries the reference's symbolic
+gradient outputs (what Compiler.compileTargets would hand over today), `<name>.primal.rir` only the primal
+log-density outputs (what the Scala wrapper of INTEGRATION.md sends).  Data-free models only: streamed models need
+their columns, which tests/bench synthesise at run time.
+    python oracle/make_fixtures.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.rainier_py import configs  # noqa: E402
+
+OUT = os.path.join(ROOT, "rainier_b200", "models")
+os.makedirs(OUT, exist_ok=True)
+
+for name, build in (("funnel10", lambda: configs.funnel(10)), ("eight_schools", configs.eight_schools)):
+    m = build()
+    rir, cols = m.compile(with_gradient=True)
+    assert not cols
+    open(os.path.join(OUT, name + ".rir"), "wb").write(rir)
+    m = build()
+    rir, cols = m.compile(with_gradient=False)
+    assert not cols
+    open(os.path.join(OUT, name + ".primal.rir"), "wb").write(rir)
+    print(name, "ok")

@@ -986,8 +986,12 @@ static void driver_sample(const Model& model, const rn_config& cfg, RNG& rng, do
     st->energy_raw = s.energyVariance.raw[0];
     st->energy_transitions2 = s.energyTransitions2;
     st->energy_samples = s.energyVariance.samples;
-    st->ring_pos = s.stepSizes.i;
-    st->ring_full = s.stepSizes.full ? 1 : 0;
+    st->ring_pos[0] = s.stepSizes.i;
+    st->ring_pos[1] = s.acceptanceRates.i;
+    st->ring_pos[2] = s.gradsPerIteration.i;
+    st->ring_full[0] = s.stepSizes.full ? 1 : 0;
+    st->ring_full[1] = s.acceptanceRates.full ? 1 : 0;
+    st->ring_full[2] = s.gradsPerIteration.full ? 1 : 0;
     st->step_sizes_mean = s.stepSizes.mean();
     st->acceptance_rates_mean = s.acceptanceRates.mean();
     st->grads_per_iteration_mean = s.gradsPerIteration.mean();

@@ -67,9 +67,9 @@ class ChainStats(C.Structure):
         ("energy_raw", C.c_double),
         ("energy_transitions2", C.c_double),
         ("energy_samples", C.c_int32),
-        ("ring_pos", C.c_int32),
-        ("ring_full", C.c_int32),
         ("reserved", C.c_int32),
+        ("ring_pos", C.c_int32 * 3),
+        ("ring_full", C.c_int32 * 3),
         ("step_sizes_mean", C.c_double),
         ("acceptance_rates_mean", C.c_double),
         ("grads_per_iteration_mean", C.c_double),

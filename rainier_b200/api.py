@@ -1,0 +1,469 @@
+"""
+rainier_b200.api -- Python host side over the C ABI of librainier_cuda.so (include/rainier_cuda.h).
+
+The reference's host side is Scala; no JVM toolchain exists in this image, so the same plugin surface is mirrored
+here in Python with the reference's own names and argument meaning, so that tests and benchmarks read like the
+reference's (rainier-sampler/src/main/scala/com/stripe/rainier/sampler/):
+
+    SamplerConfig / DefaultConfig      Sampler.scala:3-27
+    HMCSampler(nSteps)                 HMC.scala:3          HMC(warmIt, it, nSteps)            HMC.scala:26-33
+    EHMCSampler(maxSteps, minSteps, bufSize, pCount)        EHMC.scala:3-6 ; EHMC(...)          EHMC.scala:64-73
+    DualAvgTuner(delta), StaticStepSize(stepSize)           DualAvg.scala:3, Sampler.scala:36-40
+    IdentityMassMatrixTuner, DiagonalMassMatrixTuner, DenseMassMatrixTuner, StaticMassMatrix
+                                       MassMatrix.scala:120-181, Sampler.scala:47-50
+    IdentityMassMatrix / DiagonalMassMatrix / DenseMassMatrix   MassMatrix.scala:3-32
+    CudaModel.sample(config, nChains)  <- Model.sample (rainier-core/.../core/Model.scala:13-24)
+    CudaModel.density()                <- Model.density(): DensityFunction (Model.scala:38-50)
+
+Python is plumbing only: every number is produced by the CUDA path.  There is no CPU fallback -- when the
+library or a GPU is missing the calls raise RainierCudaError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import ChainStats, Config, RngState
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class RainierCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rainier_cuda error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Loads rainier_b200/librainier_cuda.so (built in-tree by __graft_entry__.build / csrc/Makefile)."""
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "librainier_cuda.so")
+        if not os.path.exists(path):
+            raise RainierCudaError(abi.RN_E_CUDA, "librainier_cuda.so is not built (run __graft_entry__.build()); "
+                                   "there is no CPU fallback")
+        L = C.CDLL(path)
+        L.rn_last_error.restype = C.c_char_p
+        L.rn_version.restype = C.c_char_p
+        L.rn_config_default.argtypes = [C.POINTER(Config)]
+        L.rn_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
+        L.rn_model_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+                                      C.c_int, C.POINTER(C.c_void_p)]
+        L.rn_model_nvars.argtypes = [C.c_void_p]
+        L.rn_model_destroy.argtypes = [C.c_void_p]
+        L.rn_model_op_counts.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(C.c_double)]
+        L.rn_density_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.rn_emit_source.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rn_emit_cubin.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rn_sample.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rn_sampler_create.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.rn_sampler_warmup.argtypes = [C.c_void_p, C.c_int]
+        L.rn_sampler_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.rn_sampler_sync.argtypes = [C.c_void_p]
+        L.rn_sampler_positions.argtypes = [C.c_void_p, C.c_void_p]
+        L.rn_sampler_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rn_sampler_stream.argtypes = [C.c_void_p]
+        L.rn_sampler_stream.restype = C.c_void_p
+        L.rn_sampler_launches.argtypes = [C.c_void_p]
+        L.rn_sampler_launches.restype = C.c_int64
+        L.rn_sampler_destroy.argtypes = [C.c_void_p]
+        L.rn_sampler_enable_trace.argtypes = [C.c_void_p]
+        L.rn_sampler_read_trace.argtypes = [C.c_void_p, C.c_void_p]
+        sizes = (C.c_int32 * 4)()
+        L.rn_abi_sizes(sizes)
+        if sizes[0] != C.sizeof(Config) or sizes[1] != C.sizeof(ChainStats) or sizes[2] != C.sizeof(RngState):
+            raise RainierCudaError(abi.RN_E_INVALID, "ABI struct size mismatch between abi.py and librainier_cuda.so")
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise RainierCudaError(rc, lib().rn_last_error().decode(errors="replace"))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# MassMatrix ADT  (sampler/MassMatrix.scala:3-32)
+# ----------------------------------------------------------------------------------------------------------
+class MassMatrix:
+    pass
+
+
+class _Identity(MassMatrix):
+    def __repr__(self):
+        return "IdentityMassMatrix"
+
+
+IdentityMassMatrix = _Identity()
+
+
+class DiagonalMassMatrix(MassMatrix):
+    def __init__(self, elements):
+        self.elements = np.asarray(elements, dtype=np.float64)
+        if np.any(self.elements == 0.0):
+            raise ValueError("requirement failed")  # MassMatrix.scala:8
+
+
+class DenseMassMatrix(MassMatrix):
+    def __init__(self, elements):
+        self.elements = np.asarray(elements, dtype=np.float64).reshape(-1)
+        if np.any(self.elements == 0.0):
+            raise ValueError("requirement failed")  # MassMatrix.scala:16
+
+
+# ----------------------------------------------------------------------------------------------------------
+# samplers / tuners  (descriptors that lower to rn_config)
+# ----------------------------------------------------------------------------------------------------------
+class Sampler:
+    pass
+
+
+class HMCSampler(Sampler):
+    def __init__(self, nSteps):
+        self.nSteps = int(nSteps)
+
+
+class EHMCSampler(Sampler):
+    def __init__(self, maxSteps, minSteps=1, bufSize=100, pCount=0.1):
+        self.maxSteps, self.minSteps, self.bufSize, self.pCount = int(maxSteps), int(minSteps), int(bufSize), float(pCount)
+
+
+class StepSizeTuner:
+    pass
+
+
+class DualAvgTuner(StepSizeTuner):
+    def __init__(self, delta):
+        self.delta = float(delta)
+
+
+class StaticStepSize(StepSizeTuner):
+    def __init__(self, stepSize):
+        self.stepSize = float(stepSize)
+
+
+class MassMatrixTuner:
+    pass
+
+
+class IdentityMassMatrixTuner(MassMatrixTuner):
+    pass
+
+
+class DiagonalMassMatrixTuner(MassMatrixTuner):
+    def __init__(self, initialWindowSize, windowExpansion, skipFirst, skipLast):
+        self.initialWindowSize, self.windowExpansion = int(initialWindowSize), float(windowExpansion)
+        self.skipFirst, self.skipLast = int(skipFirst), int(skipLast)
+
+
+class DenseMassMatrixTuner(DiagonalMassMatrixTuner):
+    pass
+
+
+class StaticMassMatrix(MassMatrixTuner):
+    def __init__(self, mass):
+        self.mass = mass
+
+
+class SamplerConfig:
+    """sampler/Sampler.scala:3-11.  Subclass or pass keyword overrides, like `new DefaultConfig { override ... }`."""
+    iterations = 1000
+    warmupIterations = 1000
+    statsWindow = 100
+
+    def __init__(self, **overrides):
+        for k, v in overrides.items():
+            setattr(self, k, v)
+
+    def stepSizeTuner(self):
+        return getattr(self, "_stepSizeTuner", None) or DualAvgTuner(0.8)
+
+    def massMatrixTuner(self):
+        return getattr(self, "_massMatrixTuner", None) or DiagonalMassMatrixTuner(50, 1.5, 50, 50)
+
+    def sampler(self):
+        return getattr(self, "_sampler", None) or EHMCSampler(1024)
+
+    # extensions of the CUDA path (not in the reference)
+    mathMode = abi.RN_MATH_PARITY
+    gradientMode = abi.RN_GRAD_AUTO
+    adaptation = abi.RN_ADAPT_PER_CHAIN
+    launchIterations = 0
+
+
+DefaultConfig = SamplerConfig
+
+
+def make_config(iterations=1000, warmupIterations=1000, statsWindow=100, sampler=None, stepSizeTuner=None,
+                massMatrixTuner=None, **ext):
+    c = SamplerConfig(iterations=iterations, warmupIterations=warmupIterations, statsWindow=statsWindow, **ext)
+    c._sampler, c._stepSizeTuner, c._massMatrixTuner = sampler, stepSizeTuner, massMatrixTuner
+    return c
+
+
+def HMC(warmIt, it, nSteps):  # HMC.scala:26-33
+    return make_config(iterations=it, warmupIterations=warmIt, sampler=HMCSampler(nSteps))
+
+
+def EHMC(warmIt, it, minSteps=1, numLengths=100):  # EHMC.scala:64-73
+    return make_config(iterations=it, warmupIterations=warmIt, sampler=EHMCSampler(1000, minSteps, numLengths, 0.1))
+
+
+def lower_config(config):
+    """SamplerConfig -> (rn_config, keepalive).  A user-defined Sampler/tuner subclass cannot be lowered to the
+    GPU and is an explicit error (no CPU fallback)."""
+    c = Config()
+    lib().rn_config_default(C.byref(c))
+    keep = []
+    c.iterations, c.warmup_iterations, c.stats_window = int(config.iterations), int(config.warmupIterations), int(config.statsWindow)
+    s = config.sampler()
+    if type(s) is HMCSampler:
+        c.sampler, c.n_steps = abi.RN_SAMPLER_HMC, s.nSteps
+    elif type(s) is EHMCSampler:
+        c.sampler = abi.RN_SAMPLER_EHMC
+        c.max_steps, c.min_steps, c.buf_size, c.p_count = s.maxSteps, s.minSteps, s.bufSize, s.pCount
+    else:
+        raise RainierCudaError(abi.RN_E_UNSUPPORTED, "only the built-in HMCSampler/EHMCSampler can be lowered to the GPU")
+    t = config.stepSizeTuner()
+    if type(t) is DualAvgTuner:
+        c.step_size_tuner, c.delta = abi.RN_STEP_DUAL_AVG, t.delta
+    elif type(t) is StaticStepSize:
+        c.step_size_tuner, c.static_step_size = abi.RN_STEP_STATIC, t.stepSize
+    else:
+        raise RainierCudaError(abi.RN_E_UNSUPPORTED, "only DualAvgTuner/StaticStepSize can be lowered to the GPU")
+    m = config.massMatrixTuner()
+    if type(m) is IdentityMassMatrixTuner:
+        c.mass_tuner = abi.RN_MASS_IDENTITY
+    elif type(m) in (DiagonalMassMatrixTuner, DenseMassMatrixTuner):
+        c.mass_tuner = abi.RN_MASS_DIAGONAL if type(m) is DiagonalMassMatrixTuner else abi.RN_MASS_DENSE
+        c.initial_window_size, c.window_expansion = m.initialWindowSize, m.windowExpansion
+        c.skip_first, c.skip_last = m.skipFirst, m.skipLast
+    elif type(m) is StaticMassMatrix:
+        c.mass_tuner = abi.RN_MASS_STATIC
+        if m.mass is IdentityMassMatrix:
+            c.static_matrix = abi.RN_MATRIX_IDENTITY
+        else:
+            c.static_matrix = abi.RN_MATRIX_DIAGONAL if isinstance(m.mass, DiagonalMassMatrix) else abi.RN_MATRIX_DENSE
+            arr = np.ascontiguousarray(m.mass.elements, dtype=np.float64)
+            keep.append(arr)
+            c.static_matrix_elements = arr.ctypes.data_as(C.POINTER(C.c_double))
+    else:
+        raise RainierCudaError(abi.RN_E_UNSUPPORTED, "unknown MassMatrixTuner")
+    c.math_mode, c.gradient_mode = int(config.mathMode), int(config.gradientMode)
+    c.adaptation, c.launch_iterations = int(config.adaptation), int(config.launchIterations)
+    return c, keep
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Stats / Trace
+# ----------------------------------------------------------------------------------------------------------
+class Stats:
+    """sampler/Stats.scala:3-17, rebuilt on the host from rn_chain_stats."""
+
+    def __init__(self, st, rings=None):
+        self.gradientEvaluations = st.gradient_evaluations
+        self.leapfrogSteps = st.leapfrog_steps
+        self.iterations = st.iterations
+        self.divergences = st.divergences
+        self.accepted = st.accepted
+        self.stepSize = st.step_size
+        self.energyTransitions2 = st.energy_transitions2
+        self.energyVarianceRaw = st.energy_raw
+        self.energyVarianceMean = st.energy_mean
+        self.stepSizesMean = st.step_sizes_mean
+        self.acceptanceRatesMean = st.acceptance_rates_mean
+        self.gradsPerIterationMean = st.grads_per_iteration_mean
+        self.rings = rings
+        self.rng = (st.rng.seed48, st.rng.next_gaussian, st.rng.have_next)
+
+    @property
+    def bfmi(self):
+        return self.energyTransitions2 / self.energyVarianceRaw
+
+
+class Trace:
+    """rainier-core/.../core/Trace.scala:6-9: chains[chain][iteration][variable], mass per chain, stats per chain."""
+
+    def __init__(self, chains, mass, stats):
+        self.chains, self.mass, self.stats = chains, mass, stats
+
+
+# ----------------------------------------------------------------------------------------------------------
+# model
+# ----------------------------------------------------------------------------------------------------------
+class CudaModel:
+    """Replaces Compiler.compileTargets(targetGroup) (compute/Compiler.scala:14-20): frozen DAG (RIR bytes) + data
+    columns -> emitted, NVRTC-compiled sm_100a kernels."""
+
+    def __init__(self, rir, cols=(), device=0):
+        L = lib()
+        self._rir = bytes(rir)
+        self._cols = [np.ascontiguousarray(c, dtype=np.float64) for c in cols]
+        n = len(self._cols)
+        ptrs = (C.c_void_p * max(n, 1))(*[c.ctypes.data for c in self._cols])
+        rows = (C.c_int64 * max(n, 1))(*[len(c) for c in self._cols])
+        h = C.c_void_p()
+        _check(L.rn_model_create(self._rir, len(self._rir), ptrs, rows, n, int(device), C.byref(h)))
+        self.h = h
+        self.nVars = L.rn_model_nvars(h)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rn_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- debug (the analogue of rainier-decompile) --
+    def emit_source(self, config=None):
+        cfg = lower_config(config)[0] if config is not None else None
+        need = C.c_size_t()
+        _check(lib().rn_emit_source(self.h, C.byref(cfg) if cfg else None, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().rn_emit_source(self.h, C.byref(cfg) if cfg else None, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
+    def emit_cubin(self, config=None):
+        cfg = lower_config(config)[0] if config is not None else None
+        need = C.c_size_t()
+        _check(lib().rn_emit_cubin(self.h, C.byref(cfg) if cfg else None, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().rn_emit_cubin(self.h, C.byref(cfg) if cfg else None, buf, need.value, C.byref(need)))
+        return buf.raw
+
+    def op_counts(self, config=None):
+        cfg = lower_config(config)[0] if config is not None else None
+        out = (C.c_double * 4)()
+        _check(lib().rn_model_op_counts(self.h, C.byref(cfg) if cfg else None, out))
+        return {"flops_invariant": out[0], "special_invariant": out[1], "flops_rows": out[2], "special_rows": out[3]}
+
+    # -- DensityFunction seam (sampler/DensityFunction.scala:3-8), batched --
+    def density_batch(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.nVars)
+        out = np.empty((q.shape[0], self.nVars + 1), dtype=np.float64)
+        _check(lib().rn_density_batch(self.h, q.ctypes.data, q.shape[0], out.ctypes.data))
+        return out
+
+    def density(self):
+        model = self
+
+        class _DF:  # DensityFunction
+            nVars = model.nVars
+
+            def update(self, vars):
+                self._out = model.density_batch(np.asarray(vars, dtype=np.float64)[None, :])[0]
+
+            @property
+            def density(self):
+                return self._out[0]
+
+            def gradient(self, index):
+                return self._out[index + 1]
+
+        return _DF()
+
+    # -- Model.sample --
+    def sample(self, config=None, nChains=4, seeds=None, rng_states=None, dense_mass=None):
+        """Model.sample(config, nChains) (core/Model.scala:13-24).  Chain c behaves exactly like a single-chain
+        reference run with ScalaRNG(seeds[c]).  Returns a Trace with numpy arrays."""
+        config = config or SamplerConfig()
+        cfg, keep = lower_config(config)
+        if rng_states is not None:
+            nChains = len(rng_states)
+            arr = (RngState * nChains)(*rng_states)
+            cfg.rng_states = C.cast(arr, C.POINTER(RngState))
+            seeds_a = np.zeros(nChains, dtype=np.int64)
+        else:
+            if seeds is None:
+                seeds = np.arange(nChains, dtype=np.int64) + 1
+            seeds_a = np.ascontiguousarray(seeds, dtype=np.int64)
+            nChains = len(seeds_a)
+        n = self.nVars
+        dense = cfg.mass_tuner == abi.RN_MASS_DENSE or (cfg.mass_tuner == abi.RN_MASS_STATIC and cfg.static_matrix == abi.RN_MATRIX_DENSE)
+        samples = np.empty((nChains, cfg.iterations, n), dtype=np.float64)
+        mass = np.empty((nChains, n * n if dense else n), dtype=np.float64)
+        stats = (ChainStats * nChains)()
+        rings = np.zeros((nChains, 3, cfg.stats_window), dtype=np.float64)
+        cfg.stats_rings = rings.ctypes.data_as(C.POINTER(C.c_double))
+        _check(lib().rn_sample(self.h, C.byref(cfg), seeds_a.ctypes.data, nChains, samples.ctypes.data, mass.ctypes.data,
+                               C.cast(stats, C.c_void_p)))
+        return Trace(samples, mass, [Stats(stats[c], rings[c]) for c in range(nChains)])
+
+
+class CudaSampler:
+    """Staged, device-resident sampling (what rn_sample is built from); used by bench.py and the parity tests."""
+
+    def __init__(self, model, config, seeds=None, rng_states=None, trace=False):
+        self.model = model
+        self.cfg, self._keep = lower_config(config)
+        if rng_states is not None:
+            self.chains = len(rng_states)
+            arr = (RngState * self.chains)(*rng_states)
+            self._keep.append(arr)
+            self.cfg.rng_states = C.cast(arr, C.POINTER(RngState))
+            seeds_a = np.zeros(self.chains, dtype=np.int64)
+        else:
+            seeds_a = np.ascontiguousarray(seeds, dtype=np.int64)
+            self.chains = len(seeds_a)
+        h = C.c_void_p()
+        _check(lib().rn_sampler_create(model.h, C.byref(self.cfg), seeds_a.ctypes.data, self.chains, C.byref(h)))
+        self.h = h
+        self._trace = trace
+        if trace:
+            _check(lib().rn_sampler_enable_trace(self.h))
+
+    def warmup(self, iterations=-1):
+        _check(lib().rn_sampler_warmup(self.h, int(iterations)))
+
+    def run(self, iterations, d_samples=None):
+        """d_samples: device pointer (int) to [iterations][n][chains] float64, or None."""
+        _check(lib().rn_sampler_run(self.h, int(iterations), C.c_void_p(d_samples) if d_samples else None))
+
+    def sync(self):
+        _check(lib().rn_sampler_sync(self.h))
+
+    @property
+    def stream(self):
+        return lib().rn_sampler_stream(self.h)
+
+    @property
+    def launches(self):
+        return lib().rn_sampler_launches(self.h)
+
+    def positions(self):
+        q = np.empty((self.chains, self.model.nVars), dtype=np.float64)
+        _check(lib().rn_sampler_positions(self.h, q.ctypes.data))
+        return q
+
+    def stats(self):
+        n = self.model.nVars
+        stats = (ChainStats * self.chains)()
+        dense = self.cfg.mass_tuner == abi.RN_MASS_DENSE or (self.cfg.mass_tuner == abi.RN_MASS_STATIC and self.cfg.static_matrix == abi.RN_MATRIX_DENSE)
+        mass = np.empty((self.chains, n * n if dense else n), dtype=np.float64)
+        rings = np.zeros((self.chains, 3, self.cfg.stats_window), dtype=np.float64)
+        _check(lib().rn_sampler_stats(self.h, C.cast(stats, C.c_void_p), mass.ctypes.data, rings.ctypes.data))
+        return [Stats(stats[c], rings[c]) for c in range(self.chains)], mass
+
+    def read_trace(self):
+        total = self.cfg.warmup_iterations + self.cfg.iterations
+        out = np.zeros((self.chains, total, 4), dtype=np.float64)
+        _check(lib().rn_sampler_read_trace(self.h, out.ctypes.data))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rn_sampler_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

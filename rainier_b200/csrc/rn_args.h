@@ -1,0 +1,55 @@
+// rn_args.h -- kernel argument block shared verbatim by the host runtime (rn_runtime.cpp) and the device code
+// (embedded in front of rn_sampler.cuh).  Plain C: only int / long long / double / pointers.
+#ifndef RN_ARGS_H
+#define RN_ARGS_H
+#ifndef RN_PRELUDE_CUH
+typedef long long rn_i64;
+#endif
+
+struct RnArgs {
+  int chains;  // number of chains == leading dimension of every SoA array
+  int pad0;
+  // ---- chain state, [field][chains] ----
+  double* params;   // [2N+1]: p(0..N-1), q(N..2N-1), U   (LeapFrog.scala:118-126)
+  double* grad;     // [N] gradient of log-density at params.q
+  rn_i64* rng_seed;
+  double* rng_nng;
+  int* rng_have;
+  double* da;       // [5]: stepSize, logStepSize, logStepSizeBar, avgError, shrinkageTarget
+  int* da_iter;
+  double* mass;     // diagonal: [N] variances; dense: [N*N]
+  double* chol;     // dense: packed upper Cholesky factor [N(N+1)/2]
+  double* est_mean; // [N]
+  double* est_raw;  // [N]
+  double* est_cov;  // [N*N] (dense tuner)
+  double* ring;     // EHMC trajectory-length ring [buf_size]
+  int* ring_i;
+  int* ring_full;
+  // ---- stats (Stats.scala) ----
+  rn_i64* st_grads;
+  rn_i64* st_steps;
+  int* st_iters;
+  int* st_accepted;
+  int* st_err;
+  double* st_energy;   // [3]: energyVariance.mean, energyVariance.raw, energyTransitions2
+  int* st_energy_n;
+  double* st_rings;    // [3][stats_window]: stepSizes, acceptanceRates, gradsPerIteration
+  int* st_ring_i;      // [3]
+  int* st_ring_full;   // [3]
+  // ---- data / outputs ----
+  const double* data;
+  double* samples;     // [n_iter][N][chains] or NULL
+  double* trace;       // [n_iter][4][chains] or NULL (test instrumentation)
+  // ---- configuration (uniform over chains) ----
+  int sampler, n_steps, max_steps, min_steps, buf_size, step_tuner;
+  double p_count, delta, static_step;
+  int mass_tuner, mass_kind;     // mass_kind: MassMatrix in force at the start of this launch (0 id, 1 diag, 2 dense)
+  int win_size, win_i, win_j, total_warmup, skip_first, skip_last, est_samples;
+  double win_expansion;
+  int stats_window;
+  int n_iter;                    // iterations in this launch
+  int phase;                     // 0 warmup, 1 sampling
+  int pad1;
+};
+
+#endif

@@ -1,0 +1,190 @@
+// rn_emit.cpp -- see rn_emit.hpp.
+#include "rn_emit.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <sstream>
+
+namespace rn {
+
+extern const char* kPreludeSource;  // rn_prelude.cuh, embedded at build time
+extern const char* kSamplerSource;  // rn_sampler.cuh
+
+namespace {
+
+std::string lit(double v) {
+  if (std::isnan(v)) return "RN_NAN";
+  if (std::isinf(v)) return v > 0 ? "RN_INF" : "(-RN_INF)";
+  char buf[64];
+  std::snprintf(buf, sizeof(buf), "%a", v);  // exact hex-float literal
+  std::string s(buf);
+  if (v < 0 || (v == 0 && std::signbit(v))) return "(" + s + ")";
+  return s;
+}
+
+struct Emitter {
+  const Program& P;
+  const EmitOptions& opt;
+  std::ostringstream os;
+  Emitter(const Program& p, const EmitOptions& o) : P(p), opt(o) {}
+
+  std::string val(int id) const {
+    const Node& n = P.nodes[id];
+    if (n.kind == K_CONST) return lit(n.value);
+    if (n.kind == K_INPUT) {
+      if ((uint32_t)n.a < P.n_params) return "q[" + std::to_string(n.a) + "]";
+      return "c" + std::to_string(n.a - (int)P.n_params);
+    }
+    return "v" + std::to_string(id);
+  }
+
+  std::string pow_expr(int a, int b) const {
+    const Node& e = P.nodes[b];
+    const std::string x = val(a);
+    if (e.kind == K_CONST) {
+      const double c = e.value;
+      if (c == 1.0) return x;
+      if (c == 2.0) return "(" + x + " * " + x + ")";
+      if (c == -1.0) return "(1.0 / " + x + ")";
+      if (opt.fast_math) {
+        if (c == 3.0) return "(" + x + " * " + x + " * " + x + ")";
+        if (c == 4.0) return "((" + x + " * " + x + ") * (" + x + " * " + x + "))";
+        if (c == -2.0) return "(1.0 / (" + x + " * " + x + "))";
+        if (c == 0.5) return "sqrt(" + x + ")";
+        if (c == -0.5) return "rsqrt(" + x + ")";
+        if (c == 1.5) return "(" + x + " * sqrt(" + x + "))";
+      }
+    }
+    return "rn_pow(" + x + ", " + val(b) + ")";
+  }
+
+  void stmt(int id, const char* indent) {
+    const Node& n = P.nodes[id];
+    if (n.kind == K_CONST || n.kind == K_INPUT) return;
+    os << indent << "const double v" << id << " = ";
+    switch (n.kind) {
+      case K_UNARY: {
+        const std::string x = val(n.a);
+        switch (n.op) {
+          case RIR_U_EXP: os << "exp(" << x << ")"; break;
+          case RIR_U_LOG: os << "log(" << x << ")"; break;
+          case RIR_U_ABS: os << "fabs(" << x << ")"; break;
+          case RIR_U_NOOP: os << x; break;
+          case RIR_U_SIN: os << "sin(" << x << ")"; break;
+          case RIR_U_COS: os << "cos(" << x << ")"; break;
+          case RIR_U_TAN: os << "tan(" << x << ")"; break;
+          case RIR_U_ASIN: os << "asin(" << x << ")"; break;
+          case RIR_U_ACOS: os << "acos(" << x << ")"; break;
+          case RIR_U_ATAN: os << "atan(" << x << ")"; break;
+          case U_NEG: os << "(-" << x << ")"; break;
+          case U_RECIP: os << "(1.0 / " << x << ")"; break;
+          case U_SQRT: os << "sqrt(" << x << ")"; break;
+        }
+        break;
+      }
+      case K_BINARY: {
+        const std::string x = val(n.a), y = val(n.b);
+        switch (n.op) {
+          case RIR_B_ADD: os << "(" << x << " + " << y << ")"; break;
+          case RIR_B_MUL: os << "(" << x << " * " << y << ")"; break;
+          case RIR_B_SUB: os << "(" << x << " - " << y << ")"; break;
+          case RIR_B_DIV: os << "(" << x << " / " << y << ")"; break;
+          case RIR_B_POW: os << pow_expr(n.a, n.b); break;
+          case RIR_B_COMPARE: os << "rn_compare(" << x << ", " << y << ")"; break;
+        }
+        break;
+      }
+      case K_LOOKUP: {
+        // D2I ; tableswitch ; default -> throw (ir/ExprMethodGenerator.scala:50-56): flag + NaN instead of a fault
+        os << "rn_lookup" << id << "(" << val(n.a);
+        for (int k = 0; k < n.c; k++) os << ", " << val(P.lookup_refs[n.b + k]);
+        os << ", err)";
+        break;
+      }
+      case K_SELEQ: os << "((rn_d2i(" << val(n.a) << ") == " << n.d << ") ? " << val(n.b) << " : " << val(n.c) << ")"; break;
+      case K_ACC: os << "acc[" << n.a << "]"; break;
+    }
+    os << ";\n";
+  }
+
+  // small lookups become a helper with a switch (keeps operands in registers)
+  void lookup_helpers() {
+    for (size_t id = 0; id < P.nodes.size(); id++) {
+      const Node& n = P.nodes[id];
+      if (n.kind != K_LOOKUP) continue;
+      os << "RN_DEVICE double rn_lookup" << id << "(double idx";
+      for (int k = 0; k < n.c; k++) os << ", double e" << k;
+      os << ", int& err) {\n  switch (rn_d2i(idx) - (" << n.d << ")) {\n";
+      for (int k = 0; k < n.c; k++) os << "    case " << k << ": return e" << k << ";\n";
+      os << "    default: err |= 1; return RN_NAN;\n  }\n}\n";
+    }
+  }
+
+  void density_tpc() {
+    os << "// ---- emitted: log-density and gradient of the frozen DAG (" << (P.symbolic ? "symbolic" : "adjoint")
+       << " gradient) ----\n";
+    lookup_helpers();
+    os << "RN_DEVICE void rn_density(const double (&q)[RN_N], double& dens, double (&grad)[RN_N], "
+          "const double* RN_RESTRICT data, int& err) {\n";
+    os << "  (void)data; (void)err;\n";
+    os << "  double acc[RN_NSLOTS];\n  for (int s = 0; s < RN_NSLOTS; s++) acc[s] = 0.0;\n";
+    for (int id : P.inv_fwd) stmt(id, "  ");
+    for (size_t t = 0; t < P.targets.size(); t++) {
+      const TargetInfo& T = P.targets[t];
+      os << "  // target " << t << (T.streamed() ? " (streamed)" : " (data-free)") << "\n";
+      const char* ind = "  ";
+      if (T.streamed()) {
+        os << "  for (long long row = 0; row < " << (long long)T.n_rows << "LL; row++) {\n";
+        ind = "    ";
+        std::set<int> used;
+        for (int id : T.row_fwd)
+          if (P.nodes[id].kind == K_INPUT) used.insert(P.nodes[id].a - (int)P.n_params);
+        for (int k : used)
+          os << ind << "const double c" << k << " = RN_LDG(data + " << (unsigned long long)opt.col_offsets[k]
+             << "ULL + row);\n";
+        for (int id : T.row_fwd) stmt(id, ind);
+        for (int id : T.row_bwd) stmt(id, ind);
+      }
+      for (const AccStmt& a : T.row_acc) os << ind << "acc[" << a.slot << "] += " << val(a.node) << ";\n";
+      for (const ScatterStmt& sc : T.row_scatter) {
+        os << ind << "{ const int k = rn_d2i(" << val(sc.index_node) << ") - (" << sc.low << "); if (k < 0 || k >= "
+           << sc.len << ") err |= 1; else acc[" << sc.slot_base << " + k] += " << val(sc.node) << "; }\n";
+      }
+      if (T.streamed()) os << "  }\n";
+    }
+    os << "  dens = acc[0];\n";
+    if (P.symbolic) {
+      os << "  RN_UNROLL\n  for (int i = 0; i < RN_N; i++) grad[i] = acc[1 + i];\n";
+    } else {
+      for (int id : P.inv_bwd) stmt(id, "  ");
+      for (uint32_t i = 0; i < P.n_params; i++) os << "  grad[" << i << "] = " << val(P.grad_nodes[i]) << ";\n";
+    }
+    os << "}\n";
+  }
+};
+
+}  // namespace
+
+std::string emit_density(const Program& P, const EmitOptions& opt) {
+  Emitter E(P, opt);
+  E.density_tpc();
+  return E.os.str();
+}
+
+std::string emit_source(const Program& P, const EmitOptions& opt) {
+  std::ostringstream os;
+  os << "// generated by rainier_b200 (CUDA source emitter) -- do not edit\n";
+  os << "#define RN_N " << P.n_params << "\n";
+  os << "#define RN_NSLOTS " << P.n_slots << "\n";
+  os << "#define RN_BACKEND " << opt.backend << "\n";
+  os << "#define RN_MASS_MAX " << opt.mass_max << "\n";
+  os << "#define RN_ENABLE_EHMC " << (opt.enable_ehmc ? 1 : 0) << "\n";
+  os << kPreludeSource << "\n";
+  os << emit_density(P, opt) << "\n";
+  os << kSamplerSource << "\n";
+  return os.str();
+}
+
+}  // namespace rn

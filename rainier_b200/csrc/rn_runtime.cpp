@@ -1,0 +1,978 @@
+// rn_runtime.cpp -- librainier_cuda.so: the C ABI of include/rainier_cuda.h.
+//
+// rn_model   : parses the RIR, owns the device copy of the data columns and the NVRTC-compiled modules
+//              (one per emit configuration); replaces Compiler.compileTargets + ir.CompiledFunction.
+// rn_sampler : owns per-chain device state and drives the fused kernels; replaces Driver.sample for a whole
+//              batch of chains (rainier-sampler/.../sampler/Driver.scala:7-119).
+// No CPU fallback: anything that needs to execute fails with RN_E_CUDA when there is no driver/device.
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/rainier_cuda.h"
+#include "rn_args.h"
+#include "rn_cuda_api.hpp"
+#include "rn_emit.hpp"
+#include "rn_graph.hpp"
+
+using namespace rn;
+using namespace rn::cu;
+
+// ---------------------------------------------------------------------------------------------------------
+// driver loader
+// ---------------------------------------------------------------------------------------------------------
+namespace rn {
+namespace cu {
+const Api* api(std::string* why) {
+  static Api a;
+  static bool tried = false, ok = false;
+  static std::string err;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      err = std::string("cannot load the CUDA driver (libcuda.so.1): ") + dlerror();
+    } else {
+      ok = true;
+#define RN_SYM(field, name)                                       \
+  a.field = (decltype(a.field))dlsym(h, name);                    \
+  if (!a.field) {                                                 \
+    ok = false;                                                   \
+    err = std::string("CUDA driver lacks symbol ") + name;        \
+  }
+      RN_SYM(cuInit, "cuInit")
+      RN_SYM(cuDeviceGet, "cuDeviceGet")
+      RN_SYM(cuDeviceGetCount, "cuDeviceGetCount")
+      RN_SYM(cuDeviceGetAttribute, "cuDeviceGetAttribute")
+      RN_SYM(cuDevicePrimaryCtxRetain, "cuDevicePrimaryCtxRetain")
+      RN_SYM(cuDevicePrimaryCtxRelease, "cuDevicePrimaryCtxRelease_v2")
+      RN_SYM(cuCtxSetCurrent, "cuCtxSetCurrent")
+      RN_SYM(cuCtxGetCurrent, "cuCtxGetCurrent")
+      RN_SYM(cuModuleLoadData, "cuModuleLoadData")
+      RN_SYM(cuModuleUnload, "cuModuleUnload")
+      RN_SYM(cuModuleGetFunction, "cuModuleGetFunction")
+      RN_SYM(cuMemAlloc, "cuMemAlloc_v2")
+      RN_SYM(cuMemFree, "cuMemFree_v2")
+      RN_SYM(cuMemAllocHost, "cuMemAllocHost_v2")
+      RN_SYM(cuMemFreeHost, "cuMemFreeHost")
+      RN_SYM(cuMemcpyHtoD, "cuMemcpyHtoD_v2")
+      RN_SYM(cuMemcpyDtoH, "cuMemcpyDtoH_v2")
+      RN_SYM(cuMemcpyHtoDAsync, "cuMemcpyHtoDAsync_v2")
+      RN_SYM(cuMemcpyDtoHAsync, "cuMemcpyDtoHAsync_v2")
+      RN_SYM(cuMemcpy2DAsync, "cuMemcpy2DAsync_v2")
+      RN_SYM(cuMemsetD8Async, "cuMemsetD8Async")
+      RN_SYM(cuStreamCreate, "cuStreamCreate")
+      RN_SYM(cuStreamDestroy, "cuStreamDestroy_v2")
+      RN_SYM(cuStreamSynchronize, "cuStreamSynchronize")
+      RN_SYM(cuStreamWaitEvent, "cuStreamWaitEvent")
+      RN_SYM(cuEventCreate, "cuEventCreate")
+      RN_SYM(cuEventDestroy, "cuEventDestroy_v2")
+      RN_SYM(cuEventRecord, "cuEventRecord")
+      RN_SYM(cuEventSynchronize, "cuEventSynchronize")
+      RN_SYM(cuLaunchKernel, "cuLaunchKernel")
+      RN_SYM(cuFuncGetAttribute, "cuFuncGetAttribute")
+      RN_SYM(cuGetErrorString, "cuGetErrorString")
+#undef RN_SYM
+      if (ok) {
+        CUresult r = a.cuInit(0);
+        if (r != 0) {
+          ok = false;
+          const char* s = nullptr;
+          a.cuGetErrorString(r, &s);
+          err = std::string("cuInit failed: ") + (s ? s : "?");
+        }
+      }
+    }
+  }
+  if (!ok) {
+    if (why) *why = err;
+    return nullptr;
+  }
+  return &a;
+}
+}  // namespace cu
+}  // namespace rn
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int cufail(const Api* A, CUresult r, const char* what) {
+  const char* s = nullptr;
+  if (A) A->cuGetErrorString(r, &s);
+  return fail(RN_E_CUDA, std::string(what) + ": " + (s ? s : "CUDA error ") + " (" + std::to_string(r) + ")");
+}
+#define CU(call)                                  \
+  do {                                            \
+    CUresult _r = (call);                         \
+    if (_r != 0) return cufail(A, _r, #call);     \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------------------
+struct KernelKey {
+  bool adjoint, fast, ehmc;
+  int mass_max, backend;
+  bool operator<(const KernelKey& o) const {
+    return std::tie(adjoint, fast, ehmc, mass_max, backend) < std::tie(o.adjoint, o.fast, o.ehmc, o.mass_max, o.backend);
+  }
+};
+struct Kernel {
+  std::string source;
+  std::vector<char> cubin;
+  CUmodule mod = nullptr;
+  CUfunction k_init = nullptr, k_iter = nullptr, k_density = nullptr, k_transpose = nullptr;
+  const Program* prog = nullptr;
+};
+
+struct rn_model {
+  std::vector<uint8_t> rir;
+  uint32_t n_params = 0, n_inputs = 0;
+  bool rir_has_gradient = false;
+  int device = -1;
+  CUcontext ctx = nullptr;
+  CUdeviceptr d_data = 0;
+  std::vector<uint64_t> col_offsets;
+  std::vector<int64_t> col_rows;
+  std::map<std::pair<bool, bool>, std::unique_ptr<Program>> programs;  // (adjoint, fast)
+  std::map<KernelKey, std::unique_ptr<Kernel>> kernels;
+};
+
+static int make_current(const Api* A, rn_model* m) {
+  CU(A->cuCtxSetCurrent(m->ctx));
+  return RN_OK;
+}
+
+static int get_program(rn_model* m, bool adjoint, bool fast, const Program** out) {
+  if (!m->rir_has_gradient) adjoint = true;
+  auto key = std::make_pair(adjoint, fast);
+  auto it = m->programs.find(key);
+  if (it == m->programs.end()) {
+    std::unique_ptr<Program> P(new Program());
+    std::string e = build_program(m->rir.data(), m->rir.size(), adjoint, fast, *P);
+    if (!e.empty()) return fail(RN_E_INVALID, e);
+    it = m->programs.emplace(key, std::move(P)).first;
+  }
+  *out = it->second.get();
+  return RN_OK;
+}
+
+static KernelKey key_for(const rn_model* m, const rn_config* cfg) {
+  KernelKey k;
+  const int gm = cfg ? cfg->gradient_mode : RN_GRAD_AUTO;
+  k.adjoint = (gm == RN_GRAD_ADJOINT) || !m->rir_has_gradient;
+  k.fast = cfg && cfg->math_mode == RN_MATH_FAST;
+  k.ehmc = cfg && cfg->sampler == RN_SAMPLER_EHMC;
+  k.mass_max = 0;
+  if (cfg) {
+    if (cfg->mass_tuner == RN_MASS_DIAGONAL) k.mass_max = 1;
+    if (cfg->mass_tuner == RN_MASS_DENSE) k.mass_max = 2;
+    if (cfg->mass_tuner == RN_MASS_STATIC) k.mass_max = cfg->static_matrix == RN_MATRIX_DENSE ? 2 : (cfg->static_matrix == RN_MATRIX_DIAGONAL ? 1 : 0);
+  }
+  k.backend = 0;
+  return k;
+}
+
+// emit + NVRTC (no device needed)
+static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
+  KernelKey key = key_for(m, cfg);
+  auto it = m->kernels.find(key);
+  if (it != m->kernels.end()) {
+    *out = it->second.get();
+    return RN_OK;
+  }
+  const Program* P = nullptr;
+  int rc = get_program(m, key.adjoint, key.fast, &P);
+  if (rc) return rc;
+  std::unique_ptr<Kernel> K(new Kernel());
+  K->prog = P;
+  EmitOptions eo;
+  eo.backend = key.backend;
+  eo.fast_math = key.fast;
+  eo.mass_max = key.mass_max;
+  eo.enable_ehmc = key.ehmc;
+  eo.col_offsets = m->col_offsets;
+  K->source = emit_source(*P, eo);
+
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, K->source.c_str(), "rainier_model.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    return fail(RN_E_COMPILE, "nvrtcCreateProgram failed");
+  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+  opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
+  nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    if (const char* dump = getenv("RN_DUMP_FAILED_SOURCE")) {
+      FILE* f = fopen(dump, "w");
+      if (f) {
+        fputs(K->source.c_str(), f);
+        fclose(f);
+      }
+    }
+    return fail(RN_E_COMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log);
+  }
+  size_t n = 0;
+  nvrtcGetCUBINSize(prog, &n);
+  K->cubin.resize(n);
+  nvrtcGetCUBIN(prog, K->cubin.data());
+  nvrtcDestroyProgram(&prog);
+  *out = K.get();
+  m->kernels.emplace(key, std::move(K));
+  return RN_OK;
+}
+
+static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
+  if (K->mod) return RN_OK;
+  int rc = make_current(A, m);
+  if (rc) return rc;
+  CU(A->cuModuleLoadData(&K->mod, K->cubin.data()));
+  CU(A->cuModuleGetFunction(&K->k_init, K->mod, "rn_k_init"));
+  CU(A->cuModuleGetFunction(&K->k_iter, K->mod, "rn_k_iter"));
+  CU(A->cuModuleGetFunction(&K->k_density, K->mod, "rn_k_density"));
+  CU(A->cuModuleGetFunction(&K->k_transpose, K->mod, "rn_k_transpose"));
+  return RN_OK;
+}
+
+extern "C" {
+
+const char* rn_last_error(void) { return g_err.c_str(); }
+const char* rn_version(void) { return "rainier_b200 0.1 (sm_100a, NVRTC)"; }
+
+void rn_config_default(rn_config* c) {  // DefaultConfig, sampler/Sampler.scala:17-27
+  std::memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(*c);
+  c->iterations = 1000;
+  c->warmup_iterations = 1000;
+  c->stats_window = 100;
+  c->sampler = RN_SAMPLER_EHMC;
+  c->n_steps = 1;
+  c->max_steps = 1024;
+  c->min_steps = 1;
+  c->buf_size = 100;
+  c->p_count = 0.1;
+  c->step_size_tuner = RN_STEP_DUAL_AVG;
+  c->delta = 0.8;
+  c->static_step_size = 1.0;
+  c->mass_tuner = RN_MASS_DIAGONAL;
+  c->initial_window_size = 50;
+  c->window_expansion = 1.5;
+  c->skip_first = 50;
+  c->skip_last = 50;
+}
+
+// sizes of the ABI structs, for the binding's self-check
+void rn_abi_sizes(int32_t out[4]) {
+  out[0] = (int32_t)sizeof(rn_config);
+  out[1] = (int32_t)sizeof(rn_chain_stats);
+  out[2] = (int32_t)sizeof(rn_rng_state);
+  out[3] = (int32_t)sizeof(RnArgs);
+}
+
+int rn_model_create(const void* rir, size_t len, const double* const* cols, const int64_t* col_rows, int n_cols,
+                    int device, rn_model** out) {
+  if (!rir || !out) return fail(RN_E_INVALID, "null argument");
+  std::unique_ptr<rn_model> m(new rn_model());
+  m->rir.assign((const uint8_t*)rir, (const uint8_t*)rir + len);
+  if (len < sizeof(rir_header)) return fail(RN_E_INVALID, "RIR: truncated header");
+  rir_header h;
+  std::memcpy(&h, rir, sizeof(h));
+  m->n_params = h.n_params;
+  m->n_inputs = h.n_inputs;
+  m->rir_has_gradient = (h.flags & RIR_FLAG_GRADIENT) != 0;
+  if ((int)(h.n_inputs - h.n_params) != n_cols) return fail(RN_E_INVALID, "column count does not match the RIR's inputs");
+  // validates the container (and caches the default program)
+  const Program* P = nullptr;
+  int rc = get_program(m.get(), !m->rir_has_gradient, false, &P);
+  if (rc) return rc;
+  for (const TargetInfo& T : P->targets)
+    for (uint32_t j = 0; j < T.n_cols; j++)
+      if ((uint64_t)col_rows[T.first_input - h.n_params + j] != T.n_rows)
+        return fail(RN_E_INVALID, "column length does not match its target's row count");
+  uint64_t off = 0;
+  for (int i = 0; i < n_cols; i++) {
+    m->col_offsets.push_back(off);
+    m->col_rows.push_back(col_rows[i]);
+    off += ((uint64_t)col_rows[i] + 3) & ~3ull;  // keep every column 32-byte aligned
+  }
+  m->device = device;
+  if (device >= 0) {
+    std::string why;
+    const Api* A = api(&why);
+    if (!A) return fail(RN_E_CUDA, why);
+    CUdevice dev;
+    CU(A->cuDeviceGet(&dev, device));
+    CU(A->cuDevicePrimaryCtxRetain(&m->ctx, dev));
+    CU(A->cuCtxSetCurrent(m->ctx));
+    if (off > 0) {
+      CU(A->cuMemAlloc(&m->d_data, off * 8));
+      for (int i = 0; i < n_cols; i++)
+        CU(A->cuMemcpyHtoD(m->d_data + m->col_offsets[i] * 8, cols[i], (size_t)col_rows[i] * 8));
+    }
+  }
+  *out = m.release();
+  return RN_OK;
+}
+
+int rn_model_nvars(const rn_model* m) { return m ? (int)m->n_params : RN_E_INVALID; }
+
+void rn_model_destroy(rn_model* m) {
+  if (!m) return;
+  std::string why;
+  const Api* A = m->device >= 0 ? api(&why) : nullptr;
+  if (A && m->ctx) {
+    A->cuCtxSetCurrent(m->ctx);
+    for (auto& kv : m->kernels)
+      if (kv.second->mod) A->cuModuleUnload(kv.second->mod);
+    if (m->d_data) A->cuMemFree(m->d_data);
+    CUdevice dev;
+    if (A->cuDeviceGet(&dev, m->device) == 0) A->cuDevicePrimaryCtxRelease(dev);
+  }
+  delete m;
+}
+
+int rn_emit_source(rn_model* m, const rn_config* cfg, char* buf, size_t cap, size_t* needed) {
+  if (!m) return fail(RN_E_INVALID, "null model");
+  Kernel* K = nullptr;
+  int rc = get_kernel(m, cfg, &K);
+  if (rc) return rc;
+  if (needed) *needed = K->source.size() + 1;
+  if (buf && cap) {
+    size_t n = std::min(cap - 1, K->source.size());
+    std::memcpy(buf, K->source.data(), n);
+    buf[n] = 0;
+  }
+  return RN_OK;
+}
+
+int rn_emit_cubin(rn_model* m, const rn_config* cfg, void* buf, size_t cap, size_t* needed) {
+  if (!m) return fail(RN_E_INVALID, "null model");
+  Kernel* K = nullptr;
+  int rc = get_kernel(m, cfg, &K);
+  if (rc) return rc;
+  if (needed) *needed = K->cubin.size();
+  if (buf && cap) std::memcpy(buf, K->cubin.data(), std::min(cap, K->cubin.size()));
+  return RN_OK;
+}
+
+// static op counts of one gradient evaluation: out = [flops_invariant, special_invariant, sum over streamed
+// targets of rows*flops_row, sum of rows*special_row]
+int rn_model_op_counts(rn_model* m, const rn_config* cfg, double out[4]) {
+  KernelKey key = key_for(m, cfg);
+  const Program* P = nullptr;
+  int rc = get_program(m, key.adjoint, key.fast, &P);
+  if (rc) return rc;
+  out[0] = P->counts.flops_inv;
+  out[1] = P->counts.special_inv;
+  out[2] = out[3] = 0;
+  for (size_t t = 0; t < P->targets.size(); t++) {
+    out[2] += P->counts.flops_row[t] * (double)P->targets[t].n_rows;
+    out[3] += P->counts.special_row[t] * (double)P->targets[t].n_rows;
+  }
+  return RN_OK;
+}
+
+int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
+  if (!m || !q || !out || chains <= 0) return fail(RN_E_INVALID, "bad argument");
+  if (m->device < 0) return fail(RN_E_CUDA, "model was created without a device (no CPU fallback)");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  Kernel* K = nullptr;
+  int rc = get_kernel(m, nullptr, &K);
+  if (rc) return rc;
+  rc = load_kernel(A, m, K);
+  if (rc) return rc;
+  const int n = (int)m->n_params;
+  std::vector<double> qt((size_t)n * chains), ot((size_t)(n + 1) * chains);
+  for (int c = 0; c < chains; c++)
+    for (int i = 0; i < n; i++) qt[(size_t)i * chains + c] = q[(size_t)c * n + i];
+  CUdeviceptr dq = 0, dout = 0, derr = 0;
+  CU(A->cuMemAlloc(&dq, qt.size() * 8 + 8));
+  CU(A->cuMemAlloc(&dout, ot.size() * 8));
+  CU(A->cuMemAlloc(&derr, 4));
+  CU(A->cuMemsetD8Async(derr, 0, 4, nullptr));
+  CU(A->cuMemcpyHtoD(dq, qt.data(), qt.size() * 8));
+  CUdeviceptr ddata = m->d_data;
+  int ch = chains;
+  void* params[] = {&dq, &dout, &ddata, &derr, &ch};
+  CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + 127) / 128), 1, 1, 128, 1, 1, 0, nullptr, params, nullptr));
+  CU(A->cuMemcpyDtoH(ot.data(), dout, ot.size() * 8));
+  int err = 0;
+  CU(A->cuMemcpyDtoH(&err, derr, 4));
+  A->cuMemFree(dq);
+  A->cuMemFree(dout);
+  A->cuMemFree(derr);
+  for (int c = 0; c < chains; c++)
+    for (int i = 0; i <= n; i++) out[(size_t)c * (n + 1) + i] = ot[(size_t)i * chains + c];
+  if (err & 1) return fail(RN_E_LOOKUP, "lookup index out of range");
+  return RN_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// sampler
+// ---------------------------------------------------------------------------------------------------------
+struct rn_sampler {
+  rn_model* m = nullptr;
+  rn_config cfg;
+  int chains = 0;
+  Kernel* K = nullptr;
+  CUstream stream = nullptr;
+  CUdeviceptr arena = 0;
+  size_t arena_bytes = 0;
+  size_t stats_off = 0, stats_bytes = 0;  // the block that `new Stats` zeroes
+  RnArgs args;                            // device pointers + uniform config
+  bool initialized = false;
+  int warm_done = 0;
+  bool stats_reset_for_sampling = false;
+  // host mirror of WindowedMassMatrixTuner's counters (identical for every chain)
+  int win_size = 0, win_i = 0, win_j = 0, est_samples = 0, mass_kind = 0;
+  int64_t launches = 0;
+  CUdeviceptr d_trace = 0;  // optional test instrumentation, [warmup+iterations][4][chains]
+  size_t trace_iters = 0, trace_pos = 0;
+  rn_comm* comm = nullptr;
+};
+
+namespace {
+
+struct Arena {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  }
+};
+
+int launch(const Api* A, rn_sampler* s, CUfunction f) {
+  void* params[] = {&s->args};
+  const unsigned block = 128;
+  const unsigned grid = (unsigned)((s->chains + block - 1) / block);
+  CU(A->cuLaunchKernel(f, grid, 1, 1, block, 1, 1, 0, s->stream, params, nullptr));
+  s->launches++;
+  return RN_OK;
+}
+
+// DenseMassMatrix.choleskyUpperTriangular, sampler/MassMatrix.scala:76-117 (host side, for StaticMassMatrix)
+std::vector<double> cholesky_upper(const double* matrix, int n) {
+  auto tri = [](int k) { return (k * (k + 1)) / 2; };
+  std::vector<double> lower(tri(n), 0.0), upper(tri(n), 0.0);
+  int l = 0;
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k <= i; k++) {
+      double sum = 0.0;
+      for (int j = 0; j < k; j++) sum += lower[tri(i) + j] * lower[tri(k) + j];
+      double x = matrix[i * n + k] - sum;
+      lower[l++] = (i == k) ? std::sqrt(x) : (1.0 / lower[tri(k + 1) - 1] * x);
+    }
+  l = 0;
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < n - i; k++) upper[l++] = lower[tri(k + i) + i];
+  return upper;
+}
+
+void advance_window(rn_sampler* s, int iters) {  // mirrors the device-side WindowedMassMatrixTuner.update
+  const rn_config& c = s->cfg;
+  if (c.mass_tuner != RN_MASS_DIAGONAL && c.mass_tuner != RN_MASS_DENSE) return;
+  for (int k = 0; k < iters; k++) {
+    s->win_j += 1;
+    if (s->win_j < c.skip_first || (c.warmup_iterations - s->win_j) < c.skip_last) continue;
+    s->win_i += 1;
+    s->est_samples += 1;
+    if (s->win_i == s->win_size) {
+      s->win_i = 0;
+      double w = s->win_size * c.window_expansion;
+      s->win_size = (w >= 2147483647.0) ? 2147483647 : (int)w;
+      s->mass_kind = c.mass_tuner == RN_MASS_DIAGONAL ? RN_MATRIX_DIAGONAL : RN_MATRIX_DENSE;
+    }
+  }
+}
+
+int check_config(const rn_model* m, const rn_config* c, int chains) {
+  if (!c) return fail(RN_E_INVALID, "null config");
+  if (c->struct_size != (int32_t)sizeof(rn_config)) return fail(RN_E_INVALID, "rn_config.struct_size mismatch");
+  if (chains <= 0) return fail(RN_E_INVALID, "chains must be positive");
+  if (c->iterations < 0 || c->warmup_iterations < 0 || c->stats_window <= 0) return fail(RN_E_INVALID, "bad iteration counts");
+  if (c->sampler == RN_SAMPLER_HMC) {
+    if (c->n_steps < 0) return fail(RN_E_INVALID, "n_steps < 0");
+  } else if (c->sampler == RN_SAMPLER_EHMC) {
+    if (c->max_steps < 1 || c->min_steps < 1 || c->buf_size < 1) return fail(RN_E_INVALID, "bad EHMC parameters");
+  } else {
+    return fail(RN_E_UNSUPPORTED, "only the built-in HMCSampler / EHMCSampler can be lowered to the GPU");
+  }
+  if (c->step_size_tuner != RN_STEP_DUAL_AVG && c->step_size_tuner != RN_STEP_STATIC)
+    return fail(RN_E_UNSUPPORTED, "unknown step size tuner");
+  if (c->mass_tuner < RN_MASS_IDENTITY || c->mass_tuner > RN_MASS_STATIC) return fail(RN_E_UNSUPPORTED, "unknown mass matrix tuner");
+  if (c->mass_tuner == RN_MASS_STATIC && c->static_matrix != RN_MATRIX_IDENTITY && !c->static_matrix_elements)
+    return fail(RN_E_INVALID, "static mass matrix without elements");
+  if ((c->mass_tuner == RN_MASS_DENSE || (c->mass_tuner == RN_MASS_STATIC && c->static_matrix == RN_MATRIX_DENSE)) && m->n_params > 64)
+    return fail(RN_E_UNSUPPORTED, "dense mass matrix supported for n <= 64");
+  if (c->adaptation == RN_ADAPT_POOLED && c->mass_tuner != RN_MASS_DIAGONAL)
+    return fail(RN_E_UNSUPPORTED, "pooled adaptation is implemented for the diagonal mass-matrix tuner");
+  return RN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, rn_sampler** out) {
+  if (!m || !out) return fail(RN_E_INVALID, "null argument");
+  int rc = check_config(m, cfg, chains);
+  if (rc) return rc;
+  if (!seeds && !cfg->rng_states) return fail(RN_E_INVALID, "need seeds or rng_states");
+  if (m->device < 0) return fail(RN_E_CUDA, "model was created without a device (no CPU fallback)");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  std::unique_ptr<rn_sampler> s(new rn_sampler());
+  s->m = m;
+  s->cfg = *cfg;
+  s->chains = chains;
+  rc = get_kernel(m, cfg, &s->K);
+  if (rc) return rc;
+  rc = load_kernel(A, m, s->K);
+  if (rc) return rc;
+  CU(A->cuStreamCreate(&s->stream, 1 /*CU_STREAM_NON_BLOCKING*/));
+
+  const size_t C = (size_t)chains, n = m->n_params, W = (size_t)cfg->stats_window;
+  const bool dense = s->K && (key_for(m, cfg).mass_max == 2);
+  const bool diag = key_for(m, cfg).mass_max >= 1;
+  const bool ehmc = cfg->sampler == RN_SAMPLER_EHMC;
+  Arena ar;
+  const size_t o_params = ar.take((2 * n + 1) * C * 8), o_grad = ar.take(n * C * 8), o_seed = ar.take(C * 8),
+               o_nng = ar.take(C * 8), o_have = ar.take(C * 4), o_da = ar.take(5 * C * 8), o_dait = ar.take(C * 4),
+               o_mass = ar.take((dense ? n * n : (diag ? n : 0)) * C * 8 + 8),
+               o_chol = ar.take((dense ? n * (n + 1) / 2 : 0) * C * 8 + 8), o_emean = ar.take((diag ? n : 0) * C * 8 + 8),
+               o_eraw = ar.take((diag ? n : 0) * C * 8 + 8), o_ecov = ar.take((dense ? n * n : 0) * C * 8 + 8),
+               o_ring = ar.take((ehmc ? (size_t)cfg->buf_size : 0) * C * 8 + 8), o_ri = ar.take(C * 4), o_rf = ar.take(C * 4),
+               o_err = ar.take(C * 4);
+  s->stats_off = ar.off;
+  const size_t o_sg = ar.take(C * 8), o_ss = ar.take(C * 8), o_si = ar.take(C * 4), o_sa = ar.take(C * 4),
+               o_se = ar.take(3 * C * 8), o_sen = ar.take(C * 4), o_sr = ar.take(3 * W * C * 8), o_sri = ar.take(3 * C * 4),
+               o_srf = ar.take(3 * C * 4);
+  s->stats_bytes = ar.off - s->stats_off;
+  s->arena_bytes = ar.off;
+  CU(A->cuMemAlloc(&s->arena, s->arena_bytes));
+  CU(A->cuMemsetD8Async(s->arena, 0, s->arena_bytes, s->stream));
+
+  RnArgs& a = s->args;
+  std::memset(&a, 0, sizeof(a));
+  auto P = [&](size_t o) { return (void*)(uintptr_t)(s->arena + o); };
+  a.chains = chains;
+  a.params = (double*)P(o_params);
+  a.grad = (double*)P(o_grad);
+  a.rng_seed = (rn_i64*)P(o_seed);
+  a.rng_nng = (double*)P(o_nng);
+  a.rng_have = (int*)P(o_have);
+  a.da = (double*)P(o_da);
+  a.da_iter = (int*)P(o_dait);
+  a.mass = (double*)P(o_mass);
+  a.chol = (double*)P(o_chol);
+  a.est_mean = (double*)P(o_emean);
+  a.est_raw = (double*)P(o_eraw);
+  a.est_cov = (double*)P(o_ecov);
+  a.ring = (double*)P(o_ring);
+  a.ring_i = (int*)P(o_ri);
+  a.ring_full = (int*)P(o_rf);
+  a.st_err = (int*)P(o_err);
+  a.st_grads = (rn_i64*)P(o_sg);
+  a.st_steps = (rn_i64*)P(o_ss);
+  a.st_iters = (int*)P(o_si);
+  a.st_accepted = (int*)P(o_sa);
+  a.st_energy = (double*)P(o_se);
+  a.st_energy_n = (int*)P(o_sen);
+  a.st_rings = (double*)P(o_sr);
+  a.st_ring_i = (int*)P(o_sri);
+  a.st_ring_full = (int*)P(o_srf);
+  a.data = (const double*)(uintptr_t)m->d_data;
+  a.sampler = cfg->sampler;
+  a.n_steps = cfg->n_steps;
+  a.max_steps = cfg->max_steps;
+  a.min_steps = cfg->min_steps;
+  a.buf_size = cfg->buf_size;
+  a.step_tuner = cfg->step_size_tuner;
+  a.p_count = cfg->p_count;
+  a.delta = cfg->delta;
+  a.static_step = cfg->static_step_size;
+  a.mass_tuner = cfg->mass_tuner;
+  a.total_warmup = cfg->warmup_iterations;
+  a.skip_first = cfg->skip_first;
+  a.skip_last = cfg->skip_last;
+  a.win_expansion = cfg->window_expansion;
+  a.stats_window = cfg->stats_window;
+  s->win_size = cfg->initial_window_size;
+
+  // RNG state: ScalaRNG(seed) = new java.util.Random(seed): scrambled seed (sampler/RNG.scala:20-26)
+  std::vector<int64_t> seed48(C);
+  std::vector<double> nng(C, 0.0);
+  std::vector<int32_t> have(C, 0);
+  for (size_t c = 0; c < C; c++) {
+    if (cfg->rng_states) {
+      seed48[c] = cfg->rng_states[c].seed48;
+      nng[c] = cfg->rng_states[c].next_gaussian;
+      have[c] = cfg->rng_states[c].have_next;
+    } else {
+      seed48[c] = (seeds[c] ^ 0x5DEECE66DLL) & ((1LL << 48) - 1);
+    }
+  }
+  CU(A->cuMemcpyHtoDAsync(s->arena + o_seed, seed48.data(), C * 8, s->stream));
+  CU(A->cuMemcpyHtoDAsync(s->arena + o_nng, nng.data(), C * 8, s->stream));
+  CU(A->cuMemcpyHtoDAsync(s->arena + o_have, have.data(), C * 4, s->stream));
+  // StaticMassMatrix: replicate the shared matrix to every chain (and factor it once, on the host)
+  if (cfg->mass_tuner == RN_MASS_STATIC && cfg->static_matrix != RN_MATRIX_IDENTITY) {
+    const size_t ne = cfg->static_matrix == RN_MATRIX_DENSE ? n * n : n;
+    std::vector<double> rep(ne * C);
+    for (size_t e = 0; e < ne; e++) {
+      if (cfg->static_matrix_elements[e] == 0.0)
+        return fail(RN_E_INVALID, "requirement failed: mass matrix contains 0.0 (MassMatrix.scala:8,16)");
+      for (size_t c = 0; c < C; c++) rep[e * C + c] = cfg->static_matrix_elements[e];
+    }
+    CU(A->cuMemcpyHtoDAsync(s->arena + o_mass, rep.data(), rep.size() * 8, s->stream));
+    if (cfg->static_matrix == RN_MATRIX_DENSE) {
+      std::vector<double> up = cholesky_upper(cfg->static_matrix_elements, (int)n);
+      std::vector<double> repu(up.size() * C);
+      for (size_t e = 0; e < up.size(); e++)
+        for (size_t c = 0; c < C; c++) repu[e * C + c] = up[e];
+      CU(A->cuMemcpyHtoDAsync(s->arena + o_chol, repu.data(), repu.size() * 8, s->stream));
+    }
+    CU(A->cuStreamSynchronize(s->stream));
+  }
+  CU(A->cuStreamSynchronize(s->stream));
+  *out = s.release();
+  return RN_OK;
+}
+
+// test instrumentation: per-iteration trace [warmup+iterations][4][chains] kept on the device
+int rn_sampler_enable_trace(rn_sampler* s) {
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  s->trace_iters = (size_t)s->cfg.warmup_iterations + (size_t)s->cfg.iterations;
+  CU(A->cuMemAlloc(&s->d_trace, std::max<size_t>(1, s->trace_iters) * 4 * (size_t)s->chains * 8));
+  return RN_OK;
+}
+int rn_sampler_read_trace(rn_sampler* s, double* out /*[chains][iters][4]*/) {
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  CU(A->cuStreamSynchronize(s->stream));
+  const size_t C = (size_t)s->chains, I = s->trace_pos;
+  std::vector<double> tmp(I * 4 * C);
+  CU(A->cuMemcpyDtoH(tmp.data(), s->d_trace, tmp.size() * 8));
+  for (size_t c = 0; c < C; c++)
+    for (size_t i = 0; i < I; i++)
+      for (size_t k = 0; k < 4; k++) out[(c * s->trace_iters + i) * 4 + k] = tmp[(i * 4 + k) * C + c];
+  return RN_OK;
+}
+
+static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, double* d_samples) {
+  const int per_launch = s->cfg.launch_iterations > 0 ? s->cfg.launch_iterations : 1000;
+  int done = 0;
+  while (done < iterations) {
+    const int k = std::min(per_launch, iterations - done);
+    RnArgs& a = s->args;
+    a.phase = phase;
+    a.n_iter = k;
+    a.mass_kind = s->mass_kind;
+    a.win_size = s->win_size;
+    a.win_i = s->win_i;
+    a.win_j = s->win_j;
+    a.est_samples = s->est_samples;
+    a.samples = (phase == 1 && d_samples) ? d_samples + (size_t)done * s->m->n_params * (size_t)s->chains : nullptr;
+    a.trace = s->d_trace ? (double*)(uintptr_t)(s->d_trace + s->trace_pos * 4 * (size_t)s->chains * 8) : nullptr;
+    int rc = launch(A, s, s->K->k_iter);
+    if (rc) return rc;
+    if (phase == 0) advance_window(s, k);
+    if (s->d_trace) s->trace_pos += (size_t)k;
+    done += k;
+  }
+  return RN_OK;
+}
+
+int rn_sampler_warmup(rn_sampler* s, int iterations) {
+  if (!s) return fail(RN_E_INVALID, "null sampler");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  if (!s->initialized) {
+    s->args.mass_kind = 0;
+    int rc = launch(A, s, s->K->k_init);  // LeapFrog.initialize + tuner initialisation
+    if (rc) return rc;
+    s->initialized = true;
+    if (s->cfg.mass_tuner == RN_MASS_STATIC) s->mass_kind = s->cfg.static_matrix;  // StaticMassMatrix.initialize
+  }
+  const int left = s->cfg.warmup_iterations - s->warm_done;
+  const int k = (iterations < 0 || iterations > left) ? left : iterations;
+  int rc = run_phase(A, s, 0, k, nullptr);
+  if (rc) return rc;
+  s->warm_done += k;
+  return RN_OK;
+}
+
+int rn_sampler_run(rn_sampler* s, int iterations, double* d_samples) {
+  if (!s) return fail(RN_E_INVALID, "null sampler");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  if (!s->initialized) {
+    int rc = rn_sampler_warmup(s, 0);
+    if (rc) return rc;
+  }
+  if (!s->stats_reset_for_sampling) {  // lf.resetStats(), Driver.scala:31
+    CU(A->cuMemsetD8Async(s->arena + s->stats_off, 0, s->stats_bytes, s->stream));
+    s->stats_reset_for_sampling = true;
+  }
+  return run_phase(A, s, 1, iterations, d_samples);
+}
+
+int rn_sampler_sync(rn_sampler* s) {
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  CU(A->cuStreamSynchronize(s->stream));
+  return RN_OK;
+}
+
+void* rn_sampler_stream(rn_sampler* s) { return s ? (void*)s->stream : nullptr; }
+int64_t rn_sampler_launches(const rn_sampler* s) { return s ? s->launches : 0; }
+
+int rn_sampler_positions(rn_sampler* s, double* q) {
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  CU(A->cuStreamSynchronize(s->stream));
+  const size_t C = (size_t)s->chains, n = s->m->n_params;
+  std::vector<double> tmp(n * C);
+  CU(A->cuMemcpyDtoH(tmp.data(), (CUdeviceptr)(uintptr_t)s->args.params + n * C * 8, n * C * 8));
+  for (size_t c = 0; c < C; c++)
+    for (size_t i = 0; i < n; i++) q[c * n + i] = tmp[i * C + c];
+  return RN_OK;
+}
+
+int rn_sampler_stats(rn_sampler* s, rn_chain_stats* stats, double* mass, double* stats_rings) {
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  CU(A->cuStreamSynchronize(s->stream));
+  const size_t C = (size_t)s->chains, n = s->m->n_params, W = (size_t)s->cfg.stats_window;
+  const RnArgs& a = s->args;
+  auto D = [](const void* p) { return (CUdeviceptr)(uintptr_t)p; };
+  std::vector<int32_t> err(C);
+  CU(A->cuMemcpyDtoH(err.data(), D(a.st_err), C * 4));
+  int any_err = 0;
+  for (size_t c = 0; c < C; c++) any_err |= err[c];
+  if (stats) {
+    std::vector<int64_t> sg(C), ss(C), seed(C);
+    std::vector<int32_t> si(C), sa(C), sen(C), sri(3 * C), srf(3 * C), have(C);
+    std::vector<double> se(3 * C), da(5 * C), rings(3 * W * C), nng(C);
+    CU(A->cuMemcpyDtoH(sg.data(), D(a.st_grads), C * 8));
+    CU(A->cuMemcpyDtoH(ss.data(), D(a.st_steps), C * 8));
+    CU(A->cuMemcpyDtoH(si.data(), D(a.st_iters), C * 4));
+    CU(A->cuMemcpyDtoH(sa.data(), D(a.st_accepted), C * 4));
+    CU(A->cuMemcpyDtoH(sen.data(), D(a.st_energy_n), C * 4));
+    CU(A->cuMemcpyDtoH(sri.data(), D(a.st_ring_i), 3 * C * 4));
+    CU(A->cuMemcpyDtoH(srf.data(), D(a.st_ring_full), 3 * C * 4));
+    CU(A->cuMemcpyDtoH(se.data(), D(a.st_energy), 3 * C * 8));
+    CU(A->cuMemcpyDtoH(da.data(), D(a.da), 5 * C * 8));
+    CU(A->cuMemcpyDtoH(rings.data(), D(a.st_rings), 3 * W * C * 8));
+    CU(A->cuMemcpyDtoH(seed.data(), D(a.rng_seed), C * 8));
+    CU(A->cuMemcpyDtoH(nng.data(), D(a.rng_nng), C * 8));
+    CU(A->cuMemcpyDtoH(have.data(), D(a.rng_have), C * 4));
+    for (size_t c = 0; c < C; c++) {
+      rn_chain_stats& o = stats[c];
+      std::memset(&o, 0, sizeof(o));
+      o.gradient_evaluations = sg[c];
+      o.leapfrog_steps = ss[c];
+      o.iterations = si[c];
+      o.accepted = sa[c];
+      o.error_flags = err[c];
+      // stepSizeTuner.stepSize: exp(logStepSizeBar) for DualAvg (DualAvg.scala:23-25)
+      o.step_size = s->cfg.step_size_tuner == RN_STEP_DUAL_AVG ? std::exp(da[2 * C + c]) : s->cfg.static_step_size;
+      o.energy_mean = se[0 * C + c];
+      o.energy_raw = se[1 * C + c];
+      o.energy_transitions2 = se[2 * C + c];
+      o.energy_samples = sen[c];
+      double means[3];
+      for (int r = 0; r < 3; r++) {
+        o.ring_pos[r] = sri[r * C + c];
+        o.ring_full[r] = srf[r * C + c];
+        double sum = 0.0;  // RingBuffer.mean, Stats.scala:47-58
+        for (size_t j = 0; j < W; j++) sum += rings[((size_t)r * W + j) * C + c];
+        means[r] = o.ring_full[r] ? sum / (double)W : sum / (double)o.ring_pos[r];
+        if (stats_rings)
+          for (size_t j = 0; j < W; j++) stats_rings[(c * 3 + r) * W + j] = rings[((size_t)r * W + j) * C + c];
+      }
+      o.step_sizes_mean = means[0];
+      o.acceptance_rates_mean = means[1];
+      o.grads_per_iteration_mean = means[2];
+      o.rng.seed48 = seed[c];
+      o.rng.next_gaussian = nng[c];
+      o.rng.have_next = have[c];
+    }
+  }
+  if (mass) {
+    const bool dense = s->cfg.mass_tuner == RN_MASS_DENSE || (s->cfg.mass_tuner == RN_MASS_STATIC && s->cfg.static_matrix == RN_MATRIX_DENSE);
+    const size_t ne = dense ? n * n : n;
+    if (s->mass_kind == RN_MATRIX_IDENTITY) {
+      for (size_t c = 0; c < C; c++)
+        for (size_t e = 0; e < ne; e++) mass[c * ne + e] = dense ? ((e / n == e % n) ? 1.0 : 0.0) : 1.0;
+    } else {
+      std::vector<double> tmp(ne * C);
+      CU(A->cuMemcpyDtoH(tmp.data(), D(a.mass), ne * C * 8));
+      for (size_t c = 0; c < C; c++)
+        for (size_t e = 0; e < ne; e++) mass[c * ne + e] = tmp[e * C + c];
+    }
+  }
+  if (any_err & 1) return fail(RN_E_LOOKUP, "lookup index out of range on at least one chain");
+  if (any_err & 2) return fail(RN_E_INVALID, "requirement failed: adapted mass matrix contains 0.0 (MassMatrix.scala:8,16)");
+  return RN_OK;
+}
+
+int rn_sampler_set_comm(rn_sampler* s, rn_comm* comm) {
+  s->comm = comm;
+  return RN_OK;
+}
+
+void rn_sampler_destroy(rn_sampler* s) {
+  if (!s) return;
+  std::string why;
+  const Api* A = api(&why);
+  if (A) {
+    A->cuCtxSetCurrent(s->m->ctx);
+    if (s->stream) {
+      A->cuStreamSynchronize(s->stream);
+      A->cuStreamDestroy(s->stream);
+    }
+    if (s->arena) A->cuMemFree(s->arena);
+    if (s->d_trace) A->cuMemFree(s->d_trace);
+  }
+  delete s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// rn_sample: Model.sample lowered to one call.  Host buffers in and out; the device->host copy of sample
+// chunk k overlaps the kernels of chunk k+1.
+// ---------------------------------------------------------------------------------------------------------
+int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, double* samples, double* mass,
+              rn_chain_stats* stats) {
+  rn_sampler* s = nullptr;
+  int rc = rn_sampler_create(m, cfg, seeds, chains, &s);
+  if (rc) return rc;
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  struct Guard {
+    rn_sampler* s;
+    const Api* A;
+    CUdeviceptr b[4] = {0, 0, 0, 0};
+    CUevent ev[2] = {nullptr, nullptr};
+    CUstream copy = nullptr;
+    ~Guard() {
+      for (auto p : b)
+        if (p) A->cuMemFree(p);
+      for (auto e : ev)
+        if (e) A->cuEventDestroy(e);
+      if (copy) A->cuStreamDestroy(copy);
+      rn_sampler_destroy(s);
+    }
+  } g{s, A};
+  rc = rn_sampler_warmup(s, -1);
+  if (rc) return rc;
+  const size_t C = (size_t)chains, n = m->n_params, I = (size_t)cfg->iterations;
+  if (I > 0 && samples) {
+    // chunk so that two [chunk][n][C] + two [C][chunk][n] buffers stay below ~2 GiB each
+    size_t chunk = std::max<size_t>(1, std::min<size_t>(I, ((size_t)1 << 31) / (n * C * 8 + 1)));
+    if (cfg->launch_iterations > 0) chunk = std::min<size_t>(chunk, (size_t)cfg->launch_iterations);
+    const size_t bytes = chunk * n * C * 8;
+    for (int k = 0; k < 4; k++) CU(A->cuMemAlloc(&g.b[k], bytes));
+    CU(A->cuStreamCreate(&g.copy, 1));
+    CU(A->cuEventCreate(&g.ev[0], 2 /*disable timing*/));
+    CU(A->cuEventCreate(&g.ev[1], 2));
+    CUevent copied[2] = {nullptr, nullptr};
+    CU(A->cuEventCreate(&copied[0], 2));
+    CU(A->cuEventCreate(&copied[1], 2));
+    size_t done = 0;
+    int buf = 0;
+    bool used[2] = {false, false};
+    while (done < I) {
+      const size_t k = std::min(chunk, I - done);
+      if (used[buf]) CU(A->cuStreamWaitEvent(s->stream, copied[buf], 0));  // buffer reuse
+      rc = rn_sampler_run(s, (int)k, (double*)(uintptr_t)g.b[buf]);
+      if (rc) return rc;
+      {  // [k][n][C] -> [C][k][n]
+        CUdeviceptr src = g.b[buf], dst = g.b[2 + buf];
+        int rows = (int)(k * n), cols = (int)C;
+        void* params[] = {&src, &dst, &rows, &cols};
+        CU(A->cuLaunchKernel(s->K->k_transpose, (unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), 1, 32, 8, 1, 0,
+                             s->stream, params, nullptr));
+        s->launches++;
+      }
+      CU(A->cuEventRecord(g.ev[buf], s->stream));
+      CU(A->cuStreamWaitEvent(g.copy, g.ev[buf], 0));
+      CUDA_MEMCPY2D cp;
+      std::memset(&cp, 0, sizeof(cp));
+      cp.srcMemoryType = CU_MEMORYTYPE_DEVICE;
+      cp.srcDevice = g.b[2 + buf];
+      cp.srcPitch = k * n * 8;
+      cp.dstMemoryType = CU_MEMORYTYPE_HOST;
+      cp.dstHost = samples + done * n;
+      cp.dstPitch = I * n * 8;
+      cp.WidthInBytes = k * n * 8;
+      cp.Height = C;
+      CU(A->cuMemcpy2DAsync(&cp, g.copy));
+      CU(A->cuEventRecord(copied[buf], g.copy));
+      used[buf] = true;
+      buf ^= 1;
+      done += k;
+    }
+    CU(A->cuStreamSynchronize(g.copy));
+    A->cuEventDestroy(copied[0]);
+    A->cuEventDestroy(copied[1]);
+  } else if (I > 0) {
+    rc = rn_sampler_run(s, (int)I, nullptr);
+    if (rc) return rc;
+  }
+  rc = rn_sampler_stats(s, stats, mass, cfg->stats_rings);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// communicator (NCCL) -- not wired yet
+// ---------------------------------------------------------------------------------------------------------
+int rn_comm_unique_id(char*) { return fail(RN_E_UNSUPPORTED, "NCCL communicator not available in this build"); }
+int rn_comm_create(const char*, int, int, int, rn_comm**) { return fail(RN_E_UNSUPPORTED, "NCCL communicator not available in this build"); }
+void rn_comm_destroy(rn_comm*) {}
+
+}  // extern "C"

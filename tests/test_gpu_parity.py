@@ -1,0 +1,149 @@
+"""
+GPU parity tests proper: the CUDA path, called through the C ABI (librainier_cuda.so), against the CPU oracle on the
+same seeded inputs -- bit-exact accept decisions / trajectory lengths / RNG stream position, samples within 1e-9
+relative (BASELINE.json north_star) -- and against the reference's own golden vectors.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.rainier_py import configs, sbc_models
+from oracle.rainier_py.binding import OracleModel
+from rainier_b200 import abi, api
+
+import parity
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sbc_goldsets.json")))
+
+
+def _cfg(it, warm, sampler, step, mass, **kw):
+    return api.make_config(iterations=it, warmupIterations=warm, sampler=sampler, stepSizeTuner=step,
+                           massMatrixTuner=mass, **kw)
+
+
+@pytest.fixture(scope="module")
+def funnel():
+    return configs.funnel().compile(True)
+
+
+@pytest.fixture(scope="module")
+def schools():
+    return configs.eight_schools().compile(True)
+
+
+def test_density_batch_funnel(funnel):
+    rir, cols = funnel
+    q = np.random.default_rng(1).normal(size=(257, 10)) * 1.5
+    g = api.CudaModel(rir, cols).density_batch(q)
+    o = OracleModel(rir, cols).density_batch(q)
+    assert parity.rel_err(g, o) < 1e-12
+
+
+def test_density_batch_adjoint_gradient(funnel):
+    """the emitter's own reverse-mode adjoints agree with the reference's symbolic gradient to 1e-9"""
+    primal = configs.funnel().compile(False)[0]
+    q = np.random.default_rng(2).normal(size=(64, 10))
+    g = api.CudaModel(primal, []).density_batch(q)
+    o = OracleModel(*funnel).density_batch(q)
+    assert parity.rel_err(g, o) < 1e-9
+
+
+def test_hmc_static_step_funnel(funnel):
+    r = parity.run_both(*funnel, _cfg(60, 0, api.HMCSampler(5), api.StaticStepSize(0.1), api.IdentityMassMatrixTuner()),
+                        seeds=np.arange(300) + 1000)
+    parity.assert_parity(r)
+
+
+def test_hmc_dualavg_funnel(funnel):
+    r = parity.run_both(*funnel, _cfg(50, 200, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()),
+                        seeds=np.arange(200) + 7)
+    parity.assert_parity(r)
+
+
+def test_launch_chunking_is_invisible(funnel):
+    """splitting the same run into many kernel launches must not change a single bit"""
+    a = parity.run_both(*funnel, _cfg(40, 120, api.HMCSampler(3), api.DualAvgTuner(0.8), api.DiagonalMassMatrixTuner(20, 1.5, 10, 10),
+                                     launchIterations=7), seeds=np.arange(64) + 3)
+    b = parity.run_both(*funnel, _cfg(40, 120, api.HMCSampler(3), api.DualAvgTuner(0.8), api.DiagonalMassMatrixTuner(20, 1.5, 10, 10)),
+                        seeds=np.arange(64) + 3)
+    assert np.array_equal(a["gpu"], b["gpu"])
+    parity.assert_parity(a)
+
+
+def test_default_config_eight_schools(schools):
+    """DefaultConfig: EHMCSampler(1024) + DualAvgTuner(0.8) + DiagonalMassMatrixTuner(50,1.5,50,50) (Sampler.scala:17-27)"""
+    cfg = api.SamplerConfig(iterations=100, warmupIterations=400)
+    r = parity.run_both(*schools, cfg, seeds=np.arange(128) + 11)
+    parity.assert_parity(r)
+
+
+def test_dense_mass_tuner_eight_schools(schools):
+    cfg = _cfg(50, 300, api.EHMCSampler(64, 1, 20, 0.1), api.DualAvgTuner(0.8), api.DenseMassMatrixTuner(40, 1.5, 20, 20))
+    r = parity.run_both(*schools, cfg, seeds=np.arange(64) + 5)
+    parity.assert_parity(r, tol=1e-8)
+
+
+def test_static_mass_matrices(funnel):
+    n = 10
+    diag = api.DiagonalMassMatrix(np.linspace(0.5, 2.0, n))
+    r = parity.run_both(*funnel, _cfg(30, 50, api.HMCSampler(4), api.DualAvgTuner(0.8), api.StaticMassMatrix(diag)), seeds=np.arange(32) + 1)
+    parity.assert_parity(r)
+    A = np.random.default_rng(3).normal(size=(n, n)) * 0.2 + np.eye(n) * 1.5
+    dense = api.DenseMassMatrix((A @ A.T).reshape(-1))
+    r = parity.run_both(*funnel, _cfg(30, 50, api.HMCSampler(4), api.DualAvgTuner(0.8), api.StaticMassMatrix(dense)), seeds=np.arange(32) + 1)
+    parity.assert_parity(r, tol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["SBCUniformNormal", "SBCBernoulli", "SBCExponential", "SBCLogNormal", "SBCBinomial"])
+def test_reference_goldsets_on_gpu(name):
+    """The reference's own golden vectors (SBCModel.scala:46-267, 1e-10 as in SBCTest.scala:7-15), reproduced by the
+    CUDA path: same RNG stream, 10000 warmup iterations of HMCSampler(1)/DualAvgTuner(0.8), then predict."""
+    from oracle.rainier_py.compute import Evaluator
+
+    gold = GOLD["models"][name]["goldset"]
+    model, real, rng, _ = sbc_models.build(name)
+    rir, cols = model.compile(True)
+    cfg = _cfg(len(gold), 10000, api.HMCSampler(1), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner())
+    tr = api.CudaModel(rir, cols).sample(cfg, rng_states=[rng.rand.state()])
+    params = model.parameters
+    for a, b in zip(tr.chains[0], gold):
+        v = Evaluator({p: float(x) for p, x in zip(params, a)}).toDouble(real)
+        assert abs((v - b) / b) < 1e-10
+
+
+def test_streamed_targets_match_oracle():
+    """non-inlinable likelihoods stream their data rows (Laplace: 27 columns x 125 rows + 8 rows)"""
+    model, real, rng, _ = sbc_models.build("SBCLaplace")
+    rir, cols = model.compile(True)
+    assert len(cols) > 0
+    r = parity.run_both(rir, cols, _cfg(30, 150, api.HMCSampler(2), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()),
+                        seeds=np.arange(96) + 1)
+    parity.assert_parity(r)
+
+
+def test_rn_sample_host_buffers(schools):
+    """the one-call path Model.sample lowers to: host buffers in/out, chunked D2H with on-device transpose"""
+    cfg = api.SamplerConfig(iterations=64, warmupIterations=200, launchIterations=24)
+    seeds = np.arange(50) + 100
+    tr = api.CudaModel(*schools).sample(cfg, seeds=seeds)
+    ref = OracleModel(*schools).sample(api.lower_config(cfg)[0], seeds=seeds)
+    assert parity.rel_err(tr.chains, ref["samples"]) < 1e-9
+    assert parity.rel_err(tr.mass, ref["mass"]) < 1e-8
+    for g, o in zip(tr.stats, ref["stats"]):
+        assert g.gradientEvaluations == o.gradient_evaluations and g.accepted == o.accepted
+
+
+def test_lookup_out_of_range_is_an_error():
+    """out-of-range LookupIR index: NullPointerException in the reference (ir/MethodGenerator.scala:164-167) -> RN_E_LOOKUP"""
+    from oracle.rainier_py.compute import Real, lookup_apply
+    from oracle.rainier_py.core import Model, Normal
+
+    x = Normal(0, 1).latent()
+    m = Model.likelihood(lookup_apply(x * 100, [Real.zero, Real.one], 0))
+    rir, cols = m.compile(True)
+    with pytest.raises(api.RainierCudaError) as e:
+        api.CudaModel(rir, cols).density_batch(np.array([[0.5]]))
+    assert e.value.code == abi.RN_E_LOOKUP
