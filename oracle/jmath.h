@@ -100,6 +100,247 @@ static inline double strict_log(double x) {
   }
 }
 
+static inline double with_lo_zero(double x) {
+  uint64_t u;
+  std::memcpy(&u, &x, 8);
+  u &= 0xffffffff00000000ull;
+  std::memcpy(&x, &u, 8);
+  return x;
+}
+static inline double from_words(int32_t hi, uint32_t lo) {
+  uint64_t u = ((uint64_t)(uint32_t)hi << 32) | lo;
+  double x;
+  std::memcpy(&x, &u, 8);
+  return x;
+}
+
+/* ---- fdlibm __ieee754_exp (StrictMath.exp) ---- */
+static inline double strict_exp(double x) {
+  const double one = 1.0, huge = 1.0e+300, twom1000 = 9.33263618503218878990e-302,
+               o_threshold = 7.09782712893383973096e+02, u_threshold = -7.45133219101941108420e+02,
+               invln2 = 1.44269504088896338700e+00, P1 = 1.66666666666666019037e-01,
+               P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+               P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08,
+               ln2HI0 = 6.93147180369123816490e-01, ln2LO0 = 1.90821492927058770002e-10;
+  double y, hi = 0.0, lo = 0.0, c, t;
+  int k = 0, xsb;
+  unsigned hx;
+  hx = (unsigned)hi_word(x);
+  xsb = (int)((hx >> 31) & 1u);
+  hx &= 0x7fffffffu;
+  if (hx >= 0x40862E42u) {
+    if (hx >= 0x7ff00000u) {
+      if (((hx & 0xfffffu) | lo_word(x)) != 0) return x + x;
+      return (xsb == 0) ? x : 0.0;
+    }
+    if (x > o_threshold) return huge * huge;
+    if (x < u_threshold) return twom1000 * twom1000;
+  }
+  if (hx > 0x3fd62e42u) {
+    if (hx < 0x3FF0A2B2u) {
+      hi = x - (xsb ? -ln2HI0 : ln2HI0);
+      lo = xsb ? -ln2LO0 : ln2LO0;
+      k = 1 - xsb - xsb;
+    } else {
+      k = (int)(invln2 * x + (xsb ? -0.5 : 0.5));
+      t = k;
+      hi = x - t * ln2HI0;
+      lo = t * ln2LO0;
+    }
+    x = hi - lo;
+  } else if (hx < 0x3e300000u) {
+    if (huge + x > one) return one + x;
+  } else
+    k = 0;
+  t = x * x;
+  c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  if (k == 0) return one - ((x * c) / (c - 2.0) - x);
+  y = one - ((lo - (x * c) / (2.0 - c)) - hi);
+  if (k >= -1021) return with_hi_word(y, hi_word(y) + (k << 20));
+  y = with_hi_word(y, hi_word(y) + ((k + 1000) << 20));
+  return y * twom1000;
+}
+
+/* ---- fdlibm __ieee754_pow (StrictMath.pow) ---- */
+static inline double strict_pow(double x, double y) {
+  const double zero = 0.0, one = 1.0, two = 2.0, two53 = 9007199254740992.0, huge = 1.0e300, tiny = 1.0e-300,
+               L1 = 5.99999999999994648725e-01, L2 = 4.28571428578550184252e-01, L3 = 3.33333329818377432918e-01,
+               L4 = 2.72728123808534006489e-01, L5 = 2.30660745775561754067e-01, L6 = 2.06975017800338417784e-01,
+               P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+               P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08, lg2 = 6.93147180559945286227e-01,
+               lg2_h = 6.93147182464599609375e-01, lg2_l = -1.90465429995776804525e-09,
+               ovt = 8.0085662595372944372e-0017, cp = 9.61796693925975554329e-01, cp_h = 9.61796700954437255859e-01,
+               cp_l = -7.02846165095275826516e-09, ivln2 = 1.44269504088896338700e+00,
+               ivln2_h = 1.44269502162933349609e+00, ivln2_l = 1.92596299112661746887e-08;
+  double z, ax, z_h, z_l, p_h, p_l;
+  double y1, t1, t2, r, s, t, u, v, w;
+  int i, j, k, yisint, n;
+  int hx, hy, ix, iy;
+  unsigned lx, ly;
+  hx = hi_word(x);
+  lx = lo_word(x);
+  hy = hi_word(y);
+  ly = lo_word(y);
+  ix = hx & 0x7fffffff;
+  iy = hy & 0x7fffffff;
+  if ((iy | ly) == 0) return one;
+  if (ix > 0x7ff00000 || ((ix == 0x7ff00000) && (lx != 0)) || iy > 0x7ff00000 || ((iy == 0x7ff00000) && (ly != 0)))
+    return x + y;
+  yisint = 0;
+  if (hx < 0) {
+    if (iy >= 0x43400000)
+      yisint = 2;
+    else if (iy >= 0x3ff00000) {
+      k = (iy >> 20) - 0x3ff;
+      if (k > 20) {
+        j = (int)(ly >> (52 - k));
+        if (((unsigned)j << (52 - k)) == ly) yisint = 2 - (j & 1);
+      } else if (ly == 0) {
+        j = iy >> (20 - k);
+        if ((j << (20 - k)) == iy) yisint = 2 - (j & 1);
+      }
+    }
+  }
+  if (ly == 0) {
+    if (iy == 0x7ff00000) {
+      if (((ix - 0x3ff00000) | lx) == 0) return y - y;
+      if (ix >= 0x3ff00000) return (hy >= 0) ? y : zero;
+      return (hy < 0) ? -y : zero;
+    }
+    if (iy == 0x3ff00000) {
+      if (hy < 0) return one / x;
+      return x;
+    }
+    if (hy == 0x40000000) return x * x;
+    if (hy == 0x3fe00000) {
+      if (hx >= 0) return std::sqrt(x);
+    }
+  }
+  ax = std::fabs(x);
+  if (lx == 0) {
+    if (ix == 0x7ff00000 || ix == 0 || ix == 0x3ff00000) {
+      z = ax;
+      if (hy < 0) z = one / z;
+      if (hx < 0) {
+        if (((ix - 0x3ff00000) | yisint) == 0) {
+          z = (z - z) / (z - z);
+        } else if (yisint == 1)
+          z = -z;
+      }
+      return z;
+    }
+  }
+  n = (hx < 0) ? 0 : 1; /* fdlibm: n = (hx>>31)+1 with an arithmetic shift */
+  if ((n | yisint) == 0) return (x - x) / (x - x);
+  s = one;
+  if ((n | (yisint - 1)) == 0) s = -one;
+  if (iy > 0x41e00000) {
+    if (iy > 0x43f00000) {
+      if (ix <= 0x3fefffff) return (hy < 0) ? huge * huge : tiny * tiny;
+      if (ix >= 0x3ff00000) return (hy > 0) ? huge * huge : tiny * tiny;
+    }
+    if (ix < 0x3fefffff) return (hy < 0) ? s * huge * huge : s * tiny * tiny;
+    if (ix > 0x3ff00000) return (hy > 0) ? s * huge * huge : s * tiny * tiny;
+    t = ax - one;
+    w = (t * t) * (0.5 - t * (0.3333333333333333333333 - t * 0.25));
+    u = ivln2_h * t;
+    v = t * ivln2_l - w * ivln2;
+    t1 = u + v;
+    t1 = with_lo_zero(t1);
+    t2 = v - (t1 - u);
+  } else {
+    double ss, s2, s_h, s_l, t_h, t_l, bpk, dphk, dplk;
+    n = 0;
+    if (ix < 0x00100000) {
+      ax *= two53;
+      n -= 53;
+      ix = hi_word(ax);
+    }
+    n += ((ix) >> 20) - 0x3ff;
+    j = ix & 0x000fffff;
+    ix = j | 0x3ff00000;
+    if (j <= 0x3988E)
+      k = 0;
+    else if (j < 0xBB67A)
+      k = 1;
+    else {
+      k = 0;
+      n += 1;
+      ix -= 0x00100000;
+    }
+    ax = with_hi_word(ax, ix);
+    bpk = k ? 1.5 : 1.0;
+    dphk = k ? 5.84962487220764160156e-01 : 0.0;
+    dplk = k ? 1.35003920212974897128e-08 : 0.0;
+    u = ax - bpk;
+    v = one / (ax + bpk);
+    ss = u * v;
+    s_h = with_lo_zero(ss);
+    t_h = from_words(((ix >> 1) | 0x20000000) + 0x00080000 + (k << 18), 0u);
+    t_l = ax - (t_h - bpk);
+    s_l = v * ((u - s_h * t_h) - s_h * t_l);
+    s2 = ss * ss;
+    r = s2 * s2 * (L1 + s2 * (L2 + s2 * (L3 + s2 * (L4 + s2 * (L5 + s2 * L6)))));
+    r += s_l * (s_h + ss);
+    s2 = s_h * s_h;
+    t_h = 3.0 + s2 + r;
+    t_h = with_lo_zero(t_h);
+    t_l = r - ((t_h - 3.0) - s2);
+    u = s_h * t_h;
+    v = s_l * t_h + t_l * ss;
+    p_h = u + v;
+    p_h = with_lo_zero(p_h);
+    p_l = v - (p_h - u);
+    z_h = cp_h * p_h;
+    z_l = cp_l * p_h + p_l * cp + dplk;
+    t = (double)n;
+    t1 = (((z_h + z_l) + dphk) + t);
+    t1 = with_lo_zero(t1);
+    t2 = z_l - (((t1 - t) - dphk) - z_h);
+  }
+  y1 = with_lo_zero(y);
+  p_l = (y - y1) * t1 + y * t2;
+  p_h = y1 * t1;
+  z = p_l + p_h;
+  j = hi_word(z);
+  i = (int)lo_word(z);
+  if (j >= 0x40900000) {
+    if (((j - 0x40900000) | i) != 0) return s * huge * huge;
+    if (p_l + ovt > z - p_h) return s * huge * huge;
+  } else if ((j & 0x7fffffff) >= 0x4090cc00) {
+    if (((j - (int)0xc090cc00) | i) != 0) return s * tiny * tiny;
+    if (p_l <= z - p_h) return s * tiny * tiny;
+  }
+  i = j & 0x7fffffff;
+  k = (i >> 20) - 0x3ff;
+  n = 0;
+  if (i > 0x3fe00000) {
+    n = j + (0x00100000 >> (k + 1));
+    k = ((n & 0x7fffffff) >> 20) - 0x3ff;
+    t = from_words(n & ~(0x000fffff >> k), 0u);
+    n = ((n & 0x000fffff) | 0x00100000) >> (20 - k);
+    if (j < 0) n = -n;
+    p_h -= t;
+  }
+  t = p_l + p_h;
+  t = with_lo_zero(t);
+  u = t * lg2_h;
+  v = (p_l - (t - p_h)) * lg2 + t * lg2_l;
+  z = u + v;
+  w = v - (z - u);
+  t = z * z;
+  t1 = z - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  r = (z * t1) / (t1 - two) - (w + z * w);
+  z = one - (r - z);
+  j = hi_word(z);
+  j += (n << 20);
+  if ((j >> 20) <= 0)
+    z = std::scalbn(z, n);
+  else
+    z = with_hi_word(z, hi_word(z) + (n << 20));
+  return s * z;
+}
+
 /* ---- java.util.Random ----------------------------------------------------------------------------------- */
 struct JRandom {
   int64_t seed; /* scrambled 48-bit state */
@@ -139,12 +380,13 @@ struct JRandom {
 };
 
 /* ---- java.lang.Math corner cases -------------------------------------------------------------------------- */
-static inline double jpow(double x, double y) {
-  if (y == 0.0) return 1.0;
-  if (std::isnan(y)) return std::numeric_limits<double>::quiet_NaN();
-  if (std::isinf(y) && std::fabs(x) == 1.0) return std::numeric_limits<double>::quiet_NaN();
-  return std::pow(x, y);
-}
+/* java.lang.Math.{exp,log,pow} are specified only to 1 ulp and may delegate to StrictMath (they do when HotSpot's
+ * intrinsics are off).  The oracle pins them to StrictMath = fdlibm, a bit-specified choice the JVM spec allows, so
+ * that the CUDA path (which carries the same fdlibm restatement) can be compared bit for bit even where HMC
+ * dynamics are chaotic (early warmup). */
+static inline double jpow(double x, double y) { return strict_pow(x, y); }
+static inline double jexp(double x) { return strict_exp(x); }
+static inline double jlog(double x) { return strict_log(x); }
 /* Math.min: NaN if either is NaN; -0.0 < +0.0 */
 static inline double jmin(double a, double b) {
   if (a != a) return a;

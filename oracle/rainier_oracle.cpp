@@ -241,8 +241,8 @@ struct RirDensity : DensityFunction {
       case RIR_UNARY: {
         double x = vals[nd.a];
         switch (nd.op) { /* IR/MethodGenerator.scala:74-94 : java.lang.Math.* */
-          case RIR_U_EXP: r = std::exp(x); break;
-          case RIR_U_LOG: r = std::log(x); break;
+          case RIR_U_EXP: r = jexp(x); break;
+          case RIR_U_LOG: r = jlog(x); break;
           case RIR_U_ABS: r = std::fabs(x); break;
           case RIR_U_NOOP: r = x; break;
           case RIR_U_SIN: r = std::sin(x); break;
@@ -549,7 +549,7 @@ struct LeapFrog {
     double deltaH = endH - startH;
     double a = logAcceptanceProb(deltaH);
     lastLogAcceptanceProb = a;
-    if (a > std::log(rng.standardUniform())) {
+    if (a > jlog(rng.standardUniform())) {
       copy(pqBuf, params);
       stats.energyVariance.update1(endH);
       stats.energyTransitions2 += jpow(endH - prevH, 2);
@@ -559,7 +559,7 @@ struct LeapFrog {
       stats.energyTransitions2 += jpow(startH - prevH, 2);
     }
     stats.iterations += 1;
-    stats.acceptanceRates.add(std::exp(a));
+    stats.acceptanceRates.add(jexp(a));
     stats.gradsPerIteration.add((double)(stats.gradientEvaluations - iterationStartGrads));
     return a;
   }
@@ -595,7 +595,7 @@ struct LeapFrog {
   }
 
   static double logAcceptanceProb(double deltaH) { /* :141-145 */
-    if (deltaH != deltaH) return std::log(0.0);
+    if (deltaH != deltaH) return jlog(0.0);
     return jmin(-deltaH, 0.0);
   }
 
@@ -757,10 +757,10 @@ struct DualAvg { /* S/DualAvg.scala:44-77 */
   double stepSizeUpdateDenom = 0.05;
   int acceptanceProbUpdateDenom = 10;
   double decayRate = 0.75;
-  double stepSize() const { return std::exp(logStepSize); }
-  double finalStepSize() const { return std::exp(logStepSizeBar); }
+  double stepSize() const { return jexp(logStepSize); }
+  double finalStepSize() const { return jexp(logStepSizeBar); }
   void update(double logAcceptanceProb) { /* :58-77 */
-    double newAcceptanceProb = std::exp(logAcceptanceProb);
+    double newAcceptanceProb = jexp(logAcceptanceProb);
     iteration = iteration + 1;
     double avgErrorMultiplier = 1.0 / ((double)iteration + acceptanceProbUpdateDenom);
     double stepSizeMultiplier = jpow((double)iteration, -decayRate);
@@ -771,11 +771,11 @@ struct DualAvg { /* S/DualAvg.scala:44-77 */
   static DualAvg apply(double delta, double stepSize) { /* :80-90 */
     DualAvg d;
     d.delta = delta;
-    d.logStepSize = std::log(stepSize);
+    d.logStepSize = jlog(stepSize);
     d.logStepSizeBar = 0.0;
     d.avgError = 0.0;
     d.iteration = 0;
-    d.shrinkageTarget = std::log(10 * stepSize);
+    d.shrinkageTarget = jlog(10 * stepSize);
     return d;
   }
 };
@@ -803,9 +803,9 @@ struct DualAvgTuner : StepSizeTuner { /* S/DualAvg.scala:3-42 */
   double findReasonableStepSize(std::vector<double>& params, LeapFrog& lf, const MassMatrix& mass) { /* :27-41 */
     double stepSize = 1.0;
     double logAcceptanceProb = lf.tryStepping(params, stepSize, mass);
-    double exponent = (logAcceptanceProb > std::log(0.5)) ? 1.0 : -1.0;
+    double exponent = (logAcceptanceProb > jlog(0.5)) ? 1.0 : -1.0;
     double doubleOrHalf = jpow(2, exponent);
-    while (stepSize != 0.0 && (exponent * logAcceptanceProb > -exponent * std::log(2))) {
+    while (stepSize != 0.0 && (exponent * logAcceptanceProb > -exponent * jlog(2))) {
       stepSize *= doubleOrHalf;
       logAcceptanceProb = lf.tryStepping(params, stepSize, mass);
     }
@@ -1174,5 +1174,9 @@ void rno_jr_gaussians(rn_rng_state* st, double* out, int64_t n) {
 }
 double rno_strict_log(double x) { return strict_log(x); }
 double rno_jpow(double x, double y) { return jpow(x, y); }
+double rno_strict_exp(double x) { return strict_exp(x); }
+void rno_vec_math(int which, const double* x, const double* y, double* out, int64_t n) {
+  for (int64_t i = 0; i < n; i++) out[i] = which == 0 ? strict_exp(x[i]) : (which == 1 ? strict_log(x[i]) : strict_pow(x[i], y[i]));
+}
 
 } /* extern "C" */

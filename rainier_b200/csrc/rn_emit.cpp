@@ -68,8 +68,8 @@ struct Emitter {
       case K_UNARY: {
         const std::string x = val(n.a);
         switch (n.op) {
-          case RIR_U_EXP: os << "exp(" << x << ")"; break;
-          case RIR_U_LOG: os << "log(" << x << ")"; break;
+          case RIR_U_EXP: os << "rn_exp(" << x << ")"; break;
+          case RIR_U_LOG: os << "rn_log(" << x << ")"; break;
           case RIR_U_ABS: os << "fabs(" << x << ")"; break;
           case RIR_U_NOOP: os << x; break;
           case RIR_U_SIN: os << "sin(" << x << ")"; break;
@@ -181,6 +181,7 @@ std::string emit_source(const Program& P, const EmitOptions& opt) {
   os << "#define RN_BACKEND " << opt.backend << "\n";
   os << "#define RN_MASS_MAX " << opt.mass_max << "\n";
   os << "#define RN_ENABLE_EHMC " << (opt.enable_ehmc ? 1 : 0) << "\n";
+  if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
   os << kPreludeSource << "\n";
   os << emit_density(P, opt) << "\n";
   os << kSamplerSource << "\n";

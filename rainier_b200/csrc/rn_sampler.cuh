@@ -262,10 +262,10 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
       lap = rn_log_accept(rn_energy(A, c, M, s.p, s.U) - H0);
     }
     // DualAvg.apply, DualAvg.scala:80-90
-    RN_AT(A.da, 1, c) = log(stepSize);
+    RN_AT(A.da, 1, c) = rn_log(stepSize);
     RN_AT(A.da, 2, c) = 0.0;
     RN_AT(A.da, 3, c) = 0.0;
-    RN_AT(A.da, 4, c) = log(10 * stepSize);
+    RN_AT(A.da, 4, c) = rn_log(10 * stepSize);
     A.da_iter[c] = 0;
   } else {
     stepSize = A.static_step;
@@ -303,7 +303,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
   rn_load_mass(A, c, M);
 
   // step size in force: warmup uses the tuner's running value; sampling uses stepSizeTuner.stepSize
-  // (= exp(logStepSizeBar) for DualAvg, Driver.scala:37 / DualAvg.scala:23-25)
+  // (= rn_exp(logStepSizeBar) for DualAvg, Driver.scala:37 / DualAvg.scala:23-25)
   double stepSize = RN_AT(A.da, 0, c);
   double logStepSize = 0, logStepSizeBar = 0, avgError = 0, shrinkageTarget = 0;
   int daIter = 0;
@@ -313,7 +313,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     avgError = RN_AT(A.da, 3, c);
     shrinkageTarget = RN_AT(A.da, 4, c);
     daIter = A.da_iter[c];
-    if (A.phase == 1) stepSize = exp(logStepSizeBar);
+    if (A.phase == 1) stepSize = rn_exp(logStepSizeBar);
   }
   int win_size = A.win_size, win_i = A.win_i, win_j = A.win_j, est_samples = A.est_samples;
 #if RN_ENABLE_EHMC
@@ -390,7 +390,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     const double endH = rn_energy(A, c, M, s.p, s.U);
     const double deltaH = endH - startH;
     const double a = rn_log_accept(deltaH);
-    const bool accept = a > log(rn_uniform(rng));
+    const bool accept = a > rn_log(rn_uniform(rng));
     double eH;
     if (accept) {
       RN_UNROLL
@@ -418,7 +418,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
       S.trans2 += d * d;
     }
     S.iters += 1;
-    rn_ring_add(A, c, S, 1, exp(a));
+    rn_ring_add(A, c, S, 1, rn_exp(a));
     rn_ring_add(A, c, S, 2, (double)(S.grads - iterationStartGrads));
 
     if (A.trace) {
@@ -432,14 +432,14 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     if (A.phase == 0) {
       // ---------------- stepSizeTuner.update, Driver.scala:69 / DualAvg.scala:58-77 ----------------
       if (A.step_tuner == 0) {
-        const double newAcceptanceProb = exp(a);
+        const double newAcceptanceProb = rn_exp(a);
         daIter = daIter + 1;
         const double avgErrorMultiplier = 1.0 / ((double)daIter + 10);
         const double stepSizeMultiplier = rn_pow((double)daIter, -0.75);
         avgError = ((1.0 - avgErrorMultiplier) * avgError + (avgErrorMultiplier * (A.delta - newAcceptanceProb)));
         logStepSize = (shrinkageTarget - (avgError * sqrt((double)daIter) / 0.05));
         logStepSizeBar = (stepSizeMultiplier * logStepSize + (1.0 - stepSizeMultiplier) * logStepSizeBar);
-        stepSize = exp(logStepSize);
+        stepSize = rn_exp(logStepSize);
       }
       // ---------------- massMatrixTuner.update(sample), Driver.scala:74-80 / MassMatrix.scala:147-164 -------
 #if RN_MASS_MAX >= 1
@@ -518,12 +518,12 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
 #endif
             // stepSize = stepSizeTuner.reset(), Driver.scala:78 / DualAvg.scala:17-21
             if (A.step_tuner == 0) {
-              const double ss = exp(logStepSizeBar);
-              logStepSize = log(ss);
+              const double ss = rn_exp(logStepSizeBar);
+              logStepSize = rn_log(ss);
               logStepSizeBar = 0.0;
               avgError = 0.0;
               daIter = 0;
-              shrinkageTarget = log(10 * ss);
+              shrinkageTarget = rn_log(10 * ss);
               stepSize = ss;
             }
           }
