@@ -164,7 +164,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--chains", type=int, default=131072, help="chains per GPU")
+    ap.add_argument("--chains", type=int, default=151552,
+                    help="chains per GPU; default = 148 SMs x 4 resident CTAs x 128 threads x 2 waves")
     ap.add_argument("--iters", type=int, default=100, help="HMC iterations per step")
     ap.add_argument("--math", default="parity", choices=["parity", "fast"])
     ap.add_argument("--grad", default="auto", choices=["auto", "symbolic", "adjoint"])

@@ -12,11 +12,15 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -218,6 +222,17 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
     return fail(RN_E_COMPILE, "nvrtcCreateProgram failed");
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
+  std::string maxreg;
+  {
+    // registers/thread: the fused iteration kernel is latency-bound on dependent fp64 chains, so occupancy matters
+    // more than a few spills (profiles/r1_ncu_rn_k_iter_funnel_*: 240 regs -> 8 warps/SM, fp64 pipe 30% busy)
+    int cap = P->n_params <= 16 ? 128 : 0;
+    if (const char* e = getenv("RN_MAXRREGCOUNT")) cap = atoi(e);
+    if (cap > 0) {
+      maxreg = "--maxrregcount=" + std::to_string(cap);
+      opts.push_back(maxreg.c_str());
+    }
+  }
   nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   if (r != NVRTC_SUCCESS) {
     size_t n = 0;
@@ -470,7 +485,7 @@ struct Arena {
 
 int launch(const Api* A, rn_sampler* s, CUfunction f) {
   void* params[] = {&s->args};
-  const unsigned block = 128;
+  static const unsigned block = getenv("RN_BLOCK") ? (unsigned)atoi(getenv("RN_BLOCK")) : 128u;
   const unsigned grid = (unsigned)((s->chains + block - 1) / block);
   CU(A->cuLaunchKernel(f, grid, 1, 1, block, 1, 1, 0, s->stream, params, nullptr));
   s->launches++;
@@ -882,9 +897,131 @@ void rn_sampler_destroy(rn_sampler* s) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// rn_sample: Model.sample lowered to one call.  Host buffers in and out; the device->host copy of sample
-// chunk k overlaps the kernels of chunk k+1.
+// rn_sample: Model.sample lowered to one call.  Host buffers in and out.
+//
+// Samples are produced chain-fastest ([iteration][n][chain], coalesced stores), re-laid on the device into the
+// caller's [chain][iteration][n] order, and drained to the (pageable) caller buffer through a ring of pinned
+// staging buffers: slice k's PCIe copy overlaps the host-side memcpy of slice k-1 (worker threads).
 // ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+struct PinnedRing {  // process-wide, grown on demand, never freed (pinning is expensive)
+  static constexpr int R = 4;
+  void* buf[R] = {nullptr, nullptr, nullptr, nullptr};
+  size_t bytes = 0;
+  std::mutex mu;
+};
+PinnedRing g_ring;
+
+class Workers {  // tiny job pool for the pinned->user memcpy
+ public:
+  explicit Workers(int n) {
+    for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
+  }
+  ~Workers() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void submit(int group, std::function<void()> f) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      pending_[group]++;
+      q_.push_back({group, std::move(f)});
+    }
+    cv_.notify_one();
+  }
+  void wait(int group) {
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_[group] == 0; });
+  }
+
+ private:
+  void loop() {
+    for (;;) {
+      std::pair<int, std::function<void()>> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;
+        job = std::move(q_.front());
+        q_.pop_front();
+      }
+      job.second();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        pending_[job.first]--;
+      }
+      done_.notify_all();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::deque<std::pair<int, std::function<void()>>> q_;
+  std::map<int, int> pending_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  bool stop_ = false;
+};
+
+int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, size_t bytes) {
+  const size_t slice = (size_t)32 << 20;
+  {
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    if (g_ring.bytes < slice) {
+      for (int r = 0; r < PinnedRing::R; r++) CU(A->cuMemAllocHost(&g_ring.buf[r], slice));
+      g_ring.bytes = slice;
+    }
+  }
+  std::lock_guard<std::mutex> lk(g_ring.mu);  // one drain at a time per process
+  const int T = 4;
+  Workers pool(T);
+  CUevent ev[PinnedRing::R];
+  for (int r = 0; r < PinnedRing::R; r++) CU(A->cuEventCreate(&ev[r], 2));
+  const size_t n_slices = (bytes + slice - 1) / slice;
+  auto finish = [&](size_t k) -> int {  // slice k has landed in pinned memory: fan its memcpy out
+    const int slot = (int)(k % PinnedRing::R);
+    CU(A->cuEventSynchronize(ev[slot]));
+    const size_t off = k * slice, len = std::min(slice, bytes - off);
+    const size_t part = ((len / T) + 4095) & ~(size_t)4095;
+    for (int t = 0; t < T; t++) {
+      const size_t o = (size_t)t * part;
+      if (o >= len) break;
+      const size_t l = std::min(part, len - o);
+      char* d = (char*)dst + off + o;
+      const char* sp = (const char*)g_ring.buf[slot] + o;
+      pool.submit(slot, [d, sp, l] { std::memcpy(d, sp, l); });
+    }
+    return RN_OK;
+  };
+  for (size_t k = 0; k < n_slices; k++) {
+    const int slot = (int)(k % PinnedRing::R);
+    pool.wait(slot);  // previous occupant of this slot fully copied out
+    const size_t off = k * slice, len = std::min(slice, bytes - off);
+    CU(A->cuMemcpyDtoHAsync(g_ring.buf[slot], src + off, len, copy));
+    CU(A->cuEventRecord(ev[slot], copy));
+    if (k >= 1) {
+      int rc = finish(k - 1);
+      if (rc) return rc;
+    }
+  }
+  if (n_slices) {
+    int rc = finish(n_slices - 1);
+    if (rc) return rc;
+  }
+  for (int r = 0; r < PinnedRing::R; r++) pool.wait(r);
+  for (int r = 0; r < PinnedRing::R; r++) A->cuEventDestroy(ev[r]);
+  return RN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, double* samples, double* mass,
               rn_chain_stats* stats) {
   rn_sampler* s = nullptr;
@@ -896,14 +1033,13 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
   struct Guard {
     rn_sampler* s;
     const Api* A;
-    CUdeviceptr b[4] = {0, 0, 0, 0};
-    CUevent ev[2] = {nullptr, nullptr};
+    CUdeviceptr b[2] = {0, 0};
     CUstream copy = nullptr;
+    CUevent done = nullptr;
     ~Guard() {
       for (auto p : b)
         if (p) A->cuMemFree(p);
-      for (auto e : ev)
-        if (e) A->cuEventDestroy(e);
+      if (done) A->cuEventDestroy(done);
       if (copy) A->cuStreamDestroy(copy);
       rn_sampler_destroy(s);
     }
@@ -912,54 +1048,54 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
   if (rc) return rc;
   const size_t C = (size_t)chains, n = m->n_params, I = (size_t)cfg->iterations;
   if (I > 0 && samples) {
-    // chunk so that two [chunk][n][C] + two [C][chunk][n] buffers stay below ~2 GiB each
-    size_t chunk = std::max<size_t>(1, std::min<size_t>(I, ((size_t)1 << 31) / (n * C * 8 + 1)));
+    const size_t total = C * I * n * 8;
+    // the whole [C][I][n] result stays on the device while it is produced; runs larger than the cap are cut into
+    // passes over the iteration axis (each pass drained with a strided copy)
+    size_t cap = (size_t)32 << 30;
+    if (const char* e = getenv("RN_SAMPLE_DEVICE_CAP_MB")) cap = (size_t)atoll(e) << 20;
+    const size_t pass_iters = std::max<size_t>(1, std::min<size_t>(I, cap / std::max<size_t>(1, C * n * 8)));
+    size_t chunk = std::max<size_t>(1, std::min<size_t>(pass_iters, ((size_t)1 << 30) / (n * C * 8 + 1)));
     if (cfg->launch_iterations > 0) chunk = std::min<size_t>(chunk, (size_t)cfg->launch_iterations);
-    const size_t bytes = chunk * n * C * 8;
-    for (int k = 0; k < 4; k++) CU(A->cuMemAlloc(&g.b[k], bytes));
+    CU(A->cuMemAlloc(&g.b[0], chunk * n * C * 8));       // [chunk][n][C] scratch
+    CU(A->cuMemAlloc(&g.b[1], pass_iters * n * C * 8));  // [C][pass_iters][n]
     CU(A->cuStreamCreate(&g.copy, 1));
-    CU(A->cuEventCreate(&g.ev[0], 2 /*disable timing*/));
-    CU(A->cuEventCreate(&g.ev[1], 2));
-    CUevent copied[2] = {nullptr, nullptr};
-    CU(A->cuEventCreate(&copied[0], 2));
-    CU(A->cuEventCreate(&copied[1], 2));
-    size_t done = 0;
-    int buf = 0;
-    bool used[2] = {false, false};
-    while (done < I) {
-      const size_t k = std::min(chunk, I - done);
-      if (used[buf]) CU(A->cuStreamWaitEvent(s->stream, copied[buf], 0));  // buffer reuse
-      rc = rn_sampler_run(s, (int)k, (double*)(uintptr_t)g.b[buf]);
-      if (rc) return rc;
-      {  // [k][n][C] -> [C][k][n]
-        CUdeviceptr src = g.b[buf], dst = g.b[2 + buf];
+    CU(A->cuEventCreate(&g.done, 2));
+    (void)total;
+    for (size_t p0 = 0; p0 < I; p0 += pass_iters) {
+      const size_t pi = std::min(pass_iters, I - p0);
+      for (size_t done = 0; done < pi;) {
+        const size_t k = std::min(chunk, pi - done);
+        rc = rn_sampler_run(s, (int)k, (double*)(uintptr_t)g.b[0]);
+        if (rc) return rc;
+        CUdeviceptr src = g.b[0], dst = g.b[1];
         int rows = (int)(k * n), cols = (int)C;
-        void* params[] = {&src, &dst, &rows, &cols};
+        long long ld = (long long)(pi * n), off = (long long)(done * n);
+        void* params[] = {&src, &dst, &rows, &cols, &ld, &off};
         CU(A->cuLaunchKernel(s->K->k_transpose, (unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), 1, 32, 8, 1, 0,
                              s->stream, params, nullptr));
         s->launches++;
+        done += k;
       }
-      CU(A->cuEventRecord(g.ev[buf], s->stream));
-      CU(A->cuStreamWaitEvent(g.copy, g.ev[buf], 0));
-      CUDA_MEMCPY2D cp;
-      std::memset(&cp, 0, sizeof(cp));
-      cp.srcMemoryType = CU_MEMORYTYPE_DEVICE;
-      cp.srcDevice = g.b[2 + buf];
-      cp.srcPitch = k * n * 8;
-      cp.dstMemoryType = CU_MEMORYTYPE_HOST;
-      cp.dstHost = samples + done * n;
-      cp.dstPitch = I * n * 8;
-      cp.WidthInBytes = k * n * 8;
-      cp.Height = C;
-      CU(A->cuMemcpy2DAsync(&cp, g.copy));
-      CU(A->cuEventRecord(copied[buf], g.copy));
-      used[buf] = true;
-      buf ^= 1;
-      done += k;
+      CU(A->cuEventRecord(g.done, s->stream));
+      CU(A->cuStreamWaitEvent(g.copy, g.done, 0));
+      if (pi == I) {
+        rc = drain_to_host(A, g.copy, g.b[1], samples, C * I * n * 8);
+        if (rc) return rc;
+      } else {  // strided pass: rows of pi*n doubles into a pitch of I*n
+        CUDA_MEMCPY2D cp;
+        std::memset(&cp, 0, sizeof(cp));
+        cp.srcMemoryType = CU_MEMORYTYPE_DEVICE;
+        cp.srcDevice = g.b[1];
+        cp.srcPitch = pi * n * 8;
+        cp.dstMemoryType = CU_MEMORYTYPE_HOST;
+        cp.dstHost = samples + p0 * n;
+        cp.dstPitch = I * n * 8;
+        cp.WidthInBytes = pi * n * 8;
+        cp.Height = C;
+        CU(A->cuMemcpy2DAsync(&cp, g.copy));
+        CU(A->cuStreamSynchronize(g.copy));
+      }
     }
-    CU(A->cuStreamSynchronize(g.copy));
-    A->cuEventDestroy(copied[0]);
-    A->cuEventDestroy(copied[1]);
   } else if (I > 0) {
     rc = rn_sampler_run(s, (int)I, nullptr);
     if (rc) return rc;

@@ -327,21 +327,18 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
   for (int it = 0; it < A.n_iter; it++) {
     // ---------------- lf.startIteration, LeapFrog.scala:52-59 ----------------
     RnPQ s;
-    double cq[RN_N];
     RN_UNROLL
-    for (int i = 0; i < RN_N; i++) {
-      s.p[i] = RN_AT(A.params, i, c);  // old momentum, for prevH
-      cq[i] = RN_AT(A.params, RN_N + i, c);
-      s.q[i] = cq[i];
-      s.g[i] = RN_AT(A.grad, i, c);
-    }
+    for (int i = 0; i < RN_N; i++) s.p[i] = RN_AT(A.params, i, c);  // old momentum, for prevH
     const double cU = RN_AT(A.params, 2 * RN_N, c);
-    s.U = cU;
     const double prevH = rn_energy(A, c, M, s.p, cU);
     rn_initialize_ps(A, c, M, rng, s.p);
-    double p0[RN_N];
     RN_UNROLL
-    for (int i = 0; i < RN_N; i++) p0[i] = s.p[i];
+    for (int i = 0; i < RN_N; i++) {
+      RN_AT(A.params, i, c) = s.p[i];  // initializePs writes into params (LeapFrog.scala:55); kept on reject
+      s.q[i] = RN_AT(A.params, RN_N + i, c);
+      s.g[i] = RN_AT(A.grad, i, c);
+    }
+    s.U = cU;
     const double startH = rn_energy(A, c, M, s.p, cU);  // finishIteration's energy(params), :62
     const rn_i64 iterationStartGrads = S.grads;
     const rn_i64 steps0 = S.steps;
@@ -361,7 +358,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
         for (;;) {
           double out = 0.0;  // lf.isUTurn(params), LeapFrog.scala:35-47
           RN_UNROLL
-          for (int i = 0; i < RN_N; i++) out += (s.q[i] - cq[i]) * s.p[i];
+          for (int i = 0; i < RN_N; i++) out += (s.q[i] - RN_AT(A.params, RN_N + i, c)) * s.p[i];
           const bool uturn = (out != out) ? true : (out < 0);
           if (uturn || !(l < A.max_steps)) break;
           l += 1;
@@ -398,14 +395,13 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
         RN_AT(A.params, i, c) = s.p[i];
         RN_AT(A.params, RN_N + i, c) = s.q[i];
         RN_AT(A.grad, i, c) = s.g[i];
-        cq[i] = s.q[i];
       }
       RN_AT(A.params, 2 * RN_N, c) = s.U;
       eH = endH;
       S.accepted += 1;
     } else {
       RN_UNROLL
-      for (int i = 0; i < RN_N; i++) RN_AT(A.params, i, c) = p0[i];
+      for (int i = 0; i < RN_N; i++) s.q[i] = RN_AT(A.params, RN_N + i, c);  // s.q := current position either way
       eH = startH;
     }
     {  // stats.energyVariance.update(eH); energyTransitions2 += pow(eH - prevH, 2)
@@ -452,9 +448,9 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
           RN_UNROLL
           for (int i = 0; i < RN_N; i++) {
             double mean = RN_AT(A.est_mean, i, c);
-            oldDiff[i] = cq[i] - mean;
+            oldDiff[i] = s.q[i] - mean;
             mean += (oldDiff[i] / (double)est_samples);
-            newDiff[i] = cq[i] - mean;
+            newDiff[i] = s.q[i] - mean;
             RN_AT(A.est_mean, i, c) = mean;
             RN_AT(A.est_raw, i, c) += oldDiff[i] * newDiff[i];
           }
@@ -533,7 +529,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     } else if (A.samples) {  // lf.variables(params, output), Driver.scala:105-107
       double* out = A.samples + (size_t)it * RN_N * (size_t)A.chains;
       RN_UNROLL
-      for (int i = 0; i < RN_N; i++) out[(size_t)i * (size_t)A.chains + c] = cq[i];
+      for (int i = 0; i < RN_N; i++) out[(size_t)i * (size_t)A.chains + c] = s.q[i];
     }
   }
 
@@ -587,7 +583,9 @@ RN_GLOBAL void rn_k_density(const double* RN_RESTRICT qin, double* RN_RESTRICT o
 // device->host copy of rn_sample).  32x32 tiles through shared memory, both sides coalesced.
 // =============================================================================================================
 #ifndef RN_HOST_EMULATION
-RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT dst, int rows, int cols) {
+RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT dst, int rows, int cols,
+                              long long dst_ld, long long dst_off) {
+  // dst[c * dst_ld + dst_off + r] = src[r * cols + c]
   __shared__ double tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += 8) {
@@ -597,7 +595,7 @@ RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int c = c0 + j, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    if (r < rows && c < cols) dst[(size_t)c * (size_t)dst_ld + (size_t)dst_off + r] = tile[threadIdx.x][j];
   }
 }
 #endif
