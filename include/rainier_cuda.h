@@ -59,6 +59,9 @@ enum { RN_MATRIX_IDENTITY = 0, RN_MATRIX_DIAGONAL = 1, RN_MATRIX_DENSE = 2 }; /*
 enum { RN_ADAPT_PER_CHAIN = 0, RN_ADAPT_POOLED = 1 };
 enum { RN_MATH_PARITY = 0, RN_MATH_FAST = 1 };
 enum { RN_GRAD_AUTO = 0, RN_GRAD_SYMBOLIC = 1, RN_GRAD_ADJOINT = 2 };
+/* kernel shape: one thread per chain (data-free / small models: state in registers, exact sequential row order) or one
+ * warp per chain (streamed data: rows across lanes, shuffle reduction).  AUTO picks by rows and parameter count. */
+enum { RN_BACKEND_AUTO = 0, RN_BACKEND_THREAD = 1, RN_BACKEND_WARP = 2 };
 
 /* java.util.Random state (48-bit LCG + cached second Gaussian), so that a chain can continue a stream the
  * host already drew from (the reference shares one RNG between data synthesis and sampling,
@@ -84,7 +87,7 @@ typedef struct rn_config {
   int32_t max_steps;         /* EHMC, default 1024 (DefaultConfig) */
   int32_t min_steps;         /* EHMC, default 1 */
   int32_t buf_size;          /* EHMC, default 100 */
-  int32_t reserved0;
+  int32_t backend;           /* RN_BACKEND_AUTO (default) | RN_BACKEND_THREAD | RN_BACKEND_WARP, see below */
   double p_count;            /* EHMC, default 0.1 */
 
   /* stepSizeTuner(): DualAvgTuner(delta) DualAvg.scala:3 | StaticStepSize(stepSize) Sampler.scala:36-40 */

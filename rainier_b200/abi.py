@@ -14,6 +14,7 @@ RN_MATRIX_IDENTITY, RN_MATRIX_DIAGONAL, RN_MATRIX_DENSE = 0, 1, 2
 RN_ADAPT_PER_CHAIN, RN_ADAPT_POOLED = 0, 1
 RN_MATH_PARITY, RN_MATH_FAST = 0, 1
 RN_GRAD_AUTO, RN_GRAD_SYMBOLIC, RN_GRAD_ADJOINT = 0, 1, 2
+RN_BACKEND_AUTO, RN_BACKEND_THREAD, RN_BACKEND_WARP = 0, 1, 2
 
 
 class RngState(C.Structure):
@@ -31,7 +32,7 @@ class Config(C.Structure):
         ("max_steps", C.c_int32),
         ("min_steps", C.c_int32),
         ("buf_size", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("backend", C.c_int32),
         ("p_count", C.c_double),
         ("step_size_tuner", C.c_int32),
         ("reserved1", C.c_int32),

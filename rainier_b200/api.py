@@ -191,6 +191,7 @@ class SamplerConfig:
     gradientMode = abi.RN_GRAD_AUTO
     adaptation = abi.RN_ADAPT_PER_CHAIN
     launchIterations = 0
+    backend = abi.RN_BACKEND_AUTO
 
 
 DefaultConfig = SamplerConfig
@@ -253,6 +254,7 @@ def lower_config(config):
         raise RainierCudaError(abi.RN_E_UNSUPPORTED, "unknown MassMatrixTuner")
     c.math_mode, c.gradient_mode = int(config.mathMode), int(config.gradientMode)
     c.adaptation, c.launch_iterations = int(config.adaptation), int(config.launchIterations)
+    c.backend = int(config.backend)
     return c, keep
 
 

@@ -68,6 +68,7 @@ struct Api {
   CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                              void**, void**);
   CUresult (*cuFuncGetAttribute)(int*, int, CUfunction);
+  CUresult (*cuFuncSetAttribute)(CUfunction, int, int);
   CUresult (*cuGetErrorString)(CUresult, const char**);
 };
 

@@ -4,13 +4,15 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <set>
 #include <sstream>
 
 namespace rn {
 
 extern const char* kPreludeSource;  // rn_prelude.cuh, embedded at build time
-extern const char* kSamplerSource;  // rn_sampler.cuh
+extern const char* kSamplerSource;     // rn_args.h + rn_sampler.cuh
+extern const char* kSamplerWpcSource;  // rn_args.h + rn_sampler_wpc.cuh
 
 namespace {
 
@@ -28,7 +30,23 @@ struct Emitter {
   const Program& P;
   const EmitOptions& opt;
   std::ostringstream os;
+  bool wpc = false;
+  std::vector<int> smem_slot;             // slot -> index in the shared accumulator block, or -1 (register)
+  std::map<int, int> tab_off;             // large-lookup node id -> offset of its table in scratch
+  int n_smem_acc = 0, tab_doubles = 0;
   Emitter(const Program& p, const EmitOptions& o) : P(p), opt(o) {}
+
+  std::string acc_ref(int slot) const {
+    if (!wpc) return "acc[" + std::to_string(slot) + "]";
+    if (smem_slot[slot] >= 0) return "scr[" + std::to_string(tab_doubles + smem_slot[slot]) + "]";
+    return "a" + std::to_string(slot);
+  }
+  bool is_big_table(const Node& n) const {
+    if (n.kind != K_LOOKUP || n.c <= 8) return false;
+    for (int k = 0; k < n.c; k++)
+      if (P.nodes[P.lookup_refs[n.b + k]].region != R_INV_FWD && P.nodes[P.lookup_refs[n.b + k]].region != R_INV_BWD) return false;
+    return true;
+  }
 
   std::string val(int id) const {
     const Node& n = P.nodes[id];
@@ -98,13 +116,17 @@ struct Emitter {
       }
       case K_LOOKUP: {
         // D2I ; tableswitch ; default -> throw (ir/ExprMethodGenerator.scala:50-56): flag + NaN instead of a fault
+        if (wpc && tab_off.count(id)) {
+          os << "rn_tab_lookup(scr + " << tab_off.at(id) << ", " << n.c << ", " << n.d << ", " << val(n.a) << ", err)";
+          break;
+        }
         os << "rn_lookup" << id << "(" << val(n.a);
         for (int k = 0; k < n.c; k++) os << ", " << val(P.lookup_refs[n.b + k]);
         os << ", err)";
         break;
       }
       case K_SELEQ: os << "((rn_d2i(" << val(n.a) << ") == " << n.d << ") ? " << val(n.b) << " : " << val(n.c) << ")"; break;
-      case K_ACC: os << "acc[" << n.a << "]"; break;
+      case K_ACC: os << acc_ref(n.a); break;
     }
     os << ";\n";
   }
@@ -114,6 +136,7 @@ struct Emitter {
     for (size_t id = 0; id < P.nodes.size(); id++) {
       const Node& n = P.nodes[id];
       if (n.kind != K_LOOKUP) continue;
+      if (wpc && tab_off.count((int)id)) continue;
       os << "RN_DEVICE double rn_lookup" << id << "(double idx";
       for (int k = 0; k < n.c; k++) os << ", double e" << k;
       os << ", int& err) {\n  switch (rn_d2i(idx) - (" << n.d << ")) {\n";
@@ -163,17 +186,90 @@ struct Emitter {
     }
     os << "}\n";
   }
+
+  void density_wpc() {
+    wpc = true;
+    // which accumulator slots live in shared memory (targets of a scatter) and which in registers
+    smem_slot.assign(P.n_slots, -1);
+    for (const TargetInfo& T : P.targets)
+      for (const ScatterStmt& sc : T.row_scatter)
+        for (int k = 0; k < sc.len; k++)
+          if (smem_slot[sc.slot_base + k] < 0) smem_slot[sc.slot_base + k] = n_smem_acc++;
+    for (const TargetInfo& T : P.targets)
+      for (int id : T.row_fwd)
+        if (is_big_table(P.nodes[id])) {
+          tab_off[id] = tab_doubles;
+          tab_doubles += P.nodes[id].c;
+        }
+    os << "// ---- emitted: log-density and gradient of the frozen DAG (" << (P.symbolic ? "symbolic" : "adjoint")
+       << " gradient), warp-per-chain: rows across lanes ----\n";
+    os << "#define RN_WPC_SCRATCH " << (tab_doubles + n_smem_acc) << "\n";
+    os << "RN_DEVICE double rn_tab_lookup(const double* tab, int len, int low, double idx, int& err) {\n"
+          "  const int k = rn_d2i(idx) - low;\n  if (k < 0 || k >= len) { err |= 1; return RN_NAN; }\n  return tab[k];\n}\n";
+    os << "RN_DEVICE double rn_warp_sum(double x) {\n  RN_UNROLL\n  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);\n  return x;\n}\n";
+    lookup_helpers();
+    os << "RN_DEVICE void rn_density(const double* q, double& dens, double* grad, double* scr, "
+          "const double* RN_RESTRICT data, int& err) {\n";
+    os << "  (void)data; (void)scr;\n  const int lane = (int)(threadIdx.x & 31);\n  (void)lane;\n";
+    if (n_smem_acc) os << "  for (int k = lane; k < " << n_smem_acc << "; k += 32) scr[" << tab_doubles << " + k] = 0.0;\n";
+    for (int id : P.inv_fwd) stmt(id, "  ");
+    for (auto& kv : tab_off) {
+      const Node& n = P.nodes[kv.first];
+      for (int k = 0; k < n.c; k++) os << "  scr[" << (kv.second + k) << "] = " << val(P.lookup_refs[n.b + k]) << ";\n";
+    }
+    os << "  __syncwarp();\n";
+    for (int sl = 0; sl < P.n_slots; sl++)
+      if (smem_slot[sl] < 0) os << "  double a" << sl << " = 0.0;\n";
+    for (size_t t = 0; t < P.targets.size(); t++) {
+      const TargetInfo& T = P.targets[t];
+      os << "  // target " << t << (T.streamed() ? " (streamed, rows across lanes)" : " (data-free)") << "\n";
+      if (T.streamed()) {
+        os << "  for (long long row = lane; row < " << (long long)T.n_rows << "LL; row += 32) {\n";
+        std::set<int> used;
+        for (int id : T.row_fwd)
+          if (P.nodes[id].kind == K_INPUT) used.insert(P.nodes[id].a - (int)P.n_params);
+        for (int k : used)
+          os << "    const double c" << k << " = RN_LDG(data + " << (unsigned long long)opt.col_offsets[k] << "ULL + row);\n";
+        for (int id : T.row_fwd) stmt(id, "    ");
+        for (int id : T.row_bwd) stmt(id, "    ");
+        for (const AccStmt& a : T.row_acc) os << "    " << acc_ref(a.slot) << " += " << val(a.node) << ";\n";
+        for (const ScatterStmt& sc : T.row_scatter) {
+          os << "    { const int k = rn_d2i(" << val(sc.index_node) << ") - (" << sc.low << "); if (k < 0 || k >= " << sc.len
+             << ") err |= 1; else atomicAdd(&scr[" << (tab_doubles + smem_slot[sc.slot_base]) << " + k], " << val(sc.node) << "); }\n";
+        }
+        os << "  }\n";
+      } else {
+        os << "  if (lane == 0) {\n";  // counted once by the butterfly below
+        for (const AccStmt& a : T.row_acc) os << "    " << acc_ref(a.slot) << " += " << val(a.node) << ";\n";
+        os << "  }\n";
+      }
+    }
+    for (int sl = 0; sl < P.n_slots; sl++)
+      if (smem_slot[sl] < 0) os << "  a" << sl << " = rn_warp_sum(a" << sl << ");\n";
+    os << "  err = (int)__reduce_or_sync(0xffffffffu, (unsigned)err);\n  __syncwarp();\n";
+    os << "  dens = a0;\n";
+    if (P.symbolic) {
+      for (uint32_t i = 0; i < P.n_params; i++) os << "  if (lane == 0) grad[" << i << "] = " << acc_ref(1 + (int)i) << ";\n";
+    } else {
+      for (int id : P.inv_bwd) stmt(id, "  ");
+      for (uint32_t i = 0; i < P.n_params; i++) os << "  if (lane == 0) grad[" << i << "] = " << val(P.grad_nodes[i]) << ";\n";
+    }
+    os << "  __syncwarp();\n}\n";
+  }
 };
 
 }  // namespace
 
 std::string emit_density(const Program& P, const EmitOptions& opt) {
   Emitter E(P, opt);
-  E.density_tpc();
+  if (opt.backend == 1)
+    E.density_wpc();
+  else
+    E.density_tpc();
   return E.os.str();
 }
 
-std::string emit_source(const Program& P, const EmitOptions& opt) {
+std::string emit_source(const Program& P, const EmitOptions& opt, int* wpc_smem_doubles) {
   std::ostringstream os;
   os << "// generated by rainier_b200 (CUDA source emitter) -- do not edit\n";
   os << "#define RN_N " << P.n_params << "\n";
@@ -184,7 +280,17 @@ std::string emit_source(const Program& P, const EmitOptions& opt) {
   if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
   os << kPreludeSource << "\n";
   os << emit_density(P, opt) << "\n";
-  os << kSamplerSource << "\n";
+  if (opt.backend == 1) {
+    os << "#define RN_WPC_SMEM_DOUBLES (" << (opt.enable_ehmc ? 7 : 4) << " * RN_N + RN_WPC_SCRATCH)\n";
+    os << kSamplerWpcSource << "\n";
+    if (wpc_smem_doubles) {
+      Emitter E(P, opt);
+      E.density_wpc();
+      *wpc_smem_doubles = (opt.enable_ehmc ? 7 : 4) * (int)P.n_params + E.tab_doubles + E.n_smem_acc;
+    }
+  } else {
+    os << kSamplerSource << "\n";
+  }
   return os.str();
 }
 

@@ -9,6 +9,7 @@
 #include <nvrtc.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -89,6 +90,7 @@ const Api* api(std::string* why) {
       RN_SYM(cuEventSynchronize, "cuEventSynchronize")
       RN_SYM(cuLaunchKernel, "cuLaunchKernel")
       RN_SYM(cuFuncGetAttribute, "cuFuncGetAttribute")
+      RN_SYM(cuFuncSetAttribute, "cuFuncSetAttribute")
       RN_SYM(cuGetErrorString, "cuGetErrorString")
 #undef RN_SYM
       if (ok) {
@@ -146,6 +148,9 @@ struct Kernel {
   CUmodule mod = nullptr;
   CUfunction k_init = nullptr, k_iter = nullptr, k_density = nullptr, k_transpose = nullptr;
   const Program* prog = nullptr;
+  int backend = 0;            // 0 thread per chain, 1 warp per chain
+  int wpc_smem_doubles = 0;   // per-warp dynamic shared memory (backend 1)
+  int warps_per_cta = 4;
 };
 
 struct rn_model {
@@ -159,6 +164,8 @@ struct rn_model {
   std::vector<int64_t> col_rows;
   std::map<std::pair<bool, bool>, std::unique_ptr<Program>> programs;  // (adjoint, fast)
   std::map<KernelKey, std::unique_ptr<Kernel>> kernels;
+  CUdeviceptr pool[2] = {0, 0};  // grow-only scratch reused by rn_sample calls (cuMemAlloc/cuMemFree of GBs is slow)
+  size_t pool_bytes[2] = {0, 0};
 };
 
 static int make_current(const Api* A, rn_model* m) {
@@ -192,7 +199,19 @@ static KernelKey key_for(const rn_model* m, const rn_config* cfg) {
     if (cfg->mass_tuner == RN_MASS_DENSE) k.mass_max = 2;
     if (cfg->mass_tuner == RN_MASS_STATIC) k.mass_max = cfg->static_matrix == RN_MATRIX_DENSE ? 2 : (cfg->static_matrix == RN_MATRIX_DIAGONAL ? 1 : 0);
   }
-  k.backend = 0;
+  // kernel shape: warp per chain when rows are streamed (or the state cannot live in registers)
+  int want = cfg ? cfg->backend : RN_BACKEND_AUTO;
+  if (const char* e = getenv("RN_BACKEND")) want = atoi(e);
+  if (want == RN_BACKEND_AUTO) {
+    uint64_t rows = 0;
+    auto it = m->programs.begin();
+    if (it != m->programs.end())
+      for (const TargetInfo& T : it->second->targets)
+        if (T.streamed()) rows += T.n_rows;
+    want = (rows >= 2048 || m->n_params > 48) ? RN_BACKEND_WARP : RN_BACKEND_THREAD;
+    if (k.mass_max == 2) want = RN_BACKEND_THREAD;  // dense mass lives in the thread-per-chain kernels
+  }
+  k.backend = want == RN_BACKEND_WARP ? 1 : 0;
   return k;
 }
 
@@ -215,7 +234,17 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
   eo.mass_max = key.mass_max;
   eo.enable_ehmc = key.ehmc;
   eo.col_offsets = m->col_offsets;
-  K->source = emit_source(*P, eo);
+  if (eo.backend == 1 && eo.mass_max == 2) return fail(RN_E_UNSUPPORTED, "dense mass matrices need the thread-per-chain backend");
+  if (eo.backend == 1 && P->symbolic && P->n_params > 96)
+    return fail(RN_E_UNSUPPORTED, "warp-per-chain with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
+  K->backend = eo.backend;
+  K->source = emit_source(*P, eo, &K->wpc_smem_doubles);
+  if (eo.backend == 1) {
+    const size_t per_warp = (size_t)K->wpc_smem_doubles * 8;
+    int w = (int)std::min<size_t>(8, (200 * 1024) / std::max<size_t>(per_warp, 1));
+    if (w < 1) return fail(RN_E_UNSUPPORTED, "model state does not fit one warp's shared memory slice");
+    K->warps_per_cta = w;
+  }
 
   nvrtcProgram prog;
   if (nvrtcCreateProgram(&prog, K->source.c_str(), "rainier_model.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
@@ -226,7 +255,7 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
   {
     // registers/thread: the fused iteration kernel is latency-bound on dependent fp64 chains, so occupancy matters
     // more than a few spills (profiles/r1_ncu_rn_k_iter_funnel_*: 240 regs -> 8 warps/SM, fp64 pipe 30% busy)
-    int cap = P->n_params <= 16 ? 128 : 0;
+    int cap = (P->n_params <= 16 && eo.backend == 0) ? 128 : 0;
     if (const char* e = getenv("RN_MAXRREGCOUNT")) cap = atoi(e);
     if (cap > 0) {
       maxreg = "--maxrregcount=" + std::to_string(cap);
@@ -268,6 +297,11 @@ static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
   CU(A->cuModuleGetFunction(&K->k_iter, K->mod, "rn_k_iter"));
   CU(A->cuModuleGetFunction(&K->k_density, K->mod, "rn_k_density"));
   CU(A->cuModuleGetFunction(&K->k_transpose, K->mod, "rn_k_transpose"));
+  if (K->backend == 1) {
+    const int bytes = K->warps_per_cta * K->wpc_smem_doubles * 8;
+    for (CUfunction f : {K->k_init, K->k_iter, K->k_density})
+      CU(A->cuFuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, bytes));
+  }
   return RN_OK;
 }
 
@@ -362,6 +396,8 @@ void rn_model_destroy(rn_model* m) {
     for (auto& kv : m->kernels)
       if (kv.second->mod) A->cuModuleUnload(kv.second->mod);
     if (m->d_data) A->cuMemFree(m->d_data);
+    for (auto p : m->pool)
+      if (p) A->cuMemFree(p);
     CUdevice dev;
     if (A->cuDeviceGet(&dev, m->device) == 0) A->cuDevicePrimaryCtxRelease(dev);
   }
@@ -433,7 +469,13 @@ int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
   CUdeviceptr ddata = m->d_data;
   int ch = chains;
   void* params[] = {&dq, &dout, &ddata, &derr, &ch};
-  CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + 127) / 128), 1, 1, 128, 1, 1, 0, nullptr, params, nullptr));
+  if (K->backend == 1) {
+    const unsigned w = (unsigned)K->warps_per_cta;
+    CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + w - 1) / w), 1, 1, w * 32, 1, 1,
+                         w * (unsigned)K->wpc_smem_doubles * 8, nullptr, params, nullptr));
+  } else {
+    CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + 127) / 128), 1, 1, 128, 1, 1, 0, nullptr, params, nullptr));
+  }
   CU(A->cuMemcpyDtoH(ot.data(), dout, ot.size() * 8));
   int err = 0;
   CU(A->cuMemcpyDtoH(&err, derr, 4));
@@ -485,6 +527,13 @@ struct Arena {
 
 int launch(const Api* A, rn_sampler* s, CUfunction f) {
   void* params[] = {&s->args};
+  if (s->K->backend == 1) {
+    const unsigned w = (unsigned)s->K->warps_per_cta;
+    const unsigned grid = (unsigned)((s->chains + w - 1) / w);
+    CU(A->cuLaunchKernel(f, grid, 1, 1, w * 32, 1, 1, w * (unsigned)s->K->wpc_smem_doubles * 8, s->stream, params, nullptr));
+    s->launches++;
+    return RN_OK;
+  }
   static const unsigned block = getenv("RN_BLOCK") ? (unsigned)atoi(getenv("RN_BLOCK")) : 128u;
   const unsigned grid = (unsigned)((s->chains + block - 1) / block);
   CU(A->cuLaunchKernel(f, grid, 1, 1, block, 1, 1, 0, s->stream, params, nullptr));
@@ -1024,9 +1073,19 @@ extern "C" {
 
 int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, double* samples, double* mass,
               rn_chain_stats* stats) {
+  const bool timing = getenv("RN_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    double t1 = now();
+    fprintf(stderr, "[rn_sample] %-18s %8.2f ms\n", what, (t1 - t0) * 1e3);
+    t0 = t1;
+  };
   rn_sampler* s = nullptr;
   int rc = rn_sampler_create(m, cfg, seeds, chains, &s);
   if (rc) return rc;
+  lap("sampler_create");
   std::string why;
   const Api* A = api(&why);
   if (!A) return fail(RN_E_CUDA, why);
@@ -1037,8 +1096,6 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
     CUstream copy = nullptr;
     CUevent done = nullptr;
     ~Guard() {
-      for (auto p : b)
-        if (p) A->cuMemFree(p);
       if (done) A->cuEventDestroy(done);
       if (copy) A->cuStreamDestroy(copy);
       rn_sampler_destroy(s);
@@ -1046,6 +1103,8 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
   } g{s, A};
   rc = rn_sampler_warmup(s, -1);
   if (rc) return rc;
+  if (timing) rn_sampler_sync(s);
+  lap("warmup");
   const size_t C = (size_t)chains, n = m->n_params, I = (size_t)cfg->iterations;
   if (I > 0 && samples) {
     const size_t total = C * I * n * 8;
@@ -1056,8 +1115,17 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
     const size_t pass_iters = std::max<size_t>(1, std::min<size_t>(I, cap / std::max<size_t>(1, C * n * 8)));
     size_t chunk = std::max<size_t>(1, std::min<size_t>(pass_iters, ((size_t)1 << 30) / (n * C * 8 + 1)));
     if (cfg->launch_iterations > 0) chunk = std::min<size_t>(chunk, (size_t)cfg->launch_iterations);
-    CU(A->cuMemAlloc(&g.b[0], chunk * n * C * 8));       // [chunk][n][C] scratch
-    CU(A->cuMemAlloc(&g.b[1], pass_iters * n * C * 8));  // [C][pass_iters][n]
+    const size_t want[2] = {chunk * n * C * 8 /* [chunk][n][C] scratch */, pass_iters * n * C * 8 /* [C][pass_iters][n] */};
+    for (int k = 0; k < 2; k++) {
+      if (m->pool_bytes[k] < want[k]) {
+        if (m->pool[k]) A->cuMemFree(m->pool[k]);
+        m->pool[k] = 0;
+        m->pool_bytes[k] = 0;
+        CU(A->cuMemAlloc(&m->pool[k], want[k]));
+        m->pool_bytes[k] = want[k];
+      }
+      g.b[k] = m->pool[k];
+    }
     CU(A->cuStreamCreate(&g.copy, 1));
     CU(A->cuEventCreate(&g.done, 2));
     (void)total;
@@ -1078,6 +1146,10 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
       }
       CU(A->cuEventRecord(g.done, s->stream));
       CU(A->cuStreamWaitEvent(g.copy, g.done, 0));
+      if (timing) {
+        rn_sampler_sync(s);
+        lap("kernels");
+      }
       if (pi == I) {
         rc = drain_to_host(A, g.copy, g.b[1], samples, C * I * n * 8);
         if (rc) return rc;
@@ -1100,7 +1172,9 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
     rc = rn_sampler_run(s, (int)I, nullptr);
     if (rc) return rc;
   }
+  lap("drain");
   rc = rn_sampler_stats(s, stats, mass, cfg->stats_rings);
+  lap("stats");
   return rc;
 }
 

@@ -1,0 +1,492 @@
+// rn_sampler_wpc.cuh -- "warp per chain" variant of the fused HMC/EHMC iteration kernels (RN_BACKEND == 1).
+//
+// Used when the frozen DAG streams observation rows (or has too many parameters for registers): the 32 lanes of
+// a warp own ONE chain.  Rows of a streamed target are spread over the lanes (coalesced 256-byte column reads,
+// per-lane partial sums, butterfly __shfl_xor reduction -- see the emitted rn_density()); the chain's vectors
+// (q, p, gradient, mass) live in the warp's slice of shared memory and are updated lane-parallel; every scalar
+// decision (energies, RNG draws, accept test, step-size adaptation) is computed redundantly and identically by
+// all lanes, so the control flow stays warp-uniform and follows the reference exactly as in rn_sampler.cuh
+// (same file:line citations apply).  Sequential reductions of the reference (dot products, LeapFrog.scala:221-231)
+// keep their left-to-right order; only the row sum of the density changes order (tree instead of sequential),
+// which moves results in the last ~3 digits.
+//
+// Supported here: HMC / EHMC, DualAvg / static step size, identity / diagonal mass (adaptive or static).  Dense
+// mass matrices use the thread-per-chain backend.
+#ifndef RN_SAMPLER_WPC_CUH
+#define RN_SAMPLER_WPC_CUH
+
+#define RN_LN2 0.6931471805599453
+#define RN_AT(ptr, field, c) (ptr)[(size_t)(field) * (size_t)A.chains + (size_t)(c)]
+#define RN_LANE ((int)(threadIdx.x & 31))
+#define RN_FOR_LANES(i) for (int i = RN_LANE; i < RN_N; i += 32)
+
+struct RnStats {
+  rn_i64 grads, steps;
+  int iters, accepted, err;
+  double e_mean, e_raw, trans2;
+  int e_n;
+  int ring_i[3], ring_full[3];
+};
+
+// per-warp shared-memory slice
+struct RnW {
+  double* q;   // pqBuf.q
+  double* p;   // pqBuf.p
+  double* g;   // gradient at q
+  double* m;   // diagonal mass (variances)
+  double* sq;  // EHMC snapshot
+  double* sp;
+  double* sg;
+  double* scr;  // emitted density scratch (lookup tables, scatter accumulators)
+  double U;     // potential of pqBuf (replicated in registers)
+  int mass_kind;
+};
+
+RN_DEVICE void rn_w_setup(RnW& w, double* base) {
+  w.q = base;
+  w.p = base + RN_N;
+  w.g = base + 2 * RN_N;
+  w.m = base + 3 * RN_N;
+#if RN_ENABLE_EHMC
+  w.sq = base + 4 * RN_N;
+  w.sp = base + 5 * RN_N;
+  w.sg = base + 6 * RN_N;
+  w.scr = base + 7 * RN_N;
+#else
+  w.sq = w.sp = w.sg = base;
+  w.scr = base + 4 * RN_N;
+#endif
+}
+
+RN_DEVICE void rn_ring_add(const RnArgs& A, int c, RnStats& S, int which, double value) {  // Stats.scala:24-30
+  int i = S.ring_i[which] + 1;
+  if (i == A.stats_window) S.ring_full[which] = 1;
+  i = i % A.stats_window;
+  S.ring_i[which] = i;
+  if (RN_LANE == 0) RN_AT(A.st_rings, which * A.stats_window + i, c) = value;
+}
+
+// energy = potential + dot(velocity, p)/2, sequential order (LeapFrog.scala:134-139,205-231)
+RN_DEVICE double rn_energy(const RnW& w, const double* p, double U) {
+  double k = 0.0;
+  if (w.mass_kind == 1) {
+    for (int i = 0; i < RN_N; i++) k += ((p[i] * w.m[i]) * p[i]);
+  } else {
+    for (int i = 0; i < RN_N; i++) k += (p[i] * p[i]);
+  }
+  return U + k / 2.0;
+}
+RN_DEVICE double rn_log_accept(double deltaH) {  // LeapFrog.scala:141-145
+  if (deltaH != deltaH) return -RN_INF;
+  return rn_jmin0(-deltaH);
+}
+RN_DEVICE void rn_update(const RnArgs& A, RnW& w, RnStats& S) {
+  double dens;
+  rn_density(w.q, dens, w.g, w.scr, A.data, S.err);
+  w.U = dens * -1;
+  S.grads += 1;
+}
+RN_DEVICE void rn_full_ps(RnW& w, double stepSize, RnStats& S) {  // LeapFrog.scala:168-176
+  S.grads += 1;
+  RN_FOR_LANES(i) w.p[i] += stepSize * w.g[i];
+  __syncwarp();
+}
+RN_DEVICE void rn_new_qs(RnW& w, double stepSize) {  // LeapFrog.scala:147-154
+  if (w.mass_kind == 1) {
+    RN_FOR_LANES(i) w.q[i] += (stepSize * (w.p[i] * w.m[i]));
+  } else {
+    RN_FOR_LANES(i) w.q[i] += (stepSize * w.p[i]);
+  }
+  __syncwarp();
+}
+RN_DEVICE void rn_leapfrog(const RnArgs& A, RnW& w, int l, double stepSize, RnStats& S) {  // :24-33,156-191
+  rn_full_ps(w, stepSize / 2.0, S);
+  rn_new_qs(w, stepSize);
+  rn_update(A, w, S);
+  for (int i = 1; i < l; i++) {
+    rn_full_ps(w, stepSize, S);
+    rn_new_qs(w, stepSize);
+    rn_update(A, w, S);
+  }
+  rn_full_ps(w, stepSize / 2.0, S);
+}
+RN_DEVICE void rn_take_steps(const RnArgs& A, int c, RnW& w, int l, double stepSize, RnStats& S) {
+  rn_ring_add(A, c, S, 0, stepSize);
+  rn_leapfrog(A, w, l, stepSize, S);
+  S.steps += l;
+}
+// momentum draw into dst (LeapFrog.scala:233-255): every lane draws the whole stream, lane i%32 keeps element i
+RN_DEVICE void rn_initialize_ps(const RnW& w, RnRng& rng, double* dst) {
+  for (int i = 0; i < RN_N; i++) {
+    const double z = rn_normal(rng);
+    if ((i & 31) == RN_LANE) dst[i] = (w.mass_kind == 1) ? z / sqrt(w.m[i]) : z;
+  }
+  __syncwarp();
+}
+
+RN_DEVICE void rn_load_stats(const RnArgs& A, int c, RnStats& S) {
+  S.grads = A.st_grads[c];
+  S.steps = A.st_steps[c];
+  S.iters = A.st_iters[c];
+  S.accepted = A.st_accepted[c];
+  S.err = A.st_err[c];
+  S.e_mean = RN_AT(A.st_energy, 0, c);
+  S.e_raw = RN_AT(A.st_energy, 1, c);
+  S.trans2 = RN_AT(A.st_energy, 2, c);
+  S.e_n = A.st_energy_n[c];
+  for (int r = 0; r < 3; r++) {
+    S.ring_i[r] = RN_AT(A.st_ring_i, r, c);
+    S.ring_full[r] = RN_AT(A.st_ring_full, r, c);
+  }
+}
+RN_DEVICE void rn_store_stats(const RnArgs& A, int c, const RnStats& S) {
+  if (RN_LANE != 0) return;
+  A.st_grads[c] = S.grads;
+  A.st_steps[c] = S.steps;
+  A.st_iters[c] = S.iters;
+  A.st_accepted[c] = S.accepted;
+  A.st_err[c] = S.err;
+  RN_AT(A.st_energy, 0, c) = S.e_mean;
+  RN_AT(A.st_energy, 1, c) = S.e_raw;
+  RN_AT(A.st_energy, 2, c) = S.trans2;
+  A.st_energy_n[c] = S.e_n;
+  for (int r = 0; r < 3; r++) {
+    RN_AT(A.st_ring_i, r, c) = S.ring_i[r];
+    RN_AT(A.st_ring_full, r, c) = S.ring_full[r];
+  }
+}
+
+extern __shared__ double rn_smem[];
+
+// =============================================================================================================
+RN_GLOBAL void rn_k_init(const RnArgs A) {
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (c >= A.chains) return;  // whole warp exits
+  RnW w;
+  rn_w_setup(w, rn_smem + (size_t)(threadIdx.x >> 5) * RN_WPC_SMEM_DOUBLES);
+  w.mass_kind = 0;
+  RnRng rng;
+  rng.seed = A.rng_seed[c];
+  rng.nng = A.rng_nng[c];
+  rng.have = A.rng_have[c];
+  RnStats S;
+  rn_load_stats(A, c, S);
+
+  // LeapFrog.initialize, LeapFrog.scala:102-116
+  for (int i = 0; i < RN_N; i++) {
+    const double z = rn_normal(rng);
+    if ((i & 31) == RN_LANE) {
+      w.q[i] = z;
+      w.p[i] = 0.0;
+    }
+  }
+  __syncwarp();
+  rn_update(A, w, S);
+  const double cU = w.U;
+  RN_FOR_LANES(i) {
+    RN_AT(A.params, RN_N + i, c) = w.q[i];
+    RN_AT(A.grad, i, c) = w.g[i];
+  }
+  rn_initialize_ps(w, rng, w.p);
+  RN_FOR_LANES(i) RN_AT(A.params, i, c) = w.p[i];
+  if (RN_LANE == 0) RN_AT(A.params, 2 * RN_N, c) = cU;
+
+  double stepSize;
+  if (A.step_tuner == 0) {  // DualAvgTuner.findReasonableStepSize, DualAvg.scala:27-41
+    const double H0 = rn_energy(w, w.p, cU);
+    stepSize = 1.0;
+    rn_leapfrog(A, w, 1, stepSize, S);  // tryStepping, LeapFrog.scala:14-22 (pqBuf == params here)
+    double lap = rn_log_accept(rn_energy(w, w.p, w.U) - H0);
+    const double exponent = (lap > -RN_LN2) ? 1.0 : -1.0;
+    const double doubleOrHalf = (exponent > 0) ? 2.0 : 0.5;
+    while (stepSize != 0.0 && (exponent * lap > -exponent * RN_LN2)) {
+      stepSize *= doubleOrHalf;
+      __syncwarp();
+      RN_FOR_LANES(i) {  // copy(params, pqBuf)
+        w.p[i] = RN_AT(A.params, i, c);
+        w.q[i] = RN_AT(A.params, RN_N + i, c);
+        w.g[i] = RN_AT(A.grad, i, c);
+      }
+      w.U = cU;
+      __syncwarp();
+      rn_leapfrog(A, w, 1, stepSize, S);
+      lap = rn_log_accept(rn_energy(w, w.p, w.U) - H0);
+    }
+    if (RN_LANE == 0) {
+      RN_AT(A.da, 1, c) = rn_log(stepSize);
+      RN_AT(A.da, 2, c) = 0.0;
+      RN_AT(A.da, 3, c) = 0.0;
+      RN_AT(A.da, 4, c) = rn_log(10 * stepSize);
+      A.da_iter[c] = 0;
+    }
+  } else {
+    stepSize = A.static_step;
+  }
+  if (RN_LANE == 0) {
+    RN_AT(A.da, 0, c) = stepSize;
+    A.rng_seed[c] = rng.seed;
+    A.rng_nng[c] = rng.nng;
+    A.rng_have[c] = rng.have;
+  }
+  rn_store_stats(A, c, S);
+}
+
+// =============================================================================================================
+RN_GLOBAL void rn_k_iter(const RnArgs A) {
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (c >= A.chains) return;
+  RnW w;
+  rn_w_setup(w, rn_smem + (size_t)(threadIdx.x >> 5) * RN_WPC_SMEM_DOUBLES);
+  w.mass_kind = A.mass_kind;
+  RnRng rng;
+  rng.seed = A.rng_seed[c];
+  rng.nng = A.rng_nng[c];
+  rng.have = A.rng_have[c];
+  RnStats S;
+  rn_load_stats(A, c, S);
+  if (w.mass_kind == 1) {
+    RN_FOR_LANES(i) w.m[i] = RN_AT(A.mass, i, c);
+    __syncwarp();
+  }
+  double stepSize = RN_AT(A.da, 0, c);
+  double logStepSize = 0, logStepSizeBar = 0, avgError = 0, shrinkageTarget = 0;
+  int daIter = 0;
+  if (A.step_tuner == 0) {
+    logStepSize = RN_AT(A.da, 1, c);
+    logStepSizeBar = RN_AT(A.da, 2, c);
+    avgError = RN_AT(A.da, 3, c);
+    shrinkageTarget = RN_AT(A.da, 4, c);
+    daIter = A.da_iter[c];
+    if (A.phase == 1) stepSize = rn_exp(logStepSizeBar);
+  }
+  int win_size = A.win_size, win_i = A.win_i, win_j = A.win_j, est_samples = A.est_samples;
+  int ring_i = 0, ring_full = 0;
+  if (A.sampler == 1) {
+    ring_i = A.ring_i[c];
+    ring_full = A.ring_full[c];
+  }
+
+  for (int it = 0; it < A.n_iter; it++) {
+    // ---- startIteration, LeapFrog.scala:52-59 ----
+    __syncwarp();
+    RN_FOR_LANES(i) w.p[i] = RN_AT(A.params, i, c);
+    __syncwarp();
+    const double cU = RN_AT(A.params, 2 * RN_N, c);
+    const double prevH = rn_energy(w, w.p, cU);
+    __syncwarp();
+    rn_initialize_ps(w, rng, w.p);
+    RN_FOR_LANES(i) {
+      RN_AT(A.params, i, c) = w.p[i];
+      w.q[i] = RN_AT(A.params, RN_N + i, c);
+      w.g[i] = RN_AT(A.grad, i, c);
+    }
+    w.U = cU;
+    __syncwarp();
+    const double startH = rn_energy(w, w.p, cU);
+    const rn_i64 iterationStartGrads = S.grads;
+    const rn_i64 steps0 = S.steps;
+    const double usedStep = stepSize;
+
+    if (A.sampler == 0) {
+      rn_take_steps(A, c, w, A.n_steps, stepSize, S);
+    } else {  // EHMC.scala:15-61
+      bool count = false;
+      if (A.phase == 0) count = (!ring_full) || (rn_uniform(rng) < A.p_count);
+      if (count) {
+        double sU = 0.0;
+        int l = 0;
+        for (;;) {
+          double out = 0.0;  // isUTurn(params): sequential order, params.q read back from global memory
+          for (int i = 0; i < RN_N; i++) out += (w.q[i] - RN_AT(A.params, RN_N + i, c)) * w.p[i];
+          const bool uturn = (out != out) ? true : (out < 0);
+          if (uturn || !(l < A.max_steps)) break;
+          l += 1;
+          rn_take_steps(A, c, w, 1, stepSize, S);
+          if (l == A.min_steps) {  // snapshot
+            RN_FOR_LANES(i) {
+              w.sq[i] = w.q[i];
+              w.sp[i] = w.p[i];
+              w.sg[i] = w.g[i];
+            }
+            sU = w.U;
+            __syncwarp();
+          }
+        }
+        if (l < A.min_steps) {
+          rn_take_steps(A, c, w, A.min_steps - l, stepSize, S);
+        } else {  // restore
+          RN_FOR_LANES(i) {
+            w.q[i] = w.sq[i];
+            w.p[i] = w.sp[i];
+            w.g[i] = w.sg[i];
+          }
+          w.U = sU;
+          __syncwarp();
+        }
+        ring_i += 1;
+        if (ring_i == A.buf_size) ring_full = 1;
+        ring_i = ring_i % A.buf_size;
+        if (RN_LANE == 0) RN_AT(A.ring, ring_i, c) = (double)l;
+        __syncwarp();
+      } else {
+        const int idx = ring_full ? rn_rng_int(rng, A.buf_size) : rn_rng_int(rng, ring_i + 1);
+        const int nsteps = rn_d2i(RN_AT(A.ring, idx, c));
+        rn_take_steps(A, c, w, nsteps, stepSize, S);
+      }
+    }
+
+    // ---- finishIteration, LeapFrog.scala:61-82 ----
+    const double endH = rn_energy(w, w.p, w.U);
+    const double deltaH = endH - startH;
+    const double a = rn_log_accept(deltaH);
+    const bool accept = a > rn_log(rn_uniform(rng));
+    double eH;
+    __syncwarp();
+    if (accept) {
+      RN_FOR_LANES(i) {
+        RN_AT(A.params, i, c) = w.p[i];
+        RN_AT(A.params, RN_N + i, c) = w.q[i];
+        RN_AT(A.grad, i, c) = w.g[i];
+      }
+      if (RN_LANE == 0) RN_AT(A.params, 2 * RN_N, c) = w.U;
+      eH = endH;
+      S.accepted += 1;
+    } else {
+      RN_FOR_LANES(i) w.q[i] = RN_AT(A.params, RN_N + i, c);
+      eH = startH;
+    }
+    __syncwarp();
+    {
+      S.e_n += 1;
+      const double oldDiff = eH - S.e_mean;
+      S.e_mean += (oldDiff / (double)S.e_n);
+      const double newDiff = eH - S.e_mean;
+      S.e_raw += oldDiff * newDiff;
+      const double d = eH - prevH;
+      S.trans2 += d * d;
+    }
+    S.iters += 1;
+    rn_ring_add(A, c, S, 1, rn_exp(a));
+    rn_ring_add(A, c, S, 2, (double)(S.grads - iterationStartGrads));
+    if (A.trace && RN_LANE == 0) {
+      double* tr = A.trace + (size_t)it * 4 * (size_t)A.chains;
+      tr[0 * (size_t)A.chains + c] = a;
+      tr[1 * (size_t)A.chains + c] = accept ? 1.0 : 0.0;
+      tr[2 * (size_t)A.chains + c] = usedStep;
+      tr[3 * (size_t)A.chains + c] = (double)(S.steps - steps0);
+    }
+
+    if (A.phase == 0) {
+      if (A.step_tuner == 0) {  // DualAvg.update, DualAvg.scala:58-77
+        const double newAcceptanceProb = rn_exp(a);
+        daIter = daIter + 1;
+        const double avgErrorMultiplier = 1.0 / ((double)daIter + 10);
+        const double stepSizeMultiplier = rn_pow((double)daIter, -0.75);
+        avgError = ((1.0 - avgErrorMultiplier) * avgError + (avgErrorMultiplier * (A.delta - newAcceptanceProb)));
+        logStepSize = (shrinkageTarget - (avgError * sqrt((double)daIter) / 0.05));
+        logStepSizeBar = (stepSizeMultiplier * logStepSize + (1.0 - stepSizeMultiplier) * logStepSizeBar);
+        stepSize = rn_exp(logStepSize);
+      }
+      if (A.mass_tuner == 1) {  // DiagonalMassMatrixTuner, MassMatrix.scala:147-164
+        win_j += 1;
+        if (!(win_j < A.skip_first || (A.total_warmup - win_j) < A.skip_last)) {
+          win_i += 1;
+          est_samples += 1;
+          const bool window_end = (win_i == win_size);
+          RN_FOR_LANES(i) {  // VarianceEstimator.update, MassMatrixEstimator.scala:69-83
+            double mean = RN_AT(A.est_mean, i, c);
+            const double oldDiff = w.q[i] - mean;
+            mean += (oldDiff / (double)est_samples);
+            const double newDiff = w.q[i] - mean;
+            double raw = RN_AT(A.est_raw, i, c) + oldDiff * newDiff;
+            if (window_end) {
+              const double var = raw / (double)est_samples;
+              if (var == 0.0) S.err |= 2;
+              w.m[i] = var;
+              RN_AT(A.mass, i, c) = var;
+              mean = 0.0;
+              raw = 0.0;
+            }
+            RN_AT(A.est_mean, i, c) = mean;
+            RN_AT(A.est_raw, i, c) = raw;
+          }
+          if (window_end) {
+            S.err |= __reduce_or_sync(0xffffffffu, (unsigned)(S.err & 2));
+            win_i = 0;
+            win_size = rn_d2i(win_size * A.win_expansion);
+            w.mass_kind = 1;
+            if (A.step_tuner == 0) {  // stepSizeTuner.reset(), DualAvg.scala:17-21
+              const double ss = rn_exp(logStepSizeBar);
+              logStepSize = rn_log(ss);
+              logStepSizeBar = 0.0;
+              avgError = 0.0;
+              daIter = 0;
+              shrinkageTarget = rn_log(10 * ss);
+              stepSize = ss;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    } else if (A.samples) {
+      double* out = A.samples + (size_t)it * RN_N * (size_t)A.chains;
+      RN_FOR_LANES(i) out[(size_t)i * (size_t)A.chains + c] = w.q[i];
+    }
+  }
+
+  if (RN_LANE == 0) {
+    if (A.phase == 0) {
+      RN_AT(A.da, 0, c) = stepSize;
+      if (A.step_tuner == 0) {
+        RN_AT(A.da, 1, c) = logStepSize;
+        RN_AT(A.da, 2, c) = logStepSizeBar;
+        RN_AT(A.da, 3, c) = avgError;
+        RN_AT(A.da, 4, c) = shrinkageTarget;
+        A.da_iter[c] = daIter;
+      }
+    }
+    if (A.sampler == 1) {
+      A.ring_i[c] = ring_i;
+      A.ring_full[c] = ring_full;
+    }
+    A.rng_seed[c] = rng.seed;
+    A.rng_nng[c] = rng.nng;
+    A.rng_have[c] = rng.have;
+  }
+  rn_store_stats(A, c, S);
+}
+
+// =============================================================================================================
+RN_GLOBAL void rn_k_density(const double* RN_RESTRICT qin, double* RN_RESTRICT out, const double* data, int* err,
+                            int chains) {
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (c >= chains) return;
+  RnW w;
+  rn_w_setup(w, rn_smem + (size_t)(threadIdx.x >> 5) * RN_WPC_SMEM_DOUBLES);
+  RN_FOR_LANES(i) w.q[i] = qin[(size_t)i * chains + c];
+  __syncwarp();
+  int e = 0;
+  double dens;
+  rn_density(w.q, dens, w.g, w.scr, data, e);
+  __syncwarp();
+  if (RN_LANE == 0) out[c] = dens;
+  RN_FOR_LANES(i) out[(size_t)(i + 1) * chains + c] = w.g[i];
+  if (e && RN_LANE == 0) atomicOr(err, e);
+}
+
+RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT dst, int rows, int cols,
+                              long long dst_ld, long long dst_off) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(size_t)c * (size_t)dst_ld + (size_t)dst_off + r] = tile[threadIdx.x][j];
+  }
+}
+
+#endif  // RN_SAMPLER_WPC_CUH

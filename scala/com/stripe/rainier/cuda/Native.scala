@@ -1,0 +1,25 @@
+package com.stripe.rainier.cuda
+
+import java.nio.ByteBuffer
+
+/** JNI surface of librainier_jni.so (jni/rainier_jni.cpp), a 1:1 forward to the C ABI in include/rainier_cuda.h.
+  * NOT COMPILED in the rainier_b200 repository (no JVM toolchain in its build image); see INTEGRATION.md. */
+object Native {
+  System.loadLibrary("rainier_jni") // which links librainier_cuda.so
+
+  @native def create(rir: ByteBuffer, cols: Array[Array[Double]], device: Int): Long
+  @native def nvars(handle: Long): Int
+  @native def densityBatch(handle: Long, q: Array[Double], chains: Int, out: Array[Double]): Unit
+  @native def sample(handle: Long,
+                     config: ByteBuffer,
+                     seeds: Array[Long],
+                     samples: Array[Double],
+                     mass: Array[Double],
+                     stats: ByteBuffer): Unit
+  @native def emitSource(handle: Long, config: ByteBuffer): String
+  @native def configSize(): Int
+  @native def statsSize(): Int
+  @native def defaultConfig(config: ByteBuffer): Unit
+  @native def destroy(handle: Long): Unit
+  @native def lastError(): String
+}

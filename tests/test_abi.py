@@ -71,3 +71,23 @@ def test_user_defined_sampler_cannot_be_lowered():
     with pytest.raises(api.RainierCudaError) as e:
         api.lower_config(api.make_config(sampler=MySampler()))
     assert e.value.code == abi.RN_E_UNSUPPORTED
+
+
+def test_scala_side_offsets():
+    """scala/com/stripe/rainier/cuda/CudaSampling.scala hard-codes rn_config / rn_chain_stats field offsets (it cannot
+    be compiled here); keep them pinned to the real struct layout."""
+    src = open(os.path.join(ROOT, "scala", "com", "stripe", "rainier", "cuda", "CudaSampling.scala")).read()
+    offs = dict((k, int(v)) for k, v in re.findall(r"private val (Off\w+) = (\d+)", src))
+    expect = {"OffIterations": "iterations", "OffWarmup": "warmup_iterations", "OffStatsWindow": "stats_window",
+              "OffSampler": "sampler", "OffNSteps": "n_steps", "OffMaxSteps": "max_steps", "OffMinSteps": "min_steps",
+              "OffBufSize": "buf_size", "OffPCount": "p_count", "OffStepTuner": "step_size_tuner", "OffDelta": "delta",
+              "OffStaticStep": "static_step_size", "OffMassTuner": "mass_tuner", "OffInitWindow": "initial_window_size",
+              "OffExpansion": "window_expansion", "OffSkipFirst": "skip_first", "OffSkipLast": "skip_last"}
+    for k, f in expect.items():
+        assert offs[k] == getattr(abi.Config, f).offset, k
+    assert "configSize() == %d" % C.sizeof(abi.Config) in src
+    for field, off in (("gradient_evaluations", 0), ("iterations", 16), ("divergences", 20), ("energy_mean", 40),
+                       ("energy_raw", 48), ("energy_transitions2", 56), ("energy_samples", 64), ("step_sizes_mean", 96),
+                       ("acceptance_rates_mean", 104), ("grads_per_iteration_mean", 112)):
+        assert getattr(abi.ChainStats, field).offset == off
+        assert "o + %d" % off in src or off == 0

@@ -147,3 +147,58 @@ def test_lookup_out_of_range_is_an_error():
     with pytest.raises(api.RainierCudaError) as e:
         api.CudaModel(rir, cols).density_batch(np.array([[0.5]]))
     assert e.value.code == abi.RN_E_LOOKUP
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# warp-per-chain backend (rows across lanes, shuffle reduction): same sampler semantics, tree-ordered row sums
+# ---------------------------------------------------------------------------------------------------------------
+def test_wpc_data_free_models_stay_bit_exact(funnel, schools):
+    """data-free targets are added once (lane 0) before the butterfly, so nothing is reordered"""
+    r = parity.run_both(*funnel, _cfg(40, 150, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner(),
+                                      backend=abi.RN_BACKEND_WARP), seeds=np.arange(70) + 3)
+    parity.assert_parity(r)
+    r = parity.run_both(*schools, api.SamplerConfig(iterations=60, warmupIterations=300, backend=abi.RN_BACKEND_WARP),
+                        seeds=np.arange(40) + 3)
+    parity.assert_parity(r)
+
+
+def test_wpc_streamed_laplace():
+    model, real, rng, _ = sbc_models.build("SBCLaplace")
+    rir, cols = model.compile(True)
+    r = parity.run_both(rir, cols, _cfg(30, 150, api.HMCSampler(2), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner(),
+                                        backend=abi.RN_BACKEND_WARP), seeds=np.arange(33) + 1)
+    parity.assert_parity(r, tol=1e-9)
+
+
+@pytest.mark.parametrize("gm", [abi.RN_GRAD_SYMBOLIC, abi.RN_GRAD_ADJOINT])
+def test_wpc_logistic_regression(gm):
+    rir, cols = configs.logreg(3000, 8).compile(True)
+    cfg = _cfg(30, 120, api.HMCSampler(3), api.DualAvgTuner(0.8), api.DiagonalMassMatrixTuner(20, 1.5, 10, 10),
+               backend=abi.RN_BACKEND_WARP, gradientMode=gm)
+    r = parity.run_both(rir, cols, cfg, seeds=np.arange(48) + 9)
+    parity.assert_parity(r, tol=1e-8)
+
+
+def test_wpc_poisson_glm_scatter_gradient():
+    """primal-only RIR (what the Scala wrapper sends): large Lookup table in shared memory, adjoint = atomic scatter-add;
+    the oracle evaluates the reference-style one-hot symbolic gradient of the same model."""
+    rir, cols = configs.poisson_glm(40, 2560).compile(True)
+    prir, pcols = configs.poisson_glm(40, 2560).compile(False)
+    q = np.random.default_rng(5).normal(size=(16, 43)) * 0.3
+    g = api.CudaModel(prir, pcols).density_batch(q)
+    o = OracleModel(rir, cols).density_batch(q)
+    assert parity.rel_err(g, o, 1e-9) < 1e-9
+    cfg = _cfg(20, 60, api.HMCSampler(3), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner(), backend=abi.RN_BACKEND_WARP)
+    om = OracleModel(rir, cols)
+    ref = om.sample(api.lower_config(cfg)[0], seeds=np.arange(12) + 1)
+    tr = api.CudaModel(prir, pcols).sample(cfg, seeds=np.arange(12) + 1)
+    assert parity.rel_err(tr.chains, ref["samples"], 1e-9) < 1e-6
+
+
+def test_auto_backend_picks_warp_for_streamed_models():
+    rir, cols = configs.linreg(4000, covariates=5).compile(True)
+    m = api.CudaModel(rir, cols)
+    assert "warp-per-chain" in m.emit_source(api.SamplerConfig())
+    r = parity.run_both(rir, cols, _cfg(20, 100, api.HMCSampler(4), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()),
+                        seeds=np.arange(40) + 1)
+    parity.assert_parity(r, tol=1e-8)
