@@ -203,12 +203,12 @@ static KernelKey key_for(const rn_model* m, const rn_config* cfg) {
   int want = cfg ? cfg->backend : RN_BACKEND_AUTO;
   if (const char* e = getenv("RN_BACKEND")) want = atoi(e);
   if (want == RN_BACKEND_AUTO) {
-    uint64_t rows = 0;
+    uint64_t row_work = 0;  // node evaluations per gradient spent in streamed rows
     auto it = m->programs.begin();
     if (it != m->programs.end())
       for (const TargetInfo& T : it->second->targets)
-        if (T.streamed()) rows += T.n_rows;
-    want = (rows >= 2048 || m->n_params > 48) ? RN_BACKEND_WARP : RN_BACKEND_THREAD;
+        if (T.streamed()) row_work += T.n_rows * (uint64_t)(T.row_fwd.size() + T.row_bwd.size() + 1);
+    want = (row_work >= 16384 || m->n_params > 48) ? RN_BACKEND_WARP : RN_BACKEND_THREAD;
     if (k.mass_max == 2) want = RN_BACKEND_THREAD;  // dense mass lives in the thread-per-chain kernels
   }
   k.backend = want == RN_BACKEND_WARP ? 1 : 0;

@@ -162,20 +162,45 @@ def test_wpc_data_free_models_stay_bit_exact(funnel, schools):
     parity.assert_parity(r)
 
 
+def _static(it, nsteps, eps, **kw):
+    return _cfg(it, 0, api.HMCSampler(nsteps), api.StaticStepSize(eps), api.IdentityMassMatrixTuner(), **kw)
+
+
+def _wpc_density_matches(rir, cols, n, seed=0, tol=1e-12, rir_gpu=None, cols_gpu=None):
+    q = np.random.default_rng(seed).normal(size=(37, n)) * 0.3
+    g = api.CudaModel(rir_gpu or rir, cols_gpu if cols_gpu is not None else cols)
+    src = g.emit_source(api.SamplerConfig(backend=abi.RN_BACKEND_WARP))
+    assert "warp-per-chain" in src
+    import ctypes as C
+    cfg = api.lower_config(api.SamplerConfig(backend=abi.RN_BACKEND_WARP))[0]
+    # rn_density_batch uses the model's default kernel; force the warp backend through the environment override
+    os.environ["RN_BACKEND"] = "2"
+    try:
+        out = api.CudaModel(rir_gpu or rir, cols_gpu if cols_gpu is not None else cols).density_batch(q)
+    finally:
+        del os.environ["RN_BACKEND"]
+    ref = OracleModel(rir, cols).density_batch(q)
+    assert parity.rel_err(out, ref, 1e-9) < tol, parity.rel_err(out, ref, 1e-9)
+
+
+# With rows spread over lanes the row sum is a tree, not the reference's sequential loop: densities agree to ~1e-13 but
+# not bit for bit, so in the chaotic part of warmup (huge trial step sizes) decisions may legitimately flip
+# (SURVEY.md 7.3-2).  Parity of this backend is therefore pinned by (a) density/gradient values, (b) whole trajectories
+# in the stable regime (static, small step size), (c) the bit-exact data-free case above; RN_BACKEND_THREAD remains
+# available when bit-exact streamed parity is wanted.
 def test_wpc_streamed_laplace():
     model, real, rng, _ = sbc_models.build("SBCLaplace")
     rir, cols = model.compile(True)
-    r = parity.run_both(rir, cols, _cfg(30, 150, api.HMCSampler(2), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner(),
-                                        backend=abi.RN_BACKEND_WARP), seeds=np.arange(33) + 1)
+    _wpc_density_matches(rir, cols, 1)
+    r = parity.run_both(rir, cols, _static(60, 3, 0.004, backend=abi.RN_BACKEND_WARP), seeds=np.arange(33) + 1)
     parity.assert_parity(r, tol=1e-9)
 
 
 @pytest.mark.parametrize("gm", [abi.RN_GRAD_SYMBOLIC, abi.RN_GRAD_ADJOINT])
 def test_wpc_logistic_regression(gm):
     rir, cols = configs.logreg(3000, 8).compile(True)
-    cfg = _cfg(30, 120, api.HMCSampler(3), api.DualAvgTuner(0.8), api.DiagonalMassMatrixTuner(20, 1.5, 10, 10),
-               backend=abi.RN_BACKEND_WARP, gradientMode=gm)
-    r = parity.run_both(rir, cols, cfg, seeds=np.arange(48) + 9)
+    _wpc_density_matches(rir, cols, 8)
+    r = parity.run_both(rir, cols, _static(40, 4, 0.02, backend=abi.RN_BACKEND_WARP, gradientMode=gm), seeds=np.arange(48) + 9)
     parity.assert_parity(r, tol=1e-8)
 
 
@@ -184,21 +209,28 @@ def test_wpc_poisson_glm_scatter_gradient():
     the oracle evaluates the reference-style one-hot symbolic gradient of the same model."""
     rir, cols = configs.poisson_glm(40, 2560).compile(True)
     prir, pcols = configs.poisson_glm(40, 2560).compile(False)
-    q = np.random.default_rng(5).normal(size=(16, 43)) * 0.3
-    g = api.CudaModel(prir, pcols).density_batch(q)
-    o = OracleModel(rir, cols).density_batch(q)
-    assert parity.rel_err(g, o, 1e-9) < 1e-9
-    cfg = _cfg(20, 60, api.HMCSampler(3), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner(), backend=abi.RN_BACKEND_WARP)
-    om = OracleModel(rir, cols)
-    ref = om.sample(api.lower_config(cfg)[0], seeds=np.arange(12) + 1)
+    _wpc_density_matches(rir, cols, 43, tol=1e-9, rir_gpu=prir, cols_gpu=pcols)
+    cfg = _static(30, 3, 0.01, backend=abi.RN_BACKEND_WARP)
+    ref = OracleModel(rir, cols).sample(api.lower_config(cfg)[0], seeds=np.arange(12) + 1)
     tr = api.CudaModel(prir, pcols).sample(cfg, seeds=np.arange(12) + 1)
-    assert parity.rel_err(tr.chains, ref["samples"], 1e-9) < 1e-6
+    assert parity.rel_err(tr.chains, ref["samples"], 1e-9) < 1e-7
 
 
 def test_auto_backend_picks_warp_for_streamed_models():
     rir, cols = configs.linreg(4000, covariates=5).compile(True)
     m = api.CudaModel(rir, cols)
     assert "warp-per-chain" in m.emit_source(api.SamplerConfig())
-    r = parity.run_both(rir, cols, _cfg(20, 100, api.HMCSampler(4), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()),
-                        seeds=np.arange(40) + 1)
+    r = parity.run_both(rir, cols, _static(30, 4, 0.005), seeds=np.arange(40) + 1)
     parity.assert_parity(r, tol=1e-8)
+
+
+def test_wpc_and_tpc_agree_statistically():
+    """full DefaultConfig run (chaotic warmup included) of a streamed model on both kernel shapes: posterior means agree
+    within Monte-Carlo error"""
+    rir, cols = configs.logreg(2000, 4).compile(True)
+    means = []
+    for be in (abi.RN_BACKEND_THREAD, abi.RN_BACKEND_WARP):
+        tr = api.CudaModel(rir, cols).sample(api.SamplerConfig(iterations=200, warmupIterations=300, backend=be), seeds=np.arange(256) + 1)
+        means.append(tr.chains.reshape(-1, 4).mean(axis=0))
+        sd = tr.chains.reshape(-1, 4).std(axis=0)
+    assert np.all(np.abs(means[0] - means[1]) < 0.05 * sd + 1e-3)
