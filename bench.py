@@ -243,15 +243,19 @@ def main():
     seeds_host = np.ascontiguousarray(seeds)
 
     def e2e_step():
+        t_call = time.perf_counter()
         rc = api.lib().rn_sample(model.h, CT.byref(e2e_cfg), seeds_host.ctypes.data, C_, samples_host.ctypes.data, None, None)
         if rc != 0:
             raise RuntimeError(api.lib().rn_last_error().decode())
+        if os.environ.get("RN_TIMING"):
+            print("[bench] rn_sample call %.1f ms" % ((time.perf_counter() - t_call) * 1e3), file=sys.stderr)
 
-    e2e_step()  # warm (page-faults the host buffer, loads nothing new on the device)
+    for _ in range(3):  # warm: page-faults the host buffer, pins the staging ring, grows the device scratch pool
+        e2e_step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    n_e2e = max(2, min(args.steps, 5))
+    n_e2e = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(n_e2e):
         e2e_step()

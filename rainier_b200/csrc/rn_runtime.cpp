@@ -1095,12 +1095,17 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
     CUdeviceptr b[2] = {0, 0};
     CUstream copy = nullptr;
     CUevent done = nullptr;
+    bool timing = false;
     ~Guard() {
+      auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+      const double t0 = now();
       if (done) A->cuEventDestroy(done);
       if (copy) A->cuStreamDestroy(copy);
       rn_sampler_destroy(s);
+      if (timing) fprintf(stderr, "[rn_sample] %-18s %8.2f ms\n", "teardown", (now() - t0) * 1e3);
     }
   } g{s, A};
+  g.timing = timing;
   rc = rn_sampler_warmup(s, -1);
   if (rc) return rc;
   if (timing) rn_sampler_sync(s);

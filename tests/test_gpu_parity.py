@@ -119,8 +119,8 @@ def test_streamed_targets_match_oracle():
     model, real, rng, _ = sbc_models.build("SBCLaplace")
     rir, cols = model.compile(True)
     assert len(cols) > 0
-    r = parity.run_both(rir, cols, _cfg(30, 150, api.HMCSampler(2), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()),
-                        seeds=np.arange(96) + 1)
+    r = parity.run_both(rir, cols, _cfg(30, 150, api.HMCSampler(2), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner(),
+                                        backend=abi.RN_BACKEND_THREAD), seeds=np.arange(96) + 1)
     parity.assert_parity(r)
 
 
