@@ -71,6 +71,10 @@ def lib():
         L.rn_sampler_destroy.argtypes = [C.c_void_p]
         L.rn_sampler_enable_trace.argtypes = [C.c_void_p]
         L.rn_sampler_read_trace.argtypes = [C.c_void_p, C.c_void_p]
+        L.rn_sampler_set_comm.argtypes = [C.c_void_p, C.c_void_p]
+        L.rn_comm_unique_id.argtypes = [C.c_char_p]
+        L.rn_comm_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rn_comm_destroy.argtypes = [C.c_void_p]
         sizes = (C.c_int32 * 4)()
         L.rn_abi_sizes(sizes)
         if sizes[0] != C.sizeof(Config) or sizes[1] != C.sizeof(ChainStats) or sizes[2] != C.sizeof(RngState):
@@ -399,6 +403,36 @@ class CudaModel:
         return Trace(samples, mass, [Stats(stats[c], rings[c]) for c in range(nChains)])
 
 
+class Comm:
+    """NCCL communicator of the library (rn_comm_*): used only by RN_ADAPT_POOLED's warmup-phase all-reduce.  The
+    128-byte unique id is exchanged through torch.distributed (any backend), which is plumbing only."""
+
+    def __init__(self, handle, rank, world):
+        self.h, self.rank, self.world = handle, rank, world
+
+    @staticmethod
+    def from_torch_distributed(device):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _check(lib().rn_comm_unique_id(buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda(device)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        h = C.c_void_p()
+        _check(lib().rn_comm_create(raw, rank, world, int(device), C.byref(h)))
+        return Comm(h, rank, world)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rn_comm_destroy(self.h)
+            self.h = None
+
+
 class CudaSampler:
     """Staged, device-resident sampling (what rn_sample is built from); used by bench.py and the parity tests."""
 
@@ -420,6 +454,10 @@ class CudaSampler:
         self._trace = trace
         if trace:
             _check(lib().rn_sampler_enable_trace(self.h))
+
+    def set_comm(self, comm):
+        self._comm = comm
+        _check(lib().rn_sampler_set_comm(self.h, comm.h))
 
     def warmup(self, iterations=-1):
         _check(lib().rn_sampler_warmup(self.h, int(iterations)))

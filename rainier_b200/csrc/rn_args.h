@@ -49,7 +49,7 @@ struct RnArgs {
   int stats_window;
   int n_iter;                    // iterations in this launch
   int phase;                     // 0 warmup, 1 sampling
-  int pad1;
+  int adaptation;                // 0 per chain (reference semantics), 1 pooled over chains/ranks (extension)
 };
 
 #endif

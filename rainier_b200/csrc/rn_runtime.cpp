@@ -146,7 +146,8 @@ struct Kernel {
   std::string source;
   std::vector<char> cubin;
   CUmodule mod = nullptr;
-  CUfunction k_init = nullptr, k_iter = nullptr, k_density = nullptr, k_transpose = nullptr;
+  CUfunction k_init = nullptr, k_iter = nullptr, k_density = nullptr, k_transpose = nullptr, k_pool_reduce = nullptr,
+             k_pool_apply = nullptr;
   const Program* prog = nullptr;
   int backend = 0;            // 0 thread per chain, 1 warp per chain
   int wpc_smem_doubles = 0;   // per-warp dynamic shared memory (backend 1)
@@ -297,6 +298,8 @@ static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
   CU(A->cuModuleGetFunction(&K->k_iter, K->mod, "rn_k_iter"));
   CU(A->cuModuleGetFunction(&K->k_density, K->mod, "rn_k_density"));
   CU(A->cuModuleGetFunction(&K->k_transpose, K->mod, "rn_k_transpose"));
+  CU(A->cuModuleGetFunction(&K->k_pool_reduce, K->mod, "rn_k_pool_reduce"));
+  CU(A->cuModuleGetFunction(&K->k_pool_apply, K->mod, "rn_k_pool_apply"));
   if (K->backend == 1) {
     const int bytes = K->warps_per_cta * K->wpc_smem_doubles * 8;
     for (CUfunction f : {K->k_init, K->k_iter, K->k_density})
@@ -491,6 +494,56 @@ int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------
+// communicator: NCCL loaded with dlopen (torch-bundled or system libnccl.so.2); only the warmup-phase all-reduce
+// of pooled mass-matrix statistics uses it -- the sampling path has no collective.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct NcclId {
+  char b[128];
+};
+typedef int (*nccl_init_fn)(void**, int, NcclId, int);
+struct Nccl {
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  nccl_init_fn CommInitRank = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, void*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+const Nccl* nccl(std::string* why) {
+  static Nccl n;
+  static bool tried = false, ok = false;
+  static std::string err;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      err = std::string("cannot load libnccl.so.2: ") + dlerror();
+    } else {
+      n.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+      n.CommInitRank = (nccl_init_fn)dlsym(h, "ncclCommInitRank");
+      n.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, void*))dlsym(h, "ncclAllReduce");
+      n.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+      n.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+      ok = n.GetUniqueId && n.CommInitRank && n.AllReduce && n.CommDestroy;
+      if (!ok) err = "libnccl lacks a required symbol";
+    }
+  }
+  if (!ok) {
+    if (why) *why = err;
+    return nullptr;
+  }
+  return &n;
+}
+}  // namespace
+
+struct rn_comm {
+  void* comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+  CUcontext ctx = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------
 // sampler
 // ---------------------------------------------------------------------------------------------------------
 struct rn_sampler {
@@ -512,6 +565,7 @@ struct rn_sampler {
   CUdeviceptr d_trace = 0;  // optional test instrumentation, [warmup+iterations][4][chains]
   size_t trace_iters = 0, trace_pos = 0;
   rn_comm* comm = nullptr;
+  CUdeviceptr d_pool = 0;  // [2n+1] pooled window statistics (RN_ADAPT_POOLED)
 };
 
 namespace {
@@ -559,21 +613,39 @@ std::vector<double> cholesky_upper(const double* matrix, int n) {
   return upper;
 }
 
-void advance_window(rn_sampler* s, int iters) {  // mirrors the device-side WindowedMassMatrixTuner.update
+// mirrors the device-side WindowedMassMatrixTuner.update; returns the length of the window that closed on the LAST
+// of these iterations (0 if none closed there)
+int advance_window(rn_sampler* s, int iters) {
   const rn_config& c = s->cfg;
-  if (c.mass_tuner != RN_MASS_DIAGONAL && c.mass_tuner != RN_MASS_DENSE) return;
+  if (c.mass_tuner != RN_MASS_DIAGONAL && c.mass_tuner != RN_MASS_DENSE) return 0;
+  int closed = 0;
   for (int k = 0; k < iters; k++) {
+    closed = 0;
     s->win_j += 1;
     if (s->win_j < c.skip_first || (c.warmup_iterations - s->win_j) < c.skip_last) continue;
     s->win_i += 1;
     s->est_samples += 1;
     if (s->win_i == s->win_size) {
+      closed = s->win_size;
       s->win_i = 0;
       double w = s->win_size * c.window_expansion;
       s->win_size = (w >= 2147483647.0) ? 2147483647 : (int)w;
       s->mass_kind = c.mass_tuner == RN_MASS_DIAGONAL ? RN_MATRIX_DIAGONAL : RN_MATRIX_DENSE;
     }
   }
+  return closed;
+}
+// number of iterations from now up to and including the next window end (or `limit` if none within it)
+int iterations_to_window_end(const rn_sampler* s, int limit) {
+  const rn_config& c = s->cfg;
+  int j = s->win_j, i = s->win_i;
+  for (int k = 1; k <= limit; k++) {
+    j += 1;
+    if (j < c.skip_first || (c.warmup_iterations - j) < c.skip_last) continue;
+    i += 1;
+    if (i == s->win_size) return k;
+  }
+  return limit;
 }
 
 int check_config(const rn_model* m, const rn_config* c, int chains) {
@@ -642,6 +714,7 @@ int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, i
   s->stats_bytes = ar.off - s->stats_off;
   s->arena_bytes = ar.off;
   CU(A->cuMemAlloc(&s->arena, s->arena_bytes));
+  CU(A->cuMemAlloc(&s->d_pool, (2 * n + 1) * 8));
   CU(A->cuMemsetD8Async(s->arena, 0, s->arena_bytes, s->stream));
 
   RnArgs& a = s->args;
@@ -756,14 +829,45 @@ int rn_sampler_read_trace(rn_sampler* s, double* out /*[chains][iters][4]*/) {
   return RN_OK;
 }
 
+static int pool_window(const Api* A, rn_sampler* s, int window_len) {
+  const size_t n = s->m->n_params;
+  CU(A->cuMemsetD8Async(s->d_pool, 0, (2 * n + 1) * 8, s->stream));
+  {
+    CUdeviceptr pool = s->d_pool;
+    int wl = window_len;
+    void* params[] = {&s->args, &pool, &wl};
+    const unsigned grid = (unsigned)std::min<size_t>(296, ((size_t)s->chains + 255) / 256);
+    CU(A->cuLaunchKernel(s->K->k_pool_reduce, grid, 1, 1, 256, 1, 1, 0, s->stream, params, nullptr));
+    s->launches++;
+  }
+  if (s->comm && s->comm->world > 1) {
+    std::string why;
+    const Nccl* N = nccl(&why);
+    if (!N) return fail(RN_E_NCCL, why);
+    int r = N->AllReduce((const void*)(uintptr_t)s->d_pool, (void*)(uintptr_t)s->d_pool, 2 * n + 1, 8 /*ncclFloat64*/,
+                         0 /*ncclSum*/, s->comm->comm, (void*)s->stream);
+    if (r != 0) return fail(RN_E_NCCL, std::string("ncclAllReduce: ") + (N->GetErrorString ? N->GetErrorString(r) : "?"));
+  }
+  {
+    CUdeviceptr pool = s->d_pool;
+    void* params[] = {&s->args, &pool};
+    CU(A->cuLaunchKernel(s->K->k_pool_apply, (unsigned)((s->chains + 127) / 128), 1, 1, 128, 1, 1, 0, s->stream, params, nullptr));
+    s->launches++;
+  }
+  return RN_OK;
+}
+
 static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, double* d_samples) {
   const int per_launch = s->cfg.launch_iterations > 0 ? s->cfg.launch_iterations : 1000;
+  const bool pooled = phase == 0 && s->cfg.adaptation == RN_ADAPT_POOLED && s->cfg.mass_tuner == RN_MASS_DIAGONAL;
   int done = 0;
   while (done < iterations) {
-    const int k = std::min(per_launch, iterations - done);
+    int k = std::min(per_launch, iterations - done);
+    if (pooled) k = iterations_to_window_end(s, k);  // launches end exactly at window ends
     RnArgs& a = s->args;
     a.phase = phase;
     a.n_iter = k;
+    a.adaptation = s->cfg.adaptation == RN_ADAPT_POOLED ? 1 : 0;
     a.mass_kind = s->mass_kind;
     a.win_size = s->win_size;
     a.win_i = s->win_i;
@@ -773,7 +877,13 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.trace = s->d_trace ? (double*)(uintptr_t)(s->d_trace + s->trace_pos * 4 * (size_t)s->chains * 8) : nullptr;
     int rc = launch(A, s, s->K->k_iter);
     if (rc) return rc;
-    if (phase == 0) advance_window(s, k);
+    if (phase == 0) {
+      const int closed = advance_window(s, k);
+      if (pooled && closed > 0) {
+        rc = pool_window(A, s, closed);
+        if (rc) return rc;
+      }
+    }
     if (s->d_trace) s->trace_pos += (size_t)k;
     done += k;
   }
@@ -940,6 +1050,7 @@ void rn_sampler_destroy(rn_sampler* s) {
       A->cuStreamDestroy(s->stream);
     }
     if (s->arena) A->cuMemFree(s->arena);
+    if (s->d_pool) A->cuMemFree(s->d_pool);
     if (s->d_trace) A->cuMemFree(s->d_trace);
   }
   delete s;
@@ -1184,10 +1295,49 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// communicator (NCCL) -- not wired yet
+// communicator (NCCL); the unique id is exchanged by the caller (e.g. torch.distributed broadcast of 128 bytes)
 // ---------------------------------------------------------------------------------------------------------
-int rn_comm_unique_id(char*) { return fail(RN_E_UNSUPPORTED, "NCCL communicator not available in this build"); }
-int rn_comm_create(const char*, int, int, int, rn_comm**) { return fail(RN_E_UNSUPPORTED, "NCCL communicator not available in this build"); }
-void rn_comm_destroy(rn_comm*) {}
-
+int rn_comm_unique_id(char id[128]) {
+  std::string why;
+  const Nccl* N = nccl(&why);
+  if (!N) return fail(RN_E_NCCL, why);
+  NcclId u;
+  int r = N->GetUniqueId(&u);
+  if (r != 0) return fail(RN_E_NCCL, "ncclGetUniqueId failed");
+  std::memcpy(id, u.b, 128);
+  return RN_OK;
+}
+int rn_comm_create(const char id[128], int rank, int world, int device, rn_comm** out) {
+  std::string why;
+  const Nccl* N = nccl(&why);
+  if (!N) return fail(RN_E_NCCL, why);
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  std::unique_ptr<rn_comm> c(new rn_comm());
+  c->rank = rank;
+  c->world = world;
+  c->device = device;
+  CUdevice dev;
+  CU(A->cuDeviceGet(&dev, device));
+  CU(A->cuDevicePrimaryCtxRetain(&c->ctx, dev));
+  CU(A->cuCtxSetCurrent(c->ctx));
+  NcclId u;
+  std::memcpy(u.b, id, 128);
+  int r = N->CommInitRank(&c->comm, world, u, rank);
+  if (r != 0) return fail(RN_E_NCCL, std::string("ncclCommInitRank: ") + (N->GetErrorString ? N->GetErrorString(r) : "?"));
+  *out = c.release();
+  return RN_OK;
+}
+void rn_comm_destroy(rn_comm* c) {
+  if (!c) return;
+  std::string why;
+  const Nccl* N = nccl(&why);
+  if (N && c->comm) N->CommDestroy(c->comm);
+  const Api* A = api(&why);
+  if (A && c->ctx) {
+    CUdevice dev;
+    if (A->cuDeviceGet(&dev, c->device) == 0) A->cuDevicePrimaryCtxRelease(dev);
+  }
+  delete c;
+}
 }  // extern "C"

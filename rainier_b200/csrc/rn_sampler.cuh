@@ -441,7 +441,22 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
 #if RN_MASS_MAX >= 1
       if (A.mass_tuner == 1 || A.mass_tuner == 2) {
         win_j += 1;
-        if (!(win_j < A.skip_first || (A.total_warmup - win_j) < A.skip_last)) {
+        if (A.adaptation == 1) {
+          // pooled extension: plain window sums per chain; the host reduces them over chains (and ranks) at the
+          // window end (rn_k_pool_reduce / rn_k_pool_apply) -- launches are cut at window ends in this mode
+          if (!(win_j < A.skip_first || (A.total_warmup - win_j) < A.skip_last)) {
+            win_i += 1;
+            RN_UNROLL
+            for (int i = 0; i < RN_N; i++) {
+              RN_AT(A.est_mean, i, c) += s.q[i];
+              RN_AT(A.est_raw, i, c) += s.q[i] * s.q[i];
+            }
+            if (win_i == win_size) {
+              win_i = 0;
+              win_size = rn_d2i(win_size * A.win_expansion);
+            }
+          }
+        } else if (!(win_j < A.skip_first || (A.total_warmup - win_j) < A.skip_last)) {
           win_i += 1;
           est_samples += 1;  // VarianceEstimator.update, MassMatrixEstimator.scala:69-83
           double oldDiff[RN_N], newDiff[RN_N];
@@ -596,6 +611,54 @@ RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int c = c0 + j, r = r0 + threadIdx.x;
     if (r < rows && c < cols) dst[(size_t)c * (size_t)dst_ld + (size_t)dst_off + r] = tile[threadIdx.x][j];
+  }
+}
+#endif
+
+// =============================================================================================================
+// Pooled mass-matrix adaptation (RN_ADAPT_POOLED; an extension, not reference semantics): at a window end the
+// per-chain window sums {sum q_i, sum q_i^2} are reduced over all chains of this GPU into pool[1..2n] (pool[0] =
+// number of draws), all-reduced over ranks by the host (NCCL) and applied to every chain: one shared diagonal
+// mass matrix, sums cleared, DualAvg restarted from each chain's averaged step size (Driver.scala:75-80).
+// =============================================================================================================
+#ifndef RN_HOST_EMULATION
+RN_GLOBAL void rn_k_pool_reduce(const RnArgs A, double* pool, int window_len) {
+  __shared__ double red[256];
+  for (int i = 0; i < 2 * RN_N; i++) {
+    const double* src = (i < RN_N) ? (A.est_mean + (size_t)i * A.chains) : (A.est_raw + (size_t)(i - RN_N) * A.chains);
+    double acc = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.chains; c += gridDim.x * blockDim.x) acc += src[c];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(&pool[1 + i], red[0]);
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&pool[0], (double)A.chains * (double)window_len);
+}
+RN_GLOBAL void rn_k_pool_apply(const RnArgs A, const double* pool) {
+  const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (c >= A.chains) return;
+  const double cnt = pool[0];
+  for (int i = 0; i < RN_N; i++) {
+    const double mean = pool[1 + i] / cnt;
+    const double var = pool[1 + RN_N + i] / cnt - mean * mean;
+    if (!(var > 0.0)) A.st_err[c] |= 2;
+    RN_AT(A.mass, i, c) = var;
+    RN_AT(A.est_mean, i, c) = 0.0;
+    RN_AT(A.est_raw, i, c) = 0.0;
+  }
+  if (A.step_tuner == 0) {  // stepSizeTuner.reset(), DualAvg.scala:17-21
+    const double ss = rn_exp(RN_AT(A.da, 2, c));
+    RN_AT(A.da, 0, c) = ss;
+    RN_AT(A.da, 1, c) = rn_log(ss);
+    RN_AT(A.da, 2, c) = 0.0;
+    RN_AT(A.da, 3, c) = 0.0;
+    RN_AT(A.da, 4, c) = rn_log(10 * ss);
+    A.da_iter[c] = 0;
   }
 }
 #endif

@@ -234,3 +234,17 @@ def test_wpc_and_tpc_agree_statistically():
         means.append(tr.chains.reshape(-1, 4).mean(axis=0))
         sd = tr.chains.reshape(-1, 4).std(axis=0)
     assert np.all(np.abs(means[0] - means[1]) < 0.05 * sd + 1e-3)
+
+
+def test_pooled_adaptation_single_gpu(schools):
+    """RN_ADAPT_POOLED (extension): mass-matrix windows pool statistics over all chains -> one shared diagonal matrix."""
+    cfg = api.SamplerConfig(iterations=200, warmupIterations=400, adaptation=abi.RN_ADAPT_POOLED)
+    tr = api.CudaModel(*schools).sample(cfg, seeds=np.arange(512) + 1)
+    assert np.all(tr.mass > 0) and np.all(np.isfinite(tr.mass))
+    assert np.all(tr.mass == tr.mass[0]), "pooled mode shares one mass matrix"
+    ref = api.CudaModel(*schools).sample(api.SamplerConfig(iterations=200, warmupIterations=400), seeds=np.arange(512) + 1)
+    m0, m1 = tr.chains.reshape(-1, 10).mean(axis=0), ref.chains.reshape(-1, 10).mean(axis=0)
+    sd = ref.chains.reshape(-1, 10).std(axis=0)
+    assert np.all(np.abs(m0 - m1) < 0.1 * sd)
+    acc = np.mean([s.accepted / s.iterations for s in tr.stats])
+    assert 0.5 < acc <= 1.0
