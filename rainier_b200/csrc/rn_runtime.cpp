@@ -7,6 +7,7 @@
 // No CPU fallback: anything that needs to execute fails with RN_E_CUDA when there is no driver/device.
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -216,6 +217,7 @@ static KernelKey key_for(const rn_model* m, const rn_config* cfg) {
   return k;
 }
 
+extern "C" const char* rn_version(void);
 // emit + NVRTC (no device needed)
 static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
   KernelKey key = key_for(m, cfg);
@@ -247,9 +249,6 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
     K->warps_per_cta = w;
   }
 
-  nvrtcProgram prog;
-  if (nvrtcCreateProgram(&prog, K->source.c_str(), "rainier_model.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
-    return fail(RN_E_COMPILE, "nvrtcCreateProgram failed");
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
   std::string maxreg;
@@ -263,6 +262,40 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
       opts.push_back(maxreg.c_str());
     }
   }
+  // optional on-disk cubin cache (NVRTC + ptxas of a large emitted model can take a minute): RN_KERNEL_CACHE=<dir>
+  std::string cache_path;
+  if (const char* dir = getenv("RN_KERNEL_CACHE")) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const std::string& t) {
+      for (unsigned char ch : t) {
+        h ^= ch;
+        h *= 1099511628211ull;
+      }
+    };
+    mix(K->source);
+    for (const char* o : opts) mix(o);
+    mix(rn_version());
+    char name[64];
+    snprintf(name, sizeof(name), "/%016llx.cubin", (unsigned long long)h);
+    cache_path = std::string(dir) + name;
+    if (FILE* f = fopen(cache_path.c_str(), "rb")) {
+      fseek(f, 0, SEEK_END);
+      long sz = ftell(f);
+      fseek(f, 0, SEEK_SET);
+      K->cubin.resize((size_t)sz);
+      size_t got = fread(K->cubin.data(), 1, (size_t)sz, f);
+      fclose(f);
+      if (got == (size_t)sz && sz > 4) {
+        *out = K.get();
+        m->kernels.emplace(key, std::move(K));
+        return RN_OK;
+      }
+      K->cubin.clear();
+    }
+  }
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, K->source.c_str(), "rainier_model.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    return fail(RN_E_COMPILE, "nvrtcCreateProgram failed");
   nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   if (r != NVRTC_SUCCESS) {
     size_t n = 0;
@@ -284,6 +317,14 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
   K->cubin.resize(n);
   nvrtcGetCUBIN(prog, K->cubin.data());
   nvrtcDestroyProgram(&prog);
+  if (!cache_path.empty()) {
+    std::string tmp = cache_path + ".tmp" + std::to_string((long long)getpid());
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      fwrite(K->cubin.data(), 1, K->cubin.size(), f);
+      fclose(f);
+      rename(tmp.c_str(), cache_path.c_str());
+    }
+  }
   *out = K.get();
   m->kernels.emplace(key, std::move(K));
   return RN_OK;
