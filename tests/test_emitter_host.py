@@ -30,7 +30,7 @@ def test_emitted_density_matches_oracle(name):
     ref = om.density_batch(q)
     cm = api.CudaModel(rir, cols, device=-1)
     for gm, tol in ((abi.RN_GRAD_SYMBOLIC, 0.0), (abi.RN_GRAD_ADJOINT, 1e-9)):
-        cfg = api.make_config(sampler=api.HMCSampler(1), gradientMode=gm)
+        cfg = api.make_config(sampler=api.HMCSampler(1), gradientMode=gm, backend=abi.RN_BACKEND_THREAD)
         out, err = he.density(cm.emit_source(cfg), q, cols)
         assert err == 0
         rel = np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1e-300))
@@ -46,7 +46,7 @@ def test_primal_rir_scatter_gradient_for_large_lookup_tables():
     ref = om.density_batch(q)
     prir, pcols = configs.poisson_glm(40, 640).compile(False)
     cm = api.CudaModel(prir, pcols, device=-1)
-    src = cm.emit_source(api.make_config(sampler=api.HMCSampler(1)))
+    src = cm.emit_source(api.make_config(sampler=api.HMCSampler(1), backend=abi.RN_BACKEND_THREAD))
     assert "+ k] +=" in src  # the scatter statement
     out, err = he.density(src, q, pcols)
     assert err == 0
