@@ -236,35 +236,38 @@ def main():
     value = total_steps / (ms_max * 1e-3)
     smp.close()
 
-    # ---------------- end-to-end leg: public one-call API, host buffers ----------------
+    # ---------------- end-to-end leg: public one-call API (rn_sample over the C ABI), HOST buffers ----------------
+    # every step: seeds host->device, all samples device->host.  Headline = page-locked caller buffer (rn_host_alloc,
+    # what the JNI shim hands the JVM as a direct ByteBuffer); also reported for a pageable caller buffer.
     e2e_cfg, keep = api.lower_config(cfg)
     import ctypes as CT
-    samples_host = torch.empty((C_, I_, N_DIM), dtype=torch.float64).pin_memory() if False else np.empty((C_, I_, N_DIM))
     seeds_host = np.ascontiguousarray(seeds)
+    pin = api.PinnedBuffer((C_, I_, N_DIM), device=local_rank)
+    pageable = np.empty((C_, I_, N_DIM))
 
-    def e2e_step():
-        t_call = time.perf_counter()
-        rc = api.lib().rn_sample(model.h, CT.byref(e2e_cfg), seeds_host.ctypes.data, C_, samples_host.ctypes.data, None, None)
-        if rc != 0:
-            raise RuntimeError(api.lib().rn_last_error().decode())
-        if os.environ.get("RN_TIMING"):
-            print("[bench] rn_sample call %.1f ms" % ((time.perf_counter() - t_call) * 1e3), file=sys.stderr)
+    def e2e_leg(buf, n_rep):
+        def step():
+            rc = api.lib().rn_sample(model.h, CT.byref(e2e_cfg), seeds_host.ctypes.data, C_, buf.ctypes.data, None, None)
+            if rc != 0:
+                raise RuntimeError(api.lib().rn_last_error().decode())
+        for _ in range(3):  # warm: page-faults the host buffer, pins the staging ring, grows the device scratch pool
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_rep):
+            step()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(world) * C_ * I_ * N_STEPS * n_rep / float(t.item())
 
-    for _ in range(3):  # warm: page-faults the host buffer, pins the staging ring, grows the device scratch pool
-        e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     n_e2e = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        e2e_step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t_e2e = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = float(world) * C_ * I_ * N_STEPS * n_e2e / float(t_e2e.item())
+    e2e_value = e2e_leg(pin.array, n_e2e)
+    e2e_pageable = e2e_leg(pageable, n_e2e)
+    pin.close()
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -287,8 +290,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "leapfrog-steps*chains/s", "h2d_bytes_per_step": int(C_ * 8),
-                    "d2h_bytes_per_step": int(C_ * I_ * N_DIM * 8), "api": "rn_sample (C ABI) with host buffers",
-                    "steps": n_e2e},
+                    "d2h_bytes_per_step": int(C_ * I_ * N_DIM * 8),
+                    "api": "rn_sample (C ABI), host buffers: seeds in, [chains][iterations][n] samples out (page-locked, rn_host_alloc)",
+                    "steps": n_e2e, "pageable_caller_buffer_value": e2e_pageable},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
                          "bytes_per_leapfrog_step": bps,

@@ -170,6 +170,17 @@ void rn_model_destroy(rn_model* m);
 int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, double* samples,
               double* mass, rn_chain_stats* stats);
 
+/* ---- page-locked host buffers (optional) ----------------------------------------------------------------- */
+/* The result of rn_sample is chains*iterations*n doubles -- at the headline size 1.2 GB per call -- so the
+ * device->host copy dominates the call.  When `samples` points into page-locked memory the DMA engine writes it
+ * directly; a pageable buffer is filled through a pinned staging ring plus host memcpy threads (about half the rate).
+ * rn_host_alloc returns page-locked memory (the JVM side wraps it with NewDirectByteBuffer);
+ * rn_host_register page-locks a buffer the caller already owns (e.g. a long-lived direct ByteBuffer). */
+int rn_host_alloc(int device, size_t bytes, void** out);
+int rn_host_free(int device, void* p);
+int rn_host_register(int device, void* p, size_t bytes);
+int rn_host_unregister(int device, void* p);
+
 /* ---- staged / device-resident sampling (what rn_sample is built from) ----------------------------------- */
 int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, rn_sampler** out);
 /* LeapFrog.initialize + Driver.warmup (Driver.scala:22,48-90) for `iterations` more warmup iterations

@@ -100,6 +100,37 @@ JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_sample(JNIEnv* env, j
   if (rc != RN_OK) throw_last(env);
 }
 
+// def hostAlloc(device: Int, bytes: Long): ByteBuffer   -- page-locked memory as a direct buffer (rn_host_alloc)
+JNIEXPORT jobject JNICALL Java_com_stripe_rainier_cuda_Native_hostAlloc(JNIEnv* env, jclass, jint device, jlong bytes) {
+  void* p = nullptr;
+  if (rn_host_alloc(device, (size_t)bytes, &p) != RN_OK) {
+    throw_last(env);
+    return nullptr;
+  }
+  return env->NewDirectByteBuffer(p, bytes);
+}
+JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_hostFree(JNIEnv* env, jclass, jint device, jobject buf) {
+  if (rn_host_free(device, env->GetDirectBufferAddress(buf)) != RN_OK) throw_last(env);
+}
+
+// def sampleDirect(h: Long, config: ByteBuffer, seeds: Array[Long], samples: ByteBuffer, mass: Array[Double],
+//                  stats: ByteBuffer): Unit    -- samples is a direct buffer (ideally from hostAlloc: the device->host
+// copy of chains*iterations*n doubles then is one DMA into the buffer the JVM reads, with no staging copy)
+JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_sampleDirect(JNIEnv* env, jclass, jlong h, jobject config,
+                                                                       jlongArray seeds, jobject samples, jdoubleArray mass,
+                                                                       jobject stats) {
+  const rn_config* cfg = (const rn_config*)env->GetDirectBufferAddress(config);
+  rn_chain_stats* st = stats ? (rn_chain_stats*)env->GetDirectBufferAddress(stats) : nullptr;
+  double* out = (double*)env->GetDirectBufferAddress(samples);
+  const jint chains = env->GetArrayLength(seeds);
+  int rc;
+  {
+    Crit cs(env, seeds, JNI_ABORT), cm(env, mass);
+    rc = rn_sample((rn_model*)(intptr_t)h, cfg, (const int64_t*)cs.p, chains, out, (double*)cm.p, st);
+  }
+  if (rc != RN_OK) throw_last(env);
+}
+
 JNIEXPORT jstring JNICALL Java_com_stripe_rainier_cuda_Native_emitSource(JNIEnv* env, jclass, jlong h, jobject config) {
   const rn_config* cfg = config ? (const rn_config*)env->GetDirectBufferAddress(config) : nullptr;
   size_t need = 0;

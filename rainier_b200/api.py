@@ -75,6 +75,10 @@ def lib():
         L.rn_comm_unique_id.argtypes = [C.c_char_p]
         L.rn_comm_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.rn_comm_destroy.argtypes = [C.c_void_p]
+        L.rn_host_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.rn_host_free.argtypes = [C.c_int, C.c_void_p]
+        L.rn_host_register.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+        L.rn_host_unregister.argtypes = [C.c_int, C.c_void_p]
         sizes = (C.c_int32 * 4)()
         L.rn_abi_sizes(sizes)
         if sizes[0] != C.sizeof(Config) or sizes[1] != C.sizeof(ChainStats) or sizes[2] != C.sizeof(RngState):
@@ -86,6 +90,31 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise RainierCudaError(rc, lib().rn_last_error().decode(errors="replace"))
+
+
+class PinnedBuffer:
+    """Page-locked host memory from rn_host_alloc, viewed as a numpy array: rn_sample DMAs results straight into it
+    (the JVM analogue is a direct ByteBuffer over the same allocation)."""
+
+    def __init__(self, shape, device=0, dtype=np.float64):
+        self.device = int(device)
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(lib().rn_host_alloc(self.device, max(nbytes, 8), C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array((C.c_char * max(nbytes, 8)).from_address(self.ptr))[:nbytes].view(dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().rn_host_free(self.device, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -376,9 +405,10 @@ class CudaModel:
         return _DF()
 
     # -- Model.sample --
-    def sample(self, config=None, nChains=4, seeds=None, rng_states=None, dense_mass=None):
+    def sample(self, config=None, nChains=4, seeds=None, rng_states=None, dense_mass=None, out=None):
         """Model.sample(config, nChains) (core/Model.scala:13-24).  Chain c behaves exactly like a single-chain
-        reference run with ScalaRNG(seeds[c]).  Returns a Trace with numpy arrays."""
+        reference run with ScalaRNG(seeds[c]).  Returns a Trace with numpy arrays.  `out`: optional C-contiguous
+        float64 array [chains][iterations][n] to receive the samples (e.g. PinnedBuffer(...).array)."""
         config = config or SamplerConfig()
         cfg, keep = lower_config(config)
         if rng_states is not None:
@@ -393,7 +423,12 @@ class CudaModel:
             nChains = len(seeds_a)
         n = self.nVars
         dense = cfg.mass_tuner == abi.RN_MASS_DENSE or (cfg.mass_tuner == abi.RN_MASS_STATIC and cfg.static_matrix == abi.RN_MATRIX_DENSE)
-        samples = np.empty((nChains, cfg.iterations, n), dtype=np.float64)
+        if out is not None:
+            if out.shape != (nChains, cfg.iterations, n) or out.dtype != np.float64 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float64 array of shape (chains, iterations, n)")
+            samples = out
+        else:
+            samples = np.empty((nChains, cfg.iterations, n), dtype=np.float64)
         mass = np.empty((nChains, n * n if dense else n), dtype=np.float64)
         stats = (ChainStats * nChains)()
         rings = np.zeros((nChains, 3, cfg.stats_window), dtype=np.float64)

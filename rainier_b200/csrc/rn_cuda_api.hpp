@@ -51,6 +51,9 @@ struct Api {
   CUresult (*cuMemFree)(CUdeviceptr);
   CUresult (*cuMemAllocHost)(void**, size_t);
   CUresult (*cuMemFreeHost)(void*);
+  CUresult (*cuMemHostRegister)(void*, size_t, unsigned);
+  CUresult (*cuMemHostUnregister)(void*);
+  CUresult (*cuPointerGetAttribute)(void*, int, CUdeviceptr);
   CUresult (*cuMemcpyHtoD)(CUdeviceptr, const void*, size_t);
   CUresult (*cuMemcpyDtoH)(void*, CUdeviceptr, size_t);
   CUresult (*cuMemcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);

@@ -75,6 +75,9 @@ const Api* api(std::string* why) {
       RN_SYM(cuMemFree, "cuMemFree_v2")
       RN_SYM(cuMemAllocHost, "cuMemAllocHost_v2")
       RN_SYM(cuMemFreeHost, "cuMemFreeHost")
+      RN_SYM(cuMemHostRegister, "cuMemHostRegister_v2")
+      RN_SYM(cuMemHostUnregister, "cuMemHostUnregister")
+      RN_SYM(cuPointerGetAttribute, "cuPointerGetAttribute")
       RN_SYM(cuMemcpyHtoD, "cuMemcpyHtoD_v2")
       RN_SYM(cuMemcpyDtoH, "cuMemcpyDtoH_v2")
       RN_SYM(cuMemcpyHtoDAsync, "cuMemcpyHtoDAsync_v2")
@@ -1109,14 +1112,14 @@ void rn_sampler_destroy(rn_sampler* s) {
 namespace {
 
 struct PinnedRing {  // process-wide, grown on demand, never freed (pinning is expensive)
-  static constexpr int R = 4;
-  void* buf[R] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int R = 6;
+  void* buf[R] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t bytes = 0;
   std::mutex mu;
 };
 PinnedRing g_ring;
 
-class Workers {  // tiny job pool for the pinned->user memcpy
+class Workers {  // persistent job pool for the pinned->pageable memcpy of the drain
  public:
   explicit Workers(int n) {
     for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
@@ -1129,6 +1132,7 @@ class Workers {  // tiny job pool for the pinned->user memcpy
     cv_.notify_all();
     for (auto& t : th_) t.join();
   }
+  int size() const { return (int)th_.size(); }
   void submit(int group, std::function<void()> f) {
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -1169,8 +1173,35 @@ class Workers {  // tiny job pool for the pinned->user memcpy
   bool stop_ = false;
 };
 
+Workers& drain_workers() {  // created on first use, lives for the process (thread start-up is not free per call)
+  static Workers* w = [] {
+    int t = (int)std::thread::hardware_concurrency() / 4;
+    if (const char* e = getenv("RN_DRAIN_THREADS")) t = atoi(e);
+    return new Workers(std::max(2, std::min(t, 16)));
+  }();
+  return *w;
+}
+
+// true when [p, p+bytes) is page-locked memory the driver knows (rn_host_alloc, rn_host_register, cudaHostAlloc,
+// cudaHostRegister by the caller): the DMA engine can then write the caller's buffer directly
+bool host_is_pinned(const Api* A, const void* p, size_t bytes) {
+  if (!p || !bytes) return false;
+  unsigned mt0 = 0, mt1 = 0;
+  const char* last = (const char*)p + bytes - 1;
+  if (A->cuPointerGetAttribute(&mt0, 2 /*CU_POINTER_ATTRIBUTE_MEMORY_TYPE*/, (CUdeviceptr)(uintptr_t)p) != 0) return false;
+  if (A->cuPointerGetAttribute(&mt1, 2, (CUdeviceptr)(uintptr_t)last) != 0) return false;
+  return mt0 == CU_MEMORYTYPE_HOST && mt1 == CU_MEMORYTYPE_HOST;
+}
+
+// device -> caller's host buffer.  Page-locked destination: one DMA, no staging.  Pageable destination: a ring of
+// pinned staging slices; slice k's PCIe copy overlaps the fan-out memcpy of slices < k into the caller's pages.
 int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, size_t bytes) {
-  const size_t slice = (size_t)32 << 20;
+  if (host_is_pinned(A, dst, bytes) && !getenv("RN_DRAIN_FORCE_STAGED")) {
+    CU(A->cuMemcpyDtoHAsync(dst, src, bytes, copy));
+    CU(A->cuStreamSynchronize(copy));
+    return RN_OK;
+  }
+  const size_t slice = (size_t)16 << 20;
   {
     std::lock_guard<std::mutex> lk(g_ring.mu);
     if (g_ring.bytes < slice) {
@@ -1179,8 +1210,8 @@ int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, siz
     }
   }
   std::lock_guard<std::mutex> lk(g_ring.mu);  // one drain at a time per process
-  const int T = 4;
-  Workers pool(T);
+  Workers& pool = drain_workers();
+  const int T = pool.size();
   CUevent ev[PinnedRing::R];
   for (int r = 0; r < PinnedRing::R; r++) CU(A->cuEventCreate(&ev[r], 2));
   const size_t n_slices = (bytes + slice - 1) / slice;
@@ -1199,19 +1230,19 @@ int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, siz
     }
     return RN_OK;
   };
-  for (size_t k = 0; k < n_slices; k++) {
-    const int slot = (int)(k % PinnedRing::R);
-    pool.wait(slot);  // previous occupant of this slot fully copied out
-    const size_t off = k * slice, len = std::min(slice, bytes - off);
-    CU(A->cuMemcpyDtoHAsync(g_ring.buf[slot], src + off, len, copy));
-    CU(A->cuEventRecord(ev[slot], copy));
-    if (k >= 1) {
-      int rc = finish(k - 1);
-      if (rc) return rc;
+  // keep up to R-1 DMA slices in flight ahead of the memcpy fan-out
+  const size_t ahead = PinnedRing::R - 1;
+  size_t issued = 0, finished = 0;
+  while (finished < n_slices) {
+    while (issued < n_slices && issued < finished + ahead) {
+      const int slot = (int)(issued % PinnedRing::R);
+      pool.wait(slot);  // previous occupant of this slot fully copied out
+      const size_t off = issued * slice, len = std::min(slice, bytes - off);
+      CU(A->cuMemcpyDtoHAsync(g_ring.buf[slot], src + off, len, copy));
+      CU(A->cuEventRecord(ev[slot], copy));
+      issued++;
     }
-  }
-  if (n_slices) {
-    int rc = finish(n_slices - 1);
+    int rc = finish(finished++);
     if (rc) return rc;
   }
   for (int r = 0; r < PinnedRing::R; r++) pool.wait(r);
@@ -1333,6 +1364,66 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
   rc = rn_sampler_stats(s, stats, mass, cfg->stats_rings);
   lap("stats");
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// page-locked host buffers for the caller (the JVM side wraps them as direct ByteBuffers): rn_sample DMAs straight
+// into such a buffer instead of staging through the pinned ring
+// ---------------------------------------------------------------------------------------------------------
+static int host_ctx(const Api* A, int device) {
+  static std::mutex mu;
+  static std::map<int, CUcontext> ctxs;  // one primary-context retain per device for the life of the process
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = ctxs.find(device);
+  if (it == ctxs.end()) {
+    CUdevice dev;
+    CUcontext ctx = nullptr;
+    CU(A->cuDeviceGet(&dev, device));
+    CU(A->cuDevicePrimaryCtxRetain(&ctx, dev));
+    it = ctxs.emplace(device, ctx).first;
+  }
+  CU(A->cuCtxSetCurrent(it->second));
+  return RN_OK;
+}
+int rn_host_alloc(int device, size_t bytes, void** out) {
+  if (!out || !bytes) return fail(RN_E_INVALID, "bad argument");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  int rc = host_ctx(A, device);
+  if (rc) return rc;
+  CU(A->cuMemAllocHost(out, bytes));
+  return RN_OK;
+}
+int rn_host_free(int device, void* p) {
+  if (!p) return RN_OK;
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  int rc = host_ctx(A, device);
+  if (rc) return rc;
+  CU(A->cuMemFreeHost(p));
+  return RN_OK;
+}
+int rn_host_register(int device, void* p, size_t bytes) {
+  if (!p || !bytes) return fail(RN_E_INVALID, "bad argument");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  int rc = host_ctx(A, device);
+  if (rc) return rc;
+  CU(A->cuMemHostRegister(p, bytes, 1 /*CU_MEMHOSTREGISTER_PORTABLE*/));
+  return RN_OK;
+}
+int rn_host_unregister(int device, void* p) {
+  if (!p) return RN_OK;
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  int rc = host_ctx(A, device);
+  if (rc) return rc;
+  CU(A->cuMemHostUnregister(p));
+  return RN_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

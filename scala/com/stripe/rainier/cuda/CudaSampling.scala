@@ -31,15 +31,22 @@ object CudaSampling {
       val n = cm.nVars
       val cfg = lower(config)
       val seeds = Array.fill(nChains)((rng.standardUniform * (1L << 48)).toLong)
-      val samples = new Array[Double](nChains * config.iterations * n)
+      // results land in page-locked memory (one DMA, no staging copy); read back through a DoubleBuffer view
+      val sampleBytes = nChains.toLong * config.iterations * n * 8
+      val sampleBuf = Native.hostAlloc(device, sampleBytes).order(ByteOrder.LITTLE_ENDIAN)
+      val samples = sampleBuf.asDoubleBuffer()
+      try {
       val dense = cfg.getInt(OffMassTuner) == 2
       val mass = new Array[Double](nChains * (if (dense) n * n else n))
       val statsBuf = ByteBuffer.allocateDirect(nChains * Native.statsSize()).order(ByteOrder.LITTLE_ENDIAN)
       1.to(nChains).foreach(progress.start)
-      Native.sample(cm.handle, cfg, seeds, samples, mass, statsBuf)
+      Native.sampleDirect(cm.handle, cfg, seeds, sampleBuf, mass, statsBuf)
       val chains = 0.until(nChains).toList.map { c =>
         0.until(config.iterations).toList.map { i =>
-          java.util.Arrays.copyOfRange(samples, (c * config.iterations + i) * n, (c * config.iterations + i + 1) * n)
+          val row = new Array[Double](n)
+          samples.position((c * config.iterations + i) * n)
+          samples.get(row)
+          row
         }
       }
       val masses: List[MassMatrix] = 0.until(nChains).toList.map { c =>
@@ -52,6 +59,7 @@ object CudaSampling {
       val stats = 0.until(nChains).toList.map(c => readStats(statsBuf, c, config.statsWindow))
       stats.zip(masses).zipWithIndex.foreach { case ((s, m), c) => progress.finish(c + 1, "Complete", s, m) }
       Trace(chains, masses, stats, model)
+      } finally Native.hostFree(device, sampleBuf)
     } finally cm.close()
   }
 

@@ -16,6 +16,15 @@ object Native {
                      samples: Array[Double],
                      mass: Array[Double],
                      stats: ByteBuffer): Unit
+  /** page-locked host memory (rn_host_alloc) as a direct buffer; rn_sample DMAs straight into it */
+  @native def hostAlloc(device: Int, bytes: Long): ByteBuffer
+  @native def hostFree(device: Int, buf: ByteBuffer): Unit
+  @native def sampleDirect(handle: Long,
+                           config: ByteBuffer,
+                           seeds: Array[Long],
+                           samples: ByteBuffer,
+                           mass: Array[Double],
+                           stats: ByteBuffer): Unit
   @native def emitSource(handle: Long, config: ByteBuffer): String
   @native def configSize(): Int
   @native def statsSize(): Int

@@ -21,7 +21,23 @@ from rainier_b200 import abi, api
 
 small = "--small" in sys.argv
 precompile = "--precompile" in sys.argv  # CPU box: emit + NVRTC into $RN_KERNEL_CACHE, no device needed
+only_math = [a.split("=")[1] for a in sys.argv if a.startswith("--math=")]
+no_cpu = "--no-cpu" in sys.argv
 which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg2", "cfg2s", "cfg3", "cfg4", "cfg5"]
+
+
+def cached(name, build):
+    """RIR bytes + columns of a config, cached under build/models/ (the Python DAG restatement needs minutes for the
+    1M-row model; the cache travels to the GPU box with the snapshot)."""
+    d = os.path.join(ROOT, "build", "models")
+    os.makedirs(d, exist_ok=True)
+    f = os.path.join(d, name + ("_small" if small else "") + ".npz")
+    if os.path.exists(f):
+        z = np.load(f)
+        return z["rir"].tobytes(), [z["c%d" % i] for i in range(int(z["ncols"]))]
+    rir, cols = build()
+    np.savez(f, rir=np.frombuffer(rir, dtype=np.uint8), ncols=len(cols), **{"c%d" % i: np.asarray(c, dtype=np.float64) for i, c in enumerate(cols)})
+    return rir, cols
 
 
 def timed_run(model, cfg, chains, iters, reps=3):
@@ -70,27 +86,26 @@ for name in which:
     t0 = time.perf_counter()
     if name == "cfg2":  # README linear regression, 3 covariates: inlined by the reference -> data-free
         n_obs = 2000 if small else 10000
-        rir, cols = configs.linreg(n_obs).compile(True)
+        rir, cols = cached("cfg2", lambda: configs.linreg(n_obs).compile(True))
         chains, iters, eps, label = 4096, 200, 0.002, "linreg 3 cov, %d obs (inlined, data-free), 4096 chains" % n_obs
         prir, pcols = rir, cols
     elif name == "cfg2s":  # 5 covariates: the reference streams the data
         n_obs = 2000 if small else 10000
-        rir, cols = configs.linreg(n_obs, covariates=5).compile(True)
+        rir, cols = cached("cfg2s", lambda: configs.linreg(n_obs, covariates=5).compile(True))
         chains, iters, eps, label = 4096, 20, 0.002, "linreg 5 cov, %d obs (streamed), 4096 chains" % n_obs
         prir, pcols = rir, cols
     elif name == "cfg3":
         n_obs, d = (10000, 50) if small else (100000, 50)
-        m = configs.logreg(n_obs, d)
-        rir, cols = m.compile(True)
+        rir, cols = cached("cfg3", lambda: configs.logreg(n_obs, d).compile(True))
         chains, iters, eps, label = 2048, 2, 0.01, "logreg %d cov, %d obs, 2048 chains" % (d, n_obs)
         prir, pcols = rir, cols
     elif name == "cfg4":
-        rir, cols = configs.eight_schools().compile(True)
+        rir, cols = cached("cfg4", lambda: configs.eight_schools().compile(True))
         chains, iters, eps, label = 8192, 200, 0.1, "eight schools, 8192 chains"
         prir, pcols = rir, cols
     elif name == "cfg5":
         g, n_obs = (100, 100000) if small else (1000, 1000000)
-        prir, pcols = configs.poisson_glm(g, n_obs).compile(False)  # primal only: the symbolic gradient is infeasible
+        prir, pcols = cached("cfg5_primal", lambda: configs.poisson_glm(g, n_obs).compile(False))  # primal only: the symbolic gradient is infeasible
         rir, cols = None, None
         chains, iters, eps, label = 4096, 1, 0.001, "poisson GLM %d groups, %d obs, 4096 chains (primal RIR, adjoint gradient)" % (g, n_obs)
     build_s = time.perf_counter() - t0
@@ -104,6 +119,8 @@ for name in which:
         continue
     model = api.CudaModel(prir, pcols)
     for math_mode, mm in (("parity", abi.RN_MATH_PARITY), ("fast", abi.RN_MATH_FAST)):
+        if only_math and math_mode not in only_math:
+            continue
         cfg = static(eps, iters, mathMode=mm)
         try:
             rate, secs, acc = timed_run(model, cfg, chains, iters)
@@ -112,7 +129,7 @@ for name in which:
             res[math_mode] = {"error": str(e)[:300]}
     res["backend"] = "warp-per-chain" if "warp-per-chain" in model.emit_source(static(eps, iters)) else "thread-per-chain"
     res["op_counts"] = model.op_counts(static(eps, iters))
-    if rir is not None:
+    if rir is not None and not no_cpu:
         cpu_iters = {"cfg2": 2000, "cfg2s": 20, "cfg3": 1, "cfg4": 2000}[name]
         r, cores, dt = cpu_rate(rir, cols, static(eps, cpu_iters), cpu_iters)
         res["cpu_oracle"] = {"steps_x_chains_per_s": r, "cores": cores, "seconds": round(dt, 2)}
