@@ -80,7 +80,10 @@ RN_DEVICE double rn_log_accept(double deltaH) {  // LeapFrog.scala:141-145
   if (deltaH != deltaH) return -RN_INF;
   return rn_jmin0(-deltaH);
 }
-RN_DEVICE void rn_update(const RnArgs& A, RnW& w, RnStats& S) {
+// One out-of-line instance of the emitted density per kernel: rn_update is reached from ~10 call sites (leapfrog inside
+// HMC / EHMC count / EHMC sample / step-size search); inlining a 1000-parameter density at each of them costs minutes of
+// NVRTC time and megabytes of SASS for nothing -- the row loop dominates, not the call.
+__device__ __noinline__ void rn_update(const RnArgs& A, RnW& w, RnStats& S) {
   double dens;
   rn_density(w.q, dens, w.g, w.scr, A.data, S.err);
   w.U = dens * -1;

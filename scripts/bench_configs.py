@@ -96,9 +96,14 @@ for name in which:
         prir, pcols = rir, cols
     elif name == "cfg3":
         n_obs, d = (10000, 50) if small else (100000, 50)
-        rir, cols = cached("cfg3", lambda: configs.logreg(n_obs, d).compile(True))
-        chains, iters, eps, label = 2048, 2, 0.01, "logreg %d cov, %d obs, 2048 chains" % (d, n_obs)
-        prir, pcols = rir, cols
+        # GPU: primal RIR + the emitter's adjoint gradient (what CudaCompiler sends; 43 MB of columns, L2-resident).
+        # CPU oracle: the reference's symbolic-gradient form (its gradient columns quadruple the data to 167 MB).
+        prir, pcols = cached("cfg3_primal", lambda: configs.logreg(n_obs, d).compile(False))
+        if no_cpu or precompile or not (os.path.exists(os.path.join(ROOT, "build", "models", "cfg3.npz")) or os.path.isdir("/root/reference")):
+            rir, cols = None, None  # (the 167 MB symbolic form is not shipped to the GPU box)
+        else:
+            rir, cols = cached("cfg3", lambda: configs.logreg(n_obs, d).compile(True))
+        chains, iters, eps, label = 2048, 2, 0.01, "logreg %d cov, %d obs, 2048 chains (primal RIR, adjoint gradient)" % (d, n_obs)
     elif name == "cfg4":
         rir, cols = cached("cfg4", lambda: configs.eight_schools().compile(True))
         chains, iters, eps, label = 8192, 200, 0.1, "eight schools, 8192 chains"
