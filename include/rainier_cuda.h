@@ -159,6 +159,10 @@ int rn_density_batch(rn_model* m, const double* q, int chains, double* out);
 /* debug: emitted CUDA source of the fused kernel for `cfg` (NUL-terminated).  Returns RN_OK and the needed
  * size (incl. NUL) in *needed; copies at most cap bytes. */
 int rn_emit_source(rn_model* m, const rn_config* cfg, char* buf, size_t cap, size_t* needed);
+/* debug/test: host image of the device data buffer exactly as rn_model_create uploads it -- per streamed target a
+ * tile-major block [tile][column][32 rows] (one tile = one contiguous chunk = one TMA bulk copy).  cols as in
+ * rn_model_create; *needed receives the size in doubles; image may be NULL to query it. */
+int rn_model_pack_columns(const rn_model* m, const double* const* cols, double* image, size_t cap_doubles, size_t* needed);
 /* debug: the compiled cubin of the same kernel (for cuobjdump -sass). */
 int rn_emit_cubin(rn_model* m, const rn_config* cfg, void* buf, size_t cap, size_t* needed);
 void rn_model_destroy(rn_model* m);

@@ -52,6 +52,7 @@ def lib():
         L.rn_model_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
                                       C.c_int, C.POINTER(C.c_void_p)]
         L.rn_model_nvars.argtypes = [C.c_void_p]
+        L.rn_model_pack_columns.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.rn_model_destroy.argtypes = [C.c_void_p]
         L.rn_model_op_counts.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(C.c_double)]
         L.rn_density_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -355,6 +356,16 @@ class CudaModel:
             self.close()
         except Exception:
             pass
+
+    def pack_columns(self):
+        """debug/test: host image of the device data buffer (tile-major [tile][column][32 rows] per streamed target)"""
+        n = len(self._cols)
+        ptrs = (C.c_void_p * max(n, 1))(*[c.ctypes.data for c in self._cols])
+        need = C.c_size_t()
+        _check(lib().rn_model_pack_columns(self.h, ptrs, None, 0, C.byref(need)))
+        image = np.zeros(max(need.value, 1), dtype=np.float64)
+        _check(lib().rn_model_pack_columns(self.h, ptrs, image.ctypes.data, need.value, C.byref(need)))
+        return image
 
     # -- debug (the analogue of rainier-decompile) --
     def emit_source(self, config=None):

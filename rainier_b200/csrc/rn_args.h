@@ -50,6 +50,8 @@ struct RnArgs {
   int n_iter;                    // iterations in this launch
   int phase;                     // 0 warmup, 1 sampling
   int adaptation;                // 0 per chain (reference semantics), 1 pooled over chains/ranks (extension)
+  int tma;                       // warp-per-chain kernels: CTA-shared TMA data tiles allowed (see rn_sampler_wpc.cuh)
+  int pad1;
 };
 
 #endif

@@ -1,6 +1,7 @@
 // rn_emit.cpp -- see rn_emit.hpp.
 #include "rn_emit.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -34,7 +35,93 @@ struct Emitter {
   std::vector<int> smem_slot;             // slot -> index in the shared accumulator block, or -1 (register)
   std::map<int, int> tab_off;             // large-lookup node id -> offset of its table in scratch
   int n_smem_acc = 0, tab_doubles = 0;
+  std::string col_suffix;                 // names of column values loaded in the current region of a row body
   Emitter(const Program& p, const EmitOptions& o) : P(p), opt(o) {}
+
+  // The body of one row of a streamed target.  Keeps live ranges short, because a "row" of the reference's
+  // Model.observe is 8 unrolled observations over hundreds of columns (core/Model.scala:98-132):
+  //   * a column value is loaded right before its first use (not hoisted to the top of the row),
+  //   * the reverse sweep re-loads the columns it needs behind a compiler fence instead of keeping the forward
+  //     sweep's copies alive (2 loads per element per row; the data sits in L1/L2/shared memory),
+  //   * every accumulation / scatter is issued as soon as its operand exists (a_j += w * x_j contracts to one FMA in
+  //     fast mode).  The order of the additions into any one slot is unchanged.
+  int local_col(const TargetInfo& T, int k) const { return k - ((int)T.first_input - (int)P.n_params); }
+
+  template <class Load, class AccRef>
+  void row_body(const TargetInfo& T, const char* ind, Load load, AccRef accref, bool atomic_scatter, int scatter_base_off) {
+    std::set<int> body;
+    for (int id : T.row_fwd)
+      if (P.nodes[id].kind != K_CONST && P.nodes[id].kind != K_INPUT) body.insert(id);
+    for (int id : T.row_bwd)
+      if (P.nodes[id].kind != K_CONST && P.nodes[id].kind != K_INPUT) body.insert(id);
+    std::map<int, std::vector<const AccStmt*>> acc_at;
+    std::map<int, std::vector<const ScatterStmt*>> sc_at;
+    std::vector<const AccStmt*> acc_tail;
+    std::vector<const ScatterStmt*> sc_tail;
+    for (const AccStmt& a : T.row_acc) (body.count(a.node) ? acc_at[a.node] : acc_tail).push_back(&a);
+    for (const ScatterStmt& sc : T.row_scatter) (body.count(sc.node) ? sc_at[sc.node] : sc_tail).push_back(&sc);
+    std::set<int> declared;
+    auto need_col = [&](int o) {
+      const Node& n = P.nodes[o];
+      if (n.kind != K_INPUT || (uint32_t)n.a < P.n_params) return;
+      const int k = n.a - (int)P.n_params;
+      if (declared.insert(k).second) os << ind << "const double c" << k << col_suffix << " = " << load(k) << ";\n";
+    };
+    auto need_operands = [&](int id) {
+      const Node& n = P.nodes[id];
+      switch (n.kind) {
+        case K_UNARY: need_col(n.a); break;
+        case K_BINARY: need_col(n.a); need_col(n.b); break;
+        case K_LOOKUP:
+          need_col(n.a);
+          for (int k = 0; k < n.c; k++) need_col(P.lookup_refs[n.b + k]);
+          break;
+        case K_SELEQ: need_col(n.a); need_col(n.b); need_col(n.c); break;
+        default: break;
+      }
+    };
+    auto emit_acc = [&](const AccStmt& a) { os << ind << accref(a.slot) << " += " << val(a.node) << ";\n"; };
+    auto emit_scatter = [&](const ScatterStmt& sc) {
+      os << ind << "{ const int k = rn_d2i(" << val(sc.index_node) << ") - (" << sc.low << "); if (k < 0 || k >= " << sc.len
+         << ") err |= 1; else ";
+      if (atomic_scatter)
+        os << "atomicAdd(&scr[" << (scatter_base_off + smem_slot[sc.slot_base]) << " + k], " << val(sc.node) << "); }\n";
+      else
+        os << "acc[" << sc.slot_base << " + k] += " << val(sc.node) << "; }\n";
+    };
+    auto one = [&](int id) {
+      if (!body.count(id)) return;
+      need_operands(id);
+      stmt(id, ind);
+      auto ia = acc_at.find(id);
+      if (ia != acc_at.end())
+        for (const AccStmt* a : ia->second) emit_acc(*a);
+      auto is = sc_at.find(id);
+      if (is != sc_at.end())
+        for (const ScatterStmt* sc : is->second) {
+          need_col(sc->index_node);
+          emit_scatter(*sc);
+        }
+    };
+    col_suffix.clear();
+    for (int id : T.row_fwd) one(id);
+    if (!T.row_bwd.empty()) {
+      os << ind << "RN_FENCE();\n";
+      declared.clear();
+      col_suffix = "b";
+      for (int id : T.row_bwd) one(id);
+    }
+    for (const AccStmt* a : acc_tail) {
+      need_col(a->node);
+      emit_acc(*a);
+    }
+    for (const ScatterStmt* sc : sc_tail) {
+      need_col(sc->index_node);
+      need_col(sc->node);
+      emit_scatter(*sc);
+    }
+    col_suffix.clear();
+  }
 
   std::string acc_ref(int slot) const {
     if (!wpc) return "acc[" + std::to_string(slot) + "]";
@@ -53,7 +140,7 @@ struct Emitter {
     if (n.kind == K_CONST) return lit(n.value);
     if (n.kind == K_INPUT) {
       if ((uint32_t)n.a < P.n_params) return "q[" + std::to_string(n.a) + "]";
-      return "c" + std::to_string(n.a - (int)P.n_params);
+      return "c" + std::to_string(n.a - (int)P.n_params) + col_suffix;
     }
     return "v" + std::to_string(id);
   }
@@ -157,25 +244,17 @@ struct Emitter {
     for (size_t t = 0; t < P.targets.size(); t++) {
       const TargetInfo& T = P.targets[t];
       os << "  // target " << t << (T.streamed() ? " (streamed)" : " (data-free)") << "\n";
-      const char* ind = "  ";
       if (T.streamed()) {
         os << "  for (long long row = 0; row < " << (long long)T.n_rows << "LL; row++) {\n";
-        ind = "    ";
-        std::set<int> used;
-        for (int id : T.row_fwd)
-          if (P.nodes[id].kind == K_INPUT) used.insert(P.nodes[id].a - (int)P.n_params);
-        for (int k : used)
-          os << ind << "const double c" << k << " = RN_LDG(data + " << (unsigned long long)opt.col_offsets[k]
-             << "ULL + row);\n";
-        for (int id : T.row_fwd) stmt(id, ind);
-        for (int id : T.row_bwd) stmt(id, ind);
+        os << "    const double* RN_RESTRICT rp = data + " << (unsigned long long)opt.target_base[t] << "ULL + (row >> 5) * "
+           << (unsigned long long)T.n_cols * 32 << "LL + (row & 31);\n";
+        row_body(
+            T, "    ", [&](int k) { return "RN_LDG(rp + " + std::to_string(local_col(T, k) * 32) + ")"; },
+            [&](int slot) { return "acc[" + std::to_string(slot) + "]"; }, false, 0);
+        os << "  }\n";
+      } else {
+        for (const AccStmt& a : T.row_acc) os << "  acc[" << a.slot << "] += " << val(a.node) << ";\n";
       }
-      for (const AccStmt& a : T.row_acc) os << ind << "acc[" << a.slot << "] += " << val(a.node) << ";\n";
-      for (const ScatterStmt& sc : T.row_scatter) {
-        os << ind << "{ const int k = rn_d2i(" << val(sc.index_node) << ") - (" << sc.low << "); if (k < 0 || k >= "
-           << sc.len << ") err |= 1; else acc[" << sc.slot_base << " + k] += " << val(sc.node) << "; }\n";
-      }
-      if (T.streamed()) os << "  }\n";
     }
     os << "  dens = acc[0];\n";
     if (P.symbolic) {
@@ -209,8 +288,8 @@ struct Emitter {
     os << "RN_DEVICE double rn_warp_sum(double x) {\n  RN_UNROLL\n  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);\n  return x;\n}\n";
     lookup_helpers();
     os << "RN_DEVICE void rn_density(const double* q, double& dens, double* grad, double* scr, "
-          "const double* RN_RESTRICT data, int& err) {\n";
-    os << "  (void)data; (void)scr;\n  const int lane = (int)(threadIdx.x & 31);\n  (void)lane;\n";
+          "const double* RN_RESTRICT data, int& err, RnTma& tma) {\n";
+    os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x & 31);\n  (void)lane;\n";
     if (n_smem_acc) os << "  for (int k = lane; k < " << n_smem_acc << "; k += 32) scr[" << tab_doubles << " + k] = 0.0;\n";
     for (int id : P.inv_fwd) stmt(id, "  ");
     for (auto& kv : tab_off) {
@@ -224,20 +303,39 @@ struct Emitter {
       const TargetInfo& T = P.targets[t];
       os << "  // target " << t << (T.streamed() ? " (streamed, rows across lanes)" : " (data-free)") << "\n";
       if (T.streamed()) {
-        os << "  for (long long row = lane; row < " << (long long)T.n_rows << "LL; row += 32) {\n";
-        std::set<int> used;
-        for (int id : T.row_fwd)
-          if (P.nodes[id].kind == K_INPUT) used.insert(P.nodes[id].a - (int)P.n_params);
-        for (int k : used)
-          os << "    const double c" << k << " = RN_LDG(data + " << (unsigned long long)opt.col_offsets[k] << "ULL + row);\n";
-        for (int id : T.row_fwd) stmt(id, "    ");
-        for (int id : T.row_bwd) stmt(id, "    ");
-        for (const AccStmt& a : T.row_acc) os << "    " << acc_ref(a.slot) << " += " << val(a.node) << ";\n";
-        for (const ScatterStmt& sc : T.row_scatter) {
-          os << "    { const int k = rn_d2i(" << val(sc.index_node) << ") - (" << sc.low << "); if (k < 0 || k >= " << sc.len
-             << ") err |= 1; else atomicAdd(&scr[" << (tab_doubles + smem_slot[sc.slot_base]) << " + k], " << val(sc.node) << "); }\n";
+        const unsigned long long base = (unsigned long long)opt.target_base[t], td = (unsigned long long)T.n_cols * 32;
+        const unsigned long long n_full = T.n_rows / 32;
+        os << "  {\n    long long row0 = lane;\n";
+        if (opt.tma_stages > 0 && n_full > 0) {
+          // CTA lockstep over full tiles: tile t+S-1 in flight (one bulk copy) while all warps consume tile t from smem
+          os << "    if (tma.on) {\n"
+             << "      const unsigned n_full = " << n_full << "u, seq0 = tma.seq;\n"
+             << "      const double* RN_RESTRICT src = data + " << base << "ULL;\n"
+             << "      if (threadIdx.x == 0)\n"
+             << "        for (unsigned p = 0; p + 1 < RN_TMA_STAGES && p < n_full; p++) rn_tma_load(tma, seq0 + p, src + (size_t)p * " << td
+             << "ULL, " << td * 8 << "u);\n"
+             << "      for (unsigned tile = 0; tile < n_full; tile++) {\n"
+             << "        const unsigned seq = seq0 + tile;\n"
+             << "        if (threadIdx.x == 0 && tile + (RN_TMA_STAGES - 1) < n_full)\n"
+             << "          rn_tma_load(tma, seq + (RN_TMA_STAGES - 1), src + (size_t)(tile + (RN_TMA_STAGES - 1)) * " << td << "ULL, " << td * 8
+             << "u);\n"
+             << "        rn_mbar_wait(tma.full + (seq % RN_TMA_STAGES), (seq / RN_TMA_STAGES) & 1u);\n"
+             << "        const double* rp = tma.stage + (size_t)(seq % RN_TMA_STAGES) * RN_TMA_TILE_DOUBLES + lane;\n";
+          row_body(
+              T, "        ", [&](int k) { return "rp[" + std::to_string(local_col(T, k) * 32) + "]"; },
+              [&](int slot) { return acc_ref(slot); }, true, tab_doubles);
+          os << "        rn_cta_bar(tma.nthreads);\n"
+             << "      }\n"
+             << "      tma.seq = seq0 + n_full;\n"
+             << "      row0 += " << n_full * 32 << "LL;\n"
+             << "    }\n";
         }
-        os << "  }\n";
+        os << "    for (long long row = row0; row < " << (long long)T.n_rows << "LL; row += 32) {\n";
+        os << "      const double* RN_RESTRICT rp = data + " << base << "ULL + (row >> 5) * " << td << "LL + lane;\n";
+        row_body(
+            T, "      ", [&](int k) { return "RN_LDG(rp + " + std::to_string(local_col(T, k) * 32) + ")"; },
+            [&](int slot) { return acc_ref(slot); }, true, tab_doubles);
+        os << "    }\n  }\n";
       } else {
         os << "  if (lane == 0) {\n";  // counted once by the butterfly below
         for (const AccStmt& a : T.row_acc) os << "    " << acc_ref(a.slot) << " += " << val(a.node) << ";\n";
@@ -269,7 +367,17 @@ std::string emit_density(const Program& P, const EmitOptions& opt) {
   return E.os.str();
 }
 
-std::string emit_source(const Program& P, const EmitOptions& opt, int* wpc_smem_doubles) {
+WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
+  WpcSizes z;
+  Emitter E(P, opt);
+  E.density_wpc();
+  z.per_warp_doubles = (opt.enable_ehmc ? 7 : 4) * (int)P.n_params + E.tab_doubles + E.n_smem_acc;
+  for (const TargetInfo& T : P.targets)
+    if (T.streamed() && T.n_rows >= 32) z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * 32);
+  return z;
+}
+
+std::string emit_source(const Program& P, const EmitOptions& opt) {
   std::ostringstream os;
   os << "// generated by rainier_b200 (CUDA source emitter) -- do not edit\n";
   os << "#define RN_N " << P.n_params << "\n";
@@ -278,16 +386,15 @@ std::string emit_source(const Program& P, const EmitOptions& opt, int* wpc_smem_
   os << "#define RN_MASS_MAX " << opt.mass_max << "\n";
   os << "#define RN_ENABLE_EHMC " << (opt.enable_ehmc ? 1 : 0) << "\n";
   if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
+  if (opt.backend == 1) {
+    os << "#define RN_TMA_STAGES " << opt.tma_stages << "\n";
+    os << "#define RN_TMA_TILE_DOUBLES " << wpc_sizes(P, opt).tile_doubles << "\n";
+  }
   os << kPreludeSource << "\n";
   os << emit_density(P, opt) << "\n";
   if (opt.backend == 1) {
     os << "#define RN_WPC_SMEM_DOUBLES (" << (opt.enable_ehmc ? 7 : 4) << " * RN_N + RN_WPC_SCRATCH)\n";
     os << kSamplerWpcSource << "\n";
-    if (wpc_smem_doubles) {
-      Emitter E(P, opt);
-      E.density_wpc();
-      *wpc_smem_doubles = (opt.enable_ehmc ? 7 : 4) * (int)P.n_params + E.tab_doubles + E.n_smem_acc;
-    }
   } else {
     os << kSamplerSource << "\n";
   }

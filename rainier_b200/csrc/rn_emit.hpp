@@ -13,12 +13,20 @@ struct EmitOptions {
   bool fast_math = false; // strength-reduce constant powers beyond what Math.pow itself special-cases
   int mass_max = 0;       // 0 identity only, 1 + diagonal, 2 + dense
   bool enable_ehmc = false;
-  std::vector<uint64_t> col_offsets;  // element offset of every column placeholder inside the data buffer
+  int tma_stages = 0;     // warp per chain: shared-memory stages of the CTA-shared data-tile pipeline (0 = off)
+  std::vector<uint64_t> target_base;  // per target: element offset of its tile-major [tile][column][32] block in the data buffer
 };
 
 // the generated rn_density() only
 std::string emit_density(const Program& P, const EmitOptions& opt);
-// full translation unit; *wpc_smem_doubles receives the per-warp shared-memory footprint (backend 1)
-std::string emit_source(const Program& P, const EmitOptions& opt, int* wpc_smem_doubles = nullptr);
+// full translation unit
+std::string emit_source(const Program& P, const EmitOptions& opt);
+// shared-memory needs of the warp-per-chain kernels: doubles per warp (chain vectors + density scratch) and doubles of
+// the largest data tile (n_cols * 32 over the streamed targets; 0 when nothing is streamed)
+struct WpcSizes {
+  int per_warp_doubles = 0;
+  int tile_doubles = 0;
+};
+WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt);
 
 }  // namespace rn

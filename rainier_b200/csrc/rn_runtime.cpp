@@ -156,6 +156,13 @@ struct Kernel {
   int backend = 0;            // 0 thread per chain, 1 warp per chain
   int wpc_smem_doubles = 0;   // per-warp dynamic shared memory (backend 1)
   int warps_per_cta = 4;
+  int tma_stages = 0;         // CTA-shared data-tile pipeline (backend 1): stages, doubles per stage
+  int tile_doubles = 0;
+  unsigned smem_bytes() const {  // dynamic shared memory of one CTA: per-warp slices | 128B pad | stages | mbarriers
+    size_t d = (size_t)warps_per_cta * wpc_smem_doubles;
+    if (tma_stages > 0) d = ((d + 15) & ~(size_t)15) + (size_t)tma_stages * tile_doubles + (size_t)tma_stages;
+    return (unsigned)(d * 8);
+  }
 };
 
 struct rn_model {
@@ -165,8 +172,8 @@ struct rn_model {
   int device = -1;
   CUcontext ctx = nullptr;
   CUdeviceptr d_data = 0;
-  std::vector<uint64_t> col_offsets;
-  std::vector<int64_t> col_rows;
+  std::vector<uint64_t> target_base;  // per target: element offset of its tile-major block in the data buffer
+  uint64_t data_doubles = 0;
   std::map<std::pair<bool, bool>, std::unique_ptr<Program>> programs;  // (adjoint, fast)
   std::map<KernelKey, std::unique_ptr<Kernel>> kernels;
   CUdeviceptr pool[2] = {0, 0};  // grow-only scratch reused by rn_sample calls (cuMemAlloc/cuMemFree of GBs is slow)
@@ -239,18 +246,38 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
   eo.fast_math = key.fast;
   eo.mass_max = key.mass_max;
   eo.enable_ehmc = key.ehmc;
-  eo.col_offsets = m->col_offsets;
+  eo.target_base = m->target_base;
   if (eo.backend == 1 && eo.mass_max == 2) return fail(RN_E_UNSUPPORTED, "dense mass matrices need the thread-per-chain backend");
   if (eo.backend == 1 && P->symbolic && P->n_params > 96)
     return fail(RN_E_UNSUPPORTED, "warp-per-chain with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
   K->backend = eo.backend;
-  K->source = emit_source(*P, eo, &K->wpc_smem_doubles);
   if (eo.backend == 1) {
-    const size_t per_warp = (size_t)K->wpc_smem_doubles * 8;
-    int w = (int)std::min<size_t>(8, (200 * 1024) / std::max<size_t>(per_warp, 1));
-    if (w < 1) return fail(RN_E_UNSUPPORTED, "model state does not fit one warp's shared memory slice");
-    K->warps_per_cta = w;
+    const WpcSizes z = wpc_sizes(*P, eo);
+    K->wpc_smem_doubles = z.per_warp_doubles;
+    K->tile_doubles = z.tile_doubles;
+    const size_t per_warp = (size_t)z.per_warp_doubles * 8, tile = (size_t)z.tile_doubles * 8;
+    const size_t cap = 227 * 1024 - 2048;  // opt-in dynamic shared memory per CTA on sm_100, minus static/reserved
+    int wmax = 8;
+    if (const char* e = getenv("RN_WPC_WARPS")) wmax = std::max(1, std::min(32, atoi(e)));
+    if (per_warp > cap) return fail(RN_E_UNSUPPORTED, "model state does not fit one warp's shared memory slice");
+    // data-tile stages: two (prefetch overlaps compute) when at least 4 chains still fit beside them, else one, else off
+    int stages = 0;
+    if (tile > 0) {
+      if (2 * tile + std::min<size_t>(4, wmax) * per_warp + 256 <= cap)
+        stages = 2;
+      else if (tile + std::min<size_t>(2, wmax) * per_warp + 256 <= cap)
+        stages = 1;
+    }
+    if (const char* e = getenv("RN_TMA")) {
+      const int want_stages = atoi(e);
+      if (want_stages == 0 || (size_t)want_stages * tile + per_warp + 256 <= cap) stages = tile > 0 ? want_stages : 0;
+    }
+    K->tma_stages = stages;
+    const size_t left = cap - (size_t)stages * tile - (stages ? 256 : 0);
+    K->warps_per_cta = (int)std::max<size_t>(1, std::min<size_t>((size_t)wmax, left / std::max<size_t>(per_warp, 1)));
+    eo.tma_stages = stages;
   }
+  K->source = emit_source(*P, eo);
 
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
@@ -345,11 +372,44 @@ static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
   CU(A->cuModuleGetFunction(&K->k_pool_reduce, K->mod, "rn_k_pool_reduce"));
   CU(A->cuModuleGetFunction(&K->k_pool_apply, K->mod, "rn_k_pool_apply"));
   if (K->backend == 1) {
-    const int bytes = K->warps_per_cta * K->wpc_smem_doubles * 8;
+    const int bytes = (int)K->smem_bytes();
     for (CUfunction f : {K->k_init, K->k_iter, K->k_density})
       CU(A->cuFuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, bytes));
   }
   return RN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Device layout of the observation columns: per streamed target a TILE-MAJOR block [tile][column][32 rows], tiles of
+// 32 consecutive rows (the last one zero-padded), every block 128-byte aligned.  One tile is one contiguous chunk of
+// n_cols*256 bytes: the warp-per-chain kernels fetch it with a single cp.async.bulk (TMA) into shared memory, and a
+// plain load of (column j, row r) is base + (r>>5)*n_cols*32 + j*32 + (r&31) -- still 256-byte coalesced across a warp.
+// (The reference keeps one JVM array per column, ir/DataFunction.scala:13-30, and gathers per row.)
+// ---------------------------------------------------------------------------------------------------------
+static uint64_t data_layout(const Program& P, std::vector<uint64_t>& target_base) {
+  uint64_t off = 0;
+  target_base.assign(P.targets.size(), 0);
+  for (size_t t = 0; t < P.targets.size(); t++) {
+    const TargetInfo& T = P.targets[t];
+    if (!T.streamed()) continue;
+    target_base[t] = off;
+    const uint64_t tiles = (T.n_rows + 31) / 32;
+    off += tiles * (uint64_t)T.n_cols * 32;
+    off = (off + 15) & ~15ull;
+  }
+  return off;
+}
+static void pack_columns(const Program& P, const std::vector<uint64_t>& target_base, const double* const* cols, double* image) {
+  for (size_t t = 0; t < P.targets.size(); t++) {
+    const TargetInfo& T = P.targets[t];
+    if (!T.streamed()) continue;
+    const uint64_t td = (uint64_t)T.n_cols * 32;
+    for (uint32_t j = 0; j < T.n_cols; j++) {
+      const double* src = cols[T.first_input - P.n_params + j];
+      double* dst = image + target_base[t] + (uint64_t)j * 32;
+      for (uint64_t r = 0; r < T.n_rows; r++) dst[(r >> 5) * td + (r & 31)] = src[r];
+    }
+  }
 }
 
 extern "C" {
@@ -407,12 +467,7 @@ int rn_model_create(const void* rir, size_t len, const double* const* cols, cons
     for (uint32_t j = 0; j < T.n_cols; j++)
       if ((uint64_t)col_rows[T.first_input - h.n_params + j] != T.n_rows)
         return fail(RN_E_INVALID, "column length does not match its target's row count");
-  uint64_t off = 0;
-  for (int i = 0; i < n_cols; i++) {
-    m->col_offsets.push_back(off);
-    m->col_rows.push_back(col_rows[i]);
-    off += ((uint64_t)col_rows[i] + 3) & ~3ull;  // keep every column 32-byte aligned
-  }
+  m->data_doubles = data_layout(*P, m->target_base);
   m->device = device;
   if (device >= 0) {
     std::string why;
@@ -422,13 +477,28 @@ int rn_model_create(const void* rir, size_t len, const double* const* cols, cons
     CU(A->cuDeviceGet(&dev, device));
     CU(A->cuDevicePrimaryCtxRetain(&m->ctx, dev));
     CU(A->cuCtxSetCurrent(m->ctx));
-    if (off > 0) {
-      CU(A->cuMemAlloc(&m->d_data, off * 8));
-      for (int i = 0; i < n_cols; i++)
-        CU(A->cuMemcpyHtoD(m->d_data + m->col_offsets[i] * 8, cols[i], (size_t)col_rows[i] * 8));
+    if (m->data_doubles > 0) {
+      std::vector<double> image(m->data_doubles, 0.0);
+      pack_columns(*P, m->target_base, cols, image.data());
+      CU(A->cuMemAlloc(&m->d_data, m->data_doubles * 8));
+      CU(A->cuMemcpyHtoD(m->d_data, image.data(), m->data_doubles * 8));
     }
   }
   *out = m.release();
+  return RN_OK;
+}
+
+// test/debug: the packed image of the data buffer exactly as rn_model_create uploads it (host emulation of the emitted
+// source needs the same layout)
+int rn_model_pack_columns(const rn_model* m, const double* const* cols, double* image, size_t cap_doubles, size_t* needed) {
+  if (!m) return fail(RN_E_INVALID, "null model");
+  if (needed) *needed = (size_t)m->data_doubles;
+  if (!image) return RN_OK;
+  if (cap_doubles < m->data_doubles) return fail(RN_E_INVALID, "buffer too small");
+  auto it = m->programs.begin();
+  if (it == m->programs.end()) return fail(RN_E_INVALID, "model has no program");
+  std::memset(image, 0, (size_t)m->data_doubles * 8);
+  pack_columns(*it->second, m->target_base, cols, image);
   return RN_OK;
 }
 
@@ -519,7 +589,7 @@ int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
   if (K->backend == 1) {
     const unsigned w = (unsigned)K->warps_per_cta;
     CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + w - 1) / w), 1, 1, w * 32, 1, 1,
-                         w * (unsigned)K->wpc_smem_doubles * 8, nullptr, params, nullptr));
+                         K->smem_bytes(), nullptr, params, nullptr));
   } else {
     CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + 127) / 128), 1, 1, 128, 1, 1, 0, nullptr, params, nullptr));
   }
@@ -628,7 +698,7 @@ int launch(const Api* A, rn_sampler* s, CUfunction f) {
   if (s->K->backend == 1) {
     const unsigned w = (unsigned)s->K->warps_per_cta;
     const unsigned grid = (unsigned)((s->chains + w - 1) / w);
-    CU(A->cuLaunchKernel(f, grid, 1, 1, w * 32, 1, 1, w * (unsigned)s->K->wpc_smem_doubles * 8, s->stream, params, nullptr));
+    CU(A->cuLaunchKernel(f, grid, 1, 1, w * 32, 1, 1, s->K->smem_bytes(), s->stream, params, nullptr));
     s->launches++;
     return RN_OK;
   }
@@ -912,6 +982,7 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.phase = phase;
     a.n_iter = k;
     a.adaptation = s->cfg.adaptation == RN_ADAPT_POOLED ? 1 : 0;
+    a.tma = s->K->tma_stages > 0 ? 1 : 0;
     a.mass_kind = s->mass_kind;
     a.win_size = s->win_size;
     a.win_i = s->win_i;

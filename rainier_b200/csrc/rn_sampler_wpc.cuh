@@ -28,6 +28,13 @@ struct RnStats {
   int ring_i[3], ring_full[3];
 };
 
+// ---- shared data tiles (RN_TMA_STAGES > 0) --------------------------------------------------------------------
+// The observation columns are laid out tile-major ([tile][column][32 rows], rn_runtime.cpp), so one tile of a streamed
+// target is one contiguous chunk.  When every chain of the CTA evaluates the density the same number of times (HMC:
+// control flow is uniform over chains), the CTA walks the tiles in lockstep: one thread fetches tile t+S-1 with a single
+// cp.async.bulk (TMA, completion on an mbarrier) while all warps consume tile t from shared memory, so a tile crosses
+// L2 -> SM once per CTA instead of once per chain.  EHMC (per-chain trajectory lengths) and the init kernel keep the
+// independent per-warp path (__ldg from L2/L1).  struct RnTma and the mbarrier / bulk-copy helpers live in rn_prelude.cuh.
 // per-warp shared-memory slice
 struct RnW {
   double* q;   // pqBuf.q
@@ -40,9 +47,15 @@ struct RnW {
   double* scr;  // emitted density scratch (lookup tables, scatter accumulators)
   double U;     // potential of pqBuf (replicated in registers)
   int mass_kind;
+  RnTma tma;    // shared data-tile pipeline of the CTA (off unless the kernel enables it)
 };
 
 RN_DEVICE void rn_w_setup(RnW& w, double* base) {
+  w.tma.on = 0;
+  w.tma.seq = 0;
+  w.tma.nthreads = 0;
+  w.tma.stage = nullptr;
+  w.tma.full = nullptr;
   w.q = base;
   w.p = base + RN_N;
   w.g = base + 2 * RN_N;
@@ -85,7 +98,7 @@ RN_DEVICE double rn_log_accept(double deltaH) {  // LeapFrog.scala:141-145
 // NVRTC time and megabytes of SASS for nothing -- the row loop dominates, not the call.
 __device__ __noinline__ void rn_update(const RnArgs& A, RnW& w, RnStats& S) {
   double dens;
-  rn_density(w.q, dens, w.g, w.scr, A.data, S.err);
+  rn_density(w.q, dens, w.g, w.scr, A.data, S.err, w.tma);
   w.U = dens * -1;
   S.grads += 1;
 }
@@ -159,7 +172,7 @@ RN_DEVICE void rn_store_stats(const RnArgs& A, int c, const RnStats& S) {
   }
 }
 
-extern __shared__ double rn_smem[];
+extern __shared__ __align__(128) double rn_smem[];
 
 // =============================================================================================================
 RN_GLOBAL void rn_k_init(const RnArgs A) {
@@ -237,9 +250,32 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
 // =============================================================================================================
 RN_GLOBAL void rn_k_iter(const RnArgs A) {
   const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+#if RN_TMA_STAGES > 0
+  const int warps = (int)(blockDim.x >> 5);
+  double* const stage0 = rn_smem + (((size_t)warps * RN_WPC_SMEM_DOUBLES + 15) & ~(size_t)15);
+  unsigned long long* const bars = (unsigned long long*)(stage0 + (size_t)RN_TMA_STAGES * RN_TMA_TILE_DOUBLES);
+  const bool lockstep = (A.sampler == 0) && (A.tma != 0);  // HMC: every chain calls the density equally often
+  if (lockstep) {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < RN_TMA_STAGES; s++) rn_mbar_init(&bars[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+#endif
   if (c >= A.chains) return;
   RnW w;
   rn_w_setup(w, rn_smem + (size_t)(threadIdx.x >> 5) * RN_WPC_SMEM_DOUBLES);
+#if RN_TMA_STAGES > 0
+  if (lockstep) {
+    const int first = (int)(blockIdx.x * (blockDim.x >> 5));
+    const int active = (A.chains - first) < warps ? (A.chains - first) : warps;
+    w.tma.on = 1;
+    w.tma.stage = stage0;
+    w.tma.full = bars;
+    w.tma.nthreads = (unsigned)active * 32u;
+  }
+#endif
   w.mass_kind = A.mass_kind;
   RnRng rng;
   rng.seed = A.rng_seed[c];
@@ -482,7 +518,7 @@ RN_GLOBAL void rn_k_density(const double* RN_RESTRICT qin, double* RN_RESTRICT o
   __syncwarp();
   int e = 0;
   double dens;
-  rn_density(w.q, dens, w.g, w.scr, data, e);
+  rn_density(w.q, dens, w.g, w.scr, data, e, w.tma);
   __syncwarp();
   if (RN_LANE == 0) out[c] = dens;
   RN_FOR_LANES(i) out[(size_t)(i + 1) * chains + c] = w.g[i];

@@ -36,21 +36,15 @@ def compile_source(src, fast=False):
     return C.CDLL(so)
 
 
-def density(src, q, cols, col_offsets=None, fast=False):
-    """q: [chains][n] -> [chains][n+1] using the emitted code."""
+def density(src, q, cols, model, fast=False):
+    """q: [chains][n] -> [chains][n+1] using the emitted code.  `model`: the CudaModel the source came from (its
+    rn_model_pack_columns lays the columns out exactly as rn_model_create uploads them: tile-major per target)."""
     L = compile_source(src, fast)
     q = np.ascontiguousarray(q, dtype=np.float64)
     chains, n = q.shape
     qt = np.ascontiguousarray(q.T)
     out = np.zeros((n + 1, chains))
-    # data buffer laid out like rn_model_create does: each column padded to a multiple of 4 doubles
-    offs, off = [], 0
-    for c in cols:
-        offs.append(off)
-        off += (len(c) + 3) & ~3
-    data = np.zeros(max(off, 1))
-    for o, c in zip(offs, cols):
-        data[o:o + len(c)] = c
+    data = model.pack_columns()
     err = C.c_int(0)
     L.emu_density(C.c_void_p(qt.ctypes.data), chains, C.c_void_p(out.ctypes.data), C.c_void_p(data.ctypes.data), C.byref(err))
     return np.ascontiguousarray(out.T), err.value

@@ -31,7 +31,7 @@ def test_emitted_density_matches_oracle(name):
     cm = api.CudaModel(rir, cols, device=-1)
     for gm, tol in ((abi.RN_GRAD_SYMBOLIC, 0.0), (abi.RN_GRAD_ADJOINT, 1e-9)):
         cfg = api.make_config(sampler=api.HMCSampler(1), gradientMode=gm, backend=abi.RN_BACKEND_THREAD)
-        out, err = he.density(cm.emit_source(cfg), q, cols)
+        out, err = he.density(cm.emit_source(cfg), q, cols, cm)
         assert err == 0
         rel = np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1e-300))
         assert rel <= tol, (name, gm, rel)
@@ -48,6 +48,6 @@ def test_primal_rir_scatter_gradient_for_large_lookup_tables():
     cm = api.CudaModel(prir, pcols, device=-1)
     src = cm.emit_source(api.make_config(sampler=api.HMCSampler(1), backend=abi.RN_BACKEND_THREAD))
     assert "+ k] +=" in src  # the scatter statement
-    out, err = he.density(src, q, pcols)
+    out, err = he.density(src, q, pcols, cm)
     assert err == 0
     assert np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-9
