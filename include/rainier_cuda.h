@@ -198,6 +198,10 @@ int rn_sampler_sync(rn_sampler* s);
 /* current q of every chain -> host [chains][n] */
 int rn_sampler_positions(rn_sampler* s, double* q);
 int rn_sampler_stats(rn_sampler* s, rn_chain_stats* stats, double* mass, double* stats_rings);
+/* Trace.diagnostics (rainier-core/.../core/Trace.scala:11-21,49-121): rHat and effective sample size per parameter
+ * over a DEVICE-resident sample block, reduced on the device (only n*2 numbers cross PCIe).  layout 0 =
+ * [iterations][n][chains] (as rn_sampler_run writes it), 1 = [chains][iterations][n].  out: host [n][2]. */
+int rn_sampler_diagnostics(rn_sampler* s, const double* d_samples, int iterations, int layout, double* out);
 /* the CUstream the sampler launches on (for CUDA-event timing by the caller) */
 void* rn_sampler_stream(rn_sampler* s);
 /* number of kernel launches issued so far on this sampler */

@@ -65,6 +65,7 @@ def lib():
         L.rn_sampler_sync.argtypes = [C.c_void_p]
         L.rn_sampler_positions.argtypes = [C.c_void_p, C.c_void_p]
         L.rn_sampler_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rn_sampler_diagnostics.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.rn_sampler_stream.argtypes = [C.c_void_p]
         L.rn_sampler_stream.restype = C.c_void_p
         L.rn_sampler_launches.argtypes = [C.c_void_p]
@@ -522,6 +523,14 @@ class CudaSampler:
     @property
     def launches(self):
         return lib().rn_sampler_launches(self.h)
+
+    def diagnostics(self, d_samples, iterations, layout=0):
+        """Trace.diagnostics (core/Trace.scala:11-21) of a device-resident sample block, reduced on the device.
+        d_samples: device pointer; layout 0 = [iterations][n][chains], 1 = [chains][iterations][n].
+        Returns an array [n][2] = (rHat, effectiveSampleSize)."""
+        out = np.empty((self.model.nVars, 2), dtype=np.float64)
+        _check(lib().rn_sampler_diagnostics(self.h, C.c_void_p(d_samples), int(iterations), int(layout), out.ctypes.data))
+        return out
 
     def positions(self):
         q = np.empty((self.chains, self.model.nVars), dtype=np.float64)

@@ -151,7 +151,7 @@ struct Kernel {
   std::vector<char> cubin;
   CUmodule mod = nullptr;
   CUfunction k_init = nullptr, k_iter = nullptr, k_density = nullptr, k_transpose = nullptr, k_pool_reduce = nullptr,
-             k_pool_apply = nullptr;
+             k_pool_apply = nullptr, k_diag_chain = nullptr, k_diag_reduce = nullptr;
   const Program* prog = nullptr;
   int backend = 0;            // 0 thread per chain, 1 warp per chain
   int wpc_smem_doubles = 0;   // per-warp dynamic shared memory (backend 1)
@@ -371,6 +371,8 @@ static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
   CU(A->cuModuleGetFunction(&K->k_transpose, K->mod, "rn_k_transpose"));
   CU(A->cuModuleGetFunction(&K->k_pool_reduce, K->mod, "rn_k_pool_reduce"));
   CU(A->cuModuleGetFunction(&K->k_pool_apply, K->mod, "rn_k_pool_apply"));
+  CU(A->cuModuleGetFunction(&K->k_diag_chain, K->mod, "rn_k_diag_chain"));
+  CU(A->cuModuleGetFunction(&K->k_diag_reduce, K->mod, "rn_k_diag_reduce"));
   if (K->backend == 1) {
     const int bytes = (int)K->smem_bytes();
     for (CUfunction f : {K->k_init, K->k_iter, K->k_density})
@@ -1146,6 +1148,92 @@ int rn_sampler_stats(rn_sampler* s, rn_chain_stats* stats, double* mass, double*
   }
   if (any_err & 1) return fail(RN_E_LOOKUP, "lookup index out of range on at least one chain");
   if (any_err & 2) return fail(RN_E_INVALID, "requirement failed: adapted mass matrix contains 0.0 (MassMatrix.scala:8,16)");
+  return RN_OK;
+}
+
+// Trace.diagnostics (core/Trace.scala:11-21,49-121) over a device-resident sample block: per-chain sums and the
+// cross-chain reductions on the device (rn_diag.cuh), the scalar epilogue here.  layout 0: [iterations][n][chains] (what
+// rn_sampler_run writes), 1: [chains][iterations][n] (the caller-facing order).  out: host [n][2] = rHat, ess.
+int rn_sampler_diagnostics(rn_sampler* s, const double* d_samples, int iterations, int layout, double* out) {
+  if (!s || !d_samples || !out) return fail(RN_E_INVALID, "null argument");
+  if (s->chains < 2) return fail(RN_E_INVALID, "requirement failed: diagnostics requires multiple chains (Trace.scala:12)");
+  if (iterations < 2) return fail(RN_E_INVALID, "diagnostics needs at least 2 iterations");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  const int n = (int)s->m->n_params, C = s->chains, I = iterations;
+  const int L = std::min(100, I - 1);  // lags whose variogram has a non-empty sum; lag == I gives 0/0 (see epilogue)
+  const size_t nC = (size_t)n * C;
+  CUdeviceptr scratch = 0;
+  const size_t n_sums = (size_t)(3 + L) * n;  // [mean sums | var sums | vario sums (L*n) | squared deviations]
+  CU(A->cuMemAlloc(&scratch, ((2 + (size_t)L) * nC + n_sums + n) * 8));
+  struct Free {
+    const Api* A;
+    CUdeviceptr p;
+    ~Free() { A->cuMemFree(p); }
+  } guard{A, scratch};
+  CUdeviceptr d_mean = scratch, d_var = scratch + nC * 8, d_vario = scratch + 2 * nC * 8, d_sums = scratch + (2 + (size_t)L) * nC * 8,
+              d_shift = d_sums + n_sums * 8;
+  {
+    CUdeviceptr src = (CUdeviceptr)(uintptr_t)d_samples;
+    long long st, si, sc;
+    int i_fastest;
+    if (layout == 0) {
+      st = (long long)n * C, si = C, sc = 1, i_fastest = 0;
+    } else {
+      st = n, si = 1, sc = (long long)I * n, i_fastest = 1;
+    }
+    int I_ = I, n_ = n, C_ = C, L_ = L;
+    void* params[] = {&src, &st, &si, &sc, &I_, &n_, &C_, &L_, &i_fastest, &d_mean, &d_var, &d_vario};
+    CU(A->cuLaunchKernel(s->K->k_diag_chain, (unsigned)((nC + 127) / 128), 1, 1, 128, 1, 1, 0, s->stream, params, nullptr));
+    s->launches++;
+  }
+  auto reduce = [&](CUdeviceptr in, int q, CUdeviceptr shift, CUdeviceptr outp) -> int {
+    int C_ = C;
+    void* params[] = {&in, &C_, &shift, &outp};
+    CU(A->cuLaunchKernel(s->K->k_diag_reduce, (unsigned)q, 1, 1, 256, 1, 1, 0, s->stream, params, nullptr));
+    s->launches++;
+    return RN_OK;
+  };
+  int rc = reduce(d_mean, n, 0, d_sums);
+  if (!rc) rc = reduce(d_var, n, 0, d_sums + (size_t)n * 8);
+  if (!rc && L > 0) rc = reduce(d_vario, L * n, 0, d_sums + 2 * (size_t)n * 8);
+  if (rc) return rc;
+  std::vector<double> sums(n_sums);
+  CU(A->cuStreamSynchronize(s->stream));
+  CU(A->cuMemcpyDtoH(sums.data(), d_sums, (size_t)n * 8));
+  const double m = (double)C, nn = (double)I;
+  std::vector<double> meanMean(n);
+  for (int i = 0; i < n; i++) meanMean[i] = sums[i] / m;  // means.sum / m, Trace.scala:73
+  CU(A->cuMemcpyHtoD(d_shift, meanMean.data(), (size_t)n * 8));
+  rc = reduce(d_mean, n, d_shift, d_sums + (2 + (size_t)L) * n * 8);
+  if (rc) return rc;
+  CU(A->cuStreamSynchronize(s->stream));
+  CU(A->cuMemcpyDtoH(sums.data(), d_sums, n_sums * 8));
+  for (int i = 0; i < n; i++) {
+    const double b = (nn / (m - 1)) * sums[(2 + (size_t)L) * n + i];  // Trace.scala:75-77
+    const double w = sums[n + i] / m;                                  // :88
+    const double v = (nn - 1) / nn * w + b / nn;                       // :90-92
+    const double rHat = std::sqrt(v / w);
+    double acc = 0.0;
+    for (int lag = 1;; lag++) {  // Trace.autocorrelation, :97-109 (tail recursion as a loop)
+      double vt;
+      if (lag <= L)
+        vt = sums[(2 + (size_t)(lag - 1)) * n + i] / m;
+      else if (lag == I)
+        vt = std::nan("");  // variogram: 0.0 / 0
+      else
+        vt = -0.0;          // lag > trace.size: empty sum over a negative count
+      const double pt = 1.0 - (vt / (2.0 * v));
+      if (pt > 0.0 && lag < 100)
+        acc += pt;
+      else
+        break;
+    }
+    out[2 * i] = rHat;
+    out[2 * i + 1] = nn * m / (1 + (2 * acc));  // :60
+  }
   return RN_OK;
 }
 

@@ -264,3 +264,29 @@ def test_pooled_adaptation_single_gpu(schools):
     assert np.all(np.abs(m0 - m1) < 0.1 * sd)
     acc = np.mean([s.accepted / s.iterations for s in tr.stats])
     assert 0.5 < acc <= 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Trace.diagnostics reduced on the device
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("iters", [40, 150])
+def test_device_diagnostics_match_trace_restatement(schools, iters):
+    """rn_sampler_diagnostics over the device-resident samples == the line-by-line restatement of Trace.diagnostics
+    (Trace.scala:49-121) over the same samples on the host; both layouts; iterations below and above the 100-lag cap."""
+    import torch
+    from oracle.rainier_py.diagnostics import trace_diagnostics
+
+    cfg = api.SamplerConfig(iterations=iters, warmupIterations=300)
+    m = api.CudaModel(*schools)
+    s = api.CudaSampler(m, cfg, seeds=np.arange(24) + 1)
+    d = torch.empty((iters, m.nVars, 24), dtype=torch.float64, device="cuda")
+    s.warmup(-1)
+    s.run(iters, d.data_ptr())
+    s.sync()
+    got = s.diagnostics(d.data_ptr(), iters, layout=0)
+    chain_major = d.permute(2, 0, 1).contiguous()
+    got2 = s.diagnostics(chain_major.data_ptr(), iters, layout=1)
+    ref = np.array(trace_diagnostics(chain_major.cpu().numpy()))
+    assert parity.rel_err(got, ref, 1e-9) < 1e-9, (got, ref)
+    assert parity.rel_err(got2, ref, 1e-9) < 1e-9
+    s.close()
