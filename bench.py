@@ -43,24 +43,53 @@ def bytes_per_leapfrog_step(n, L):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML every ~5 ms (nvidia-smi every 200 ms when the
+    NVML binding is missing)."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.sm, self.max_sm, self.reasons = [], None, set()
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for nm, b in bits.items():
+                if r & b:
+                    self.reasons.add(nm)
+            self._stop.wait(0.005)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                self.sm.append(float(r[0]))
+                self.max_sm = float(r[1])
+                for k, nm in enumerate(self.NAMES):
+                    if r[2 + k].lower().startswith("active"):
+                        self.reasons.add(nm)
             except Exception:
                 pass
             self._stop.wait(0.2)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def __enter__(self):
         self._t.start()
@@ -71,12 +100,14 @@ class ClockSampler:
         self._t.join(timeout=5)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": [n for n in self.NAMES if n in self.reasons], "samples": len(self.sm)}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE rn_k_iter launch at the default workload (151552 chains x 100
+# iterations), from `ncu --set full` (profiles/r1_ncu_funnel_{parity,fast}_v2.csv): the 46 MB of chain state stays in
+# L2, so what reaches DRAM is the 1.2 GB sample stream plus write-allocate traffic -- below the algorithmic bytes.
+NCU_DRAM_BYTES_PER_LAUNCH = {"parity": 55083520 + 1776891000, "fast": 54043904 + 1686160000}
 
 
 def measured_peaks():
@@ -294,7 +325,10 @@ def main():
                     "api": "rn_sample (C ABI), host buffers: seeds in, [chains][iterations][n] samples out (page-locked, rn_host_alloc)",
                     "steps": n_e2e, "pageable_caller_buffer_value": e2e_pageable},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                         "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH[args.math] if (C_, I_) == (151552, 100) else None,
+                         "traffic_unit": "bytes per rn_k_iter launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "algorithmic_bytes_per_launch": bps * C_ * I_ * N_STEPS, "peak_source": peak_kind,
                          "bytes_per_leapfrog_step": bps,
                          "note": "compulsory-traffic accounting (SURVEY.md 8d); the kernel is FP64-pipe bound, see fp64"},
             "fp64": {"flops_per_leapfrog_step": flops_step, "special_per_leapfrog_step": counts["special_invariant"] * evals_per_step,

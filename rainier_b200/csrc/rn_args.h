@@ -51,6 +51,8 @@ struct RnArgs {
   int phase;                     // 0 warmup, 1 sampling
   int adaptation;                // 0 per chain (reference semantics), 1 pooled over chains/ranks (extension)
   int tma;                       // warp-per-chain kernels: CTA-shared TMA data tiles allowed (see rn_sampler_wpc.cuh)
+  int chain_begin;               // rn_k_iter works on chains [chain_begin, chain_end): rn_sample pipelines chain blocks
+  int chain_end;                 //   against the device->host copy of the previous block
   int pad1;
 };
 

@@ -54,6 +54,8 @@ struct Api {
   CUresult (*cuMemHostRegister)(void*, size_t, unsigned);
   CUresult (*cuMemHostUnregister)(void*);
   CUresult (*cuPointerGetAttribute)(void*, int, CUdeviceptr);
+  CUresult (*cuCtxGetDevice)(CUdevice*);
+  CUresult (*cuDeviceGetPCIBusId)(char*, int, CUdevice);
   CUresult (*cuMemcpyHtoD)(CUdeviceptr, const void*, size_t);
   CUresult (*cuMemcpyDtoH)(void*, CUdeviceptr, size_t);
   CUresult (*cuMemcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);

@@ -34,6 +34,7 @@ struct Emitter {
   bool wpc = false;
   std::vector<int> smem_slot;             // slot -> index in the shared accumulator block, or -1 (register)
   std::map<int, int> tab_off;             // large-lookup node id -> offset of its table in scratch
+  std::vector<int> tab_fill;              // one representative lookup node per distinct table
   int n_smem_acc = 0, tab_doubles = 0;
   std::string col_suffix;                 // names of column values loaded in the current region of a row body
   Emitter(const Program& p, const EmitOptions& o) : P(p), opt(o) {}
@@ -274,11 +275,19 @@ struct Emitter {
       for (const ScatterStmt& sc : T.row_scatter)
         for (int k = 0; k < sc.len; k++)
           if (smem_slot[sc.slot_base + k] < 0) smem_slot[sc.slot_base + k] = n_smem_acc++;
+    std::map<std::vector<int>, int> tab_by_refs;  // Lookups over the same entries (the 8 observe splits) share a table
     for (const TargetInfo& T : P.targets)
       for (int id : T.row_fwd)
         if (is_big_table(P.nodes[id])) {
-          tab_off[id] = tab_doubles;
-          tab_doubles += P.nodes[id].c;
+          const Node& n = P.nodes[id];
+          std::vector<int> refs(P.lookup_refs.begin() + n.b, P.lookup_refs.begin() + n.b + n.c);
+          auto it = tab_by_refs.find(refs);
+          if (it == tab_by_refs.end()) {
+            it = tab_by_refs.emplace(refs, tab_doubles).first;
+            tab_fill.push_back(id);
+            tab_doubles += n.c;
+          }
+          tab_off[id] = it->second;
         }
     os << "// ---- emitted: log-density and gradient of the frozen DAG (" << (P.symbolic ? "symbolic" : "adjoint")
        << " gradient), warp-per-chain: rows across lanes ----\n";
@@ -292,9 +301,9 @@ struct Emitter {
     os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x & 31);\n  (void)lane;\n";
     if (n_smem_acc) os << "  for (int k = lane; k < " << n_smem_acc << "; k += 32) scr[" << tab_doubles << " + k] = 0.0;\n";
     for (int id : P.inv_fwd) stmt(id, "  ");
-    for (auto& kv : tab_off) {
-      const Node& n = P.nodes[kv.first];
-      for (int k = 0; k < n.c; k++) os << "  scr[" << (kv.second + k) << "] = " << val(P.lookup_refs[n.b + k]) << ";\n";
+    for (int id : tab_fill) {
+      const Node& n = P.nodes[id];
+      for (int k = 0; k < n.c; k++) os << "  scr[" << (tab_off.at(id) + k) << "] = " << val(P.lookup_refs[n.b + k]) << ";\n";
     }
     os << "  __syncwarp();\n";
     for (int sl = 0; sl < P.n_slots; sl++)

@@ -372,6 +372,7 @@ std::string build_program(const void* rir, size_t len, bool want_adjoint, bool f
     std::map<int, std::vector<int>> inv_slots;  // invariant node -> accumulator slots feeding its adjoint
     std::map<int, std::vector<double>> inv_seeds;  // invariant node -> constant seeds
     std::map<int, int> direct_slot;             // invariant node -> its own frontier slot
+    std::map<std::vector<int>, int> scatter_base;  // table entries of a large Lookup -> its block of scatter slots
     auto frontier_slot = [&](int node) {
       auto it = direct_slot.find(node);
       if (it != direct_slot.end()) return it->second;
@@ -409,11 +410,21 @@ std::string build_program(const void* rir, size_t len, bool want_adjoint, bool f
           for (int j = 0; j < nd.c; j++)
             if (B.dep[P.lookup_refs[nd.b + j]] != -1) all_inv = false;
           if (all_inv) {
-            int base = P.n_slots;
-            P.n_slots += nd.c;
-            for (int j = 0; j < nd.c; j++) {
-              int e = P.lookup_refs[nd.b + j];
-              if (B.active[e]) inv_slots[e].push_back(base + j);
+            // the 8 unrolled observation splits of Model.observe (core/Model.scala:98-132) each carry their own Lookup
+            // over the SAME table entries: they share one block of scatter accumulators
+            std::vector<int> refs(P.lookup_refs.begin() + nd.b, P.lookup_refs.begin() + nd.b + nd.c);
+            auto sb = scatter_base.find(refs);
+            int base;
+            if (sb != scatter_base.end()) {
+              base = sb->second;
+            } else {
+              base = P.n_slots;
+              P.n_slots += nd.c;
+              scatter_base[refs] = base;
+              for (int j = 0; j < nd.c; j++) {
+                int e = refs[j];
+                if (B.active[e]) inv_slots[e].push_back(base + j);
+              }
             }
             T.row_scatter.push_back({base, nd.c, nd.d, nd.a, a});
             continue;

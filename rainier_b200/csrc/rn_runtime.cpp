@@ -7,9 +7,12 @@
 // No CPU fallback: anything that needs to execute fails with RN_E_CUDA when there is no driver/device.
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -78,6 +81,8 @@ const Api* api(std::string* why) {
       RN_SYM(cuMemHostRegister, "cuMemHostRegister_v2")
       RN_SYM(cuMemHostUnregister, "cuMemHostUnregister")
       RN_SYM(cuPointerGetAttribute, "cuPointerGetAttribute")
+      a.cuCtxGetDevice = (decltype(a.cuCtxGetDevice))dlsym(h, "cuCtxGetDevice");        // optional (NUMA placement)
+      a.cuDeviceGetPCIBusId = (decltype(a.cuDeviceGetPCIBusId))dlsym(h, "cuDeviceGetPCIBusId");
       RN_SYM(cuMemcpyHtoD, "cuMemcpyHtoD_v2")
       RN_SYM(cuMemcpyDtoH, "cuMemcpyDtoH_v2")
       RN_SYM(cuMemcpyHtoDAsync, "cuMemcpyHtoDAsync_v2")
@@ -281,6 +286,7 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
 
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
+  if (getenv("RN_LIBM_INLINE")) opts.push_back("-DRN_LIBM_INLINE=1");
   std::string maxreg;
   {
     // registers/thread: the fused iteration kernel is latency-bound on dependent fp64 chains, so occupancy matters
@@ -695,17 +701,18 @@ struct Arena {
   }
 };
 
-int launch(const Api* A, rn_sampler* s, CUfunction f) {
+int launch(const Api* A, rn_sampler* s, CUfunction f, int count = -1) {
   void* params[] = {&s->args};
+  const size_t chains = count < 0 ? (size_t)s->chains : (size_t)count;
   if (s->K->backend == 1) {
     const unsigned w = (unsigned)s->K->warps_per_cta;
-    const unsigned grid = (unsigned)((s->chains + w - 1) / w);
+    const unsigned grid = (unsigned)((chains + w - 1) / w);
     CU(A->cuLaunchKernel(f, grid, 1, 1, w * 32, 1, 1, s->K->smem_bytes(), s->stream, params, nullptr));
     s->launches++;
     return RN_OK;
   }
   static const unsigned block = getenv("RN_BLOCK") ? (unsigned)atoi(getenv("RN_BLOCK")) : 128u;
-  const unsigned grid = (unsigned)((s->chains + block - 1) / block);
+  const unsigned grid = (unsigned)((chains + block - 1) / block);
   CU(A->cuLaunchKernel(f, grid, 1, 1, block, 1, 1, 0, s->stream, params, nullptr));
   s->launches++;
   return RN_OK;
@@ -973,7 +980,9 @@ static int pool_window(const Api* A, rn_sampler* s, int window_len) {
   return RN_OK;
 }
 
-static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, double* d_samples) {
+static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, double* d_samples, int chain_begin = 0,
+                     int chain_end = -1) {
+  if (chain_end < 0) chain_end = s->chains;
   const int per_launch = s->cfg.launch_iterations > 0 ? s->cfg.launch_iterations : 1000;
   const bool pooled = phase == 0 && s->cfg.adaptation == RN_ADAPT_POOLED && s->cfg.mass_tuner == RN_MASS_DIAGONAL;
   int done = 0;
@@ -985,6 +994,8 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.n_iter = k;
     a.adaptation = s->cfg.adaptation == RN_ADAPT_POOLED ? 1 : 0;
     a.tma = s->K->tma_stages > 0 ? 1 : 0;
+    a.chain_begin = chain_begin;
+    a.chain_end = chain_end;
     a.mass_kind = s->mass_kind;
     a.win_size = s->win_size;
     a.win_i = s->win_i;
@@ -992,7 +1003,7 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.est_samples = s->est_samples;
     a.samples = (phase == 1 && d_samples) ? d_samples + (size_t)done * s->m->n_params * (size_t)s->chains : nullptr;
     a.trace = s->d_trace ? (double*)(uintptr_t)(s->d_trace + s->trace_pos * 4 * (size_t)s->chains * 8) : nullptr;
-    int rc = launch(A, s, s->K->k_iter);
+    int rc = launch(A, s, s->K->k_iter, chain_end - chain_begin);
     if (rc) return rc;
     if (phase == 0) {
       const int closed = advance_window(s, k);
@@ -1270,6 +1281,37 @@ void rn_sampler_destroy(rn_sampler* s) {
 
 namespace {
 
+// Page-locked host memory should live on the socket the GPU hangs off: a D2H copy into the far socket crosses the
+// inter-socket link (measured on the B200 box: 57 vs 38 GB/s).  The driver allocates pinned pages in the calling
+// thread's context, so a temporary MPOL_PREFERRED policy around cuMemAllocHost places them.  Best effort: any failure
+// (single-socket box, no sysfs, seccomp) leaves the default policy.
+int gpu_numa_node(const Api* A) {
+  CUdevice dev;
+  if (!A->cuCtxGetDevice || A->cuCtxGetDevice(&dev) != 0) return -1;
+  char bus[32] = {0};
+  if (!A->cuDeviceGetPCIBusId || A->cuDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != 0) return -1;
+  for (char* p = bus; *p; p++) *p = (char)tolower(*p);
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+struct NumaScope {
+  bool set = false;
+  explicit NumaScope(int node) {
+    if (node < 0 || node >= 1024 || getenv("RN_NO_NUMA")) return;
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    set = syscall(SYS_set_mempolicy, 1 /*MPOL_PREFERRED*/, mask, 1024ul + 1) == 0;
+  }
+  ~NumaScope() {
+    if (set) syscall(SYS_set_mempolicy, 0 /*MPOL_DEFAULT*/, nullptr, 0ul);
+  }
+};
+
 struct PinnedRing {  // process-wide, grown on demand, never freed (pinning is expensive)
   static constexpr int R = 6;
   void* buf[R] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1354,16 +1396,17 @@ bool host_is_pinned(const Api* A, const void* p, size_t bytes) {
 
 // device -> caller's host buffer.  Page-locked destination: one DMA, no staging.  Pageable destination: a ring of
 // pinned staging slices; slice k's PCIe copy overlaps the fan-out memcpy of slices < k into the caller's pages.
-int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, size_t bytes) {
+int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, size_t bytes, bool sync) {
   if (host_is_pinned(A, dst, bytes) && !getenv("RN_DRAIN_FORCE_STAGED")) {
     CU(A->cuMemcpyDtoHAsync(dst, src, bytes, copy));
-    CU(A->cuStreamSynchronize(copy));
+    if (sync) CU(A->cuStreamSynchronize(copy));
     return RN_OK;
   }
-  const size_t slice = (size_t)16 << 20;
+  const size_t slice = (size_t)32 << 20;
   {
     std::lock_guard<std::mutex> lk(g_ring.mu);
     if (g_ring.bytes < slice) {
+      NumaScope numa(gpu_numa_node(A));  // staging buffers on the GPU's socket
       for (int r = 0; r < PinnedRing::R; r++) CU(A->cuMemAllocHost(&g_ring.buf[r], slice));
       g_ring.bytes = slice;
     }
@@ -1371,41 +1414,56 @@ int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, siz
   std::lock_guard<std::mutex> lk(g_ring.mu);  // one drain at a time per process
   Workers& pool = drain_workers();
   const int T = pool.size();
-  CUevent ev[PinnedRing::R];
-  for (int r = 0; r < PinnedRing::R; r++) CU(A->cuEventCreate(&ev[r], 2));
+  constexpr int R = PinnedRing::R;
+  CUevent ev[R];
+  for (int r = 0; r < R; r++) CU(A->cuEventCreate(&ev[r], 2));
   const size_t n_slices = (bytes + slice - 1) / slice;
-  auto finish = [&](size_t k) -> int {  // slice k has landed in pinned memory: fan its memcpy out
-    const int slot = (int)(k % PinnedRing::R);
-    CU(A->cuEventSynchronize(ev[slot]));
-    const size_t off = k * slice, len = std::min(slice, bytes - off);
-    const size_t part = ((len / T) + 4095) & ~(size_t)4095;
-    for (int t = 0; t < T; t++) {
-      const size_t o = (size_t)t * part;
-      if (o >= len) break;
-      const size_t l = std::min(part, len - o);
-      char* d = (char*)dst + off + o;
-      const char* sp = (const char*)g_ring.buf[slot] + o;
-      pool.submit(slot, [d, sp, l] { std::memcpy(d, sp, l); });
-    }
-    return RN_OK;
+  // Each worker owns one stripe of every slice: it waits until slice k has landed in the ring (`ready`), copies its
+  // stripe into the caller's pages and counts itself in done[k]; the DMA of slices k+1.. runs meanwhile.
+  std::atomic<size_t> ready{0};
+  std::vector<std::atomic<int>> done(n_slices);
+  for (auto& d : done) d.store(0);
+  std::atomic<bool> abort{false};
+  for (int t = 0; t < T; t++) {
+    pool.submit(0, [&, t] {
+      for (size_t k = 0; k < n_slices; k++) {
+        while (ready.load(std::memory_order_acquire) <= k) {
+          if (abort.load()) return;
+          std::this_thread::yield();
+        }
+        const size_t off = k * slice, len = std::min(slice, bytes - off);
+        const size_t part = ((len / (size_t)T) + 4095) & ~(size_t)4095;
+        const size_t o = (size_t)t * part;
+        if (o < len) std::memcpy((char*)dst + off + o, (const char*)g_ring.buf[k % R] + o, std::min(part, len - o));
+        done[k].fetch_add(1, std::memory_order_release);
+      }
+    });
+  }
+  auto fail_out = [&](int rc) {
+    abort.store(true);
+    pool.wait(0);
+    for (int r = 0; r < R; r++) A->cuEventDestroy(ev[r]);
+    return rc;
   };
-  // keep up to R-1 DMA slices in flight ahead of the memcpy fan-out
-  const size_t ahead = PinnedRing::R - 1;
-  size_t issued = 0, finished = 0;
-  while (finished < n_slices) {
-    while (issued < n_slices && issued < finished + ahead) {
-      const int slot = (int)(issued % PinnedRing::R);
-      pool.wait(slot);  // previous occupant of this slot fully copied out
+  const size_t ahead = R - 1;
+  size_t issued = 0, landed = 0;
+  while (landed < n_slices) {
+    while (issued < n_slices && issued < landed + ahead) {
+      if (issued >= (size_t)R)  // the slot's previous slice must be fully copied out
+        while (done[issued - R].load(std::memory_order_acquire) < T) std::this_thread::yield();
       const size_t off = issued * slice, len = std::min(slice, bytes - off);
-      CU(A->cuMemcpyDtoHAsync(g_ring.buf[slot], src + off, len, copy));
-      CU(A->cuEventRecord(ev[slot], copy));
+      CUresult r1 = A->cuMemcpyDtoHAsync(g_ring.buf[issued % R], src + off, len, copy);
+      if (r1 == 0) r1 = A->cuEventRecord(ev[issued % R], copy);
+      if (r1 != 0) return fail_out(cufail(A, r1, "drain: cuMemcpyDtoHAsync"));
       issued++;
     }
-    int rc = finish(finished++);
-    if (rc) return rc;
+    CUresult r2 = A->cuEventSynchronize(ev[landed % R]);
+    if (r2 != 0) return fail_out(cufail(A, r2, "drain: cuEventSynchronize"));
+    ready.store(++landed, std::memory_order_release);
   }
-  for (int r = 0; r < PinnedRing::R; r++) pool.wait(r);
-  for (int r = 0; r < PinnedRing::R; r++) A->cuEventDestroy(ev[r]);
+  pool.wait(0);
+  for (int r = 0; r < R; r++) A->cuEventDestroy(ev[r]);
+  (void)sync;
   return RN_OK;
 }
 
@@ -1475,33 +1533,75 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
     }
     CU(A->cuStreamCreate(&g.copy, 1));
     CU(A->cuEventCreate(&g.done, 2));
-    (void)total;
-    for (size_t p0 = 0; p0 < I; p0 += pass_iters) {
-      const size_t pi = std::min(pass_iters, I - p0);
-      for (size_t done = 0; done < pi;) {
-        const size_t k = std::min(chunk, pi - done);
-        rc = rn_sampler_run(s, (int)k, (double*)(uintptr_t)g.b[0]);
-        if (rc) return rc;
-        CUdeviceptr src = g.b[0], dst = g.b[1];
-        int rows = (int)(k * n), cols = (int)C;
-        long long ld = (long long)(pi * n), off = (long long)(done * n);
-        void* params[] = {&src, &dst, &rows, &cols, &ld, &off};
-        CU(A->cuLaunchKernel(s->K->k_transpose, (unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), 1, 32, 8, 1, 0,
-                             s->stream, params, nullptr));
-        s->launches++;
-        done += k;
+    auto transpose = [&](CUdeviceptr src, CUdeviceptr dst, size_t k, size_t cols, size_t pi, size_t done) -> int {
+      int rows = (int)(k * n), ncols = (int)cols;
+      long long src_ld = (long long)C, ld = (long long)(pi * n), off = (long long)(done * n);
+      void* params[] = {&src, &dst, &rows, &ncols, &src_ld, &ld, &off};
+      CU(A->cuLaunchKernel(s->K->k_transpose, (unsigned)((ncols + 31) / 32), (unsigned)((rows + 31) / 32), 1, 32, 8, 1, 0, s->stream,
+                           params, nullptr));
+      s->launches++;
+      return RN_OK;
+    };
+    if (pass_iters == I) {
+      // Everything fits on the device.  The chains are cut into blocks: block b runs all its iterations and is
+      // re-laid into the caller's [chain][iteration][n] order, then its (contiguous) slab starts crossing PCIe while
+      // block b+1 computes -- the copy, not the kernel, is the long pole of this call.
+      rc = rn_sampler_run(s, 0, nullptr);  // initialize + lf.resetStats() (Driver.scala:31), no iterations
+      if (rc) return rc;
+      size_t blocks = std::min<size_t>(8, C / 32768);
+      if (total < ((size_t)64 << 20)) blocks = 1;
+      if (const char* e = getenv("RN_SAMPLE_BLOCKS")) blocks = (size_t)atoll(e);
+      blocks = std::max<size_t>(1, std::min(blocks, C));
+      const size_t per = (((C + blocks - 1) / blocks) + 1023) & ~(size_t)1023;
+      std::vector<std::pair<size_t, size_t>> ranges;
+      for (size_t c0 = 0; c0 < C; c0 += per) ranges.push_back({c0, std::min(C, c0 + per)});
+      std::vector<CUevent> evs(ranges.size(), nullptr);
+      struct EvGuard {
+        const Api* A;
+        std::vector<CUevent>& e;
+        ~EvGuard() {
+          for (CUevent x : e)
+            if (x) A->cuEventDestroy(x);
+        }
+      } evg{A, evs};
+      for (size_t bi = 0; bi < ranges.size(); bi++) {
+        const size_t c0 = ranges[bi].first, c1 = ranges[bi].second;
+        for (size_t done = 0; done < I;) {
+          const size_t k = std::min(chunk, I - done);
+          rc = run_phase(A, s, 1, (int)k, (double*)(uintptr_t)g.b[0], (int)c0, (int)c1);
+          if (rc) return rc;
+          rc = transpose(g.b[0] + c0 * 8, g.b[1] + c0 * I * n * 8, k, c1 - c0, I, done);
+          if (rc) return rc;
+          done += k;
+        }
+        CU(A->cuEventCreate(&evs[bi], 2));
+        CU(A->cuEventRecord(evs[bi], s->stream));
       }
-      CU(A->cuEventRecord(g.done, s->stream));
-      CU(A->cuStreamWaitEvent(g.copy, g.done, 0));
       if (timing) {
         rn_sampler_sync(s);
         lap("kernels");
       }
-      if (pi == I) {
-        rc = drain_to_host(A, g.copy, g.b[1], samples, C * I * n * 8);
+      for (size_t bi = 0; bi < ranges.size(); bi++) {
+        const size_t c0 = ranges[bi].first, c1 = ranges[bi].second;
+        CU(A->cuStreamWaitEvent(g.copy, evs[bi], 0));
+        rc = drain_to_host(A, g.copy, g.b[1] + c0 * I * n * 8, samples + c0 * I * n, (c1 - c0) * I * n * 8,
+                           /*sync=*/bi + 1 == ranges.size());
         if (rc) return rc;
-      } else {  // strided pass: rows of pi*n doubles into a pitch of I*n
-        CUDA_MEMCPY2D cp;
+      }
+    } else {
+      for (size_t p0 = 0; p0 < I; p0 += pass_iters) {  // strided passes over the iteration axis
+        const size_t pi = std::min(pass_iters, I - p0);
+        for (size_t done = 0; done < pi;) {
+          const size_t k = std::min(chunk, pi - done);
+          rc = rn_sampler_run(s, (int)k, (double*)(uintptr_t)g.b[0]);
+          if (rc) return rc;
+          rc = transpose(g.b[0], g.b[1], k, C, pi, done);
+          if (rc) return rc;
+          done += k;
+        }
+        CU(A->cuEventRecord(g.done, s->stream));
+        CU(A->cuStreamWaitEvent(g.copy, g.done, 0));
+        CUDA_MEMCPY2D cp;  // rows of pi*n doubles into a pitch of I*n
         std::memset(&cp, 0, sizeof(cp));
         cp.srcMemoryType = CU_MEMORYTYPE_DEVICE;
         cp.srcDevice = g.b[1];
@@ -1551,6 +1651,7 @@ int rn_host_alloc(int device, size_t bytes, void** out) {
   if (!A) return fail(RN_E_CUDA, why);
   int rc = host_ctx(A, device);
   if (rc) return rc;
+  NumaScope numa(gpu_numa_node(A));
   CU(A->cuMemAllocHost(out, bytes));
   return RN_OK;
 }

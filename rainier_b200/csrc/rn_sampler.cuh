@@ -113,13 +113,13 @@ RN_DEVICE void rn_new_qs(const RnArgs& A, int c, const RnMass& M, RnPQ& s, doubl
 // initialHalfThenFullStep + (l-1) twoFullSteps + finalHalfStep, LeapFrog.scala:24-33,156-191.
 // `g` must hold the gradient at s.q on entry (true for params and for every state this kernel produces).
 RN_DEVICE void rn_leapfrog(const RnArgs& A, int c, const RnMass& M, RnPQ& s, int l, double stepSize, RnStats& S) {
+  // (one rn_update call site: the emitted density is inlined exactly once per use of rn_leapfrog)
   rn_full_ps(s, stepSize / 2.0, S);
-  rn_new_qs(A, c, M, s, stepSize);
-  rn_update(A, s, S);
-  for (int i = 1; i < l; i++) {
-    rn_full_ps(s, stepSize, S);
+  for (int i = 0;;) {
     rn_new_qs(A, c, M, s, stepSize);
     rn_update(A, s, S);
+    if (++i >= l) break;
+    rn_full_ps(s, stepSize, S);
   }
   rn_full_ps(s, stepSize / 2.0, S);
 }
@@ -290,8 +290,8 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
 // Driver.collectSamples (phase 1, Driver.scala:102-117)
 // =============================================================================================================
 RN_GLOBAL void rn_k_iter(const RnArgs A) {
-  const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (c >= A.chains) return;
+  const int c = A.chain_begin + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (c >= A.chain_end) return;
   RnRng rng;
   rng.seed = A.rng_seed[c];
   rng.nng = A.rng_nng[c];
@@ -599,13 +599,13 @@ RN_GLOBAL void rn_k_density(const double* RN_RESTRICT qin, double* RN_RESTRICT o
 // =============================================================================================================
 #ifndef RN_HOST_EMULATION
 RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT dst, int rows, int cols,
-                              long long dst_ld, long long dst_off) {
-  // dst[c * dst_ld + dst_off + r] = src[r * cols + c]
+                              long long src_ld, long long dst_ld, long long dst_off) {
+  // dst[c * dst_ld + dst_off + r] = src[r * src_ld + c]   (a block of `cols` chains out of src_ld)
   __shared__ double tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int r = r0 + j, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * cols + c];
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * (size_t)src_ld + c];
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += 8) {

@@ -249,7 +249,7 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
 
 // =============================================================================================================
 RN_GLOBAL void rn_k_iter(const RnArgs A) {
-  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int c = A.chain_begin + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 #if RN_TMA_STAGES > 0
   const int warps = (int)(blockDim.x >> 5);
   double* const stage0 = rn_smem + (((size_t)warps * RN_WPC_SMEM_DOUBLES + 15) & ~(size_t)15);
@@ -263,13 +263,13 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     __syncthreads();
   }
 #endif
-  if (c >= A.chains) return;
+  if (c >= A.chain_end) return;
   RnW w;
   rn_w_setup(w, rn_smem + (size_t)(threadIdx.x >> 5) * RN_WPC_SMEM_DOUBLES);
 #if RN_TMA_STAGES > 0
   if (lockstep) {
-    const int first = (int)(blockIdx.x * (blockDim.x >> 5));
-    const int active = (A.chains - first) < warps ? (A.chains - first) : warps;
+    const int first = A.chain_begin + (int)(blockIdx.x * (blockDim.x >> 5));
+    const int active = (A.chain_end - first) < warps ? (A.chain_end - first) : warps;
     w.tma.on = 1;
     w.tma.stage = stage0;
     w.tma.full = bars;
@@ -526,12 +526,13 @@ RN_GLOBAL void rn_k_density(const double* RN_RESTRICT qin, double* RN_RESTRICT o
 }
 
 RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT dst, int rows, int cols,
-                              long long dst_ld, long long dst_off) {
+                              long long src_ld, long long dst_ld, long long dst_off) {
+  // dst[c * dst_ld + dst_off + r] = src[r * src_ld + c]   (a block of `cols` chains out of src_ld)
   __shared__ double tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int r = r0 + j, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * cols + c];
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * (size_t)src_ld + c];
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += 8) {
