@@ -286,7 +286,7 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
 
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
-  if (getenv("RN_LIBM_INLINE")) opts.push_back("-DRN_LIBM_INLINE=1");
+  if (getenv("RN_LIBM_NOINLINE")) opts.push_back("-DRN_LIBM_NOINLINE=1");
   std::string maxreg;
   {
     // registers/thread: the fused iteration kernel is latency-bound on dependent fp64 chains, so occupancy matters

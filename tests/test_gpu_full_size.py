@@ -1,0 +1,120 @@
+"""
+Parity at BASELINE.json's FULL sizes (configs[0..4]), through the C ABI, by properties that do not need the oracle to
+run the whole workload:
+  * chains are independent and seed-determined: chain c of a full-size batch is bit-identical to the same seed run in a
+    tiny batch, and that tiny batch is compared with the CPU oracle;
+  * density/gradient of the full data set at a few positions against the oracle (cfg 2, 3, 4 at full size; cfg 5 at a
+    reduced size -- the reference's one-hot symbolic gradient that the oracle evaluates needs ~8 GB at 1000 groups x 1M
+    rows) and, for cfg 5, additivity of the log-likelihood over a partition of the rows.
+"""
+import numpy as np
+import pytest
+
+from oracle.rainier_py import configs
+from oracle.rainier_py.binding import OracleModel
+from rainier_b200 import abi, api
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _static(it, nsteps, eps, **kw):
+    return api.make_config(iterations=it, warmupIterations=0, sampler=api.HMCSampler(nsteps), stepSizeTuner=api.StaticStepSize(eps),
+                           massMatrixTuner=api.IdentityMassMatrixTuner(), **kw)
+
+
+def _subset_matches(rir, cols, cfg, n_chains, pick, tol=1e-9, rir_gpu=None, cols_gpu=None, seed0=1000):
+    """full batch on the GPU; the picked chains re-run alone must be bit-identical; those are checked against the oracle"""
+    seeds = np.arange(n_chains, dtype=np.int64) + seed0
+    m = api.CudaModel(rir_gpu if rir_gpu is not None else rir, cols_gpu if cols_gpu is not None else cols)
+    full = m.sample(cfg, seeds=seeds)
+    small = m.sample(cfg, seeds=seeds[pick])
+    assert np.array_equal(full.chains[pick], small.chains), "a chain's samples depend on the batch it ran in"
+    ref = OracleModel(rir, cols).sample(api.lower_config(cfg)[0], seeds=seeds[pick])
+    assert parity.rel_err(small.chains, ref["samples"], 1e-9) < tol
+    return full
+
+
+def test_cfg1_funnel_headline_batch():
+    """configs[0]/headline: Neal's funnel, HMC nSteps=5, the bench's 151552 chains (and the 1-chain plumbing case)"""
+    rir, cols = configs.funnel().compile(True)
+    cfg = _static(20, 5, 0.1)
+    pick = np.array([0, 1, 77777, 151551])
+    full = _subset_matches(rir, cols, cfg, 151552, pick)
+    assert np.all(np.isfinite(full.chains))
+    one = api.CudaModel(rir, cols).sample(cfg, seeds=[1000])
+    assert np.array_equal(one.chains[0], full.chains[0])
+
+
+def test_cfg2_linear_regression_10k_obs_4096_chains():
+    rir, cols = configs.linreg(10000).compile(True)
+    assert len(cols) == 0  # the reference inlines this likelihood into data-free polynomials
+    q = np.random.default_rng(0).normal(size=(64, 5)) * 0.3
+    assert parity.rel_err(api.CudaModel(rir, cols).density_batch(q), OracleModel(rir, cols).density_batch(q), 1e-9) < 1e-12
+    _subset_matches(rir, cols, _static(30, 5, 0.002), 4096, np.array([0, 5, 4095]))
+
+
+def test_cfg3_logistic_regression_100k_obs_50_covariates():
+    """full data (100000 x 50): density + gradient at 3 positions vs the oracle's evaluation of the reference's symbolic
+    gradient; the GPU side takes the primal RIR (what CudaCompiler sends) and differentiates it itself."""
+    model = configs.logreg(100000, 50)
+    rir, cols = model.compile(True)
+    prir, pcols = model.compile(False)
+    q = np.random.default_rng(1).normal(size=(3, 50)) * 0.2
+    ref = OracleModel(rir, cols).density_batch(q)
+    got = api.CudaModel(prir, pcols).density_batch(q)
+    assert parity.rel_err(got, ref, 1e-9) < 1e-9
+    # short trajectories of 2048 chains (the BASELINE chain count); 2 chains re-run alone and against the oracle
+    cfg = _static(2, 5, 0.01)
+    _subset_matches(rir, cols, cfg, 2048, np.array([0, 2047]), tol=1e-8, rir_gpu=prir, cols_gpu=pcols)
+
+
+def test_cfg4_eight_schools_default_config_8192_chains():
+    rir, cols = configs.eight_schools().compile(True)
+    cfg = api.SamplerConfig(iterations=50, warmupIterations=300)  # DefaultConfig: EHMC + DualAvg + diagonal mass
+    seeds = np.arange(8192, dtype=np.int64) + 1
+    m = api.CudaModel(rir, cols)
+    full = m.sample(cfg, seeds=seeds)
+    pick = np.array([0, 4096, 8191])
+    small = m.sample(cfg, seeds=seeds[pick])
+    assert np.array_equal(full.chains[pick], small.chains)
+    ref = OracleModel(rir, cols).sample(api.lower_config(cfg)[0], seeds=seeds[pick])
+    assert parity.rel_err(small.chains, ref["samples"]) < 1e-9
+    assert parity.rel_err(small.mass, ref["mass"]) < 1e-7
+
+
+def test_cfg5_poisson_glm_reduced_oracle_and_additivity():
+    """cfg 5 at 100 groups x 20000 rows against the oracle (symbolic one-hot gradient), and additivity over a row
+    partition: loglik(rows A+B) - prior = (loglik(A) - prior) + (loglik(B) - prior), gradients likewise."""
+    g, n = 100, 20000
+    rir, cols = configs.poisson_glm(g, n).compile(True)
+    prir, pcols = configs.poisson_glm(g, n).compile(False)
+    q = np.random.default_rng(2).normal(size=(4, g + 3)) * 0.2
+    ref = OracleModel(rir, cols).density_batch(q)
+    got = api.CudaModel(prir, pcols).density_batch(q)
+    assert parity.rel_err(got, ref, 1e-9) < 1e-9
+    # additivity: the prior-only model is the same DAG with zero rows
+    gidx, xs, ys = configs.poisson_glm_data(g, n)
+
+    def model_of(rows):
+        from oracle.rainier_py.compute import Vec
+        from oracle.rainier_py.core import Model, Normal, Poisson, Uniform
+        mu = Normal(0, 10).latent()
+        sd = Uniform(0, 2).latent()
+        alphas = Normal(mu, sd).latentVec(g)
+        beta = Normal(0, 10).latent()
+        rr = [(float(gidx[i]), float(xs[i])) for i in rows]
+        return Model.observe([int(ys[i]) for i in rows], Vec.from_(rr).map(lambda t: Poisson((alphas.at(t[0]) + beta * t[1]).exp())))
+
+    half = n // 2
+    a = api.CudaModel(*model_of(range(0, half)).compile(False)).density_batch(q)
+    b = api.CudaModel(*model_of(range(half, n)).compile(False)).density_batch(q)
+    # prior = density with the likelihood removed: 2*prior + lik(A) + lik(B) = a + b ; got = prior + lik(A) + lik(B)
+    from oracle.rainier_py.core import Model, Normal, Uniform
+    mu = Normal(0, 10).latent()
+    sd = Uniform(0, 2).latent()
+    alphas = Normal(mu, sd).latentVec(g)
+    beta = Normal(0, 10).latent()
+    prior = api.CudaModel(*Model.track_([mu, sd] + alphas.toList() + [beta]).compile(False)).density_batch(q)
+    assert parity.rel_err(a + b - prior, got, 1e-6) < 1e-9
