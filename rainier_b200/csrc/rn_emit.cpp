@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <set>
 #include <sstream>
@@ -47,6 +48,107 @@ struct Emitter {
   //   * every accumulation / scatter is issued as soon as its operand exists (a_j += w * x_j contracts to one FMA in
   //     fast mode).  The order of the additions into any one slot is unchanged.
   int local_col(const TargetInfo& T, int k) const { return k - ((int)T.first_input - (int)P.n_params); }
+
+  void operands(int id, std::vector<int>& out) const {
+    const Node& n = P.nodes[id];
+    out.clear();
+    switch (n.kind) {
+      case K_UNARY: out.push_back(n.a); break;
+      case K_BINARY: out.push_back(n.a); out.push_back(n.b); break;
+      case K_LOOKUP:
+        out.push_back(n.a);
+        for (int k = 0; k < n.c; k++) out.push_back(P.lookup_refs[n.b + k]);
+        break;
+      case K_SELEQ: out.push_back(n.a); out.push_back(n.b); out.push_back(n.c); break;
+      default: break;
+    }
+  }
+
+  // see row_body(): splits the row statements into independent dataflow components and merges them round-robin
+  void interleave_components(const TargetInfo& T, const std::set<int>& body, std::vector<int>& order_fwd,
+                             std::vector<int>& order_bwd) const {
+    const int BIG = 4;  // two components of at least this many statements meeting in one statement = a joiner
+    std::map<int, int> parent, size;  // union-find over statement ids
+    std::set<int> tail;
+    std::function<int(int)> find = [&](int x) {
+      while (parent[x] != x) {
+        parent[x] = parent[parent[x]];
+        x = parent[x];
+      }
+      return x;
+    };
+    std::vector<int> ops;
+    auto classify = [&](int s) {
+      operands(s, ops);
+      bool is_tail = false;
+      std::set<int> comps;
+      for (int o : ops) {
+        if (!body.count(o)) continue;
+        if (tail.count(o)) {
+          is_tail = true;
+          break;
+        }
+        comps.insert(find(o));
+      }
+      if (!is_tail && comps.size() >= 2) {
+        int big = 0;
+        for (int c : comps)
+          if (size[c] >= BIG) big++;
+        if (big >= 2) is_tail = true;
+      }
+      if (is_tail) {
+        tail.insert(s);
+        return;
+      }
+      parent[s] = s;
+      size[s] = 1;
+      for (int c : comps) {
+        const int r = find(s), q = find(c);
+        if (r == q) continue;
+        parent[q] = r;
+        size[r] += size[q];
+      }
+    };
+    std::vector<int> fwd, bwd;
+    for (int id : T.row_fwd)
+      if (body.count(id)) {
+        classify(id);
+        fwd.push_back(id);
+      }
+    for (int id : T.row_bwd)
+      if (body.count(id)) {
+        classify(id);
+        bwd.push_back(id);
+      }
+    auto schedule = [&](const std::vector<int>& region, std::vector<int>& out) {
+      std::vector<int> comp_order;
+      std::map<int, std::vector<int>> lists;
+      std::vector<int> tails;
+      for (int id : region) {
+        if (tail.count(id)) {
+          tails.push_back(id);
+          continue;
+        }
+        const int c = find(id);
+        if (!lists.count(c)) comp_order.push_back(c);
+        lists[c].push_back(id);
+      }
+      std::vector<size_t> pos(comp_order.size(), 0);
+      for (bool any = true; any;) {
+        any = false;
+        for (size_t k = 0; k < comp_order.size(); k++) {
+          const std::vector<int>& l = lists[comp_order[k]];
+          if (pos[k] < l.size()) {
+            out.push_back(l[pos[k]++]);
+            any = true;
+          }
+        }
+      }
+      out.insert(out.end(), tails.begin(), tails.end());
+    };
+    schedule(fwd, order_fwd);
+    schedule(bwd, order_bwd);
+  }
 
   template <class Load, class AccRef>
   void row_body(const TargetInfo& T, const char* ind, Load load, AccRef accref, bool atomic_scatter, int scatter_base_off) {
@@ -104,13 +206,20 @@ struct Emitter {
           emit_scatter(*sc);
         }
     };
+    // Instruction-level parallelism: the unrolled observations of a row are independent dataflow components whose
+    // results only meet in a final sum.  Emitting them one after the other leaves each warp with a single serial
+    // dependency chain (a 50-term dot product is 50 dependent FMAs; ncu: stall_wait dominates at 8 warps/SM), so the
+    // statements of the components are interleaved round-robin; "joiner" statements (and everything downstream of
+    // them) follow in their original order.  Values are unchanged (SSA); only the issue order moves.
+    std::vector<int> order_fwd, order_bwd;
+    interleave_components(T, body, order_fwd, order_bwd);
     col_suffix.clear();
-    for (int id : T.row_fwd) one(id);
-    if (!T.row_bwd.empty()) {
+    for (int id : order_fwd) one(id);
+    if (!order_bwd.empty()) {
       os << ind << "RN_FENCE();\n";
       declared.clear();
       col_suffix = "b";
-      for (int id : T.row_bwd) one(id);
+      for (int id : order_bwd) one(id);
     }
     for (const AccStmt* a : acc_tail) {
       need_col(a->node);
