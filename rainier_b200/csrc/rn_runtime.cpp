@@ -586,6 +586,16 @@ int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
   for (int c = 0; c < chains; c++)
     for (int i = 0; i < n; i++) qt[(size_t)i * chains + c] = q[(size_t)c * n + i];
   CUdeviceptr dq = 0, dout = 0, derr = 0;
+  struct Free {  // released on every exit path
+    const Api* A;
+    CUdeviceptr *a, *b, *c;
+    ~Free() {
+      for (CUdeviceptr* p : {a, b, c})
+        if (*p) A->cuMemFree(*p);
+    }
+  } guard{A, &dq, &dout, &derr};
+  rc = make_current(A, m);
+  if (rc) return rc;
   CU(A->cuMemAlloc(&dq, qt.size() * 8 + 8));
   CU(A->cuMemAlloc(&dout, ot.size() * 8));
   CU(A->cuMemAlloc(&derr, 4));
@@ -604,9 +614,6 @@ int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
   CU(A->cuMemcpyDtoH(ot.data(), dout, ot.size() * 8));
   int err = 0;
   CU(A->cuMemcpyDtoH(&err, derr, 4));
-  A->cuMemFree(dq);
-  A->cuMemFree(dout);
-  A->cuMemFree(derr);
   for (int c = 0; c < chains; c++)
     for (int i = 0; i <= n; i++) out[(size_t)c * (n + 1) + i] = ot[(size_t)i * chains + c];
   if (err & 1) return fail(RN_E_LOOKUP, "lookup index out of range");
@@ -808,7 +815,10 @@ int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, i
   std::string why;
   const Api* A = api(&why);
   if (!A) return fail(RN_E_CUDA, why);
-  std::unique_ptr<rn_sampler> s(new rn_sampler());
+  struct Destroy {
+    void operator()(rn_sampler* p) const { rn_sampler_destroy(p); }  // frees stream / arena / pools on a failed create
+  };
+  std::unique_ptr<rn_sampler, Destroy> s(new rn_sampler());
   s->m = m;
   s->cfg = *cfg;
   s->chains = chains;
@@ -1302,10 +1312,14 @@ int gpu_numa_node(const Api* A) {
 struct NumaScope {
   bool set = false;
   explicit NumaScope(int node) {
-    if (node < 0 || node >= 1024 || getenv("RN_NO_NUMA")) return;
+    if (node < 0 || node >= 1024 || getenv("RN_NO_NUMA")) {
+      if (getenv("RN_TIMING")) fprintf(stderr, "[rn numa] gpu node %d: default placement\n", node);
+      return;
+    }
     unsigned long mask[16] = {0};
     mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
     set = syscall(SYS_set_mempolicy, 1 /*MPOL_PREFERRED*/, mask, 1024ul + 1) == 0;
+    if (getenv("RN_TIMING")) fprintf(stderr, "[rn numa] gpu node %d: set_mempolicy %s\n", node, set ? "ok" : "refused");
   }
   ~NumaScope() {
     if (set) syscall(SYS_set_mempolicy, 0 /*MPOL_DEFAULT*/, nullptr, 0ul);
@@ -1552,9 +1566,22 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
       if (total < ((size_t)64 << 20)) blocks = 1;
       if (const char* e = getenv("RN_SAMPLE_BLOCKS")) blocks = (size_t)atoll(e);
       blocks = std::max<size_t>(1, std::min(blocks, C));
-      const size_t per = (((C + blocks - 1) / blocks) + 1023) & ~(size_t)1023;
+      // geometric ramp (1/16, 1/16, 1/8, 1/4, 1/2 of the chains for >= 4 blocks): the first slab reaches the copy
+      // engine after a fraction of a millisecond, later blocks keep the SMs full
       std::vector<std::pair<size_t, size_t>> ranges;
-      for (size_t c0 = 0; c0 < C; c0 += per) ranges.push_back({c0, std::min(C, c0 + per)});
+      if (blocks >= 4 && C >= 16 * 1024) {
+        const size_t unit = ((C / 16) + 1023) & ~(size_t)1023;
+        const size_t mult[5] = {1, 1, 2, 4, 8};
+        size_t c0 = 0;
+        for (int k = 0; k < 5 && c0 < C; k++) {
+          const size_t c1 = (k == 4) ? C : std::min(C, c0 + mult[k] * unit);
+          ranges.push_back({c0, c1});
+          c0 = c1;
+        }
+      } else {
+        const size_t per = (((C + blocks - 1) / blocks) + 1023) & ~(size_t)1023;
+        for (size_t c0 = 0; c0 < C; c0 += per) ranges.push_back({c0, std::min(C, c0 + per)});
+      }
       std::vector<CUevent> evs(ranges.size(), nullptr);
       struct EvGuard {
         const Api* A;

@@ -147,6 +147,14 @@ def test_rn_sample_pinned_and_pageable_buffers_agree(funnel):
     pinned = m.sample(cfg, seeds=seeds, out=pin.array).chains
     assert pinned is pin.array
     assert np.array_equal(pageable, pinned)
+    # chain blocks pipelined against the copy (normally only for >= 64K chains): same bits, both buffer kinds
+    os.environ["RN_SAMPLE_BLOCKS"] = "3"
+    try:
+        assert np.array_equal(m.sample(cfg, seeds=seeds).chains, pageable)
+        pin.array[:] = 0
+        assert np.array_equal(m.sample(cfg, seeds=seeds, out=pin.array).chains, pageable)
+    finally:
+        del os.environ["RN_SAMPLE_BLOCKS"]
     ref = OracleModel(*funnel).sample(api.lower_config(cfg)[0], seeds=seeds[:16])
     assert parity.rel_err(pinned[:16], ref["samples"]) < 1e-9
     pin.close()
