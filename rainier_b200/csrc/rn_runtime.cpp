@@ -420,6 +420,26 @@ static void pack_columns(const Program& P, const std::vector<uint64_t>& target_b
   }
 }
 
+// One primary-context retain per device that is never released: process-wide resources (the pinned staging ring of the
+// drain, rn_host_alloc buffers, the worker pool) must outlive any single model handle.  Without it, destroying the last
+// model drops the primary context's refcount to zero, the driver frees the pinned ring with the context, and the next
+// rn_sample copies through dangling pointers.
+static int host_ctx(const Api* A, int device) {
+  static std::mutex mu;
+  static std::map<int, CUcontext> ctxs;  // one primary-context retain per device for the life of the process
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = ctxs.find(device);
+  if (it == ctxs.end()) {
+    CUdevice dev;
+    CUcontext ctx = nullptr;
+    CU(A->cuDeviceGet(&dev, device));
+    CU(A->cuDevicePrimaryCtxRetain(&ctx, dev));
+    it = ctxs.emplace(device, ctx).first;
+  }
+  CU(A->cuCtxSetCurrent(it->second));
+  return RN_OK;
+}
+
 extern "C" {
 
 const char* rn_last_error(void) { return g_err.c_str(); }
@@ -482,6 +502,8 @@ int rn_model_create(const void* rir, size_t len, const double* const* cols, cons
     const Api* A = api(&why);
     if (!A) return fail(RN_E_CUDA, why);
     CUdevice dev;
+    rc = host_ctx(A, device);  // process-lifetime retain (see host_ctx)
+    if (rc) return rc;
     CU(A->cuDeviceGet(&dev, device));
     CU(A->cuDevicePrimaryCtxRetain(&m->ctx, dev));
     CU(A->cuCtxSetCurrent(m->ctx));
@@ -1656,21 +1678,6 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
 // page-locked host buffers for the caller (the JVM side wraps them as direct ByteBuffers): rn_sample DMAs straight
 // into such a buffer instead of staging through the pinned ring
 // ---------------------------------------------------------------------------------------------------------
-static int host_ctx(const Api* A, int device) {
-  static std::mutex mu;
-  static std::map<int, CUcontext> ctxs;  // one primary-context retain per device for the life of the process
-  std::lock_guard<std::mutex> lk(mu);
-  auto it = ctxs.find(device);
-  if (it == ctxs.end()) {
-    CUdevice dev;
-    CUcontext ctx = nullptr;
-    CU(A->cuDeviceGet(&dev, device));
-    CU(A->cuDevicePrimaryCtxRetain(&ctx, dev));
-    it = ctxs.emplace(device, ctx).first;
-  }
-  CU(A->cuCtxSetCurrent(it->second));
-  return RN_OK;
-}
 int rn_host_alloc(int device, size_t bytes, void** out) {
   if (!out || !bytes) return fail(RN_E_INVALID, "bad argument");
   std::string why;

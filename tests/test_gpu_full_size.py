@@ -118,3 +118,22 @@ def test_cfg5_poisson_glm_reduced_oracle_and_additivity():
     beta = Normal(0, 10).latent()
     prior = api.CudaModel(*Model.track_([mu, sd] + alphas.toList() + [beta]).compile(False)).density_batch(q)
     assert parity.rel_err(a + b - prior, got, 1e-6) < 1e-9
+
+
+def test_process_wide_staging_ring_outlives_a_model_handle():
+    """Regression: in a process where nothing else holds the CUDA primary context (no torch), destroying the only model
+    used to free the pinned staging ring with the context; the next rn_sample then copied through dangling pointers."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r);"
+        "from rainier_b200 import api;"
+        "rir = open(%r, 'rb').read();"
+        "cfg = api.make_config(iterations=8, warmupIterations=0, sampler=api.HMCSampler(2), stepSizeTuner=api.StaticStepSize(0.1),"
+        " massMatrixTuner=api.IdentityMassMatrixTuner());"
+        "a = api.CudaModel(rir, []); x = a.sample(cfg, seeds=[5, 6, 7]).chains.copy(); a.close();"
+        "b = api.CudaModel(rir, []); y = b.sample(cfg, seeds=[5, 6, 7]).chains; b.close();"
+        "assert np.array_equal(x, y) and np.all(np.isfinite(x)); print('ok')"
+    ) % (parity.__file__.rsplit('/tests/', 1)[0], parity.__file__.rsplit('/tests/', 1)[0] + "/rainier_b200/models/funnel10.rir")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
