@@ -36,6 +36,7 @@ struct Emitter {
   std::vector<int> smem_slot;             // slot -> index in the shared accumulator block, or -1 (register)
   std::map<int, int> tab_off;             // large-lookup node id -> offset of its table in scratch
   std::vector<int> tab_fill;              // one representative lookup node per distinct table
+  int red_off = 0, red_doubles = 0;       // cross-warp reduction scratch (K warps per chain)
   int n_smem_acc = 0, tab_doubles = 0;
   std::string col_suffix;                 // names of column values loaded in the current region of a row body
   Emitter(const Program& p, const EmitOptions& o) : P(p), opt(o) {}
@@ -400,29 +401,38 @@ struct Emitter {
         }
     os << "// ---- emitted: log-density and gradient of the frozen DAG (" << (P.symbolic ? "symbolic" : "adjoint")
        << " gradient), warp-per-chain: rows across lanes ----\n";
-    os << "#define RN_WPC_SCRATCH " << (tab_doubles + n_smem_acc) << "\n";
+    const int K = std::max(1, opt.wpc_k);
+    int n_reg_acc = 0;
+    for (int sl = 0; sl < P.n_slots; sl++)
+      if (smem_slot[sl] < 0) n_reg_acc++;
+    // cross-warp reduction scratch of the chain's group (K warps): [warp][register accumulators..., err]
+    red_off = tab_doubles + n_smem_acc;
+    red_doubles = K > 1 ? K * (n_reg_acc + 1) : 0;
+    os << "#define RN_WPC_SCRATCH " << (tab_doubles + n_smem_acc + red_doubles) << "\n";
+    os << "#define RN_WPC_RED_OFF " << red_off << "\n";
     os << "RN_DEVICE double rn_tab_lookup(const double* tab, int len, int low, double idx, int& err) {\n"
           "  const int k = rn_d2i(idx) - low;\n  if (k < 0 || k >= len) { err |= 1; return RN_NAN; }\n  return tab[k];\n}\n";
     os << "RN_DEVICE double rn_warp_sum(double x) {\n  RN_UNROLL\n  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);\n  return x;\n}\n";
     lookup_helpers();
     os << "RN_DEVICE void rn_density(const double* q, double& dens, double* grad, double* scr, "
           "const double* RN_RESTRICT data, int& err, RnTma& tma) {\n";
-    os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x & 31);\n  (void)lane;\n";
-    if (n_smem_acc) os << "  for (int k = lane; k < " << n_smem_acc << "; k += 32) scr[" << tab_doubles << " + k] = 0.0;\n";
+    os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x % RN_G);  // thread of the chain's group\n  (void)lane;\n";
+    if (n_smem_acc) os << "  for (int k = lane; k < " << n_smem_acc << "; k += RN_G) scr[" << tab_doubles << " + k] = 0.0;\n";
     for (int id : P.inv_fwd) stmt(id, "  ");
     for (int id : tab_fill) {
       const Node& n = P.nodes[id];
       for (int k = 0; k < n.c; k++) os << "  scr[" << (tab_off.at(id) + k) << "] = " << val(P.lookup_refs[n.b + k]) << ";\n";
     }
-    os << "  __syncwarp();\n";
+    os << "  RN_SYNC();\n";
     for (int sl = 0; sl < P.n_slots; sl++)
       if (smem_slot[sl] < 0) os << "  double a" << sl << " = 0.0;\n";
     for (size_t t = 0; t < P.targets.size(); t++) {
       const TargetInfo& T = P.targets[t];
-      os << "  // target " << t << (T.streamed() ? " (streamed, rows across lanes)" : " (data-free)") << "\n";
+      os << "  // target " << t << (T.streamed() ? " (streamed, rows across the group's threads)" : " (data-free)") << "\n";
       if (T.streamed()) {
         const unsigned long long base = (unsigned long long)opt.target_base[t], td = (unsigned long long)T.n_cols * 32;
-        const unsigned long long n_full = T.n_rows / 32;
+        const unsigned long long rows_per_tile = 32ull * K;  // a "super-tile": K consecutive 32-row tiles, one per warp
+        const unsigned long long n_full = T.n_rows / rows_per_tile;
         os << "  {\n    long long row0 = lane;\n";
         if (opt.tma_stages > 0 && n_full > 0) {
           // CTA lockstep over full tiles: tile t+S-1 in flight (one bulk copy) while all warps consume tile t from smem
@@ -430,39 +440,60 @@ struct Emitter {
              << "      const unsigned n_full = " << n_full << "u, seq0 = tma.seq;\n"
              << "      const double* RN_RESTRICT src = data + " << base << "ULL;\n"
              << "      if (threadIdx.x == 0)\n"
-             << "        for (unsigned p = 0; p + 1 < RN_TMA_STAGES && p < n_full; p++) rn_tma_load(tma, seq0 + p, src + (size_t)p * " << td
-             << "ULL, " << td * 8 << "u);\n"
+             << "        for (unsigned p = 0; p + 1 < RN_TMA_STAGES && p < n_full; p++) rn_tma_load(tma, seq0 + p, src + (size_t)p * "
+             << td * K << "ULL, " << td * K * 8 << "u);\n"
              << "      for (unsigned tile = 0; tile < n_full; tile++) {\n"
              << "        const unsigned seq = seq0 + tile;\n"
              << "        if (threadIdx.x == 0 && tile + (RN_TMA_STAGES - 1) < n_full)\n"
-             << "          rn_tma_load(tma, seq + (RN_TMA_STAGES - 1), src + (size_t)(tile + (RN_TMA_STAGES - 1)) * " << td << "ULL, " << td * 8
-             << "u);\n"
+             << "          rn_tma_load(tma, seq + (RN_TMA_STAGES - 1), src + (size_t)(tile + (RN_TMA_STAGES - 1)) * " << td * K << "ULL, "
+             << td * K * 8 << "u);\n"
              << "        rn_mbar_wait(tma.full + (seq % RN_TMA_STAGES), (seq / RN_TMA_STAGES) & 1u);\n"
-             << "        const double* rp = tma.stage + (size_t)(seq % RN_TMA_STAGES) * RN_TMA_TILE_DOUBLES + lane;\n";
+             << "        const double* rp = tma.stage + (size_t)(seq % RN_TMA_STAGES) * RN_TMA_TILE_DOUBLES + (size_t)(lane >> 5) * " << td
+             << " + (lane & 31);\n";
           row_body(
               T, "        ", [&](int k) { return "rp[" + std::to_string(local_col(T, k) * 32) + "]"; },
               [&](int slot) { return acc_ref(slot); }, true, tab_doubles);
           os << "        rn_cta_bar(tma.nthreads);\n"
              << "      }\n"
              << "      tma.seq = seq0 + n_full;\n"
-             << "      row0 += " << n_full * 32 << "LL;\n"
+             << "      row0 += " << n_full * rows_per_tile << "LL;\n"
              << "    }\n";
         }
-        os << "    for (long long row = row0; row < " << (long long)T.n_rows << "LL; row += 32) {\n";
-        os << "      const double* RN_RESTRICT rp = data + " << base << "ULL + (row >> 5) * " << td << "LL + lane;\n";
+        os << "    for (long long row = row0; row < " << (long long)T.n_rows << "LL; row += RN_G) {\n";
+        os << "      const double* RN_RESTRICT rp = data + " << base << "ULL + (row >> 5) * " << td << "LL + (row & 31);\n";
         row_body(
             T, "      ", [&](int k) { return "RN_LDG(rp + " + std::to_string(local_col(T, k) * 32) + ")"; },
             [&](int slot) { return acc_ref(slot); }, true, tab_doubles);
         os << "    }\n  }\n";
       } else {
-        os << "  if (lane == 0) {\n";  // counted once by the butterfly below
+        os << "  if (lane == 0) {\n";  // counted once by the reduction below
         for (const AccStmt& a : T.row_acc) os << "    " << acc_ref(a.slot) << " += " << val(a.node) << ";\n";
         os << "  }\n";
       }
     }
     for (int sl = 0; sl < P.n_slots; sl++)
       if (smem_slot[sl] < 0) os << "  a" << sl << " = rn_warp_sum(a" << sl << ");\n";
-    os << "  err = (int)__reduce_or_sync(0xffffffffu, (unsigned)err);\n  __syncwarp();\n";
+    os << "  err = (int)__reduce_or_sync(0xffffffffu, (unsigned)err);\n";
+    if (K > 1) {
+      // the K warps of the chain exchange their partial sums through shared memory; every thread adds them in the same
+      // order, so all of them hold identical totals afterwards
+      const int stride = n_reg_acc + 1;
+      os << "  {\n    double* red = scr + " << red_off << ";\n    const int wg = lane >> 5;\n    if ((lane & 31) == 0) {\n";
+      int idx = 0;
+      for (int sl = 0; sl < P.n_slots; sl++)
+        if (smem_slot[sl] < 0) os << "      red[wg * " << stride << " + " << idx++ << "] = a" << sl << ";\n";
+      os << "      red[wg * " << stride << " + " << idx << "] = (double)err;\n    }\n    RN_SYNC();\n";
+      idx = 0;
+      for (int sl = 0; sl < P.n_slots; sl++)
+        if (smem_slot[sl] < 0) {
+          os << "    a" << sl << " = red[" << idx << "]";
+          for (int k = 1; k < K; k++) os << " + red[" << k * stride + idx << "]";
+          os << ";\n";
+          idx++;
+        }
+      os << "    for (int k = 0; k < " << K << "; k++) err |= (int)red[k * " << stride << " + " << idx << "];\n  }\n";
+    }
+    os << "  RN_SYNC();\n";
     os << "  dens = a0;\n";
     if (P.symbolic) {
       for (uint32_t i = 0; i < P.n_params; i++) os << "  if (lane == 0) grad[" << i << "] = " << acc_ref(1 + (int)i) << ";\n";
@@ -470,7 +501,7 @@ struct Emitter {
       for (int id : P.inv_bwd) stmt(id, "  ");
       for (uint32_t i = 0; i < P.n_params; i++) os << "  if (lane == 0) grad[" << i << "] = " << val(P.grad_nodes[i]) << ";\n";
     }
-    os << "  __syncwarp();\n}\n";
+    os << "  RN_SYNC();\n}\n";
   }
 };
 
@@ -489,9 +520,10 @@ WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
   WpcSizes z;
   Emitter E(P, opt);
   E.density_wpc();
-  z.per_warp_doubles = (opt.enable_ehmc ? 7 : 4) * (int)P.n_params + E.tab_doubles + E.n_smem_acc;
+  z.per_warp_doubles = (opt.enable_ehmc ? 7 : 4) * (int)P.n_params + E.tab_doubles + E.n_smem_acc + E.red_doubles;
   for (const TargetInfo& T : P.targets)
-    if (T.streamed() && T.n_rows >= 32) z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * 32);
+    if (T.streamed() && T.n_rows >= 32ull * (uint64_t)std::max(1, opt.wpc_k))
+      z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * 32 * std::max(1, opt.wpc_k));
   return z;
 }
 
@@ -505,6 +537,7 @@ std::string emit_source(const Program& P, const EmitOptions& opt) {
   os << "#define RN_ENABLE_EHMC " << (opt.enable_ehmc ? 1 : 0) << "\n";
   if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
   if (opt.backend == 1) {
+    os << "#define RN_WPC_K " << std::max(1, opt.wpc_k) << "\n";
     os << "#define RN_TMA_STAGES " << opt.tma_stages << "\n";
     os << "#define RN_TMA_TILE_DOUBLES " << wpc_sizes(P, opt).tile_doubles << "\n";
   }

@@ -14,6 +14,7 @@ struct EmitOptions {
   int mass_max = 0;       // 0 identity only, 1 + diagonal, 2 + dense
   bool enable_ehmc = false;
   int tma_stages = 0;     // warp per chain: shared-memory stages of the CTA-shared data-tile pipeline (0 = off)
+  int wpc_k = 1;          // warp per chain: warps owning one chain (1, 2, 4 or 8; > 1 for chains with a large state)
   std::vector<uint64_t> target_base;  // per target: element offset of its tile-major [tile][column][32] block in the data buffer
 };
 
@@ -24,7 +25,7 @@ std::string emit_source(const Program& P, const EmitOptions& opt);
 // shared-memory needs of the warp-per-chain kernels: doubles per warp (chain vectors + density scratch) and doubles of
 // the largest data tile (n_cols * 32 over the streamed targets; 0 when nothing is streamed)
 struct WpcSizes {
-  int per_warp_doubles = 0;
+  int per_warp_doubles = 0;  // per CHAIN (its wpc_k warps share the slice)
   int tile_doubles = 0;
 };
 WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt);

@@ -160,7 +160,8 @@ struct Kernel {
   const Program* prog = nullptr;
   int backend = 0;            // 0 thread per chain, 1 warp per chain
   int wpc_smem_doubles = 0;   // per-warp dynamic shared memory (backend 1)
-  int warps_per_cta = 4;
+  int warps_per_cta = 4;      // backend 1: CHAINS per CTA (each owned by wpc_k warps)
+  int wpc_k = 1;
   int tma_stages = 0;         // CTA-shared data-tile pipeline (backend 1): stages, doubles per stage
   int tile_doubles = 0;
   unsigned smem_bytes() const {  // dynamic shared memory of one CTA: per-warp slices | 128B pad | stages | mbarriers
@@ -182,6 +183,11 @@ struct rn_model {
   std::map<std::pair<bool, bool>, std::unique_ptr<Program>> programs;  // (adjoint, fast)
   std::map<KernelKey, std::unique_ptr<Kernel>> kernels;
   CUdeviceptr pool[2] = {0, 0};  // grow-only scratch reused by rn_sample calls (cuMemAlloc/cuMemFree of GBs is slow)
+  // one spare set of sampler resources handed from a destroyed sampler to the next one: rn_sample creates and destroys a
+  // sampler per call, and cuMemAlloc / cuMemFree / cuStreamCreate are synchronising driver calls
+  CUdeviceptr spare_arena = 0;
+  size_t spare_arena_bytes = 0;
+  CUstream spare_stream = nullptr;
   size_t pool_bytes[2] = {0, 0};
 };
 
@@ -257,14 +263,27 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
     return fail(RN_E_UNSUPPORTED, "warp-per-chain with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
   K->backend = eo.backend;
   if (eo.backend == 1) {
+    const size_t cap = 227 * 1024 - 2048;  // opt-in dynamic shared memory per CTA on sm_100, minus static/reserved
+    int wmax = 8;
+    if (const char* e = getenv("RN_WPC_WARPS")) wmax = std::max(1, std::min(32, atoi(e)));
+    // warps per chain: one, unless the chain's shared-memory state is so large that fewer than 8 chains fit an SM
+    {
+      const WpcSizes z1 = wpc_sizes(*P, eo);
+      const size_t pc = (size_t)z1.per_warp_doubles * 8;
+      if (pc > cap) return fail(RN_E_UNSUPPORTED, "model state does not fit one chain's shared memory slice");
+      const size_t fit = std::max<size_t>(1, (cap - std::min<size_t>(cap / 4, 2 * (size_t)z1.tile_doubles * 8)) / pc);
+      int k = 1;
+      while (k < 8 && fit * (size_t)k < 8) k *= 2;
+      if (const char* e = getenv("RN_WPC_K")) k = std::max(1, std::min(8, atoi(e)));
+      if (k != 1 && k != 2 && k != 4 && k != 8) k = 1;
+      eo.wpc_k = K->wpc_k = k;
+    }
+    if (eo.wpc_k > 1) wmax = std::min(wmax, 14);  // named barriers 2..15, one per chain slot
     const WpcSizes z = wpc_sizes(*P, eo);
     K->wpc_smem_doubles = z.per_warp_doubles;
     K->tile_doubles = z.tile_doubles;
     const size_t per_warp = (size_t)z.per_warp_doubles * 8, tile = (size_t)z.tile_doubles * 8;
-    const size_t cap = 227 * 1024 - 2048;  // opt-in dynamic shared memory per CTA on sm_100, minus static/reserved
-    int wmax = 8;
-    if (const char* e = getenv("RN_WPC_WARPS")) wmax = std::max(1, std::min(32, atoi(e)));
-    if (per_warp > cap) return fail(RN_E_UNSUPPORTED, "model state does not fit one warp's shared memory slice");
+    if (per_warp > cap) return fail(RN_E_UNSUPPORTED, "model state does not fit one chain's shared memory slice");
     // data-tile stages: two (prefetch overlaps compute) when at least 4 chains still fit beside them, else one, else off
     int stages = 0;
     if (tile > 0) {
@@ -292,6 +311,10 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
     // registers/thread: the fused iteration kernel is latency-bound on dependent fp64 chains, so occupancy matters
     // more than a few spills (profiles/r1_ncu_rn_k_iter_funnel_*: 240 regs -> 8 warps/SM, fp64 pipe 30% busy)
     int cap = (P->n_params <= 16 && eo.backend == 0) ? 128 : 0;
+    if (eo.backend == 1) {  // the CTA (chains x warps per chain) must fit the 64K-register file
+      const int threads = K->warps_per_cta * K->wpc_k * 32;
+      if (threads * 255 > 65536) cap = (65536 / threads) & ~7;
+    }
     if (const char* e = getenv("RN_MAXRREGCOUNT")) cap = atoi(e);
     if (cap > 0) {
       maxreg = "--maxrregcount=" + std::to_string(cap);
@@ -545,6 +568,8 @@ void rn_model_destroy(rn_model* m) {
     if (m->d_data) A->cuMemFree(m->d_data);
     for (auto p : m->pool)
       if (p) A->cuMemFree(p);
+    if (m->spare_arena) A->cuMemFree(m->spare_arena);
+    if (m->spare_stream) A->cuStreamDestroy(m->spare_stream);
     CUdevice dev;
     if (A->cuDeviceGet(&dev, m->device) == 0) A->cuDevicePrimaryCtxRelease(dev);
   }
@@ -628,7 +653,7 @@ int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
   void* params[] = {&dq, &dout, &ddata, &derr, &ch};
   if (K->backend == 1) {
     const unsigned w = (unsigned)K->warps_per_cta;
-    CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + w - 1) / w), 1, 1, w * 32, 1, 1,
+    CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + w - 1) / w), 1, 1, w * 32 * (unsigned)K->wpc_k, 1, 1,
                          K->smem_bytes(), nullptr, params, nullptr));
   } else {
     CU(A->cuLaunchKernel(K->k_density, (unsigned)((chains + 127) / 128), 1, 1, 128, 1, 1, 0, nullptr, params, nullptr));
@@ -704,7 +729,7 @@ struct rn_sampler {
   Kernel* K = nullptr;
   CUstream stream = nullptr;
   CUdeviceptr arena = 0;
-  size_t arena_bytes = 0;
+  size_t arena_bytes = 0, arena_alloc = 0;
   size_t stats_off = 0, stats_bytes = 0;  // the block that `new Stats` zeroes
   RnArgs args;                            // device pointers + uniform config
   bool initialized = false;
@@ -736,7 +761,7 @@ int launch(const Api* A, rn_sampler* s, CUfunction f, int count = -1) {
   if (s->K->backend == 1) {
     const unsigned w = (unsigned)s->K->warps_per_cta;
     const unsigned grid = (unsigned)((chains + w - 1) / w);
-    CU(A->cuLaunchKernel(f, grid, 1, 1, w * 32, 1, 1, s->K->smem_bytes(), s->stream, params, nullptr));
+    CU(A->cuLaunchKernel(f, grid, 1, 1, w * 32 * (unsigned)s->K->wpc_k, 1, 1, s->K->smem_bytes(), s->stream, params, nullptr));
     s->launches++;
     return RN_OK;
   }
@@ -848,7 +873,12 @@ int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, i
   if (rc) return rc;
   rc = load_kernel(A, m, s->K);
   if (rc) return rc;
-  CU(A->cuStreamCreate(&s->stream, 1 /*CU_STREAM_NON_BLOCKING*/));
+  if (m->spare_stream) {
+    s->stream = m->spare_stream;
+    m->spare_stream = nullptr;
+  } else {
+    CU(A->cuStreamCreate(&s->stream, 1 /*CU_STREAM_NON_BLOCKING*/));
+  }
 
   const size_t C = (size_t)chains, n = m->n_params, W = (size_t)cfg->stats_window;
   const bool dense = s->K && (key_for(m, cfg).mass_max == 2);
@@ -868,8 +898,17 @@ int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, i
                o_srf = ar.take(3 * C * 4);
   s->stats_bytes = ar.off - s->stats_off;
   s->arena_bytes = ar.off;
-  CU(A->cuMemAlloc(&s->arena, s->arena_bytes));
-  CU(A->cuMemAlloc(&s->d_pool, (2 * n + 1) * 8));
+  const size_t pool_off = (s->arena_bytes + 255) & ~(size_t)255, need = pool_off + (2 * n + 1) * 8;
+  if (m->spare_arena && m->spare_arena_bytes >= need) {
+    s->arena = m->spare_arena;
+    s->arena_alloc = m->spare_arena_bytes;
+    m->spare_arena = 0;
+    m->spare_arena_bytes = 0;
+  } else {
+    CU(A->cuMemAlloc(&s->arena, need));
+    s->arena_alloc = need;
+  }
+  s->d_pool = s->arena + pool_off;  // [2n+1] pooled window statistics live behind the chain state
   CU(A->cuMemsetD8Async(s->arena, 0, s->arena_bytes, s->stream));
 
   RnArgs& a = s->args;
@@ -1293,10 +1332,20 @@ void rn_sampler_destroy(rn_sampler* s) {
     A->cuCtxSetCurrent(s->m->ctx);
     if (s->stream) {
       A->cuStreamSynchronize(s->stream);
-      A->cuStreamDestroy(s->stream);
+      if (!s->m->spare_stream)
+        s->m->spare_stream = s->stream;
+      else
+        A->cuStreamDestroy(s->stream);
     }
-    if (s->arena) A->cuMemFree(s->arena);
-    if (s->d_pool) A->cuMemFree(s->d_pool);
+    if (s->arena) {
+      if (s->arena_alloc > s->m->spare_arena_bytes) {  // keep the larger one as the model's spare
+        if (s->m->spare_arena) A->cuMemFree(s->m->spare_arena);
+        s->m->spare_arena = s->arena;
+        s->m->spare_arena_bytes = s->arena_alloc;
+      } else {
+        A->cuMemFree(s->arena);
+      }
+    }
     if (s->d_trace) A->cuMemFree(s->d_trace);
   }
   delete s;

@@ -17,8 +17,8 @@
 
 #define RN_LN2 0.6931471805599453
 #define RN_AT(ptr, field, c) (ptr)[(size_t)(field) * (size_t)A.chains + (size_t)(c)]
-#define RN_LANE ((int)(threadIdx.x & 31))
-#define RN_FOR_LANES(i) for (int i = RN_LANE; i < RN_N; i += 32)
+#define RN_LANE ((int)(threadIdx.x % RN_G))  // thread index inside the chain's group (RN_G, RN_SYNC: rn_prelude.cuh)
+#define RN_FOR_LANES(i) for (int i = RN_LANE; i < RN_N; i += RN_G)
 
 struct RnStats {
   rn_i64 grads, steps;
@@ -71,6 +71,21 @@ RN_DEVICE void rn_w_setup(RnW& w, double* base) {
 #endif
 }
 
+// OR over the chain's RN_G threads (red: RN_WPC_K doubles of the group's reduction scratch)
+RN_DEVICE unsigned rn_group_or(unsigned x, double* red) {
+  unsigned r = __reduce_or_sync(0xffffffffu, x);
+#if RN_WPC_K > 1
+  if ((threadIdx.x & 31) == 0) red[(threadIdx.x % RN_G) >> 5] = (double)r;
+  RN_SYNC();
+  r = 0;
+  for (int k = 0; k < RN_WPC_K; k++) r |= (unsigned)red[k];
+  RN_SYNC();
+#else
+  (void)red;
+#endif
+  return r;
+}
+
 RN_DEVICE void rn_ring_add(const RnArgs& A, int c, RnStats& S, int which, double value) {  // Stats.scala:24-30
   int i = S.ring_i[which] + 1;
   if (i == A.stats_window) S.ring_full[which] = 1;
@@ -105,7 +120,7 @@ __device__ __noinline__ void rn_update(const RnArgs& A, RnW& w, RnStats& S) {
 RN_DEVICE void rn_full_ps(RnW& w, double stepSize, RnStats& S) {  // LeapFrog.scala:168-176
   S.grads += 1;
   RN_FOR_LANES(i) w.p[i] += stepSize * w.g[i];
-  __syncwarp();
+  RN_SYNC();
 }
 RN_DEVICE void rn_new_qs(RnW& w, double stepSize) {  // LeapFrog.scala:147-154
   if (w.mass_kind == 1) {
@@ -113,7 +128,7 @@ RN_DEVICE void rn_new_qs(RnW& w, double stepSize) {  // LeapFrog.scala:147-154
   } else {
     RN_FOR_LANES(i) w.q[i] += (stepSize * w.p[i]);
   }
-  __syncwarp();
+  RN_SYNC();
 }
 RN_DEVICE void rn_leapfrog(const RnArgs& A, RnW& w, int l, double stepSize, RnStats& S) {  // :24-33,156-191
   rn_full_ps(w, stepSize / 2.0, S);
@@ -135,9 +150,9 @@ RN_DEVICE void rn_take_steps(const RnArgs& A, int c, RnW& w, int l, double stepS
 RN_DEVICE void rn_initialize_ps(const RnW& w, RnRng& rng, double* dst) {
   for (int i = 0; i < RN_N; i++) {
     const double z = rn_normal(rng);
-    if ((i & 31) == RN_LANE) dst[i] = (w.mass_kind == 1) ? z / sqrt(w.m[i]) : z;
+    if ((i % RN_G) == RN_LANE) dst[i] = (w.mass_kind == 1) ? z / sqrt(w.m[i]) : z;
   }
-  __syncwarp();
+  RN_SYNC();
 }
 
 RN_DEVICE void rn_load_stats(const RnArgs& A, int c, RnStats& S) {
@@ -176,10 +191,10 @@ extern __shared__ __align__(128) double rn_smem[];
 
 // =============================================================================================================
 RN_GLOBAL void rn_k_init(const RnArgs A) {
-  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) / RN_G);
   if (c >= A.chains) return;  // whole warp exits
   RnW w;
-  rn_w_setup(w, rn_smem + (size_t)(threadIdx.x >> 5) * RN_WPC_SMEM_DOUBLES);
+  rn_w_setup(w, rn_smem + (size_t)RN_GROUP * RN_WPC_SMEM_DOUBLES);
   w.mass_kind = 0;
   RnRng rng;
   rng.seed = A.rng_seed[c];
@@ -191,12 +206,12 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
   // LeapFrog.initialize, LeapFrog.scala:102-116
   for (int i = 0; i < RN_N; i++) {
     const double z = rn_normal(rng);
-    if ((i & 31) == RN_LANE) {
+    if ((i % RN_G) == RN_LANE) {
       w.q[i] = z;
       w.p[i] = 0.0;
     }
   }
-  __syncwarp();
+  RN_SYNC();
   rn_update(A, w, S);
   const double cU = w.U;
   RN_FOR_LANES(i) {
@@ -217,14 +232,14 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
     const double doubleOrHalf = (exponent > 0) ? 2.0 : 0.5;
     while (stepSize != 0.0 && (exponent * lap > -exponent * RN_LN2)) {
       stepSize *= doubleOrHalf;
-      __syncwarp();
+      RN_SYNC();
       RN_FOR_LANES(i) {  // copy(params, pqBuf)
         w.p[i] = RN_AT(A.params, i, c);
         w.q[i] = RN_AT(A.params, RN_N + i, c);
         w.g[i] = RN_AT(A.grad, i, c);
       }
       w.U = cU;
-      __syncwarp();
+      RN_SYNC();
       rn_leapfrog(A, w, 1, stepSize, S);
       lap = rn_log_accept(rn_energy(w, w.p, w.U) - H0);
     }
@@ -249,10 +264,10 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
 
 // =============================================================================================================
 RN_GLOBAL void rn_k_iter(const RnArgs A) {
-  const int c = A.chain_begin + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int c = A.chain_begin + (int)((blockIdx.x * blockDim.x + threadIdx.x) / RN_G);
 #if RN_TMA_STAGES > 0
-  const int warps = (int)(blockDim.x >> 5);
-  double* const stage0 = rn_smem + (((size_t)warps * RN_WPC_SMEM_DOUBLES + 15) & ~(size_t)15);
+  const int slots = (int)(blockDim.x / RN_G);  // chains per CTA
+  double* const stage0 = rn_smem + (((size_t)slots * RN_WPC_SMEM_DOUBLES + 15) & ~(size_t)15);
   unsigned long long* const bars = (unsigned long long*)(stage0 + (size_t)RN_TMA_STAGES * RN_TMA_TILE_DOUBLES);
   const bool lockstep = (A.sampler == 0) && (A.tma != 0);  // HMC: every chain calls the density equally often
   if (lockstep) {
@@ -265,15 +280,15 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
 #endif
   if (c >= A.chain_end) return;
   RnW w;
-  rn_w_setup(w, rn_smem + (size_t)(threadIdx.x >> 5) * RN_WPC_SMEM_DOUBLES);
+  rn_w_setup(w, rn_smem + (size_t)RN_GROUP * RN_WPC_SMEM_DOUBLES);
 #if RN_TMA_STAGES > 0
   if (lockstep) {
-    const int first = A.chain_begin + (int)(blockIdx.x * (blockDim.x >> 5));
-    const int active = (A.chain_end - first) < warps ? (A.chain_end - first) : warps;
+    const int first = A.chain_begin + (int)(blockIdx.x * (blockDim.x / RN_G));
+    const int active = (A.chain_end - first) < slots ? (A.chain_end - first) : slots;
     w.tma.on = 1;
     w.tma.stage = stage0;
     w.tma.full = bars;
-    w.tma.nthreads = (unsigned)active * 32u;
+    w.tma.nthreads = (unsigned)active * (unsigned)RN_G;
   }
 #endif
   w.mass_kind = A.mass_kind;
@@ -285,7 +300,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
   rn_load_stats(A, c, S);
   if (w.mass_kind == 1) {
     RN_FOR_LANES(i) w.m[i] = RN_AT(A.mass, i, c);
-    __syncwarp();
+    RN_SYNC();
   }
   double stepSize = RN_AT(A.da, 0, c);
   double logStepSize = 0, logStepSizeBar = 0, avgError = 0, shrinkageTarget = 0;
@@ -307,12 +322,12 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
 
   for (int it = 0; it < A.n_iter; it++) {
     // ---- startIteration, LeapFrog.scala:52-59 ----
-    __syncwarp();
+    RN_SYNC();
     RN_FOR_LANES(i) w.p[i] = RN_AT(A.params, i, c);
-    __syncwarp();
+    RN_SYNC();
     const double cU = RN_AT(A.params, 2 * RN_N, c);
     const double prevH = rn_energy(w, w.p, cU);
-    __syncwarp();
+    RN_SYNC();
     rn_initialize_ps(w, rng, w.p);
     RN_FOR_LANES(i) {
       RN_AT(A.params, i, c) = w.p[i];
@@ -320,7 +335,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
       w.g[i] = RN_AT(A.grad, i, c);
     }
     w.U = cU;
-    __syncwarp();
+    RN_SYNC();
     const double startH = rn_energy(w, w.p, cU);
     const rn_i64 iterationStartGrads = S.grads;
     const rn_i64 steps0 = S.steps;
@@ -348,7 +363,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
               w.sg[i] = w.g[i];
             }
             sU = w.U;
-            __syncwarp();
+            RN_SYNC();
           }
         }
         if (l < A.min_steps) {
@@ -360,13 +375,13 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
             w.g[i] = w.sg[i];
           }
           w.U = sU;
-          __syncwarp();
+          RN_SYNC();
         }
         ring_i += 1;
         if (ring_i == A.buf_size) ring_full = 1;
         ring_i = ring_i % A.buf_size;
         if (RN_LANE == 0) RN_AT(A.ring, ring_i, c) = (double)l;
-        __syncwarp();
+        RN_SYNC();
       } else {
         const int idx = ring_full ? rn_rng_int(rng, A.buf_size) : rn_rng_int(rng, ring_i + 1);
         const int nsteps = rn_d2i(RN_AT(A.ring, idx, c));
@@ -380,7 +395,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     const double a = rn_log_accept(deltaH);
     const bool accept = a > rn_log(rn_uniform(rng));
     double eH;
-    __syncwarp();
+    RN_SYNC();
     if (accept) {
       RN_FOR_LANES(i) {
         RN_AT(A.params, i, c) = w.p[i];
@@ -394,7 +409,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
       RN_FOR_LANES(i) w.q[i] = RN_AT(A.params, RN_N + i, c);
       eH = startH;
     }
-    __syncwarp();
+    RN_SYNC();
     {
       S.e_n += 1;
       const double oldDiff = eH - S.e_mean;
@@ -462,7 +477,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
             RN_AT(A.est_raw, i, c) = raw;
           }
           if (window_end) {
-            S.err |= __reduce_or_sync(0xffffffffu, (unsigned)(S.err & 2));
+            S.err |= (int)rn_group_or((unsigned)(S.err & 2), w.scr + RN_WPC_RED_OFF);
             win_i = 0;
             win_size = rn_d2i(win_size * A.win_expansion);
             w.mass_kind = 1;
@@ -476,7 +491,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
               stepSize = ss;
             }
           }
-          __syncwarp();
+          RN_SYNC();
         }
       }
     } else if (A.samples) {
@@ -510,16 +525,16 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
 // =============================================================================================================
 RN_GLOBAL void rn_k_density(const double* RN_RESTRICT qin, double* RN_RESTRICT out, const double* data, int* err,
                             int chains) {
-  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) / RN_G);
   if (c >= chains) return;
   RnW w;
-  rn_w_setup(w, rn_smem + (size_t)(threadIdx.x >> 5) * RN_WPC_SMEM_DOUBLES);
+  rn_w_setup(w, rn_smem + (size_t)RN_GROUP * RN_WPC_SMEM_DOUBLES);
   RN_FOR_LANES(i) w.q[i] = qin[(size_t)i * chains + c];
-  __syncwarp();
+  RN_SYNC();
   int e = 0;
   double dens;
   rn_density(w.q, dens, w.g, w.scr, data, e, w.tma);
-  __syncwarp();
+  RN_SYNC();
   if (RN_LANE == 0) out[c] = dens;
   RN_FOR_LANES(i) out[(size_t)(i + 1) * chains + c] = w.g[i];
   if (e && RN_LANE == 0) atomicOr(err, e);

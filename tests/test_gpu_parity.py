@@ -240,6 +240,34 @@ def test_wpc_poisson_glm_scatter_gradient():
     assert parity.rel_err(tr.chains, ref["samples"], 1e-9) < 1e-7
 
 
+@pytest.mark.parametrize("k", [2, 4])
+def test_wpc_several_warps_per_chain(k):
+    """RN_WPC_K warps own one chain (what the runtime picks when a chain's shared-memory state is large): rows strided
+    over 32*K threads, cross-warp reduction through shared memory, group-wide named barriers.  Same parity bar as K=1:
+    density/gradient vs the oracle, whole trajectories in the stable regime, EHMC + adaptation statistically."""
+    os.environ["RN_WPC_K"] = str(k)
+    try:
+        rir, cols = configs.logreg(3000, 8).compile(True)
+        _wpc_density_matches(rir, cols, 8)
+        r = parity.run_both(rir, cols, _static(40, 4, 0.02, backend=abi.RN_BACKEND_WARP), seeds=np.arange(21) + 9)
+        parity.assert_parity(r, tol=1e-8)
+        # primal RIR with a shared-memory lookup table + scatter adjoints, more chains than fit one CTA, EHMC path too
+        rir, cols = configs.poisson_glm(40, 2560).compile(True)
+        prir, pcols = configs.poisson_glm(40, 2560).compile(False)
+        _wpc_density_matches(rir, cols, 43, tol=1e-9, rir_gpu=prir, cols_gpu=pcols)
+        cfg = _static(30, 3, 0.01, backend=abi.RN_BACKEND_WARP)
+        ref = OracleModel(rir, cols).sample(api.lower_config(cfg)[0], seeds=np.arange(19) + 1)
+        tr = api.CudaModel(prir, pcols).sample(cfg, seeds=np.arange(19) + 1)
+        assert parity.rel_err(tr.chains, ref["samples"], 1e-9) < 1e-7
+        # data-free model stays bit-exact on this kernel shape as well
+        f = configs.funnel().compile(True)
+        r = parity.run_both(*f, _cfg(30, 120, api.EHMCSampler(32, 1, 10, 0.1), api.DualAvgTuner(0.8), api.DiagonalMassMatrixTuner(20, 1.5, 10, 10),
+                                     backend=abi.RN_BACKEND_WARP), seeds=np.arange(11) + 3)
+        parity.assert_parity(r)
+    finally:
+        del os.environ["RN_WPC_K"]
+
+
 def test_auto_backend_picks_warp_for_streamed_models():
     rir, cols = configs.linreg(4000, covariates=5).compile(True)
     m = api.CudaModel(rir, cols)
