@@ -272,7 +272,9 @@ def main():
     # what the JNI shim hands the JVM as a direct ByteBuffer); also reported for a pageable caller buffer.
     e2e_cfg, keep = api.lower_config(cfg)
     import ctypes as CT
-    seeds_host = np.ascontiguousarray(seeds)
+    seeds_pin = api.PinnedBuffer((C_,), device=local_rank, dtype=np.int64)  # inputs come from page-locked memory too
+    seeds_pin.array[:] = seeds
+    seeds_host = seeds_pin.array
     pin = api.PinnedBuffer((C_, I_, N_DIM), device=local_rank)
     pageable = np.empty((C_, I_, N_DIM))
 
@@ -305,6 +307,7 @@ def main():
     e2e_value, e2e_ms = e2e_leg(pin.array, n_e2e)
     e2e_pageable, e2e_pageable_ms = e2e_leg(pageable, n_e2e)
     pin.close()
+    seeds_pin.close()
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()

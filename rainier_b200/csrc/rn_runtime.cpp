@@ -266,14 +266,14 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
     const size_t cap = 227 * 1024 - 2048;  // opt-in dynamic shared memory per CTA on sm_100, minus static/reserved
     int wmax = 8;
     if (const char* e = getenv("RN_WPC_WARPS")) wmax = std::max(1, std::min(32, atoi(e)));
-    // warps per chain: one, unless the chain's shared-memory state is so large that fewer than 8 chains fit an SM
+    // warps per chain: one, unless the chain's shared-memory state is so large that fewer than 16 chains fit an SM
     {
       const WpcSizes z1 = wpc_sizes(*P, eo);
       const size_t pc = (size_t)z1.per_warp_doubles * 8;
       if (pc > cap) return fail(RN_E_UNSUPPORTED, "model state does not fit one chain's shared memory slice");
       const size_t fit = std::max<size_t>(1, (cap - std::min<size_t>(cap / 4, 2 * (size_t)z1.tile_doubles * 8)) / pc);
       int k = 1;
-      while (k < 8 && fit * (size_t)k < 8) k *= 2;
+      while (k < 8 && fit * (size_t)k < 16) k *= 2;  // aim at 16 warps per SM (cfg 5: K=1/2/4 -> 4.4e4 / 8.9e4 / 1.23e5 steps*chains/s)
       if (const char* e = getenv("RN_WPC_K")) k = std::max(1, std::min(8, atoi(e)));
       if (k != 1 && k != 2 && k != 4 && k != 8) k = 1;
       eo.wpc_k = K->wpc_k = k;
