@@ -312,8 +312,8 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
     // more than a few spills (profiles/r1_ncu_rn_k_iter_funnel_*: 240 regs -> 8 warps/SM, fp64 pipe 30% busy)
     int cap = (P->n_params <= 16 && eo.backend == 0) ? 128 : 0;
     if (eo.backend == 1) {  // the CTA (chains x warps per chain) must fit the 64K-register file
-      const int threads = K->warps_per_cta * K->wpc_k * 32;
-      if (threads * 255 > 65536) cap = (65536 / threads) & ~7;
+      const int warps = K->warps_per_cta * K->wpc_k;  // registers are allocated per warp in units of 512
+      if (warps * 32 * 255 > 65536) cap = std::min(255, ((65536 / warps) / 512) * 512 / 32);
     }
     if (const char* e = getenv("RN_MAXRREGCOUNT")) cap = atoi(e);
     if (cap > 0) {

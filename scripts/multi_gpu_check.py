@@ -43,5 +43,40 @@ assert np.all(mass == mass[0])
 if rank == 0:
     print("pooled adaptation: identical mass matrix on all %d ranks:" % world, np.round(mass[0], 4))
 s.close()
+
+# BASELINE.json configs[3]: eight schools, DefaultConfig (EHMC + DualAvg + diagonal mass), 8192 chains over the ranks,
+# warmup with the pooled mass-matrix all-reduce (NCCL over NVLink); device-resident, timed on the device, max over ranks
+import time
+total = 8192
+per = total // world
+seeds_all = np.arange(total) + 1
+cfgb = api.SamplerConfig(iterations=500, warmupIterations=500, adaptation=abi.RN_ADAPT_POOLED)
+for mode, cfg_run in (("pooled", cfgb), ("per-chain", api.SamplerConfig(iterations=500, warmupIterations=500))):
+    sb = api.CudaSampler(model, cfg_run, seeds=rdist.seeds_for_rank(seeds_all, rank, world))
+    if mode == "pooled":
+        sb.set_comm(comm)
+    stream = torch.cuda.ExternalStream(sb.stream)
+    d = torch.empty((500, model.nVars, per), dtype=torch.float64, device="cuda")
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record(stream)
+    sb.warmup(-1)
+    e1.record(stream)
+    sb.run(500, d.data_ptr())
+    e2.record(stream)
+    sb.sync()
+    torch.cuda.synchronize()
+    st, _ = sb.stats()
+    steps = float(sum(x.leapfrogSteps for x in st))
+    t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), steps], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print("cfg4 eight schools, %d chains over %d GPU(s), %s adaptation: warmup(500) %.1f ms, sampling(500) %.1f ms, "
+              "sampling-phase leapfrog-steps*chains/s %.3e" % (total, world, mode, tmax[0].item(), tmax[1].item(),
+                                                              t[2].item() / (tmax[1].item() * 1e-3)), flush=True)
+    sb.close()
 comm.close()
 dist.destroy_process_group()
