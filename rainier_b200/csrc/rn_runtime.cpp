@@ -765,7 +765,11 @@ int launch(const Api* A, rn_sampler* s, CUfunction f, int count = -1) {
     s->launches++;
     return RN_OK;
   }
-  static const unsigned block = getenv("RN_BLOCK") ? (unsigned)atoi(getenv("RN_BLOCK")) : 128u;
+  // 128 threads per CTA when there are chains to fill the chip twice over; a few thousand chains (cfg 2 / cfg 4: 4096-8192)
+  // are spread over all 148 SMs with smaller CTAs instead of packing 64 SMs and idling the rest
+  unsigned block = 128u;
+  while (block > 32u && chains < (size_t)block * 148 * 2) block >>= 1;
+  if (const char* e = getenv("RN_BLOCK")) block = (unsigned)atoi(e);
   const unsigned grid = (unsigned)((chains + block - 1) / block);
   CU(A->cuLaunchKernel(f, grid, 1, 1, block, 1, 1, 0, s->stream, params, nullptr));
   s->launches++;
