@@ -160,6 +160,32 @@ def test_rn_sample_pinned_and_pageable_buffers_agree(funnel):
     pin.close()
 
 
+@pytest.mark.parametrize("nsteps", [0, 1])
+def test_degenerate_trajectory_lengths(funnel, nsteps):
+    """takeSteps(0) still performs initialHalfThenFullStep + finalHalfStep (LeapFrog.scala:24-33) while counting 0 steps"""
+    r = parity.run_both(*funnel, _cfg(25, 40, api.HMCSampler(nsteps), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()),
+                        seeds=np.arange(37) + 1)
+    parity.assert_parity(r)
+
+
+@pytest.mark.parametrize("chains", [1, 33, 129])
+def test_ragged_chain_counts_and_empty_phases(schools, chains):
+    """chain counts that fill no warp / CTA exactly; warmup-only (iterations = 0) and sampling-only (warmup = 0) runs"""
+    seeds = np.arange(chains) + 17
+    m = api.CudaModel(*schools)
+    om = OracleModel(*schools)
+    for it, warm in ((0, 60), (12, 0), (9, 35)):
+        cfg = api.SamplerConfig(iterations=it, warmupIterations=warm)
+        tr = m.sample(cfg, seeds=seeds)
+        ref = om.sample(api.lower_config(cfg)[0], seeds=seeds)
+        assert tr.chains.shape == (chains, it, 10)
+        assert parity.rel_err(tr.chains, ref["samples"]) < 1e-9
+        assert parity.rel_err(tr.mass, ref["mass"]) < 1e-8
+        for g, o in zip(tr.stats, ref["stats"]):
+            assert g.gradientEvaluations == o.gradient_evaluations and g.iterations == o.iterations
+            assert g.rng[0] == o.rng.seed48
+
+
 def test_lookup_out_of_range_is_an_error():
     """out-of-range LookupIR index: NullPointerException in the reference (ir/MethodGenerator.scala:164-167) -> RN_E_LOOKUP"""
     from oracle.rainier_py.compute import Real, lookup_apply
