@@ -105,9 +105,9 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rn_k_iter launch at the default workload (151552 chains x 100
-# iterations), from `ncu --set full` (profiles/r1_ncu_funnel_{parity,fast}_v2.csv): the 46 MB of chain state stays in
+# iterations), from `ncu --set full` (profiles/r1_ncu_funnel_parity_v5.csv, profiles/r1_ncu_funnel_fast_v2.csv): the 46 MB of chain state stays in
 # L2, so what reaches DRAM is the 1.2 GB sample stream plus write-allocate traffic -- below the algorithmic bytes.
-NCU_DRAM_BYTES_PER_LAUNCH = {"parity": 55083520 + 1776891000, "fast": 54043904 + 1686160000}
+NCU_DRAM_BYTES_PER_LAUNCH = {"parity": 54746624 + 1809110000, "fast": 54043904 + 1686160000}
 
 
 def measured_peaks():
@@ -342,7 +342,10 @@ def main():
                          "bytes_per_leapfrog_step": bps,
                          "note": "compulsory-traffic accounting (SURVEY.md 8d); the kernel is FP64-pipe bound, see fp64"},
             "fp64": {"flops_per_leapfrog_step": flops_step, "special_per_leapfrog_step": counts["special_invariant"] * evals_per_step,
-                     "achieved_tflops": per_gpu_rate * flops_step / 1e12},
+                     "achieved_tflops": per_gpu_rate * flops_step / 1e12,
+                     "ncu_fp64_pipe_active_pct": {"parity": 46.3, "fast": 39.7}[args.math] if (C_, I_) == (151552, 100) else None,
+                     "ncu_source": "profiles/r1_ncu_funnel_parity_v5.csv, profiles/r1_ncu_funnel_fast_v2.csv "
+                                   "(sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active)"},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg()

@@ -54,6 +54,7 @@ struct Api {
   CUresult (*cuMemHostRegister)(void*, size_t, unsigned);
   CUresult (*cuMemHostUnregister)(void*);
   CUresult (*cuPointerGetAttribute)(void*, int, CUdeviceptr);
+  CUresult (*cuPointerGetAttributes)(unsigned, int*, void**, CUdeviceptr);
   CUresult (*cuCtxGetDevice)(CUdevice*);
   CUresult (*cuDeviceGetPCIBusId)(char*, int, CUdevice);
   CUresult (*cuMemcpyHtoD)(CUdeviceptr, const void*, size_t);

@@ -81,6 +81,7 @@ const Api* api(std::string* why) {
       RN_SYM(cuMemHostRegister, "cuMemHostRegister_v2")
       RN_SYM(cuMemHostUnregister, "cuMemHostUnregister")
       RN_SYM(cuPointerGetAttribute, "cuPointerGetAttribute")
+      a.cuPointerGetAttributes = (decltype(a.cuPointerGetAttributes))dlsym(h, "cuPointerGetAttributes");  // optional
       a.cuCtxGetDevice = (decltype(a.cuCtxGetDevice))dlsym(h, "cuCtxGetDevice");        // optional (NUMA placement)
       a.cuDeviceGetPCIBusId = (decltype(a.cuDeviceGetPCIBusId))dlsym(h, "cuDeviceGetPCIBusId");
       RN_SYM(cuMemcpyHtoD, "cuMemcpyHtoD_v2")
@@ -1466,6 +1467,8 @@ class Workers {  // persistent job pool for the pinned->pageable memcpy of the d
 Workers& drain_workers() {  // created on first use, lives for the process (thread start-up is not free per call)
   static Workers* w = [] {
     int t = (int)std::thread::hardware_concurrency() / 4;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE"))  // one process per GPU (torchrun): share the host's cores
+      t /= std::max(1, atoi(e));
     if (const char* e = getenv("RN_DRAIN_THREADS")) t = atoi(e);
     return new Workers(std::max(2, std::min(t, 16)));
   }();
@@ -1475,12 +1478,17 @@ Workers& drain_workers() {  // created on first use, lives for the process (thre
 // true when [p, p+bytes) is page-locked memory the driver knows (rn_host_alloc, rn_host_register, cudaHostAlloc,
 // cudaHostRegister by the caller): the DMA engine can then write the caller's buffer directly
 bool host_is_pinned(const Api* A, const void* p, size_t bytes) {
-  if (!p || !bytes) return false;
-  unsigned mt0 = 0, mt1 = 0;
-  const char* last = (const char*)p + bytes - 1;
-  if (A->cuPointerGetAttribute(&mt0, 2 /*CU_POINTER_ATTRIBUTE_MEMORY_TYPE*/, (CUdeviceptr)(uintptr_t)p) != 0) return false;
-  if (A->cuPointerGetAttribute(&mt1, 2, (CUdeviceptr)(uintptr_t)last) != 0) return false;
-  return mt0 == CU_MEMORYTYPE_HOST && mt1 == CU_MEMORYTYPE_HOST;
+  if (!p || !bytes || !A->cuPointerGetAttributes) return false;
+  // cuPointerGetAttributes (plural) reports memory type 0 for plain pageable memory instead of failing, so probing a
+  // caller's malloc'ed buffer does not raise a driver error (compute-sanitizer would count one per call)
+  auto type_of = [&](const void* q) -> unsigned {
+    unsigned mt = 0;
+    int attr = 2 /*CU_POINTER_ATTRIBUTE_MEMORY_TYPE*/;
+    void* data = &mt;
+    if (A->cuPointerGetAttributes(1, &attr, &data, (CUdeviceptr)(uintptr_t)q) != 0) return 0;
+    return mt;
+  };
+  return type_of(p) == CU_MEMORYTYPE_HOST && type_of((const char*)p + bytes - 1) == CU_MEMORYTYPE_HOST;
 }
 
 // device -> caller's host buffer.  Page-locked destination: one DMA, no staging.  Pageable destination: a ring of
@@ -1600,6 +1608,8 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
   if (timing) rn_sampler_sync(s);
   lap("warmup");
   const size_t C = (size_t)chains, n = m->n_params, I = (size_t)cfg->iterations;
+  rc = rn_sampler_run(s, 0, nullptr);  // lf.resetStats() after warmup even when no iteration follows (Driver.scala:31)
+  if (rc) return rc;
   if (I > 0 && samples) {
     const size_t total = C * I * n * 8;
     // the whole [C][I][n] result stays on the device while it is produced; runs larger than the cap are cut into

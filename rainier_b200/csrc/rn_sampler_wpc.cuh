@@ -119,6 +119,7 @@ __device__ __noinline__ void rn_update(const RnArgs& A, RnW& w, RnStats& S) {
 }
 RN_DEVICE void rn_full_ps(RnW& w, double stepSize, RnStats& S) {  // LeapFrog.scala:168-176
   S.grads += 1;
+  RN_SYNC();  // every thread of the group has finished reading p (energies, isUTurn) before anyone rewrites it
   RN_FOR_LANES(i) w.p[i] += stepSize * w.g[i];
   RN_SYNC();
 }
@@ -369,6 +370,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
         if (l < A.min_steps) {
           rn_take_steps(A, c, w, A.min_steps - l, stepSize, S);
         } else {  // restore
+          RN_SYNC();  // the isUTurn sums above read q and p of every element
           RN_FOR_LANES(i) {
             w.q[i] = w.sq[i];
             w.p[i] = w.sp[i];
