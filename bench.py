@@ -304,6 +304,24 @@ def main():
         return units / med, {"median": med * 1e3, "min": lo * 1e3, "mean": mean * 1e3, "max": hi * 1e3}
 
     n_e2e = max(3, min(args.steps, 10))
+    # supplementary: the same call returning only Trace.diagnostics (rHat / ESS reduced on the device, rn_config.diagnostics
+    # with samples == NULL) -- what the path does when the caller needs summaries rather than 1.2 GB of draws
+    diag_cfg, keep2 = api.lower_config(cfg)
+    diag_out = np.empty((N_DIM, 2))
+    diag_cfg.diagnostics = diag_out.ctypes.data_as(CT.POINTER(CT.c_double))
+
+    def diag_step():
+        rc = api.lib().rn_sample(model.h, CT.byref(diag_cfg), seeds_host.ctypes.data, C_, None, None, None)
+        if rc != 0:
+            raise RuntimeError(api.lib().rn_last_error().decode())
+    for _ in range(2):
+        diag_step()
+    tt = []
+    for _ in range(n_e2e):
+        t0 = time.perf_counter()
+        diag_step()
+        tt.append(time.perf_counter() - t0)
+    diag_ms = float(np.median(tt)) * 1e3
     e2e_value, e2e_ms = e2e_leg(pin.array, n_e2e)
     e2e_pageable, e2e_pageable_ms = e2e_leg(pageable, n_e2e)
     pin.close()
@@ -333,7 +351,10 @@ def main():
                     "d2h_bytes_per_step": int(C_ * I_ * N_DIM * 8),
                     "api": "rn_sample (C ABI), host buffers: seeds in, [chains][iterations][n] samples out (page-locked, rn_host_alloc)",
                     "steps": n_e2e, "ms_per_call": e2e_ms, "statistic": "median call (max over ranks)",
-                    "pageable_caller_buffer_value": e2e_pageable, "pageable_ms_per_call": e2e_pageable_ms},
+                    "pageable_caller_buffer_value": e2e_pageable, "pageable_ms_per_call": e2e_pageable_ms,
+                    "diagnostics_only": {"value": C_ * I_ * N_STEPS / (diag_ms * 1e-3), "ms_per_call": diag_ms, "d2h_bytes_per_step": N_DIM * 16,
+                                         "max_rhat": float(np.max(diag_out[:, 0])), "min_ess": float(np.min(diag_out[:, 1])),
+                                         "note": "per rank; same rn_sample call with samples=NULL, rn_config.diagnostics set"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH[args.math] if (C_, I_) == (151552, 100) else None,

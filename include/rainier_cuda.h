@@ -117,6 +117,9 @@ typedef struct rn_config {
   const rn_rng_state* rng_states; /* optional [chains]; overrides seeds when non-NULL */
   double* stats_rings;       /* optional host buffer [chains][3][stats_window]: the stepSizes, acceptanceRates
                                 and gradsPerIteration ring buffers in RingBuffer slot order (Stats.scala:19-59) */
+  double* diagnostics;       /* optional host buffer [n][2]: Trace.diagnostics (rHat, effectiveSampleSize per parameter,
+                                core/Trace.scala:11-21) reduced on the device over all chains and iterations of this
+                                call; with `samples == NULL` nothing but these numbers crosses PCIe */
 } rn_config;
 
 /* Stats.scala:3-17, one per chain, sampling phase (the reference resets stats after warmup, Driver.scala:31) */

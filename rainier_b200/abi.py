@@ -52,6 +52,7 @@ class Config(C.Structure):
         ("launch_iterations", C.c_int32),
         ("rng_states", C.POINTER(RngState)),
         ("stats_rings", C.POINTER(C.c_double)),
+        ("diagnostics", C.POINTER(C.c_double)),
     ]
 
 

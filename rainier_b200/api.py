@@ -417,7 +417,8 @@ class CudaModel:
         return _DF()
 
     # -- Model.sample --
-    def sample(self, config=None, nChains=4, seeds=None, rng_states=None, dense_mass=None, out=None):
+    def sample(self, config=None, nChains=4, seeds=None, rng_states=None, dense_mass=None, out=None, diagnostics=False,
+               keep_samples=True):
         """Model.sample(config, nChains) (core/Model.scala:13-24).  Chain c behaves exactly like a single-chain
         reference run with ScalaRNG(seeds[c]).  Returns a Trace with numpy arrays.  `out`: optional C-contiguous
         float64 array [chains][iterations][n] to receive the samples (e.g. PinnedBuffer(...).array)."""
@@ -445,9 +446,14 @@ class CudaModel:
         stats = (ChainStats * nChains)()
         rings = np.zeros((nChains, 3, cfg.stats_window), dtype=np.float64)
         cfg.stats_rings = rings.ctypes.data_as(C.POINTER(C.c_double))
-        _check(lib().rn_sample(self.h, C.byref(cfg), seeds_a.ctypes.data, nChains, samples.ctypes.data, mass.ctypes.data,
-                               C.cast(stats, C.c_void_p)))
-        return Trace(samples, mass, [Stats(stats[c], rings[c]) for c in range(nChains)])
+        diag = np.empty((n, 2), dtype=np.float64) if diagnostics else None
+        if diagnostics:
+            cfg.diagnostics = diag.ctypes.data_as(C.POINTER(C.c_double))
+        _check(lib().rn_sample(self.h, C.byref(cfg), seeds_a.ctypes.data, nChains, samples.ctypes.data if keep_samples else None,
+                               mass.ctypes.data, C.cast(stats, C.c_void_p)))
+        tr = Trace(samples if keep_samples else None, mass, [Stats(stats[c], rings[c]) for c in range(nChains)])
+        tr.diagnostics = diag  # [n][2] = rHat, effectiveSampleSize (Trace.diagnostics), reduced on the device
+        return tr
 
 
 class Comm:

@@ -6,6 +6,9 @@
 //              batch of chains (rainier-sampler/.../sampler/Driver.scala:7-119).
 // No CPU fallback: anything that needs to execute fails with RN_E_CUDA when there is no driver/device.
 #include <dlfcn.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <nvrtc.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -1410,6 +1413,31 @@ struct PinnedRing {  // process-wide, grown on demand, never freed (pinning is e
 };
 PinnedRing g_ring;
 
+// pinned staging slice -> caller's pageable pages with non-temporal stores: a plain memcpy of a 2 MB stripe stays below
+// glibc's non-temporal threshold, so every destination line is first read (RFO) -- with the DMA engine writing the ring
+// at PCIe rate at the same time that extra read stream is what saturates the socket's memory bandwidth
+void copy_streaming(char* dst, const char* src, size_t n) {
+#if defined(__x86_64__) && defined(__SSE2__)
+  size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+  if (head > n) head = n;
+  if (head) std::memcpy(dst, src, head);
+  dst += head, src += head, n -= head;
+  size_t body = n & ~(size_t)63;
+  for (size_t i = 0; i < body; i += 64) {
+    const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16)),
+                  c = _mm_loadu_si128((const __m128i*)(src + i + 32)), d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+    _mm_stream_si128((__m128i*)(dst + i), a);
+    _mm_stream_si128((__m128i*)(dst + i + 16), b);
+    _mm_stream_si128((__m128i*)(dst + i + 32), c);
+    _mm_stream_si128((__m128i*)(dst + i + 48), d);
+  }
+  _mm_sfence();
+  if (n > body) std::memcpy(dst + body, src + body, n - body);
+#else
+  std::memcpy(dst, src, n);
+#endif
+}
+
 class Workers {  // persistent job pool for the pinned->pageable memcpy of the drain
  public:
   explicit Workers(int n) {
@@ -1531,7 +1559,7 @@ int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, siz
         const size_t off = k * slice, len = std::min(slice, bytes - off);
         const size_t part = ((len / (size_t)T) + 4095) & ~(size_t)4095;
         const size_t o = (size_t)t * part;
-        if (o < len) std::memcpy((char*)dst + off + o, (const char*)g_ring.buf[k % R] + o, std::min(part, len - o));
+        if (o < len) copy_streaming((char*)dst + off + o, (const char*)g_ring.buf[k % R] + o, std::min(part, len - o));
         done[k].fetch_add(1, std::memory_order_release);
       }
     });
@@ -1610,7 +1638,22 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
   const size_t C = (size_t)chains, n = m->n_params, I = (size_t)cfg->iterations;
   rc = rn_sampler_run(s, 0, nullptr);  // lf.resetStats() after warmup even when no iteration follows (Driver.scala:31)
   if (rc) return rc;
-  if (I > 0 && samples) {
+  if (I > 0 && !samples && cfg->diagnostics) {
+    // summaries only: the samples stay on the device ([iterations][n][chains], as the kernels write them) and
+    // Trace.diagnostics is reduced there
+    const size_t want = I * n * C * 8;
+    if (m->pool_bytes[0] < want) {
+      if (m->pool[0]) A->cuMemFree(m->pool[0]);
+      m->pool[0] = 0;
+      m->pool_bytes[0] = 0;
+      CU(A->cuMemAlloc(&m->pool[0], want));
+      m->pool_bytes[0] = want;
+    }
+    rc = rn_sampler_run(s, (int)I, (double*)(uintptr_t)m->pool[0]);
+    if (rc) return rc;
+    rc = rn_sampler_diagnostics(s, (const double*)(uintptr_t)m->pool[0], (int)I, 0, cfg->diagnostics);
+    if (rc) return rc;
+  } else if (I > 0 && samples) {
     const size_t total = C * I * n * 8;
     // the whole [C][I][n] result stays on the device while it is produced; runs larger than the cap are cut into
     // passes over the iteration axis (each pass drained with a strided copy)
@@ -1700,7 +1743,12 @@ int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chain
                            /*sync=*/bi + 1 == ranges.size());
         if (rc) return rc;
       }
+      if (cfg->diagnostics) {  // the [chain][iteration][n] block is still resident
+        rc = rn_sampler_diagnostics(s, (const double*)(uintptr_t)g.b[1], (int)I, 1, cfg->diagnostics);
+        if (rc) return rc;
+      }
     } else {
+      if (cfg->diagnostics) return fail(RN_E_UNSUPPORTED, "diagnostics need the whole sample block on the device (raise RN_SAMPLE_DEVICE_CAP_MB)");
       for (size_t p0 = 0; p0 < I; p0 += pass_iters) {  // strided passes over the iteration axis
         const size_t pi = std::min(pass_iters, I - p0);
         for (size_t done = 0; done < pi;) {

@@ -70,7 +70,7 @@ object CudaSampling {
   private val OffStepTuner = 48; private val OffDelta = 56; private val OffStaticStep = 64
   private val OffMassTuner = 72; private val OffInitWindow = 76; private val OffExpansion = 80
   private val OffSkipFirst = 88; private val OffSkipLast = 92
-  require(Native.configSize() == 144, "rn_config layout changed")
+  require(Native.configSize() == 152, "rn_config layout changed")
 
   private def lower(config: SamplerConfig): ByteBuffer = {
     val b = ByteBuffer.allocateDirect(Native.configSize()).order(ByteOrder.LITTLE_ENDIAN)

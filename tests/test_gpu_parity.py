@@ -352,3 +352,19 @@ def test_device_diagnostics_match_trace_restatement(schools, iters):
     assert parity.rel_err(got, ref, 1e-9) < 1e-9, (got, ref)
     assert parity.rel_err(got2, ref, 1e-9) < 1e-9
     s.close()
+
+
+def test_rn_sample_diagnostics_only(schools):
+    """rn_config.diagnostics: rHat/ESS come back from rn_sample itself; with samples == NULL nothing else crosses PCIe.
+    Same numbers as the restatement of Trace.diagnostics over the samples of an identical run."""
+    from oracle.rainier_py.diagnostics import trace_diagnostics
+    cfg = api.SamplerConfig(iterations=60, warmupIterations=200)
+    seeds = np.arange(40) + 3
+    m = api.CudaModel(*schools)
+    full = m.sample(cfg, seeds=seeds, diagnostics=True)
+    only = m.sample(cfg, seeds=seeds, diagnostics=True, keep_samples=False)
+    assert only.chains is None
+    ref = np.array(trace_diagnostics(full.chains))
+    assert parity.rel_err(full.diagnostics, ref, 1e-9) < 1e-9
+    assert parity.rel_err(only.diagnostics, ref, 1e-9) < 1e-9
+    assert [s.gradientEvaluations for s in only.stats] == [s.gradientEvaluations for s in full.stats]
