@@ -5,41 +5,61 @@
 // of every sample dominate the call; here only [n][2] numbers leave the device.
 //
 //   rn_k_diag_chain   one thread per (parameter, chain): mean, variance and the variograms of lags 1..max_lag of that
-//                     chain's series, summed over iterations in the reference's sequential order.
-//   rn_k_diag_reduce  fixed-shape tree sums over chains (deterministic), optionally of squared deviations.
+//                     chain's series (summed over iterations in the reference's sequential order), reduced over the 128
+//                     chains of the block in a fixed order.
+//   rn_k_diag_reduce  fixed-shape tree sums over blocks / chains (deterministic), optionally of squared deviations.
 // The scalar epilogue (b, w, v, rHat, the lag loop with its termination rule, ess) runs on the host in rn_runtime.cpp.
 #ifndef RN_DIAG_CUH
 #define RN_DIAG_CUH
 #ifndef RN_HOST_EMULATION
 
-// sample(t, i, c) = s[t*st + i*si + c*sc];  outputs are [.][n][C], chain fastest
+// sample(t, i, c) = s[t*st + i*si + c*sc].  grid = (ceil(C/128), n), 128 threads: thread = chain, blockIdx.y = parameter.
+// The chain's series is staged once in shared memory (x[t][thread], conflict-free) when iterations*128 doubles fit
+// (`use_smem`), so the O(iterations * lags) variogram loops never touch global memory again.  Per block the 128 chains'
+// contributions are added in a fixed order (warp shuffles, then 4 warp totals) and written as one partial per
+// (quantity, parameter, block): partial[(q * n + i) * nblk + blockIdx.x], q = 0 mean, 1 variance, 2.. variogram(lag).
+extern __shared__ double rn_diag_smem[];
+RN_DEVICE double rn_diag_block_sum(double v, double* red4) {
+  RN_UNROLL
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red4[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return ((red4[0] + red4[1]) + red4[2]) + red4[3];
+}
 RN_GLOBAL void rn_k_diag_chain(const double* RN_RESTRICT s, long long st, long long si, long long sc, int I, int n, int C,
-                               int max_lag, int i_fastest, double* RN_RESTRICT mean, double* RN_RESTRICT var,
-                               double* RN_RESTRICT vario) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)n * C) return;
-  const int i = i_fastest ? (int)(gid % n) : (int)(gid / C);
-  const int c = i_fastest ? (int)(gid / n) : (int)(gid % C);
-  const double* x = s + (long long)i * si + (long long)c * sc;
-  double sum = 0.0;  // t.sum / n, Trace.scala:69-71
-  for (int t = 0; t < I; t++) sum += x[(long long)t * st];
+                               int max_lag, int use_smem, double* RN_RESTRICT mean, double* RN_RESTRICT partial) {
+  __shared__ double red4[4];
+  const int i = blockIdx.y, c = blockIdx.x * 128 + threadIdx.x, nblk = gridDim.x;
+  const bool live = c < C;
+  const double* xg = s + (long long)i * si + (long long)(live ? c : 0) * sc;
+  double* xs = rn_diag_smem + threadIdx.x;  // x[t] at xs[t * 128]
+  if (use_smem)
+    for (int t = 0; t < I; t++) xs[(size_t)t * 128] = live ? xg[(long long)t * st] : 0.0;
+#define RN_DIAG_X(t) (use_smem ? xs[(size_t)(t) * 128] : (live ? xg[(long long)(t) * st] : 0.0))
+  double sum = 0.0;  // t.sum / n, Trace.scala:69-71 (sequential over iterations, like the reference)
+  for (int t = 0; t < I; t++) sum += RN_DIAG_X(t);
   const double m = sum / (double)I;
   double ss = 0.0;  // t.map(a => pow(a - m, 2)).sum / (n - 1), Trace.scala:79-86
   for (int t = 0; t < I; t++) {
-    const double d = x[(long long)t * st] - m;
+    const double d = RN_DIAG_X(t) - m;
     ss += d * d;
   }
-  const size_t o = (size_t)i * C + c;
-  mean[o] = m;
-  var[o] = ss / (double)(I - 1);
+  if (live) mean[(size_t)i * C + c] = m;
+  double tot = rn_diag_block_sum(live ? m : 0.0, red4);
+  if (threadIdx.x == 0) partial[((size_t)0 * n + i) * nblk + blockIdx.x] = tot;
+  tot = rn_diag_block_sum(live ? ss / (double)(I - 1) : 0.0, red4);
+  if (threadIdx.x == 0) partial[((size_t)1 * n + i) * nblk + blockIdx.x] = tot;
   for (int lag = 1; lag <= max_lag; lag++) {  // Trace.variogram, Trace.scala:111-119
     double v = 0.0;
     for (int t = lag; t < I; t++) {
-      const double d = x[(long long)t * st] - x[(long long)(t - lag) * st];
+      const double d = RN_DIAG_X(t) - RN_DIAG_X(t - lag);
       v += d * d;
     }
-    vario[(size_t)(lag - 1) * n * C + o] = v / (double)(I - lag);
+    tot = rn_diag_block_sum(live ? v / (double)(I - lag) : 0.0, red4);
+    if (threadIdx.x == 0) partial[((size_t)(1 + lag) * n + i) * nblk + blockIdx.x] = tot;
   }
+#undef RN_DIAG_X
 }
 
 // out[q] = sum_c f(in[q*C + c]),  f(x) = x or (x - shift[q])^2 ; one 256-thread block per q

@@ -189,6 +189,8 @@ struct rn_model {
   CUdeviceptr pool[2] = {0, 0};  // grow-only scratch reused by rn_sample calls (cuMemAlloc/cuMemFree of GBs is slow)
   // one spare set of sampler resources handed from a destroyed sampler to the next one: rn_sample creates and destroys a
   // sampler per call, and cuMemAlloc / cuMemFree / cuStreamCreate are synchronising driver calls
+  CUdeviceptr diag_scratch = 0;  // grow-only scratch of rn_sampler_diagnostics
+  size_t diag_bytes = 0;
   CUdeviceptr spare_arena = 0;
   size_t spare_arena_bytes = 0;
   CUstream spare_stream = nullptr;
@@ -573,6 +575,7 @@ void rn_model_destroy(rn_model* m) {
     for (auto p : m->pool)
       if (p) A->cuMemFree(p);
     if (m->spare_arena) A->cuMemFree(m->spare_arena);
+    if (m->diag_scratch) A->cuMemFree(m->diag_scratch);
     if (m->spare_stream) A->cuStreamDestroy(m->spare_stream);
     CUdevice dev;
     if (A->cuDeviceGet(&dev, m->device) == 0) A->cuDevicePrimaryCtxRelease(dev);
@@ -1254,41 +1257,44 @@ int rn_sampler_diagnostics(rn_sampler* s, const double* d_samples, int iteration
   CU(A->cuCtxSetCurrent(s->m->ctx));
   const int n = (int)s->m->n_params, C = s->chains, I = iterations;
   const int L = std::min(100, I - 1);  // lags whose variogram has a non-empty sum; lag == I gives 0/0 (see epilogue)
-  const size_t nC = (size_t)n * C;
-  CUdeviceptr scratch = 0;
-  const size_t n_sums = (size_t)(3 + L) * n;  // [mean sums | var sums | vario sums (L*n) | squared deviations]
-  CU(A->cuMemAlloc(&scratch, ((2 + (size_t)L) * nC + n_sums + n) * 8));
-  struct Free {
-    const Api* A;
-    CUdeviceptr p;
-    ~Free() { A->cuMemFree(p); }
-  } guard{A, scratch};
-  CUdeviceptr d_mean = scratch, d_var = scratch + nC * 8, d_vario = scratch + 2 * nC * 8, d_sums = scratch + (2 + (size_t)L) * nC * 8,
-              d_shift = d_sums + n_sums * 8;
+  const size_t nC = (size_t)n * C, nblk = ((size_t)C + 127) / 128;
+  const size_t n_q = 2 + (size_t)L;            // quantities reduced over chains: mean, variance, variogram(1..L)
+  const size_t n_sums = (n_q + 1) * n;         // + squared deviations of the chain means
+  // scratch: [mean per chain | per-block partials | sums | shift]
+  const size_t need = (nC + n_q * n * nblk + n_sums + n) * 8;
+  if (s->m->diag_bytes < need) {
+    if (s->m->diag_scratch) A->cuMemFree(s->m->diag_scratch);
+    s->m->diag_scratch = 0;
+    s->m->diag_bytes = 0;
+    CU(A->cuMemAlloc(&s->m->diag_scratch, need));
+    s->m->diag_bytes = need;
+  }
+  CUdeviceptr d_mean = s->m->diag_scratch, d_part = d_mean + nC * 8, d_sums = d_part + n_q * n * nblk * 8, d_shift = d_sums + n_sums * 8;
   {
     CUdeviceptr src = (CUdeviceptr)(uintptr_t)d_samples;
     long long st, si, sc;
-    int i_fastest;
     if (layout == 0) {
-      st = (long long)n * C, si = C, sc = 1, i_fastest = 0;
+      st = (long long)n * C, si = C, sc = 1;
     } else {
-      st = n, si = 1, sc = (long long)I * n, i_fastest = 1;
+      st = n, si = 1, sc = (long long)I * n;
     }
     int I_ = I, n_ = n, C_ = C, L_ = L;
-    void* params[] = {&src, &st, &si, &sc, &I_, &n_, &C_, &L_, &i_fastest, &d_mean, &d_var, &d_vario};
-    CU(A->cuLaunchKernel(s->K->k_diag_chain, (unsigned)((nC + 127) / 128), 1, 1, 128, 1, 1, 0, s->stream, params, nullptr));
+    const size_t smem = (size_t)I * 128 * 8;
+    int use_smem = smem <= (size_t)200 * 1024 ? 1 : 0;
+    if (use_smem) CU(A->cuFuncSetAttribute(s->K->k_diag_chain, 8 /*MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)smem));
+    void* params[] = {&src, &st, &si, &sc, &I_, &n_, &C_, &L_, &use_smem, &d_mean, &d_part};
+    CU(A->cuLaunchKernel(s->K->k_diag_chain, (unsigned)nblk, (unsigned)n, 1, 128, 1, 1, use_smem ? (unsigned)smem : 0, s->stream, params,
+                         nullptr));
     s->launches++;
   }
-  auto reduce = [&](CUdeviceptr in, int q, CUdeviceptr shift, CUdeviceptr outp) -> int {
-    int C_ = C;
+  auto reduce = [&](CUdeviceptr in, size_t rows, size_t cols, CUdeviceptr shift, CUdeviceptr outp) -> int {
+    int C_ = (int)cols;
     void* params[] = {&in, &C_, &shift, &outp};
-    CU(A->cuLaunchKernel(s->K->k_diag_reduce, (unsigned)q, 1, 1, 256, 1, 1, 0, s->stream, params, nullptr));
+    CU(A->cuLaunchKernel(s->K->k_diag_reduce, (unsigned)rows, 1, 1, 256, 1, 1, 0, s->stream, params, nullptr));
     s->launches++;
     return RN_OK;
   };
-  int rc = reduce(d_mean, n, 0, d_sums);
-  if (!rc) rc = reduce(d_var, n, 0, d_sums + (size_t)n * 8);
-  if (!rc && L > 0) rc = reduce(d_vario, L * n, 0, d_sums + 2 * (size_t)n * 8);
+  int rc = reduce(d_part, n_q * n, nblk, 0, d_sums);  // sums[q * n + i]
   if (rc) return rc;
   std::vector<double> sums(n_sums);
   CU(A->cuStreamSynchronize(s->stream));
@@ -1297,7 +1303,7 @@ int rn_sampler_diagnostics(rn_sampler* s, const double* d_samples, int iteration
   std::vector<double> meanMean(n);
   for (int i = 0; i < n; i++) meanMean[i] = sums[i] / m;  // means.sum / m, Trace.scala:73
   CU(A->cuMemcpyHtoD(d_shift, meanMean.data(), (size_t)n * 8));
-  rc = reduce(d_mean, n, d_shift, d_sums + (2 + (size_t)L) * n * 8);
+  rc = reduce(d_mean, n, (size_t)C, d_shift, d_sums + n_q * n * 8);
   if (rc) return rc;
   CU(A->cuStreamSynchronize(s->stream));
   CU(A->cuMemcpyDtoH(sums.data(), d_sums, n_sums * 8));
