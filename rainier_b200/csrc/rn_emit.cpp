@@ -256,7 +256,10 @@ struct Emitter {
     return "v" + std::to_string(id);
   }
 
-  std::string pow_expr(int a, int b) const {
+  // `derived`: the node was created by the emitter's own reverse sweep (there is no reference operation to mirror), so
+  // constant powers are strength-reduced in parity mode as well -- d/dx x^-1 = -x^-2 would otherwise cost one fdlibm
+  // pow() per observation of a logistic regression
+  std::string pow_expr(int a, int b, bool derived) const {
     const Node& e = P.nodes[b];
     const std::string x = val(a);
     if (e.kind == K_CONST) {
@@ -264,6 +267,16 @@ struct Emitter {
       if (c == 1.0) return x;
       if (c == 2.0) return "(" + x + " * " + x + ")";
       if (c == -1.0) return "(1.0 / " + x + ")";
+      if (derived && !opt.fast_math) {
+        if (c == 3.0) return "(" + x + " * " + x + " * " + x + ")";
+        if (c == 4.0) return "((" + x + " * " + x + ") * (" + x + " * " + x + "))";
+        if (c == -2.0) return "(1.0 / (" + x + " * " + x + "))";
+        if (c == -3.0) return "(1.0 / (" + x + " * " + x + " * " + x + "))";
+        if (c == 0.5) return "sqrt(" + x + ")";
+        if (c == -0.5) return "(1.0 / sqrt(" + x + "))";
+        if (c == 1.5) return "(" + x + " * sqrt(" + x + "))";
+        if (c == -1.5) return "(1.0 / (" + x + " * sqrt(" + x + ")))";
+      }
       if (opt.fast_math) {
         if (c == 3.0) return "(" + x + " * " + x + " * " + x + ")";
         if (c == 4.0) return "((" + x + " * " + x + ") * (" + x + " * " + x + "))";
@@ -307,7 +320,7 @@ struct Emitter {
           case RIR_B_MUL: os << "(" << x << " * " << y << ")"; break;
           case RIR_B_SUB: os << "(" << x << " - " << y << ")"; break;
           case RIR_B_DIV: os << "(" << x << " / " << y << ")"; break;
-          case RIR_B_POW: os << pow_expr(n.a, n.b); break;
+          case RIR_B_POW: os << pow_expr(n.a, n.b, n.region == R_ROW_BWD || n.region == R_INV_BWD); break;
           case RIR_B_COMPARE: os << "rn_compare(" << x << ", " << y << ")"; break;
         }
         break;
