@@ -259,7 +259,7 @@ struct Emitter {
   // `derived`: the node was created by the emitter's own reverse sweep (there is no reference operation to mirror), so
   // constant powers are strength-reduced in parity mode as well -- d/dx x^-1 = -x^-2 would otherwise cost one fdlibm
   // pow() per observation of a logistic regression
-  std::string pow_expr(int a, int b, bool derived) const {
+  std::string pow_expr(int a, int b, bool derived, bool row_variant = false) const {
     const Node& e = P.nodes[b];
     const std::string x = val(a);
     if (e.kind == K_CONST) {
@@ -286,8 +286,9 @@ struct Emitter {
         if (c == 1.5) return "(" + x + " * sqrt(" + x + "))";
       }
     }
-    return "rn_pow(" + x + ", " + val(b) + ")";
+    return std::string(row_variant ? "rn_pow_libm(" : "rn_pow(") + x + ", " + val(b) + ")";
   }
+  bool row_libm(const Node& n) const { return wpc && (n.region == R_ROW_FWD || n.region == R_ROW_BWD); }
 
   void stmt(int id, const char* indent) {
     const Node& n = P.nodes[id];
@@ -297,8 +298,12 @@ struct Emitter {
       case K_UNARY: {
         const std::string x = val(n.a);
         switch (n.op) {
-          case RIR_U_EXP: os << "rn_exp(" << x << ")"; break;
-          case RIR_U_LOG: os << "rn_log(" << x << ")"; break;
+          // Row-variant transcendentals of the warp-per-chain shape use CUDA's libm (<= 1 ulp, like the JVM's own
+          // Math.exp/log intrinsics): rows are summed in tree order there, so those results are not bit-comparable with
+          // the oracle anyway (1e-13 agreement), and fdlibm costs twice the instructions.  Everything that stays
+          // bit-exact -- invariant parts, data-free targets, the thread-per-chain kernels -- keeps fdlibm.
+          case RIR_U_EXP: os << (row_libm(n) ? "exp(" : "rn_exp(") << x << ")"; break;
+          case RIR_U_LOG: os << (row_libm(n) ? "log(" : "rn_log(") << x << ")"; break;
           case RIR_U_ABS: os << "fabs(" << x << ")"; break;
           case RIR_U_NOOP: os << x; break;
           case RIR_U_SIN: os << "sin(" << x << ")"; break;
@@ -320,7 +325,7 @@ struct Emitter {
           case RIR_B_MUL: os << "(" << x << " * " << y << ")"; break;
           case RIR_B_SUB: os << "(" << x << " - " << y << ")"; break;
           case RIR_B_DIV: os << "(" << x << " / " << y << ")"; break;
-          case RIR_B_POW: os << pow_expr(n.a, n.b, n.region == R_ROW_BWD || n.region == R_INV_BWD); break;
+          case RIR_B_POW: os << pow_expr(n.a, n.b, n.region == R_ROW_BWD || n.region == R_INV_BWD, row_libm(n)); break;
           case RIR_B_COMPARE: os << "rn_compare(" << x << ", " << y << ")"; break;
         }
         break;
