@@ -51,3 +51,31 @@ def test_primal_rir_scatter_gradient_for_large_lookup_tables():
     out, err = he.density(src, q, pcols, cm)
     assert err == 0
     assert np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-9
+
+
+def test_warp_per_chain_source_shape():
+    """CPU-side checks of what the emitter writes for a streamed model on the warp-per-chain shape (the device code itself
+    is exercised by the GPU tests): TMA tile loop + per-warp fallback, no fdlibm pow in emitter-derived adjoints, CUDA libm
+    only in row regions, K-warps reduction scratch, and the same source when emitted twice (cache key stability)."""
+    rir, cols = configs.logreg(700, 4).compile(False)
+    m = api.CudaModel(rir, cols, device=-1)
+    cfg = api.make_config(sampler=api.HMCSampler(2), backend=abi.RN_BACKEND_WARP)
+    src = m.emit_source(cfg)
+    dens = src[src.index("// ---- emitted"):src.index("#define RN_WPC_SMEM_DOUBLES")]
+    assert "rn_tma_load(" in dens and "rn_mbar_wait(" in dens and "rn_cta_bar(" in dens  # CTA-shared tiles
+    assert "RN_LDG(rp +" in dens                                                          # independent per-warp path
+    assert "rn_pow(" not in dens and "rn_pow_libm(" not in dens                           # d/dx x^-1 strength-reduced
+    rows = dens[dens.index("// target 1"):]
+    assert " exp(" in rows and " log(" in rows and "rn_exp(" not in rows                  # libm in row regions only
+    assert "RN_FENCE();" in rows                                                          # reverse sweep reloads columns
+    assert "#define RN_TMA_STAGES" in src and "#define RN_WPC_K 1" in src
+    assert src == api.CudaModel(rir, cols, device=-1).emit_source(cfg)
+    import os
+    os.environ["RN_WPC_K"] = "2"
+    try:
+        src2 = api.CudaModel(rir, cols, device=-1).emit_source(cfg)
+    finally:
+        del os.environ["RN_WPC_K"]
+    assert "#define RN_WPC_K 2" in src2 and "double* red = scr +" in src2
+    cub = api.CudaModel(rir, cols, device=-1).emit_cubin(cfg)  # NVRTC accepts it for sm_100a
+    assert cub[:4] == b"\x7fELF"
