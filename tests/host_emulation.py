@@ -13,6 +13,80 @@ import tempfile
 
 import numpy as np
 
+_SAMPLER_SHIM = r"""
+#include <vector>
+#include <cstring>
+// Host emulation of rn_sampler_create / warmup / run for the THREAD-PER-CHAIN kernels (one launch per phase, one
+// "thread" at a time).  Test infrastructure only: lets the CPU test-suite run the hand-written sampler source
+// (rn_sampler.cuh) against the oracle; the product never executes this.
+struct EmuCfg {
+  int sampler, n_steps, max_steps, min_steps, buf_size, step_tuner;
+  double p_count, delta, static_step;
+  int mass_tuner, initial_window, skip_first, skip_last;
+  double win_expansion;
+  int stats_window, warmup, iterations;
+};
+extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, const double* data, double* samples,
+                          double* trace, long long* out_stats, double* mass_out, int* mass_kind_out) {
+  const size_t C = (size_t)chains, n = RN_N, W = (size_t)c->stats_window;
+  std::vector<double> params((2 * n + 1) * C), grad(n * C), nng(C), da(5 * C), mass(n * n * C + 1), chol(n * (n + 1) / 2 * C + 1),
+      emean(n * C + 1), eraw(n * C + 1), ecov(n * n * C + 1), ring((size_t)c->buf_size * C + 1), energy(3 * C), rings(3 * W * C);
+  std::vector<long long> seed(C), grads(C), steps(C);
+  std::vector<int> have(C), dait(C), ring_i(C), ring_full(C), err(C), iters(C), accepted(C), energy_n(C), sri(3 * C), srf(3 * C);
+  RnArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.chains = chains;
+  a.params = params.data(); a.grad = grad.data(); a.rng_seed = seed.data(); a.rng_nng = nng.data(); a.rng_have = have.data();
+  a.da = da.data(); a.da_iter = dait.data(); a.mass = mass.data(); a.chol = chol.data(); a.est_mean = emean.data();
+  a.est_raw = eraw.data(); a.est_cov = ecov.data(); a.ring = ring.data(); a.ring_i = ring_i.data(); a.ring_full = ring_full.data();
+  a.st_err = err.data(); a.st_grads = grads.data(); a.st_steps = steps.data(); a.st_iters = iters.data();
+  a.st_accepted = accepted.data(); a.st_energy = energy.data(); a.st_energy_n = energy_n.data(); a.st_rings = rings.data();
+  a.st_ring_i = sri.data(); a.st_ring_full = srf.data(); a.data = data;
+  a.sampler = c->sampler; a.n_steps = c->n_steps; a.max_steps = c->max_steps; a.min_steps = c->min_steps; a.buf_size = c->buf_size;
+  a.step_tuner = c->step_tuner; a.p_count = c->p_count; a.delta = c->delta; a.static_step = c->static_step;
+  a.mass_tuner = c->mass_tuner; a.total_warmup = c->warmup; a.skip_first = c->skip_first; a.skip_last = c->skip_last;
+  a.win_expansion = c->win_expansion; a.stats_window = c->stats_window;
+  a.chain_begin = 0; a.chain_end = chains;
+  for (size_t k = 0; k < C; k++) seed[k] = (seeds[k] ^ 0x5DEECE66DLL) & ((1LL << 48) - 1);  // new java.util.Random(seed)
+  auto launch = [&](void (*kern)(const RnArgs)) {
+    blockDim.x = 1; gridDim.x = (unsigned)chains; threadIdx.x = 0;
+    for (int k = 0; k < chains; k++) { blockIdx.x = (unsigned)k; kern(a); }
+  };
+  a.mass_kind = 0;
+  launch(rn_k_init);
+  int win_size = c->initial_window, win_i = 0, win_j = 0, est = 0, mass_kind = 0;
+  if (c->warmup > 0) {
+    a.phase = 0; a.n_iter = c->warmup; a.mass_kind = 0; a.win_size = win_size; a.win_i = 0; a.win_j = 0; a.est_samples = 0;
+    a.trace = trace;
+    launch(rn_k_iter);
+    if (c->mass_tuner == 1 || c->mass_tuner == 2)  // host mirror of WindowedMassMatrixTuner.update (rn_runtime.cpp: advance_window)
+      for (int k = 0; k < c->warmup; k++) {
+        win_j += 1;
+        if (win_j < c->skip_first || (c->warmup - win_j) < c->skip_last) continue;
+        win_i += 1; est += 1;
+        if (win_i == win_size) { win_i = 0; win_size = (int)(win_size * c->win_expansion); mass_kind = c->mass_tuner; }
+      }
+  }
+  // lf.resetStats(), Driver.scala:31
+  std::fill(grads.begin(), grads.end(), 0); std::fill(steps.begin(), steps.end(), 0); std::fill(iters.begin(), iters.end(), 0);
+  std::fill(accepted.begin(), accepted.end(), 0); std::fill(energy.begin(), energy.end(), 0.0); std::fill(energy_n.begin(), energy_n.end(), 0);
+  std::fill(rings.begin(), rings.end(), 0.0); std::fill(sri.begin(), sri.end(), 0); std::fill(srf.begin(), srf.end(), 0);
+  if (c->iterations > 0) {
+    a.phase = 1; a.n_iter = c->iterations; a.mass_kind = mass_kind; a.samples = samples;
+    a.trace = trace ? trace + (size_t)c->warmup * 4 * C : nullptr;
+    launch(rn_k_iter);
+  }
+  for (size_t k = 0; k < C; k++) {
+    out_stats[k * 5 + 0] = grads[k]; out_stats[k * 5 + 1] = steps[k]; out_stats[k * 5 + 2] = accepted[k]; out_stats[k * 5 + 3] = seed[k];
+    out_stats[k * 5 + 4] = err[k];
+  }
+  const size_t ne = mass_kind == 2 ? n * n : n;
+  for (size_t e = 0; e < ne * C; e++) mass_out[e] = mass_kind == 0 ? 1.0 : mass[e];
+  *mass_kind_out = mass_kind;
+  return 0;
+}
+"""
+
 _SHIM = r"""
 extern "C" void emu_density(const double* q, int chains, double* out, const double* data, int* err) {
   blockDim.x = 1; gridDim.x = (unsigned)chains; threadIdx.x = 0;
@@ -29,7 +103,7 @@ def compile_source(src, fast=False):
     if not os.path.exists(so):
         cpp = os.path.join(d, key + ".cpp")
         with open(cpp, "w") as f:
-            f.write(src + _SHIM)
+            f.write(src + _SHIM + (_SAMPLER_SHIM if "RN_BACKEND 0" in src else ""))
         flags = ["-O1", "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w"]
         flags.append("-ffp-contract=fast" if fast else "-ffp-contract=off")
         subprocess.run(["g++"] + flags + [cpp, "-o", so], check=True)
@@ -48,3 +122,35 @@ def density(src, q, cols, model, fast=False):
     err = C.c_int(0)
     L.emu_density(C.c_void_p(qt.ctypes.data), chains, C.c_void_p(out.ctypes.data), C.c_void_p(data.ctypes.data), C.byref(err))
     return np.ascontiguousarray(out.T), err.value
+
+
+class EmuCfg(C.Structure):
+    _fields_ = [("sampler", C.c_int), ("n_steps", C.c_int), ("max_steps", C.c_int), ("min_steps", C.c_int), ("buf_size", C.c_int),
+                ("step_tuner", C.c_int), ("p_count", C.c_double), ("delta", C.c_double), ("static_step", C.c_double),
+                ("mass_tuner", C.c_int), ("initial_window", C.c_int), ("skip_first", C.c_int), ("skip_last", C.c_int),
+                ("win_expansion", C.c_double), ("stats_window", C.c_int), ("warmup", C.c_int), ("iterations", C.c_int)]
+
+
+def sample(src, cfg, seeds, model):
+    """Runs the emitted thread-per-chain sampler kernels on the host.  cfg: lowered rn_config (abi.Config).
+    Returns dict(samples [chains][iters][n], trace [chains][warm+iters][4], stats [chains][5], mass, mass_kind)."""
+    L = compile_source(src)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    chains, n = len(seeds), model.nVars
+    e = EmuCfg(cfg.sampler, cfg.n_steps, cfg.max_steps, cfg.min_steps, cfg.buf_size, cfg.step_size_tuner, cfg.p_count, cfg.delta,
+               cfg.static_step_size, cfg.mass_tuner, cfg.initial_window_size, cfg.skip_first, cfg.skip_last, cfg.window_expansion,
+               cfg.stats_window, cfg.warmup_iterations, cfg.iterations)
+    it, tot = cfg.iterations, cfg.warmup_iterations + cfg.iterations
+    samples = np.zeros((max(it, 1), n, chains))
+    trace = np.zeros((max(tot, 1), 4, chains))
+    stats = np.zeros((chains, 5), dtype=np.int64)
+    mass = np.zeros((n * n, chains))
+    kind = C.c_int(0)
+    data = model.pack_columns()
+    L.emu_sample.argtypes = [C.POINTER(EmuCfg), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.POINTER(C.c_int)]
+    L.emu_sample(C.byref(e), seeds.ctypes.data, chains, data.ctypes.data, samples.ctypes.data, trace.ctypes.data, stats.ctypes.data,
+                 mass.ctypes.data, C.byref(kind))
+    ne = n * n if kind.value == 2 else n
+    return {"samples": np.ascontiguousarray(samples[:it].transpose(2, 0, 1)), "trace": np.ascontiguousarray(trace[:tot].transpose(2, 0, 1)),
+            "stats": stats, "mass": np.ascontiguousarray(mass.reshape(-1)[: ne * chains].reshape(ne, chains).T), "mass_kind": kind.value}

@@ -1,0 +1,54 @@
+"""The hand-written thread-per-chain sampler source (rn_sampler.cuh) compiled for the host and run against the oracle on
+this box (no GPU): the same LeapFrog / HMC / EHMC / DualAvg / mass-matrix logic the GPU executes, one emulated thread
+per chain (tests/host_emulation.py).  Bit-exact: g++ -ffp-contract=off + the prelude's fdlibm = the oracle's arithmetic.
+The GPU tests (-m gpu) remain the parity tests proper; this is the CPU-side safety net for the kernel source."""
+import numpy as np
+import pytest
+
+from oracle.rainier_py import configs, sbc_models
+from oracle.rainier_py.binding import OracleModel
+from rainier_b200 import abi, api
+
+import host_emulation as he
+
+
+def _run(model, config, seeds, dense=False):
+    rir, cols = model.compile(True)
+    cfg, keep = api.lower_config(config)
+    cfg.backend = abi.RN_BACKEND_THREAD
+    cm = api.CudaModel(rir, cols, device=-1)
+    config.backend = abi.RN_BACKEND_THREAD
+    got = he.sample(cm.emit_source(config), cfg, seeds, cm)
+    ref = OracleModel(rir, cols).sample(cfg, seeds=seeds, trace=True, dense_mass=dense)
+    assert np.array_equal(got["trace"][:, :, 1], ref["trace"][:, :, 1]), "accept decisions differ"
+    assert np.array_equal(got["trace"][:, :, 3], ref["trace"][:, :, 3]), "leapfrog step counts differ"
+    assert np.array_equal(got["samples"], ref["samples"]), "samples are not bit-identical"
+    for k, o in enumerate(ref["stats"]):
+        assert got["stats"][k, 0] == o.gradient_evaluations and got["stats"][k, 1] == o.leapfrog_steps
+        assert got["stats"][k, 2] == o.accepted and got["stats"][k, 3] == o.rng.seed48 and got["stats"][k, 4] == 0
+    assert np.array_equal(got["mass"], ref["mass"])
+    return got
+
+
+def _cfg(it, warm, sampler, step, mass, **kw):
+    return api.make_config(iterations=it, warmupIterations=warm, sampler=sampler, stepSizeTuner=step, massMatrixTuner=mass, **kw)
+
+
+def test_hmc_dualavg_funnel_on_host():
+    _run(configs.funnel(), _cfg(30, 120, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(6) + 7)
+
+
+def test_default_config_eight_schools_on_host():
+    """EHMC + DualAvg + windowed diagonal mass adaptation (DefaultConfig, Sampler.scala:17-27)"""
+    _run(configs.eight_schools(), api.SamplerConfig(iterations=40, warmupIterations=260), np.arange(5) + 11)
+
+
+def test_dense_mass_tuner_on_host():
+    cfg = _cfg(20, 200, api.EHMCSampler(32, 1, 10, 0.1), api.DualAvgTuner(0.8), api.DenseMassMatrixTuner(40, 1.5, 20, 20))
+    _run(configs.eight_schools(), cfg, np.arange(3) + 5, dense=True)
+
+
+def test_streamed_rows_on_host():
+    """a streamed target (sequential row order of DataFunction.compute) under HMC with a static step size"""
+    model = sbc_models.build("SBCLaplace")[0]
+    _run(model, _cfg(15, 40, api.HMCSampler(2), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(4) + 1)
