@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -302,7 +303,7 @@ struct Emitter {
           // Math.exp/log intrinsics): rows are summed in tree order there, so those results are not bit-comparable with
           // the oracle anyway (1e-13 agreement), and fdlibm costs twice the instructions.  Everything that stays
           // bit-exact -- invariant parts, data-free targets, the thread-per-chain kernels -- keeps fdlibm.
-          case RIR_U_EXP: os << (row_libm(n) ? "exp(" : "rn_exp(") << x << ")"; break;
+          case RIR_U_EXP: os << (row_libm(n) && !getenv("RN_ROW_EXP_FDLIBM") ? "exp(" : "rn_exp(") << x << ")"; break;
           case RIR_U_LOG: os << (row_libm(n) ? "log(" : "rn_log(") << x << ")"; break;
           case RIR_U_ABS: os << "fabs(" << x << ")"; break;
           case RIR_U_NOOP: os << x; break;
