@@ -188,7 +188,11 @@ RN_DEVICE void rn_store_stats(const RnArgs& A, int c, const RnStats& S) {
   }
 }
 
+#ifdef RN_HOST_EMULATION
+static double rn_smem[1 << 16];  // one emulated CTA (= one chain) at a time
+#else
 extern __shared__ __align__(128) double rn_smem[];
+#endif
 
 // =============================================================================================================
 RN_GLOBAL void rn_k_init(const RnArgs A) {
@@ -542,6 +546,7 @@ RN_GLOBAL void rn_k_density(const double* RN_RESTRICT qin, double* RN_RESTRICT o
   if (e && RN_LANE == 0) atomicOr(err, e);
 }
 
+#ifndef RN_HOST_EMULATION
 RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT dst, int rows, int cols,
                               long long src_ld, long long dst_ld, long long dst_off) {
   // dst[c * dst_ld + dst_off + r] = src[r * src_ld + c]   (a block of `cols` chains out of src_ld)
@@ -603,5 +608,7 @@ RN_GLOBAL void rn_k_pool_apply(const RnArgs A, const double* pool) {
     A.da_iter[c] = 0;
   }
 }
+
+#endif  // !RN_HOST_EMULATION
 
 #endif  // RN_SAMPLER_WPC_CUH

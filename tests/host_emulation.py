@@ -49,9 +49,7 @@ extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, c
   a.chain_begin = 0; a.chain_end = chains;
   for (size_t k = 0; k < C; k++) seed[k] = (seeds[k] ^ 0x5DEECE66DLL) & ((1LL << 48) - 1);  // new java.util.Random(seed)
   auto launch = [&](void (*kern)(const RnArgs)) {
-    blockDim.x = 1; gridDim.x = (unsigned)chains; threadIdx.x = 0;
-    for (int k = 0; k < chains; k++) { blockIdx.x = (unsigned)k; kern(a); }
-  };
+@LAUNCH@  };
   a.mass_kind = 0;
   launch(rn_k_init);
   int win_size = c->initial_window, win_i = 0, win_j = 0, est = 0, mass_kind = 0;
@@ -87,6 +85,29 @@ extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, c
 }
 """
 
+_WPC_SHIM = r"""
+#include <thread>
+#include <vector>
+#include <functional>
+// one emulated warp = 32 host threads around a pthread barrier (rn_prelude.cuh, RN_HOST_EMULATION && RN_BACKEND == 1)
+static void rn_emu_run_warp(int block, int nblocks, const std::function<void()>& body) {
+  RnEmuWarp w;
+  pthread_barrier_init(&w.bar, nullptr, 32);
+  rn_emu_warp = &w;
+  std::vector<std::thread> th;
+  for (int lane = 0; lane < 32; lane++)
+    th.emplace_back([&, lane] {
+      blockDim.x = 32; gridDim.x = (unsigned)nblocks; blockIdx.x = (unsigned)block; threadIdx.x = (unsigned)lane;
+      body();
+    });
+  for (auto& t : th) t.join();
+  pthread_barrier_destroy(&w.bar);
+}
+extern "C" void emu_density(const double* q, int chains, double* out, const double* data, int* err) {
+  for (int c = 0; c < chains; c++) rn_emu_run_warp(c, chains, [&] { rn_k_density(q, out, data, err, chains); });
+}
+"""
+
 _SHIM = r"""
 extern "C" void emu_density(const double* q, int chains, double* out, const double* data, int* err) {
   blockDim.x = 1; gridDim.x = (unsigned)chains; threadIdx.x = 0;
@@ -103,8 +124,12 @@ def compile_source(src, fast=False):
     if not os.path.exists(so):
         cpp = os.path.join(d, key + ".cpp")
         with open(cpp, "w") as f:
-            f.write(src + _SHIM + (_SAMPLER_SHIM if "RN_BACKEND 0" in src else ""))
-        flags = ["-O1", "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w"]
+            wpc = "#define RN_BACKEND 1" in src
+            launch_tpc = ("    blockDim.x = 1; gridDim.x = (unsigned)chains; threadIdx.x = 0;\n"
+                          "    for (int k = 0; k < chains; k++) { blockIdx.x = (unsigned)k; kern(a); }\n")
+            launch_wpc = "    for (int k = 0; k < chains; k++) rn_emu_run_warp(k, chains, [&] { kern(a); });\n"
+            f.write(src + (_WPC_SHIM if wpc else _SHIM) + _SAMPLER_SHIM.replace("@LAUNCH@", launch_wpc if wpc else launch_tpc))
+        flags = ["-O1", "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w", "-pthread"]
         flags.append("-ffp-contract=fast" if fast else "-ffp-contract=off")
         subprocess.run(["g++"] + flags + [cpp, "-o", so], check=True)
     return C.CDLL(so)

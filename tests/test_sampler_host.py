@@ -52,3 +52,47 @@ def test_streamed_rows_on_host():
     """a streamed target (sequential row order of DataFunction.compute) under HMC with a static step size"""
     model = sbc_models.build("SBCLaplace")[0]
     _run(model, _cfg(15, 40, api.HMCSampler(2), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(4) + 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# warp-per-chain source (rn_sampler_wpc.cuh + the emitted rows-across-lanes density) on 32 host threads per chain
+# ---------------------------------------------------------------------------------------------------------------
+def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None):
+    import os
+    rir, cols = model.compile(True)
+    config.backend = abi.RN_BACKEND_WARP
+    cfg, keep = api.lower_config(config)
+    os.environ["RN_TMA"] = "0"  # the tile pipeline (cp.async.bulk / mbarrier) has no host equivalent; K = 1
+    os.environ["RN_WPC_K"] = "1"
+    try:
+        cm = api.CudaModel(rir_gpu if rir_gpu is not None else rir, cols_gpu if cols_gpu is not None else cols, device=-1)
+        src = cm.emit_source(config)
+    finally:
+        del os.environ["RN_TMA"], os.environ["RN_WPC_K"]
+    assert "#define RN_BACKEND 1" in src
+    q = np.random.default_rng(0).normal(size=(2, cm.nVars)) * 0.3
+    om = OracleModel(rir, cols)
+    d, err = he.density(src, q, None, cm)
+    ref_d = om.density_batch(q)
+    assert err == 0 and np.max(np.abs(d - ref_d) / np.maximum(np.abs(ref_d), 1e-9)) < tol
+    got = he.sample(src, cfg, seeds, cm)
+    ref = om.sample(cfg, seeds=seeds, trace=True)
+    assert np.array_equal(got["trace"][:, :, 1], ref["trace"][:, :, 1]), "accept decisions differ"
+    assert np.array_equal(got["trace"][:, :, 3], ref["trace"][:, :, 3]), "leapfrog step counts differ"
+    assert np.max(np.abs(got["samples"] - ref["samples"]) / np.maximum(np.abs(ref["samples"]), 1e-9)) < tol
+    for k, o in enumerate(ref["stats"]):
+        assert got["stats"][k, 0] == o.gradient_evaluations and got["stats"][k, 3] == o.rng.seed48
+
+
+def test_wpc_data_free_model_is_bit_exact_on_host():
+    _run_wpc(configs.eight_schools(), api.SamplerConfig(iterations=12, warmupIterations=70), np.arange(2) + 3, tol=1e-300)
+
+
+def test_wpc_streamed_logistic_regression_on_host():
+    """rows across 32 emulated lanes, butterfly reduction, HMC with a static step size in the stable regime; the GPU
+    side differentiates the primal RIR itself (adjoint mode, what the Scala CudaCompiler sends)"""
+    model = configs.logreg(300, 3)
+    prir, pcols = model.compile(False)
+    cfg = api.make_config(iterations=6, warmupIterations=0, sampler=api.HMCSampler(3), stepSizeTuner=api.StaticStepSize(0.02),
+                          massMatrixTuner=api.IdentityMassMatrixTuner())
+    _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols)
