@@ -278,7 +278,9 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
   if (lockstep) {
     if (threadIdx.x == 0) {
       for (int s = 0; s < RN_TMA_STAGES; s++) rn_mbar_init(&bars[s], 1);
+#ifndef RN_HOST_EMULATION
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
     }
     __syncthreads();
   }

@@ -47,6 +47,9 @@ extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, c
   a.mass_tuner = c->mass_tuner; a.total_warmup = c->warmup; a.skip_first = c->skip_first; a.skip_last = c->skip_last;
   a.win_expansion = c->win_expansion; a.stats_window = c->stats_window;
   a.chain_begin = 0; a.chain_end = chains;
+#if defined(RN_TMA_STAGES) && RN_TMA_STAGES > 0
+  a.tma = 1;  // rn_runtime.cpp: run_phase
+#endif
   for (size_t k = 0; k < C; k++) seed[k] = (seeds[k] ^ 0x5DEECE66DLL) & ((1LL << 48) - 1);  // new java.util.Random(seed)
   auto launch = [&](void (*kern)(const RnArgs)) {
 @LAUNCH@  };

@@ -57,19 +57,19 @@ def test_streamed_rows_on_host():
 # ---------------------------------------------------------------------------------------------------------------
 # warp-per-chain source (rn_sampler_wpc.cuh + the emitted rows-across-lanes density) on 32 host threads per chain
 # ---------------------------------------------------------------------------------------------------------------
-def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None):
+def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None, tma="0"):
     import os
     rir, cols = model.compile(True)
     config.backend = abi.RN_BACKEND_WARP
     cfg, keep = api.lower_config(config)
-    os.environ["RN_TMA"] = "0"  # the tile pipeline (cp.async.bulk / mbarrier) has no host equivalent; K = 1
+    os.environ["RN_TMA"] = tma  # "0": per-warp loads; "2": the tile pipeline, emulated synchronously (memcpy + barriers)
     os.environ["RN_WPC_K"] = "1"
     try:
         cm = api.CudaModel(rir_gpu if rir_gpu is not None else rir, cols_gpu if cols_gpu is not None else cols, device=-1)
         src = cm.emit_source(config)
     finally:
         del os.environ["RN_TMA"], os.environ["RN_WPC_K"]
-    assert "#define RN_BACKEND 1" in src
+    assert "#define RN_BACKEND 1" in src and ("#define RN_TMA_STAGES %s" % tma) in src
     q = np.random.default_rng(0).normal(size=(2, cm.nVars)) * 0.3
     om = OracleModel(rir, cols)
     d, err = he.density(src, q, None, cm)
@@ -96,3 +96,6 @@ def test_wpc_streamed_logistic_regression_on_host():
     cfg = api.make_config(iterations=6, warmupIterations=0, sampler=api.HMCSampler(3), stepSizeTuner=api.StaticStepSize(0.02),
                           massMatrixTuner=api.IdentityMassMatrixTuner())
     _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols)
+    # same run through the data-tile pipeline: full 32-row tiles from the staged buffer, ragged remainder from global
+    # memory, two stages cycling across targets and density calls (300 observations -> 37 rows per split target)
+    _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2")
