@@ -92,19 +92,22 @@ _WPC_SHIM = r"""
 #include <thread>
 #include <vector>
 #include <functional>
-// one emulated warp = 32 host threads around a pthread barrier (rn_prelude.cuh, RN_HOST_EMULATION && RN_BACKEND == 1)
+// one emulated chain = RN_G = 32*K host threads: a barrier per warp and one for the group (rn_prelude.cuh,
+// RN_HOST_EMULATION && RN_BACKEND == 1)
 static void rn_emu_run_warp(int block, int nblocks, const std::function<void()>& body) {
-  RnEmuWarp w;
-  pthread_barrier_init(&w.bar, nullptr, 32);
-  rn_emu_warp = &w;
+  RnEmuGroup g;
+  pthread_barrier_init(&g.bar, nullptr, RN_G);
+  for (int k = 0; k < RN_WPC_K; k++) pthread_barrier_init(&g.warp[k].bar, nullptr, 32);
+  rn_emu_group = &g;
   std::vector<std::thread> th;
-  for (int lane = 0; lane < 32; lane++)
-    th.emplace_back([&, lane] {
-      blockDim.x = 32; gridDim.x = (unsigned)nblocks; blockIdx.x = (unsigned)block; threadIdx.x = (unsigned)lane;
+  for (int tid = 0; tid < RN_G; tid++)
+    th.emplace_back([&, tid] {
+      blockDim.x = RN_G; gridDim.x = (unsigned)nblocks; blockIdx.x = (unsigned)block; threadIdx.x = (unsigned)tid;
       body();
     });
   for (auto& t : th) t.join();
-  pthread_barrier_destroy(&w.bar);
+  pthread_barrier_destroy(&g.bar);
+  for (int k = 0; k < RN_WPC_K; k++) pthread_barrier_destroy(&g.warp[k].bar);
 }
 extern "C" void emu_density(const double* q, int chains, double* out, const double* data, int* err) {
   for (int c = 0; c < chains; c++) rn_emu_run_warp(c, chains, [&] { rn_k_density(q, out, data, err, chains); });

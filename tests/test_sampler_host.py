@@ -57,19 +57,19 @@ def test_streamed_rows_on_host():
 # ---------------------------------------------------------------------------------------------------------------
 # warp-per-chain source (rn_sampler_wpc.cuh + the emitted rows-across-lanes density) on 32 host threads per chain
 # ---------------------------------------------------------------------------------------------------------------
-def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None, tma="0"):
+def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None, tma="0", k="1"):
     import os
     rir, cols = model.compile(True)
     config.backend = abi.RN_BACKEND_WARP
     cfg, keep = api.lower_config(config)
     os.environ["RN_TMA"] = tma  # "0": per-warp loads; "2": the tile pipeline, emulated synchronously (memcpy + barriers)
-    os.environ["RN_WPC_K"] = "1"
+    os.environ["RN_WPC_K"] = k  # warps per chain
     try:
         cm = api.CudaModel(rir_gpu if rir_gpu is not None else rir, cols_gpu if cols_gpu is not None else cols, device=-1)
         src = cm.emit_source(config)
     finally:
         del os.environ["RN_TMA"], os.environ["RN_WPC_K"]
-    assert "#define RN_BACKEND 1" in src and ("#define RN_TMA_STAGES %s" % tma) in src
+    assert "#define RN_BACKEND 1" in src and ("#define RN_TMA_STAGES %s" % tma) in src and ("#define RN_WPC_K %s" % k) in src
     q = np.random.default_rng(0).normal(size=(2, cm.nVars)) * 0.3
     om = OracleModel(rir, cols)
     d, err = he.density(src, q, None, cm)
@@ -99,3 +99,13 @@ def test_wpc_streamed_logistic_regression_on_host():
     # same run through the data-tile pipeline: full 32-row tiles from the staged buffer, ragged remainder from global
     # memory, two stages cycling across targets and density calls (300 observations -> 37 rows per split target)
     _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2")
+
+
+def test_wpc_two_warps_per_chain_on_host():
+    """K = 2: 64 emulated threads per chain, named group barrier, cross-warp reduction scratch, 64-row super-tiles"""
+    _run_wpc(configs.eight_schools(), api.SamplerConfig(iterations=8, warmupIterations=60), np.arange(2) + 3, tol=1e-300, k="2")
+    model = configs.logreg(600, 3)
+    prir, pcols = model.compile(False)
+    cfg = api.make_config(iterations=4, warmupIterations=0, sampler=api.HMCSampler(3), stepSizeTuner=api.StaticStepSize(0.02),
+                          massMatrixTuner=api.IdentityMassMatrixTuner())
+    _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2", k="2")
