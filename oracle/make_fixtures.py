@@ -28,3 +28,12 @@ for name, build in (("funnel10", lambda: configs.funnel(10)), ("eight_schools", 
     assert not cols
     open(os.path.join(OUT, name + ".primal.rir"), "wb").write(rir)
     print(name, "ok")
+
+# one small streamed model with its columns (logistic regression, 700 observations x 4 covariates, primal flavour):
+# __graft_entry__.build()/smoke() use it to assemble and run the warp-per-chain (TMA-tiled) kernel shape
+import numpy as np  # noqa: E402
+
+rir, cols = configs.logreg(700, 4).compile(False)
+np.savez_compressed(os.path.join(OUT, "logreg_700x4.primal.npz"), rir=np.frombuffer(rir, dtype=np.uint8), ncols=len(cols),
+                    **{"c%d" % i: np.asarray(c, dtype=np.float64) for i, c in enumerate(cols)})
+print("logreg_700x4 ok")
