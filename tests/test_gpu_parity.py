@@ -368,3 +368,22 @@ def test_rn_sample_diagnostics_only(schools):
     assert parity.rel_err(full.diagnostics, ref, 1e-9) < 1e-9
     assert parity.rel_err(only.diagnostics, ref, 1e-9) < 1e-9
     assert [s.gradientEvaluations for s in only.stats] == [s.gradientEvaluations for s in full.stats]
+
+
+def test_reference_leapfrog_test_standard_normal():
+    """The reference's own LeapFrogTest (rainier-test/.../sampler/LeapFrogTest.scala:60-78): standard normal density,
+    takeSteps(1) at stepSize 1.0, 1000 iterations, seed 123; identity mass: |mean| < 0.2, |var - 1| < 0.2 on the single
+    chain the reference runs; DiagonalMassMatrix(0.1): |mean| < 0.2, |var - 1| < 0.3, here pooled over 64 chains because the
+    batched path always initialises with the identity mass like Driver.sample (Driver.scala:22), so the single-seed
+    realisation differs from LeapFrogTest's lf.initialize(mass)."""
+    from oracle.rainier_py.compute import Real
+    from oracle.rainier_py.core import Model
+    rir, cols = Model.track_(list(Real.parameters(1, lambda t: (t[0] * t[0]) / -2.0))).compile(True)
+    m = api.CudaModel(rir, cols)
+    x = m.sample(_cfg(1000, 0, api.HMCSampler(1), api.StaticStepSize(1.0), api.IdentityMassMatrixTuner()), seeds=[123]).chains[0, :, 0]
+    assert abs(x.mean()) < 0.2 and abs((x ** 2).sum() / (len(x) - 1) - 1.0) < 0.2
+    ref = OracleModel(rir, cols).sample(api.lower_config(_cfg(1000, 0, api.HMCSampler(1), api.StaticStepSize(1.0), api.IdentityMassMatrixTuner()))[0], seeds=[123])
+    assert np.array_equal(x, ref["samples"][0, :, 0])
+    cfg = _cfg(1000, 0, api.HMCSampler(1), api.StaticStepSize(1.0), api.StaticMassMatrix(api.DiagonalMassMatrix([0.1])))
+    y = m.sample(cfg, seeds=np.arange(64) + 123).chains[:, :, 0].reshape(-1)
+    assert abs(y.mean()) < 0.2 and abs((y ** 2).sum() / (len(y) - 1) - 1.0) < 0.3

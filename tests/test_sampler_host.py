@@ -109,3 +109,21 @@ def test_wpc_two_warps_per_chain_on_host():
     cfg = api.make_config(iterations=4, warmupIterations=0, sampler=api.HMCSampler(3), stepSizeTuner=api.StaticStepSize(0.02),
                           massMatrixTuner=api.IdentityMassMatrixTuner())
     _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2", k="2")
+
+
+def _standard_normal_model():
+    from oracle.rainier_py.compute import Real
+    from oracle.rainier_py.core import Model
+    # NormalDensityFunction of the reference's LeapFrogTest: density = x*x / -2.0, gradient = -x
+    return Model.track_(list(Real.parameters(1, lambda t: (t[0] * t[0]) / -2.0)))
+
+
+def test_reference_leapfrog_test_standard_normal_on_host():
+    """rainier-test/.../sampler/LeapFrogTest.scala:60-69 ("standard normal, identity matrix"): ScalaRNG(123), 1000
+    iterations of takeSteps(1) at stepSize 1.0; |mean| < 0.2 and |variance - 1| < 0.2 -- through the emitted + hand-written
+    kernel source on the host, bit-identical to the oracle's run of the same chain."""
+    cfg = _cfg(1000, 0, api.HMCSampler(1), api.StaticStepSize(1.0), api.IdentityMassMatrixTuner())
+    got = _run(_standard_normal_model(), cfg, np.array([123]))
+    x = got["samples"][0, :, 0]
+    assert abs(x.mean()) < 0.2
+    assert abs(((x - 0.0) ** 2).sum() / (len(x) - 1) - 1.0) < 0.2
