@@ -246,11 +246,15 @@ static KernelKey key_for(const rn_model* m, const rn_config* cfg) {
 
 extern "C" const char* rn_version(void);
 // emit + NVRTC (no device needed)
-static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
+// source_only: just emit (rn_emit_source, the analogue of rainier-decompile) -- no NVRTC run, nothing cached
+static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::string* source_only = nullptr) {
   KernelKey key = key_for(m, cfg);
   auto it = m->kernels.find(key);
   if (it != m->kernels.end()) {
-    *out = it->second.get();
+    if (source_only)
+      *source_only = it->second->source;
+    else
+      *out = it->second.get();
     return RN_OK;
   }
   const Program* P = nullptr;
@@ -308,6 +312,10 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out) {
     eo.tma_stages = stages;
   }
   K->source = emit_source(*P, eo);
+  if (source_only) {
+    *source_only = std::move(K->source);
+    return RN_OK;
+  }
 
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
@@ -585,13 +593,13 @@ void rn_model_destroy(rn_model* m) {
 
 int rn_emit_source(rn_model* m, const rn_config* cfg, char* buf, size_t cap, size_t* needed) {
   if (!m) return fail(RN_E_INVALID, "null model");
-  Kernel* K = nullptr;
-  int rc = get_kernel(m, cfg, &K);
+  std::string src;
+  int rc = get_kernel(m, cfg, nullptr, &src);
   if (rc) return rc;
-  if (needed) *needed = K->source.size() + 1;
+  if (needed) *needed = src.size() + 1;
   if (buf && cap) {
-    size_t n = std::min(cap - 1, K->source.size());
-    std::memcpy(buf, K->source.data(), n);
+    size_t n = std::min(cap - 1, src.size());
+    std::memcpy(buf, src.data(), n);
     buf[n] = 0;
   }
   return RN_OK;

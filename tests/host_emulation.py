@@ -122,10 +122,10 @@ extern "C" void emu_density(const double* q, int chains, double* out, const doub
 """
 
 
-def compile_source(src, fast=False):
+def compile_source(src, fast=False, opt="-O1"):
     d = os.path.join(tempfile.gettempdir(), "rn_emul")
     os.makedirs(d, exist_ok=True)
-    key = hashlib.sha1((src + str(fast)).encode()).hexdigest()[:16]
+    key = hashlib.sha1((src + str(fast) + opt).encode()).hexdigest()[:16]
     so = os.path.join(d, key + ".so")
     if not os.path.exists(so):
         cpp = os.path.join(d, key + ".cpp")
@@ -135,16 +135,16 @@ def compile_source(src, fast=False):
                           "    for (int k = 0; k < chains; k++) { blockIdx.x = (unsigned)k; kern(a); }\n")
             launch_wpc = "    for (int k = 0; k < chains; k++) rn_emu_run_warp(k, chains, [&] { kern(a); });\n"
             f.write(src + (_WPC_SHIM if wpc else _SHIM) + _SAMPLER_SHIM.replace("@LAUNCH@", launch_wpc if wpc else launch_tpc))
-        flags = ["-O1", "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w", "-pthread"]
+        flags = [opt, "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w", "-pthread"]
         flags.append("-ffp-contract=fast" if fast else "-ffp-contract=off")
         subprocess.run(["g++"] + flags + [cpp, "-o", so], check=True)
     return C.CDLL(so)
 
 
-def density(src, q, cols, model, fast=False):
+def density(src, q, cols, model, fast=False, opt="-O1"):
     """q: [chains][n] -> [chains][n+1] using the emitted code.  `model`: the CudaModel the source came from (its
     rn_model_pack_columns lays the columns out exactly as rn_model_create uploads them: tile-major per target)."""
-    L = compile_source(src, fast)
+    L = compile_source(src, fast, opt)
     q = np.ascontiguousarray(q, dtype=np.float64)
     chains, n = q.shape
     qt = np.ascontiguousarray(q.T)
