@@ -78,3 +78,16 @@ def test_random_dag(seed):
     assert np.array_equal(np.isfinite(ref[:, 0]), np.isfinite(adj[:, 0]))
     rel = np.abs(adj - ref)[fin] / np.maximum(np.abs(ref[fin]), 1e-6)
     assert rel.size == 0 or rel.max() < 1e-9, rel.max()
+    if streamed:  # the same DAG on the warp-per-chain shape (rows across 32 emulated lanes, tree-ordered sums), both modes
+        import os
+        os.environ["RN_TMA"], os.environ["RN_WPC_K"] = "2", "1"
+        try:
+            for mdl, cc, gm in ((cm, cols, abi.RN_GRAD_SYMBOLIC), (pm, pcols, abi.RN_GRAD_AUTO)):
+                src = mdl.emit_source(api.make_config(sampler=api.HMCSampler(1), gradientMode=gm, backend=abi.RN_BACKEND_WARP))
+                w, err = he.density(src, q[:2], cc, mdl, opt="-O0")
+                assert err == 0
+                f2 = np.isfinite(ref[:2]) & np.isfinite(w)
+                r2 = np.abs(w - ref[:2])[f2] / np.maximum(np.abs(ref[:2][f2]), 1e-6)
+                assert r2.size == 0 or r2.max() < 1e-9, r2.max()
+        finally:
+            del os.environ["RN_TMA"], os.environ["RN_WPC_K"]
