@@ -219,6 +219,40 @@ int rn_comm_unique_id(char id[128]);
 int rn_comm_create(const char id[128], int rank, int world, int device, rn_comm** out);
 void rn_comm_destroy(rn_comm* c);
 
+/* ---- compiled functions: posterior-predictive "requirements"  ------------------------------ */
+/* rn_function_create   <- Compiler.compile(inputs: Seq[ir.Param], outputs: Seq[(String, Real)]): ir.CompiledFunction
+ *                         rainier-compute/.../compute/Compiler.scala:22-30, as called by Generator.prepare
+ *                         (rainier-core/.../core/Generator.scala:59-94) for Trace.predict (core/Trace.scala:34-41)
+ * rn_function_eval*    <- the `0.until(cf.numOutputs).foreach(i => reqValues(i) = CompiledFunction.output(cf, array,
+ *                         globalBuf, i))` loop of Generator.scala:80-84 (ir/CompiledFunction.scala:122-140), for ALL
+ *                         posterior draws in one launch instead of once per draw
+ * rir: a RIR_FLAG_FUNCTION container (rainier_rir.h): n inputs (the model's parameters), m outputs (the generator's
+ * requirements, at most Generator.MaxRequirements = 500).  math_mode: RN_MATH_PARITY | RN_MATH_FAST.  device -1:
+ * emit/compile only.  The Scala side keeps Generator.get (the RNG-consuming closure) and feeds it the values. */
+typedef struct rn_function rn_function;
+enum { RN_LAYOUT_SAMPLER = 0, RN_LAYOUT_ROWS = 1 };
+int rn_function_create(const void* rir, size_t len, int device, int math_mode, rn_function** out);
+int rn_function_ninputs(const rn_function* f);
+int rn_function_noutputs(const rn_function* f);
+/* host buffers: x [count][n] -> out [count][m]; blocking.  RN_E_LOOKUP when a lookup index left its table. */
+int rn_function_eval(rn_function* f, const double* x, int64_t count, double* out);
+/* device-resident draws, asynchronous on `stream` (NULL: the function's own stream, rn_function_stream):
+ *   RN_LAYOUT_SAMPLER: d_x [iterations][n][chains] exactly as rn_sampler_run wrote it -> d_out [chains][iterations][m]
+ *                      (the order of Trace.predict: chains.flatMap(_.map(fn)))
+ *   RN_LAYOUT_ROWS   : d_x [iterations*chains][n] -> d_out [iterations*chains][m]
+ * rn_function_sync waits for the function's own stream and reports lookup errors of the evaluations since the last sync. */
+int rn_function_eval_device(rn_function* f, const double* d_x, int layout, int64_t iterations, int64_t chains, double* d_out,
+                            void* stream);
+int rn_function_sync(rn_function* f);
+void* rn_function_stream(rn_function* f);
+int64_t rn_function_launches(const rn_function* f);
+/* debug: emitted CUDA source / compiled cubin (as rn_emit_source / rn_emit_cubin); static fp64 op counts of one point:
+ * out = [adds+multiplies+compares, transcendental and division-class calls] */
+int rn_function_emit_source(rn_function* f, char* buf, size_t cap, size_t* needed);
+int rn_function_emit_cubin(rn_function* f, void* buf, size_t cap, size_t* needed);
+int rn_function_op_counts(const rn_function* f, double out[2]);
+void rn_function_destroy(rn_function* f);
+
 const char* rn_last_error(void);
 const char* rn_version(void);
 

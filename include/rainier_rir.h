@@ -44,6 +44,13 @@ extern "C" {
 #define RIR_VERSION 1u
 
 #define RIR_FLAG_GRADIENT 1u
+/* RIR_FLAG_FUNCTION: the container is the hand-off of the OTHER compile seam, `Compiler.compile(inputs: Seq[ir.Param],
+ * outputs: Seq[(String, Real)]): ir.CompiledFunction` (compute/Compiler.scala:22-30) as Generator.prepare uses it for the
+ * "requirements" of a posterior-predictive generator (core/Generator.scala:59-94, called from Trace.predict,
+ * core/Trace.scala:34-41): n_inputs == n_params (parameters only, no columns), n_targets == 1 with n_rows == 0,
+ * n_cols == 0 and n_outputs == m >= 1 arbitrary output nodes ("req0".."req{m-1}").  No gradient, no accumulation:
+ * output j of a point is the value of node outputs[j].  Consumed by rn_function_create (rainier_cuda.h). */
+#define RIR_FLAG_FUNCTION 2u
 
 /* node kinds */
 enum {

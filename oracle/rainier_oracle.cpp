@@ -1142,6 +1142,61 @@ int rno_sample(rno_model* mm, const rn_config* cfg, const int64_t* seeds, int ch
   return rno_sample_traced(mm, cfg, seeds, chains, samples, mass, stats, nullptr);
 }
 
+/* ---- compiled functions: Compiler.compile(inputs, outputs) (C/Compiler.scala:22-30) evaluated the way
+ * Generator.prepare does per posterior draw (K/Generator.scala:76-93): reqValues(i) = CompiledFunction.output(cf, array,
+ * globalBuf, i) for i = 0 until numOutputs, in that order (IR/CompiledFunction.scala:122-140).  The flat SSA array is
+ * evaluated in definition order, which is the order the generated output methods define their VarDefs in. ---- */
+struct rno_function {
+  Model m;
+  std::vector<int32_t> needed; /* nodes some output reaches, ascending */
+};
+
+int rno_function_create(const void* rir, size_t len, int /*device*/, int /*math_mode*/, rno_function** out) {
+  std::unique_ptr<rno_function> f(new rno_function());
+  int rc = parse_rir(rir, len, f->m);
+  if (rc) return rc;
+  const Model& m = f->m;
+  if (!(m.h.flags & RIR_FLAG_FUNCTION)) return fail(RN_E_INVALID, "RIR: not a function container");
+  if (m.h.n_inputs != m.h.n_params || m.targets.size() != 1 || m.targets[0].n_rows != 0 || m.targets[0].n_cols != 0 ||
+      m.targets[0].outputs.empty())
+    return fail(RN_E_INVALID, "RIR: malformed function container");
+  std::vector<char> need(m.h.n_nodes, 0);
+  for (uint32_t o : m.targets[0].outputs) need[o] = 1;
+  for (int i = (int)m.h.n_nodes - 1; i >= 0; i--) {
+    if (!need[i]) continue;
+    const rir_node& nd = m.nodes[i];
+    switch (nd.kind) {
+      case RIR_UNARY: need[nd.a] = 1; break;
+      case RIR_BINARY: need[nd.a] = need[nd.b] = 1; break;
+      case RIR_LOOKUP:
+        need[nd.a] = 1;
+        for (int k = 0; k < nd.c; k++) need[m.lookup_refs[nd.b + k]] = 1;
+        break;
+      default: break;
+    }
+  }
+  for (uint32_t i = 0; i < m.h.n_nodes; i++)
+    if (need[i]) f->needed.push_back((int32_t)i);
+  *out = f.release();
+  return RN_OK;
+}
+int rno_function_ninputs(const rno_function* f) { return (int)f->m.h.n_params; }
+int rno_function_noutputs(const rno_function* f) { return (int)f->m.targets[0].outputs.size(); }
+void rno_function_destroy(rno_function* f) { delete f; }
+
+/* x: [count][n] -> out: [count][m] */
+int rno_function_eval(rno_function* f, const double* x, int64_t count, double* out) {
+  const Model& m = f->m;
+  RirDensity d(m); /* reused for its node interpreter (op semantics of IR/MethodGenerator.scala) */
+  const size_t n = m.h.n_params, mo = m.targets[0].outputs.size();
+  for (int64_t p = 0; p < count; p++) {
+    if (n) std::memcpy(d.inputs.data(), x + (size_t)p * n, n * sizeof(double));
+    for (int32_t i : f->needed) d.eval_node(i);
+    for (size_t j = 0; j < mo; j++) out[(size_t)p * mo + j] = d.vals[m.targets[0].outputs[j]];
+  }
+  return d.lookup_error ? fail(RN_E_LOOKUP, "lookup index out of range") : RN_OK;
+}
+
 /* ---- java.util.Random exposed for test/bench data synthesis (so a Scala harness can reproduce inputs) ---- */
 void rno_jr_seed(rn_rng_state* st, int64_t seed) {
   JRandom r(seed);

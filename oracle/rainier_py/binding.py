@@ -39,6 +39,11 @@ def lib():
         L.rno_sample_traced.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
         L.rno_config_default.argtypes = [C.POINTER(Config)]
+        L.rno_function_create.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rno_function_ninputs.argtypes = [C.c_void_p]
+        L.rno_function_noutputs.argtypes = [C.c_void_p]
+        L.rno_function_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.rno_function_destroy.argtypes = [C.c_void_p]
         L.rno_jr_seed.argtypes = [C.POINTER(RngState), C.c_int64]
         L.rno_jr_doubles.argtypes = [C.POINTER(RngState), C.c_void_p, C.c_int64]
         L.rno_jr_gaussians.argtypes = [C.POINTER(RngState), C.c_void_p, C.c_int64]
@@ -180,3 +185,30 @@ class OracleModel:
         if rc != 0:
             raise OracleError(L.rno_last_error().decode())
         return {"samples": samples, "mass": mass, "stats": stats, "trace": tr}
+
+
+class OracleFunction:
+    """rno_function_*: Compiler.compile(inputs, outputs) + the CompiledFunction.output loop of Generator.prepare."""
+
+    def __init__(self, rir):
+        L = lib()
+        self._rir = bytes(rir)
+        h = C.c_void_p()
+        if L.rno_function_create(self._rir, len(self._rir), 0, 0, C.byref(h)) != 0:
+            raise OracleError(L.rno_last_error().decode())
+        self.h = h
+        self.nInputs = L.rno_function_ninputs(h)
+        self.nOutputs = L.rno_function_noutputs(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().rno_function_destroy(self.h)
+            self.h = None
+
+    def __call__(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, max(self.nInputs, 1))[:, : self.nInputs]
+        x = np.ascontiguousarray(x)
+        out = np.empty((x.shape[0], self.nOutputs), dtype=np.float64)
+        if lib().rno_function_eval(self.h, x.ctypes.data, x.shape[0], out.ctypes.data) != 0:
+            raise OracleError(lib().rno_last_error().decode())
+        return out

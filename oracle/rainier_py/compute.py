@@ -1846,6 +1846,33 @@ def compile_rir(group):
     return bytes(blob), cols
 
 
+RIR_FLAG_FUNCTION = 2
+
+
+def compile_function_rir(parameters, outputs):
+    """Compiler.compile(inputs: Seq[ir.Param], outputs: Seq[(String, Real)]) (C/Compiler.scala:22-30) with the bytecode
+    emitter replaced by RIR serialisation (RIR_FLAG_FUNCTION container, include/rainier_rir.h).  parameters: the model's
+    Parameter list (input order); outputs: list of Real -- one Translator over all of them, in order, exactly like the
+    `outputs.map { case (s, r) => s -> translator.toExpr(r) }` of :25-28."""
+    n = len(parameters)
+    input_index = {p.param_id: i for i, p in enumerate(parameters)}
+    tr = Translator(input_index)
+    ids = []
+    for r in outputs:
+        e = tr.toExpr(to_real(r))
+        ids.append(tr.node_id(e))
+    blob = bytearray()
+    blob += struct.pack("<8I", 0x31524952, 1, n, n, len(tr.nodes), 1, len(tr.lookup_refs), RIR_FLAG_FUNCTION)
+    for (kind, op, a, b, c, d, value) in tr.nodes:
+        blob += struct.pack("<BBHiiiiid", kind, op, 0, a, b, c, d, 0, value)
+    lr = struct.pack("<%di" % len(tr.lookup_refs), *tr.lookup_refs)
+    blob += lr + b"\0" * ((-len(lr)) % 8)
+    blob += struct.pack("<QIIII", 0, n, 0, len(ids), 0)
+    ob = struct.pack("<%dI" % len(ids), *ids)
+    blob += ob + b"\0" * ((-len(ob)) % 8)
+    return bytes(blob)
+
+
 # ------------------------------------------------------------------------------------------------------
 # Evaluator  (C/Evaluator.scala)
 # ------------------------------------------------------------------------------------------------------

@@ -17,8 +17,8 @@ import math
 
 import numpy as np
 
-from .compute import (Bounds, Column, Evaluator, Real, Scalar, TargetGroup, Vec, compile_rir, jd2i, jexp, jlog, jpow,
-                      to_real)
+from .compute import (Bounds, Column, Evaluator, Real, Scalar, TargetGroup, Vec, compile_function_rir, compile_rir, jd2i,
+                      jexp, jlog, jpow, to_real)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -75,6 +75,52 @@ class Generator:
             return Generator(self.requirements, fn=lambda r, n: [u for _ in range(n.toInt(k))])
         fromFn = self.fn
         return Generator(self.requirements, fn=lambda r, n: [fromFn(r, n) for _ in range(n.toInt(k))])
+
+    MaxRequirements = 500  # :101
+
+    def reqs(self):
+        """requirements.toList.take(Generator.MaxRequirements) (:61): `requirements` is a Set[Real] -- duplicates
+        collapse; the hash order of a Scala Set with more than 4 elements is resolved to insertion order here."""
+        seen, out = set(), []
+        for r in self.requirements:
+            r = to_real(r)
+            if r not in seen:
+                seen.add(r)
+                out.append(r)
+        return out[: Generator.MaxRequirements]
+
+    def prepare(self, parameters, rng, make_function):  # :59-94
+        """Returns fn(array) like the reference.  make_function(rir_bytes) -> callable([count][n] -> [count][m]) stands
+        for `Compiler.default.compile(parameters.map(_.param), namedReqs)` + the CompiledFunction.output loop: the CPU
+        oracle's OracleFunction or the CUDA path's CudaFunction."""
+        reqs = self.reqs()
+        if not reqs:
+            return lambda array: self.get(rng, Evaluator({p: float(v) for p, v in zip(parameters, array)}))
+        cf = make_function(compile_function_rir(parameters, reqs))
+
+        def fn(array):
+            reqValues = cf(np.asarray(array, dtype=np.float64)[None, :])[0]
+            cache = {p: float(v) for p, v in zip(parameters, array)}
+            cache.update({r: float(v) for r, v in zip(reqs, reqValues)})
+            return self.get(rng, Evaluator(cache))
+
+        return fn
+
+    def predict(self, parameters, draws, rng, make_function):
+        """Trace.predict (K/Trace.scala:34-41) over draws [count][n] given in predict's order (chain-major): the batched
+        form of prepare -- ALL draws' requirement values come from one call of the compiled function, then Generator.get
+        runs per draw on the host exactly as in the reference (same RNG consumption order)."""
+        draws = np.asarray(draws, dtype=np.float64)
+        reqs = self.reqs()
+        if not reqs:
+            return [self.get(rng, Evaluator({p: float(v) for p, v in zip(parameters, a)})) for a in draws]
+        values = make_function(compile_function_rir(parameters, reqs))(draws)
+        out = []
+        for a, rv in zip(draws, values):
+            cache = {p: float(v) for p, v in zip(parameters, a)}
+            cache.update({r: float(v) for r, v in zip(reqs, rv)})
+            out.append(self.get(rng, Evaluator(cache)))
+        return out
 
     # companion
     @staticmethod

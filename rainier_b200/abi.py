@@ -15,6 +15,7 @@ RN_ADAPT_PER_CHAIN, RN_ADAPT_POOLED = 0, 1
 RN_MATH_PARITY, RN_MATH_FAST = 0, 1
 RN_GRAD_AUTO, RN_GRAD_SYMBOLIC, RN_GRAD_ADJOINT = 0, 1, 2
 RN_BACKEND_AUTO, RN_BACKEND_THREAD, RN_BACKEND_WARP = 0, 1, 2
+RN_LAYOUT_SAMPLER, RN_LAYOUT_ROWS = 0, 1
 
 
 class RngState(C.Structure):

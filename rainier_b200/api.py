@@ -81,6 +81,20 @@ def lib():
         L.rn_host_free.argtypes = [C.c_int, C.c_void_p]
         L.rn_host_register.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
         L.rn_host_unregister.argtypes = [C.c_int, C.c_void_p]
+        L.rn_function_create.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rn_function_ninputs.argtypes = [C.c_void_p]
+        L.rn_function_noutputs.argtypes = [C.c_void_p]
+        L.rn_function_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.rn_function_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        L.rn_function_sync.argtypes = [C.c_void_p]
+        L.rn_function_stream.argtypes = [C.c_void_p]
+        L.rn_function_stream.restype = C.c_void_p
+        L.rn_function_launches.argtypes = [C.c_void_p]
+        L.rn_function_launches.restype = C.c_int64
+        L.rn_function_emit_source.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rn_function_emit_cubin.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rn_function_op_counts.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.rn_function_destroy.argtypes = [C.c_void_p]
         sizes = (C.c_int32 * 4)()
         L.rn_abi_sizes(sizes)
         if sizes[0] != C.sizeof(Config) or sizes[1] != C.sizeof(ChainStats) or sizes[2] != C.sizeof(RngState):
@@ -325,6 +339,86 @@ class Trace:
 
     def __init__(self, chains, mass, stats):
         self.chains, self.mass, self.stats = chains, mass, stats
+
+    def requirements(self, function):
+        """The device half of Trace.predict (core/Trace.scala:34-41): the values of a generator's requirements
+        (Generator.prepare, core/Generator.scala:76-84) for every draw, in predict's order (chain-major), evaluated by
+        one rn_function_eval call.  function: CudaFunction compiled from the requirements.  Returns
+        [chains*iterations][m]; the host side applies Generator.get to each row."""
+        c = np.ascontiguousarray(self.chains, dtype=np.float64)
+        return function(c.reshape(-1, c.shape[-1]))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# compiled functions (posterior-predictive requirements)
+# ----------------------------------------------------------------------------------------------------------
+class CudaFunction:
+    """Replaces Compiler.compile(inputs, outputs): CompiledFunction (compute/Compiler.scala:22-30) as Generator.prepare
+    uses it (core/Generator.scala:59-94): RIR_FLAG_FUNCTION container -> emitted rn_function() + rn_k_eval, evaluated
+    for all posterior draws at once."""
+
+    def __init__(self, rir, device=0, fast=False):
+        L = lib()
+        self._rir = bytes(rir)
+        h = C.c_void_p()
+        _check(L.rn_function_create(self._rir, len(self._rir), int(device), abi.RN_MATH_FAST if fast else abi.RN_MATH_PARITY,
+                                    C.byref(h)))
+        self.h = h
+        self.nInputs = L.rn_function_ninputs(h)
+        self.nOutputs = L.rn_function_noutputs(h)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rn_function_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, x):
+        """x: [count][nInputs] host array -> [count][nOutputs]"""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, max(self.nInputs, 1))[:, : self.nInputs]
+        x = np.ascontiguousarray(x)
+        out = np.empty((x.shape[0], self.nOutputs), dtype=np.float64)
+        _check(lib().rn_function_eval(self.h, x.ctypes.data, x.shape[0], out.ctypes.data))
+        return out
+
+    def eval_device(self, d_x, iterations, chains, d_out, layout=abi.RN_LAYOUT_SAMPLER, stream=None):
+        """device pointers (ints); asynchronous -- call sync() before reading d_out"""
+        _check(lib().rn_function_eval_device(self.h, C.c_void_p(d_x), layout, iterations, chains, C.c_void_p(d_out),
+                                             C.c_void_p(stream) if stream else None))
+
+    def sync(self):
+        _check(lib().rn_function_sync(self.h))
+
+    def stream(self):
+        return lib().rn_function_stream(self.h)
+
+    def launches(self):
+        return lib().rn_function_launches(self.h)
+
+    def emit_source(self):
+        need = C.c_size_t()
+        _check(lib().rn_function_emit_source(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().rn_function_emit_source(self.h, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
+    def emit_cubin(self):
+        need = C.c_size_t()
+        _check(lib().rn_function_emit_cubin(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().rn_function_emit_cubin(self.h, buf, need.value, C.byref(need)))
+        return buf.raw
+
+    def op_counts(self):
+        out = (C.c_double * 2)()
+        _check(lib().rn_function_op_counts(self.h, out))
+        return {"flops": out[0], "special": out[1]}
 
 
 # ----------------------------------------------------------------------------------------------------------

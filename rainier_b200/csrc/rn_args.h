@@ -56,4 +56,14 @@ struct RnArgs {
   int pad1;
 };
 
+// argument block of rn_k_eval (rn_function.cuh): batched evaluation of a compiled function, generic addressing
+struct RnEvalArgs {
+  const double* x;
+  double* out;
+  long long count;
+  long long in_inner, in_outer, in_pstride, in_estride;
+  long long out_inner, out_outer, out_pstride, out_estride;
+  int* err;  // bit 0: a lookup index fell outside its table at some point
+};
+
 #endif

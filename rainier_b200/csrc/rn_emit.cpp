@@ -16,6 +16,7 @@ namespace rn {
 extern const char* kPreludeSource;  // rn_prelude.cuh, embedded at build time
 extern const char* kSamplerSource;     // rn_args.h + rn_sampler.cuh
 extern const char* kSamplerWpcSource;  // rn_args.h + rn_sampler_wpc.cuh
+extern const char* kFunctionSource;    // rn_function.cuh
 
 namespace {
 
@@ -396,6 +397,32 @@ struct Emitter {
     os << "}\n";
   }
 
+  // Function flavour: forward evaluation of the m outputs of Compiler.compile(inputs, outputs).  An output is stored as
+  // soon as its node is defined (500 requirements -- Generator.MaxRequirements -- must not stay live to the end).
+  void function_tpc() {
+    os << "// ---- emitted: the " << P.fn_outputs.size() << " outputs of the compiled function (forward only) ----\n";
+    lookup_helpers();
+    os << "RN_DEVICE void rn_function(const double (&q)[RN_NQ], double* RN_RESTRICT out, const long long os, int& err) {\n";
+    os << "  (void)q; (void)err;\n";
+    std::map<int, std::vector<int>> out_at;
+    std::vector<int> tail;
+    for (size_t j = 0; j < P.fn_outputs.size(); j++) {
+      const Node& n = P.nodes[P.fn_outputs[j]];
+      if (n.kind == K_CONST || n.kind == K_INPUT)
+        tail.push_back((int)j);
+      else
+        out_at[P.fn_outputs[j]].push_back((int)j);
+    }
+    for (int id : P.inv_fwd) {
+      stmt(id, "  ");
+      auto it = out_at.find(id);
+      if (it != out_at.end())
+        for (int j : it->second) os << "  out[" << j << "LL * os] = " << val(id) << ";\n";
+    }
+    for (int j : tail) os << "  out[" << j << "LL * os] = " << val(P.fn_outputs[j]) << ";\n";
+    os << "}\n";
+  }
+
   void density_wpc() {
     wpc = true;
     // which accumulator slots live in shared memory (targets of a scatter) and which in registers
@@ -544,6 +571,21 @@ WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
     if (T.streamed() && T.n_rows >= 32ull * (uint64_t)std::max(1, opt.wpc_k))
       z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * 32 * std::max(1, opt.wpc_k));
   return z;
+}
+
+std::string emit_function_source(const Program& P, const EmitOptions& opt) {
+  std::ostringstream os;
+  os << "// generated by rainier_b200 (CUDA source emitter, function flavour) -- do not edit\n";
+  os << "#define RN_N " << P.n_params << "\n";
+  os << "#define RN_NQ " << std::max<uint32_t>(1, P.n_params) << "\n";
+  os << "#define RN_M " << P.fn_outputs.size() << "\n";
+  os << "#define RN_BACKEND 0\n";
+  if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
+  os << kPreludeSource << "\n";
+  Emitter E(P, opt);
+  E.function_tpc();
+  os << E.os.str() << "\n" << kFunctionSource << "\n";
+  return os.str();
 }
 
 std::string emit_source(const Program& P, const EmitOptions& opt) {

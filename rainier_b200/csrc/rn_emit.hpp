@@ -22,6 +22,9 @@ struct EmitOptions {
 std::string emit_density(const Program& P, const EmitOptions& opt);
 // full translation unit
 std::string emit_source(const Program& P, const EmitOptions& opt);
+// function flavour (Program from build_function): prelude + emitted rn_function() + rn_function.cuh (rn_k_eval); only
+// opt.fast_math is read
+std::string emit_function_source(const Program& P, const EmitOptions& opt);
 // shared-memory needs of the warp-per-chain kernels: doubles per warp (chain vectors + density scratch) and doubles of
 // the largest data tile (n_cols * 32 over the streamed targets; 0 when nothing is streamed)
 struct WpcSizes {

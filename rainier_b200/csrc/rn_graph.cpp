@@ -500,4 +500,103 @@ std::string build_program(const void* rir, size_t len, bool want_adjoint, bool f
   return "";
 }
 
+std::string build_function(const void* rir, size_t len, Program& P) {
+  const uint8_t* p = (const uint8_t*)rir;
+  const uint8_t* end = p + len;
+  rir_header h;
+  if (len < sizeof(h)) return "RIR: truncated header";
+  std::memcpy(&h, p, sizeof(h));
+  p += sizeof(h);
+  if (h.magic != RIR_MAGIC) return "RIR: bad magic";
+  if (h.version != RIR_VERSION) return "RIR: unsupported version";
+  if (!(h.flags & RIR_FLAG_FUNCTION)) return "RIR: not a function container (RIR_FLAG_FUNCTION clear)";
+  if (h.n_inputs != h.n_params) return "RIR: a function container has no column inputs";
+  if (h.n_targets != 1) return "RIR: a function container carries exactly one output list";
+  if ((size_t)(end - p) < (size_t)h.n_nodes * sizeof(rir_node)) return "RIR: truncated node array";
+  P = Program();
+  P.n_params = h.n_params;
+  P.n_inputs = h.n_inputs;
+  P.symbolic = true;
+  std::vector<rir_node> raw(h.n_nodes);
+  if (h.n_nodes) std::memcpy(raw.data(), p, (size_t)h.n_nodes * sizeof(rir_node));
+  p += (size_t)h.n_nodes * sizeof(rir_node);
+  const size_t lrb = ((size_t)h.n_lookup_refs * 4 + 7) & ~(size_t)7;
+  if ((size_t)(end - p) < lrb) return "RIR: truncated lookup refs";
+  P.lookup_refs.resize(h.n_lookup_refs);
+  if (h.n_lookup_refs) std::memcpy(P.lookup_refs.data(), p, (size_t)h.n_lookup_refs * 4);
+  p += lrb;
+  rir_target rt;
+  if ((size_t)(end - p) < sizeof(rt)) return "RIR: truncated target";
+  std::memcpy(&rt, p, sizeof(rt));
+  p += sizeof(rt);
+  if (rt.n_rows != 0 || rt.n_cols != 0) return "RIR: a function container streams no rows";
+  if (rt.n_outputs == 0) return "RIR: function without outputs";
+  if ((size_t)(end - p) < (((size_t)rt.n_outputs * 4 + 7) & ~(size_t)7)) return "RIR: truncated outputs";
+  std::vector<uint32_t> outs(rt.n_outputs);
+  std::memcpy(outs.data(), p, (size_t)rt.n_outputs * 4);
+  for (uint32_t o : outs) {
+    if (o >= h.n_nodes) return "RIR: output id out of range";
+    P.fn_outputs.push_back((int32_t)o);
+  }
+  P.nodes.resize(h.n_nodes);
+  for (uint32_t i = 0; i < h.n_nodes; i++) {
+    const rir_node& r = raw[i];
+    auto ok = [&](int32_t x) { return x >= 0 && (uint32_t)x < i; };
+    switch (r.kind) {
+      case RIR_INPUT:
+        if (r.a < 0 || (uint32_t)r.a >= h.n_inputs) return "RIR: input index out of range";
+        break;
+      case RIR_CONST: break;
+      case RIR_UNARY:
+        if (r.op > RIR_U_ATAN) return "RIR: unknown unary op";
+        if (!ok(r.a)) return "RIR: unary operand not defined before use";
+        break;
+      case RIR_BINARY:
+        if (r.op > RIR_B_COMPARE) return "RIR: unknown binary op";
+        if (!ok(r.a) || !ok(r.b)) return "RIR: binary operand not defined before use";
+        break;
+      case RIR_LOOKUP:
+        if (!ok(r.a) || r.b < 0 || r.c <= 0 || (uint32_t)(r.b + r.c) > h.n_lookup_refs) return "RIR: bad lookup";
+        for (int k = 0; k < r.c; k++)
+          if (!ok(P.lookup_refs[r.b + k])) return "RIR: lookup ref not defined before use";
+        P.has_lookup = true;
+        break;
+      default: return "RIR: unknown node kind";
+    }
+    Node& n = P.nodes[i];
+    n.kind = r.kind;
+    n.op = r.op;
+    n.region = R_INV_FWD;
+    n.target = -1;
+    n.a = r.a;
+    n.b = r.b;
+    n.c = r.c;
+    n.d = r.d;
+    n.value = r.value;
+  }
+  // only what some output needs is evaluated (the generated outputN methods evaluate their own expression tree only,
+  // ir/OutputMethodGenerator.scala:3-21); shared VarDefs are computed once, like the reference's globals
+  std::vector<char> need(h.n_nodes, 0);
+  for (int32_t o : P.fn_outputs) need[o] = 1;
+  for (int i = (int)h.n_nodes - 1; i >= 0; i--) {
+    if (!need[i]) continue;
+    const Node& n = P.nodes[i];
+    switch (n.kind) {
+      case K_UNARY: need[n.a] = 1; break;
+      case K_BINARY: need[n.a] = need[n.b] = 1; break;
+      case K_LOOKUP:
+        need[n.a] = 1;
+        for (int k = 0; k < n.c; k++) need[P.lookup_refs[n.b + k]] = 1;
+        break;
+      default: break;
+    }
+  }
+  for (uint32_t i = 0; i < h.n_nodes; i++)
+    if (need[i]) {
+      P.inv_fwd.push_back((int32_t)i);
+      count_node(P.nodes[i], P.counts.flops_inv, P.counts.special_inv);
+    }
+  return "";
+}
+
 }  // namespace rn

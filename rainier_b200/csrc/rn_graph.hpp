@@ -85,6 +85,9 @@ struct Program {
   std::vector<int32_t> grad_nodes;
   std::vector<uint8_t> slot_row_accumulated;  // slot receives per-row contributions (needs cross-lane reduce)
   bool has_lookup = false;                    // any K_LOOKUP / K_SELEQ / scatter (error flag needed)
+  // function flavour (RIR_FLAG_FUNCTION, build_function): the m output nodes of Compiler.compile(inputs, outputs);
+  // every needed node sits in inv_fwd, there are no targets, slots or gradients
+  std::vector<int32_t> fn_outputs;
   // static op counts per gradient evaluation (for the roofline): fp64 adds/muls/fmas are counted
   // as flops, transcendental calls separately.
   struct Counts {
@@ -95,5 +98,11 @@ struct Program {
 
 // returns empty string on success, else an error message
 std::string build_program(const void* rir, size_t len, bool want_adjoint, bool fast_math, Program& out);
+
+// RIR_FLAG_FUNCTION containers: Compiler.compile(inputs, outputs): CompiledFunction (compute/Compiler.scala:22-30) --
+// m named outputs over n_params inputs, forward evaluation only (Generator.prepare's "requirements",
+// core/Generator.scala:59-94).  Fills nodes / lookup_refs / inv_fwd (nodes some output needs, topological) /
+// fn_outputs / counts.flops_inv, special_inv.
+std::string build_function(const void* rir, size_t len, Program& out);
 
 }  // namespace rn

@@ -1892,3 +1892,248 @@ void rn_comm_destroy(rn_comm* c) {
   delete c;
 }
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// rn_function: the OTHER compile seam -- Compiler.compile(inputs, outputs): ir.CompiledFunction
+// (rainier-compute/.../compute/Compiler.scala:22-30) -- batched over posterior draws.  Generator.prepare
+// (rainier-core/.../core/Generator.scala:59-94) compiles a generator's "requirements" with it and Trace.predict
+// (core/Trace.scala:34-41) evaluates them once per draw through CompiledFunction.output; here one launch of rn_k_eval
+// (rn_function.cuh) evaluates all m requirements of all draws, reading the draws where rn_sampler_run left them.
+// ---------------------------------------------------------------------------------------------------------
+struct rn_function {
+  std::vector<uint8_t> rir;
+  Program prog;
+  bool fast = false;
+  int device = -1;
+  CUcontext ctx = nullptr;
+  std::string source;
+  std::vector<char> cubin;
+  CUmodule mod = nullptr;
+  CUfunction k_eval = nullptr;
+  CUstream stream = nullptr;
+  CUdeviceptr d_err = 0;
+  CUdeviceptr scratch = 0;  // grow-only staging of rn_function_eval (host buffers)
+  size_t scratch_bytes = 0;
+  int sm_count = 148;
+  int64_t launches = 0;
+};
+
+static int function_compile(rn_function* f) {
+  if (!f->cubin.empty()) return RN_OK;
+  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+  opts.push_back(f->fast ? "--fmad=true" : "--fmad=false");
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, f->source.c_str(), "rainier_function.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    return fail(RN_E_COMPILE, "nvrtcCreateProgram failed");
+  nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    return fail(RN_E_COMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log);
+  }
+  size_t n = 0;
+  nvrtcGetCUBINSize(prog, &n);
+  f->cubin.resize(n);
+  nvrtcGetCUBIN(prog, f->cubin.data());
+  nvrtcDestroyProgram(&prog);
+  return RN_OK;
+}
+
+static int function_load(const Api* A, rn_function* f) {
+  CU(A->cuCtxSetCurrent(f->ctx));
+  if (f->mod) return RN_OK;
+  int rc = function_compile(f);
+  if (rc) return rc;
+  CU(A->cuModuleLoadData(&f->mod, f->cubin.data()));
+  CU(A->cuModuleGetFunction(&f->k_eval, f->mod, "rn_k_eval"));
+  CU(A->cuStreamCreate(&f->stream, 1 /*CU_STREAM_NON_BLOCKING*/));
+  CU(A->cuMemAlloc(&f->d_err, 8));
+  CU(A->cuMemsetD8Async(f->d_err, 0, 8, f->stream));
+  CUdevice dev;
+  int sms = 0;
+  if (A->cuDeviceGet(&dev, f->device) == 0 && A->cuDeviceGetAttribute(&sms, 16 /*MULTIPROCESSOR_COUNT*/, dev) == 0 && sms > 0)
+    f->sm_count = sms;
+  return RN_OK;
+}
+
+// one launch; grid = a multiple of the SM count (grid-stride loop), 128 threads per CTA
+static int function_launch(const Api* A, rn_function* f, const RnEvalArgs& args, CUstream st) {
+  RnEvalArgs a = args;
+  a.err = (int*)(uintptr_t)f->d_err;
+  const long long ctas_needed = (a.count + 127) / 128;
+  const long long cap = (long long)f->sm_count * 16;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min(ctas_needed, cap));
+  void* params[] = {&a};
+  CU(A->cuLaunchKernel(f->k_eval, grid, 1, 1, 128, 1, 1, 0, st, params, nullptr));
+  f->launches++;
+  return RN_OK;
+}
+
+extern "C" {
+
+int rn_function_create(const void* rir, size_t len, int device, int math_mode, rn_function** out) {
+  if (!rir || !out) return fail(RN_E_INVALID, "null argument");
+  std::unique_ptr<rn_function> f(new rn_function());
+  f->rir.assign((const uint8_t*)rir, (const uint8_t*)rir + len);
+  std::string e = build_function(rir, len, f->prog);
+  if (!e.empty()) return fail(RN_E_INVALID, e);
+  f->fast = math_mode == RN_MATH_FAST;
+  EmitOptions eo;
+  eo.fast_math = f->fast;
+  f->source = emit_function_source(f->prog, eo);
+  f->device = device;
+  if (device >= 0) {
+    std::string why;
+    const Api* A = api(&why);
+    if (!A) return fail(RN_E_CUDA, why);
+    int rc = host_ctx(A, device);
+    if (rc) return rc;
+    CUdevice dev;
+    CU(A->cuDeviceGet(&dev, device));
+    CU(A->cuDevicePrimaryCtxRetain(&f->ctx, dev));
+  }
+  *out = f.release();
+  return RN_OK;
+}
+
+int rn_function_ninputs(const rn_function* f) { return f ? (int)f->prog.n_params : RN_E_INVALID; }
+int rn_function_noutputs(const rn_function* f) { return f ? (int)f->prog.fn_outputs.size() : RN_E_INVALID; }
+int64_t rn_function_launches(const rn_function* f) { return f ? f->launches : 0; }
+void* rn_function_stream(rn_function* f) { return f ? (void*)f->stream : nullptr; }
+
+int rn_function_emit_source(rn_function* f, char* buf, size_t cap, size_t* needed) {
+  if (!f) return fail(RN_E_INVALID, "null function");
+  if (needed) *needed = f->source.size() + 1;
+  if (buf && cap) {
+    size_t n = std::min(cap - 1, f->source.size());
+    std::memcpy(buf, f->source.data(), n);
+    buf[n] = 0;
+  }
+  return RN_OK;
+}
+
+int rn_function_emit_cubin(rn_function* f, void* buf, size_t cap, size_t* needed) {
+  if (!f) return fail(RN_E_INVALID, "null function");
+  int rc = function_compile(f);
+  if (rc) return rc;
+  if (needed) *needed = f->cubin.size();
+  if (buf && cap) std::memcpy(buf, f->cubin.data(), std::min(cap, f->cubin.size()));
+  return RN_OK;
+}
+
+// op counts of one point: out = [fp64 flops, transcendental calls]
+int rn_function_op_counts(const rn_function* f, double out[2]) {
+  if (!f || !out) return fail(RN_E_INVALID, "null argument");
+  out[0] = f->prog.counts.flops_inv;
+  out[1] = f->prog.counts.special_inv;
+  return RN_OK;
+}
+
+int rn_function_eval_device(rn_function* f, const double* d_x, int layout, int64_t iterations, int64_t chains, double* d_out,
+                            void* stream) {
+  if (!f || !d_out || iterations < 0 || chains < 0) return fail(RN_E_INVALID, "bad argument");
+  if (f->device < 0) return fail(RN_E_CUDA, "function was created without a device (no CPU fallback)");
+  const long long n = (long long)f->prog.n_params, m = (long long)f->prog.fn_outputs.size();
+  if (!d_x && n > 0) return fail(RN_E_INVALID, "null input");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  int rc = function_load(A, f);
+  if (rc) return rc;
+  const long long count = (long long)iterations * (long long)chains;
+  if (count == 0) return RN_OK;
+  RnEvalArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.x = d_x;
+  a.out = d_out;
+  a.count = count;
+  if (layout == RN_LAYOUT_SAMPLER) {
+    // in [iteration][n][chain] (rn_sampler_run) -> out [chain][iteration][m] (Trace.predict's order: chains.flatMap(_.map(fn)))
+    a.in_inner = chains, a.in_outer = n * chains, a.in_pstride = 1, a.in_estride = chains;
+    a.out_inner = chains, a.out_outer = m, a.out_pstride = (long long)iterations * m, a.out_estride = 1;
+  } else if (layout == RN_LAYOUT_ROWS) {
+    // in [count][n] -> out [count][m]
+    a.in_inner = count, a.in_outer = 0, a.in_pstride = n, a.in_estride = 1;
+    a.out_inner = count, a.out_outer = 0, a.out_pstride = m, a.out_estride = 1;
+  } else {
+    return fail(RN_E_INVALID, "unknown layout");
+  }
+  return function_launch(A, f, a, stream ? (CUstream)stream : f->stream);
+}
+
+int rn_function_sync(rn_function* f) {
+  if (!f) return fail(RN_E_INVALID, "null function");
+  if (f->device < 0) return fail(RN_E_CUDA, "function was created without a device (no CPU fallback)");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  if (!f->mod) return RN_OK;
+  CU(A->cuCtxSetCurrent(f->ctx));
+  CU(A->cuStreamSynchronize(f->stream));
+  int err = 0;
+  CU(A->cuMemcpyDtoH(&err, f->d_err, 4));
+  if (err) {
+    CU(A->cuMemsetD8Async(f->d_err, 0, 8, f->stream));
+    if (err & 1) return fail(RN_E_LOOKUP, "lookup index out of range");
+  }
+  return RN_OK;
+}
+
+int rn_function_eval(rn_function* f, const double* x, int64_t count, double* out) {
+  if (!f || !out || count < 0) return fail(RN_E_INVALID, "bad argument");
+  if (f->device < 0) return fail(RN_E_CUDA, "function was created without a device (no CPU fallback)");
+  const size_t n = f->prog.n_params, m = f->prog.fn_outputs.size();
+  if (!x && n > 0 && count > 0) return fail(RN_E_INVALID, "null input");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  int rc = function_load(A, f);
+  if (rc) return rc;
+  if (count == 0) return RN_OK;
+  // chunks of at most 256 MB of staging; [chunk][n] in, [chunk][m] out
+  const size_t per_point = (n + m) * 8;
+  const int64_t chunk_max = std::max<int64_t>(1, (int64_t)((size_t)256 << 20) / (int64_t)per_point);
+  const int64_t chunk = std::min<int64_t>(count, chunk_max);
+  const size_t need = (size_t)chunk * per_point + 16;
+  if (f->scratch_bytes < need) {
+    if (f->scratch) A->cuMemFree(f->scratch);
+    f->scratch = 0;
+    f->scratch_bytes = 0;
+    CU(A->cuMemAlloc(&f->scratch, need));
+    f->scratch_bytes = need;
+  }
+  const CUdeviceptr d_x = f->scratch, d_out = f->scratch + (((size_t)chunk * n * 8 + 15) & ~(size_t)15);
+  for (int64_t p0 = 0; p0 < count; p0 += chunk) {
+    const int64_t c = std::min<int64_t>(chunk, count - p0);
+    if (n > 0) CU(A->cuMemcpyHtoDAsync(d_x, x + (size_t)p0 * n, (size_t)c * n * 8, f->stream));
+    rc = rn_function_eval_device(f, (const double*)(uintptr_t)d_x, RN_LAYOUT_ROWS, 1, c, (double*)(uintptr_t)d_out, nullptr);
+    if (rc) return rc;
+    CU(A->cuMemcpyDtoHAsync(out + (size_t)p0 * m, d_out, (size_t)c * m * 8, f->stream));
+    CU(A->cuStreamSynchronize(f->stream));
+  }
+  return rn_function_sync(f);
+}
+
+void rn_function_destroy(rn_function* f) {
+  if (!f) return;
+  std::string why;
+  const Api* A = f->device >= 0 ? api(&why) : nullptr;
+  if (A && f->ctx) {
+    A->cuCtxSetCurrent(f->ctx);
+    if (f->stream) {
+      A->cuStreamSynchronize(f->stream);
+      A->cuStreamDestroy(f->stream);
+    }
+    if (f->mod) A->cuModuleUnload(f->mod);
+    if (f->d_err) A->cuMemFree(f->d_err);
+    if (f->scratch) A->cuMemFree(f->scratch);
+    CUdevice dev;
+    if (A->cuDeviceGet(&dev, f->device) == 0) A->cuDevicePrimaryCtxRelease(dev);
+  }
+  delete f;
+}
+
+}  // extern "C"

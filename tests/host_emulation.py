@@ -122,6 +122,21 @@ extern "C" void emu_density(const double* q, int chains, double* out, const doub
 """
 
 
+_FUNCTION_SHIM = r"""
+// Host emulation of one rn_k_eval launch (rn_function.cuh): `grid` CTAs of 128 "threads", one at a time.
+extern "C" void emu_eval(const double* x, double* out, long long count, const long long* lay, int* err, int grid) {
+  RnEvalArgs a;
+  a.x = x; a.out = out; a.count = count;
+  a.in_inner = lay[0]; a.in_outer = lay[1]; a.in_pstride = lay[2]; a.in_estride = lay[3];
+  a.out_inner = lay[4]; a.out_outer = lay[5]; a.out_pstride = lay[6]; a.out_estride = lay[7];
+  a.err = err;
+  blockDim.x = 128; gridDim.x = (unsigned)grid;
+  for (int b = 0; b < grid; b++)
+    for (int t = 0; t < 128; t++) { blockIdx.x = (unsigned)b; threadIdx.x = (unsigned)t; rn_k_eval(a); }
+}
+"""
+
+
 def compile_source(src, fast=False, opt="-O1"):
     d = os.path.join(tempfile.gettempdir(), "rn_emul")
     os.makedirs(d, exist_ok=True)
@@ -134,7 +149,10 @@ def compile_source(src, fast=False, opt="-O1"):
             launch_tpc = ("    blockDim.x = 1; gridDim.x = (unsigned)chains; threadIdx.x = 0;\n"
                           "    for (int k = 0; k < chains; k++) { blockIdx.x = (unsigned)k; kern(a); }\n")
             launch_wpc = "    for (int k = 0; k < chains; k++) rn_emu_run_warp(k, chains, [&] { kern(a); });\n"
-            f.write(src + (_WPC_SHIM if wpc else _SHIM) + _SAMPLER_SHIM.replace("@LAUNCH@", launch_wpc if wpc else launch_tpc))
+            if src.startswith("// generated by rainier_b200 (CUDA source emitter, function flavour)"):  # rn_function.cuh
+                f.write(src + _FUNCTION_SHIM)
+            else:
+                f.write(src + (_WPC_SHIM if wpc else _SHIM) + _SAMPLER_SHIM.replace("@LAUNCH@", launch_wpc if wpc else launch_tpc))
         flags = [opt, "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w", "-pthread"]
         flags.append("-ffp-contract=fast" if fast else "-ffp-contract=off")
         subprocess.run(["g++"] + flags + [cpp, "-o", so], check=True)
@@ -185,3 +203,25 @@ def sample(src, cfg, seeds, model):
     ne = n * n if kind.value == 2 else n
     return {"samples": np.ascontiguousarray(samples[:it].transpose(2, 0, 1)), "trace": np.ascontiguousarray(trace[:tot].transpose(2, 0, 1)),
             "stats": stats, "mass": np.ascontiguousarray(mass.reshape(-1)[: ne * chains].reshape(ne, chains).T), "mass_kind": kind.value}
+
+
+def eval_function(src, x, m, layout="rows", iterations=None, chains=None, grid=3, fast=False):
+    """Runs the emitted function source (CudaFunction.emit_source) on the host through rn_k_eval's own addressing.
+    layout "rows": x [count][n] -> [count][m].  layout "sampler": x [iterations][n][chains] (as rn_sampler_run writes
+    draws) -> [chains][iterations][m] (Trace.predict's order), the strides rn_function_eval_device passes."""
+    L = compile_source(src, fast)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if layout == "rows":
+        count, n = x.shape
+        lay = [count, 0, n, 1, count, 0, m, 1]
+        out = np.full((count, m), np.nan)
+    else:
+        n = x.shape[1]
+        count = iterations * chains
+        lay = [chains, n * chains, 1, chains, chains, m, iterations * m, 1]
+        out = np.full((chains, iterations, m), np.nan)
+    lay_a = (C.c_longlong * 8)(*[max(int(v), 0) if k not in (0, 4) else max(int(v), 1) for k, v in enumerate(lay)])
+    err = C.c_int(0)
+    L.emu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    L.emu_eval(x.ctypes.data, out.ctypes.data, count, lay_a, C.byref(err), grid)
+    return out, err.value
