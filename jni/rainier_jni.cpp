@@ -151,6 +151,29 @@ JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_defaultConfig(JNIEnv*
 JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_destroy(JNIEnv*, jclass, jlong h) {
   rn_model_destroy((rn_model*)(intptr_t)h);
 }
+// ---- compiled functions: Generator.prepare's Compiler.compile + CompiledFunction.output loop (core/Generator.scala:59-94) ----
+// def functionCreate(rir: ByteBuffer, device: Int): Long
+JNIEXPORT jlong JNICALL Java_com_stripe_rainier_cuda_Native_functionCreate(JNIEnv* env, jclass, jobject rir, jint device) {
+  rn_function* f = nullptr;
+  if (rn_function_create(env->GetDirectBufferAddress(rir), (size_t)env->GetDirectBufferCapacity(rir), device, RN_MATH_PARITY, &f) != RN_OK) {
+    throw_last(env);
+    return 0;
+  }
+  return (jlong)(intptr_t)f;
+}
+// def functionEval(handle: Long, draws: Array[Double], count: Long, out: Array[Double]): Unit   draws [count][n] -> out [count][m]
+JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_functionEval(JNIEnv* env, jclass, jlong h, jdoubleArray draws, jlong count,
+                                                                        jdoubleArray out) {
+  int rc;
+  {
+    Crit cx(env, draws, JNI_ABORT), co(env, out);
+    rc = rn_function_eval((rn_function*)(intptr_t)h, (const double*)cx.p, (int64_t)count, (double*)co.p);
+  }
+  if (rc != RN_OK) throw_last(env);
+}
+JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_functionDestroy(JNIEnv*, jclass, jlong h) {
+  rn_function_destroy((rn_function*)(intptr_t)h);
+}
 JNIEXPORT jstring JNICALL Java_com_stripe_rainier_cuda_Native_lastError(JNIEnv* env, jclass) {
   return env->NewStringUTF(rn_last_error());
 }

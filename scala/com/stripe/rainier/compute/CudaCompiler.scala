@@ -40,6 +40,16 @@ object CudaCompiler {
     new CudaModel(h, group.parameters.size)
   }
 
+  /** Drop-in for `Compiler.compile(inputs, outputs): CompiledFunction` (compute/Compiler.scala:22-30) as
+    * `Generator.prepare` calls it (core/Generator.scala:72-76): one Translator over all outputs, serialised as a
+    * RIR_FLAG_FUNCTION container (include/rainier_rir.h) for `Native.functionCreate`. */
+  def compileFunction(inputs: Seq[Param], outputs: Seq[Real]): ByteBuffer = {
+    val translator = new Translator
+    val w = new RirWriter(inputs)
+    val outs = outputs.map(r => w.node(translator.toExpr(r)))
+    w.finish(inputs.size, Seq((inputs.size, 0, 0, outs)), flags = 2)
+  }
+
   /** ir.Expr -> flat SSA.  VarDef(sym, rhs) becomes the node computing rhs, VarRef(sym) its index, SeqIR vanishes
     * (node order is evaluation order; defs precede refs by construction, compute/Translator.scala:178-179). */
   private final class RirWriter(inputs: Seq[Param]) {
@@ -90,12 +100,15 @@ object CudaCompiler {
       case MethodRef(_) => sys.error("MethodRef only exists after packing")
     }
 
-    def finish(nParams: Int, targets: Seq[(Int, Int, Int, Seq[Int])], withGradient: Boolean): ByteBuffer = {
+    def finish(nParams: Int, targets: Seq[(Int, Int, Int, Seq[Int])], withGradient: Boolean): ByteBuffer =
+      finish(nParams, targets, if (withGradient) 1 else 0)
+
+    def finish(nParams: Int, targets: Seq[(Int, Int, Int, Seq[Int])], flags: Int): ByteBuffer = {
       def pad8(n: Int) = (n + 7) & ~7
       val size = 32 + nodes.size * 32 + pad8(lookupRefs.size * 4) + targets.map(t => 24 + pad8(t._4.size * 4)).sum
       val bb = ByteBuffer.allocateDirect(size).order(ByteOrder.LITTLE_ENDIAN)
       bb.putInt(0x31524952).putInt(1).putInt(nParams).putInt(inputs.size).putInt(nodes.size)
-        .putInt(targets.size).putInt(lookupRefs.size).putInt(if (withGradient) 1 else 0)
+        .putInt(targets.size).putInt(lookupRefs.size).putInt(flags)
       nodes.foreach(bb.put)
       lookupRefs.foreach(bb.putInt)
       while (bb.position() % 8 != 0) bb.put(0.toByte)

@@ -129,4 +129,31 @@ object CudaSampling {
       def gradient(index: Int) = out(index + 1)
     }
   }
+
+  /** `Trace.predict` (core/Trace.scala:34-41) with the requirement values of ALL draws computed by one native call.
+    * Mirrors `Generator.prepare` (core/Generator.scala:59-94): same requirement list (`requirements.toList.take(
+    * Generator.MaxRequirements)`), same Evaluator contents, `get` applied per draw in the reference's order, so a
+    * generator consumes the RNG exactly as before.  `CudaCompiler.compileFunction` = the unchanged `Translator` +
+    * RIR serialisation with RIR_FLAG_FUNCTION (the `Compiler.compile(inputs, outputs)` seam, compute/Compiler.scala:22-30). */
+  def predict[T, U](trace: Trace, value: T, device: Int = 0)(implicit tg: ToGenerator[T, U], rng: RNG): List[U] = {
+    val gen = tg(value)
+    val params = trace.model.parameters
+    val reqs = gen.requirements.toList.take(Generator.MaxRequirements)
+    val draws = trace.chains.flatten
+    if (reqs.isEmpty)
+      draws.map(a => gen.get(rng, new Evaluator(params.zip(a).toMap)))
+    else {
+      val n = params.size; val m = reqs.size
+      val h = Native.functionCreate(CudaCompiler.compileFunction(params.map(_.param), reqs), device)
+      try {
+        val flat = new Array[Double](draws.size * n)
+        draws.zipWithIndex.foreach { case (a, i) => System.arraycopy(a, 0, flat, i * n, n) }
+        val out = new Array[Double](draws.size * m)
+        Native.functionEval(h, flat, draws.size.toLong, out)
+        draws.zipWithIndex.map { case (a, i) =>
+          gen.get(rng, new Evaluator((params.zip(a) ++ reqs.zipWithIndex.map { case (r, j) => r -> out(i * m + j) }).toMap))
+        }
+      } finally Native.functionDestroy(h)
+    }
+  }
 }

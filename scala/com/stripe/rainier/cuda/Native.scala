@@ -30,5 +30,9 @@ object Native {
   @native def statsSize(): Int
   @native def defaultConfig(config: ByteBuffer): Unit
   @native def destroy(handle: Long): Unit
+  /** rn_function_*: Compiler.compile(inputs, outputs) + the CompiledFunction.output loop of Generator.prepare, batched */
+  @native def functionCreate(rir: ByteBuffer, device: Int): Long
+  @native def functionEval(handle: Long, draws: Array[Double], count: Long, out: Array[Double]): Unit
+  @native def functionDestroy(handle: Long): Unit
   @native def lastError(): String
 }
