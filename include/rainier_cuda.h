@@ -253,6 +253,33 @@ int rn_function_emit_cubin(rn_function* f, void* buf, size_t cap, size_t* needed
 int rn_function_op_counts(const rn_function* f, double out[2]);
 void rn_function_destroy(rn_function* f);
 
+/* ---- MAP optimisation: batched multi-start L-BFGS ------------------------------------------ */
+/* rn_optimize          <- Optimizer.lbfgs(df: DensityFunction): Array[Double]
+ *                         rainier-sampler/.../optimizer/Optimizer.scala:6-24 driving class LBFGS
+ *                         (rainier-sampler/.../optimizer/LBFGS.java:42-190, mcsrch :240-383, mcstep :431-605),
+ *                         the body of Model.optimize (rainier-core/.../core/Model.scala:26-30)
+ * The reference optimises from the single start x = 0.  Here every start of a batch is one GPU thread that runs the whole
+ * optimisation (density + gradient + line search + history) inside one kernel; start c with x0 = NULL (or a zero row) is
+ * bit-identical to the reference's run.  Thread-per-chain models only (n*(2*history+4) <= 4096 doubles per start). */
+typedef struct rn_optimize_config {
+  int32_t struct_size;
+  int32_t history;          /* m of new LBFGS(x, m, eps); Optimizer.scala:12 uses 5 */
+  double eps;               /* terminate when ||g|| <= eps * max(1, ||x||); Optimizer.scala:13 uses 0.1 */
+  int32_t max_evaluations;  /* per start; the reference loops without a cap -- a kernel needs one (default 10000) */
+  int32_t math_mode;        /* RN_MATH_* */
+  int32_t gradient_mode;    /* RN_GRAD_* */
+  int32_t reserved;
+} rn_optimize_config;
+void rn_optimize_config_default(rn_optimize_config* cfg);
+/* x0: host [starts][n] or NULL (all starts at 0).  x: host [starts][n].  f: host [starts] = -density at x (what LBFGS
+ * minimises), may be NULL.  info: host [starts], may be NULL: 0 converged, bit 0 evaluation cap reached, bit 1 the search
+ * direction was not a descent direction (`throw new RuntimeException("dginit")`, LBFGS.java:253-254), bit 2 lookup index
+ * out of range (then the call returns RN_E_LOOKUP).  evaluations: host [starts] density evaluations used, may be NULL. */
+int rn_optimize(rn_model* m, const rn_optimize_config* cfg, const double* x0, int starts, double* x, double* f, int32_t* info,
+                int32_t* evaluations);
+int rn_optimize_emit_source(rn_model* m, const rn_optimize_config* cfg, char* buf, size_t cap, size_t* needed);
+int rn_optimize_emit_cubin(rn_model* m, const rn_optimize_config* cfg, void* buf, size_t cap, size_t* needed);
+
 const char* rn_last_error(void);
 const char* rn_version(void);
 

@@ -174,6 +174,23 @@ JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_functionEval(JNIEnv* 
 JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_functionDestroy(JNIEnv*, jclass, jlong h) {
   rn_function_destroy((rn_function*)(intptr_t)h);
 }
+// ---- Optimizer.lbfgs for a batch of starts (optimizer/Optimizer.scala:6-24) ----
+// def optimize(handle: Long, x0: Array[Double] /* [starts][n] or null */, starts: Int, m: Int, eps: Double, maxEvals: Int,
+//              x: Array[Double] /* [starts][n] */, info: Array[Int]): Unit
+JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_optimize(JNIEnv* env, jclass, jlong h, jdoubleArray x0, jint starts, jint m,
+                                                                    jdouble eps, jint maxEvals, jdoubleArray x, jintArray info) {
+  rn_optimize_config oc;
+  rn_optimize_config_default(&oc);
+  oc.history = m;
+  oc.eps = eps;
+  oc.max_evaluations = maxEvals;
+  int rc;
+  {
+    Crit c0(env, x0, JNI_ABORT), cx(env, x), ci(env, info);
+    rc = rn_optimize((rn_model*)(intptr_t)h, &oc, (const double*)c0.p, starts, (double*)cx.p, nullptr, (int32_t*)ci.p, nullptr);
+  }
+  if (rc != RN_OK) throw_last(env);
+}
 JNIEXPORT jstring JNICALL Java_com_stripe_rainier_cuda_Native_lastError(JNIEnv* env, jclass) {
   return env->NewStringUTF(rn_last_error());
 }

@@ -78,3 +78,8 @@ class ChainStats(C.Structure):
         ("grads_per_iteration_mean", C.c_double),
         ("rng", RngState),
     ]
+
+
+class OptimizeConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("history", C.c_int32), ("eps", C.c_double), ("max_evaluations", C.c_int32),
+                ("math_mode", C.c_int32), ("gradient_mode", C.c_int32), ("reserved", C.c_int32)]

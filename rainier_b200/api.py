@@ -81,6 +81,11 @@ def lib():
         L.rn_host_free.argtypes = [C.c_int, C.c_void_p]
         L.rn_host_register.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
         L.rn_host_unregister.argtypes = [C.c_int, C.c_void_p]
+        L.rn_optimize_config_default.argtypes = [C.POINTER(abi.OptimizeConfig)]
+        L.rn_optimize.argtypes = [C.c_void_p, C.POINTER(abi.OptimizeConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]
+        L.rn_optimize_emit_source.argtypes = [C.c_void_p, C.POINTER(abi.OptimizeConfig), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rn_optimize_emit_cubin.argtypes = [C.c_void_p, C.POINTER(abi.OptimizeConfig), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.rn_function_create.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.rn_function_ninputs.argtypes = [C.c_void_p]
         L.rn_function_noutputs.argtypes = [C.c_void_p]
@@ -509,6 +514,48 @@ class CudaModel:
                 return self._out[index + 1]
 
         return _DF()
+
+    # -- Model.optimize / Optimizer.lbfgs, batched over starts --
+    @staticmethod
+    def _optimize_config(m=5, eps=0.1, max_evals=10000, fast=False, gradient_mode=abi.RN_GRAD_AUTO):
+        oc = abi.OptimizeConfig()
+        lib().rn_optimize_config_default(C.byref(oc))
+        oc.history, oc.eps, oc.max_evaluations = int(m), float(eps), int(max_evals)
+        oc.math_mode = abi.RN_MATH_FAST if fast else abi.RN_MATH_PARITY
+        oc.gradient_mode = gradient_mode
+        return oc
+
+    def optimize(self, x0=None, starts=1, **kw):
+        """Optimizer.lbfgs(density()) (optimizer/Optimizer.scala:6-24; Model.optimize, core/Model.scala:26-30) for a batch
+        of starts in one kernel.  x0: [starts][n] or None (every start at 0 = the reference's only start).  Returns
+        dict(x [starts][n], f [starts] = -density, info [starts], evals [starts])."""
+        oc = self._optimize_config(**kw)
+        if x0 is not None:
+            x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nVars)
+            starts = x0.shape[0]
+        x = np.empty((starts, self.nVars), dtype=np.float64)
+        f = np.empty(starts, dtype=np.float64)
+        info = np.empty(starts, dtype=np.int32)
+        evals = np.empty(starts, dtype=np.int32)
+        _check(lib().rn_optimize(self.h, C.byref(oc), x0.ctypes.data if x0 is not None else None, starts, x.ctypes.data,
+                                 f.ctypes.data, info.ctypes.data, evals.ctypes.data))
+        return {"x": x, "f": f, "info": info, "evals": evals}
+
+    def emit_optimizer_source(self, **kw):
+        oc = self._optimize_config(**kw)
+        need = C.c_size_t()
+        _check(lib().rn_optimize_emit_source(self.h, C.byref(oc), None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().rn_optimize_emit_source(self.h, C.byref(oc), buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
+    def emit_optimizer_cubin(self, **kw):
+        oc = self._optimize_config(**kw)
+        need = C.c_size_t()
+        _check(lib().rn_optimize_emit_cubin(self.h, C.byref(oc), None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().rn_optimize_emit_cubin(self.h, C.byref(oc), buf, need.value, C.byref(need)))
+        return buf.raw
 
     # -- Model.sample --
     def sample(self, config=None, nChains=4, seeds=None, rng_states=None, dense_mass=None, out=None, diagnostics=False,

@@ -66,4 +66,17 @@ struct RnEvalArgs {
   int* err;  // bit 0: a lookup index fell outside its table at some point
 };
 
+// argument block of rn_k_lbfgs (rn_optimizer.cuh): batched multi-start L-BFGS, one thread per start
+struct RnOptArgs {
+  const double* x0;   // [N][starts] or NULL (every start at 0: Optimizer.scala:7)
+  double* x;          // [N][starts]
+  double* f;          // [starts]  -density at x
+  int* info;          // [starts]  0 converged | bit 0 evaluation cap | bit 1 "dginit" | bit 2 lookup error
+  int* evals;         // [starts]  density evaluations used
+  const double* data;
+  double eps;         // Optimizer.scala:13
+  int starts;
+  int max_evals;
+};
+
 #endif

@@ -17,6 +17,7 @@ extern const char* kPreludeSource;  // rn_prelude.cuh, embedded at build time
 extern const char* kSamplerSource;     // rn_args.h + rn_sampler.cuh
 extern const char* kSamplerWpcSource;  // rn_args.h + rn_sampler_wpc.cuh
 extern const char* kFunctionSource;    // rn_function.cuh
+extern const char* kOptimizerSource;   // rn_args.h + rn_optimizer.cuh
 
 namespace {
 
@@ -571,6 +572,21 @@ WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
     if (T.streamed() && T.n_rows >= 32ull * (uint64_t)std::max(1, opt.wpc_k))
       z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * 32 * std::max(1, opt.wpc_k));
   return z;
+}
+
+std::string emit_optimizer_source(const Program& P, const EmitOptions& opt, int history) {
+  std::ostringstream os;
+  os << "// generated by rainier_b200 (CUDA source emitter, optimizer flavour) -- do not edit\n";
+  os << "#define RN_N " << P.n_params << "\n";
+  os << "#define RN_NSLOTS " << P.n_slots << "\n";
+  os << "#define RN_BACKEND 0\n";
+  os << "#define RN_LBFGS_M " << history << "\n";
+  if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
+  os << kPreludeSource << "\n";
+  EmitOptions eo = opt;
+  eo.backend = 0;
+  os << emit_density(P, eo) << "\n" << kOptimizerSource << "\n";
+  return os.str();
 }
 
 std::string emit_function_source(const Program& P, const EmitOptions& opt) {

@@ -25,6 +25,9 @@ std::string emit_source(const Program& P, const EmitOptions& opt);
 // function flavour (Program from build_function): prelude + emitted rn_function() + rn_function.cuh (rn_k_eval); only
 // opt.fast_math is read
 std::string emit_function_source(const Program& P, const EmitOptions& opt);
+// optimizer flavour: prelude + emitted thread-per-chain rn_density() + rn_optimizer.cuh (rn_k_lbfgs, `history` = the m of
+// new LBFGS(x, m, eps)); reads opt.fast_math and opt.target_base
+std::string emit_optimizer_source(const Program& P, const EmitOptions& opt, int history);
 // shared-memory needs of the warp-per-chain kernels: doubles per warp (chain vectors + density scratch) and doubles of
 // the largest data tile (n_cols * 32 over the streamed targets; 0 when nothing is streamed)
 struct WpcSizes {

@@ -195,6 +195,14 @@ struct rn_model {
   size_t spare_arena_bytes = 0;
   CUstream spare_stream = nullptr;
   size_t pool_bytes[2] = {0, 0};
+  // rn_optimize: one module per (adjoint, fast, history) -- cubin, module, rn_k_lbfgs
+  struct OptKernel {
+    std::string source;
+    std::vector<char> cubin;
+    CUmodule mod = nullptr;
+    CUfunction k_lbfgs = nullptr;
+  };
+  std::map<std::tuple<bool, bool, int>, std::unique_ptr<OptKernel>> opt_kernels;
 };
 
 static int make_current(const Api* A, rn_model* m) {
@@ -578,6 +586,8 @@ void rn_model_destroy(rn_model* m) {
   if (A && m->ctx) {
     A->cuCtxSetCurrent(m->ctx);
     for (auto& kv : m->kernels)
+      if (kv.second->mod) A->cuModuleUnload(kv.second->mod);
+    for (auto& kv : m->opt_kernels)
       if (kv.second->mod) A->cuModuleUnload(kv.second->mod);
     if (m->d_data) A->cuMemFree(m->d_data);
     for (auto p : m->pool)
@@ -2134,6 +2144,160 @@ void rn_function_destroy(rn_function* f) {
     if (A->cuDeviceGet(&dev, f->device) == 0) A->cuDevicePrimaryCtxRelease(dev);
   }
   delete f;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// rn_optimize: Optimizer.lbfgs (rainier-sampler/.../optimizer/Optimizer.scala:6-24) for a batch of starts, fused into
+// one kernel (rn_optimizer.cuh).  Model.optimize (rainier-core/.../core/Model.scala:26-30) = start 0 of a batch whose
+// x0 is NULL.
+// ---------------------------------------------------------------------------------------------------------
+static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::OptKernel** out) {
+  const bool fast = oc && oc->math_mode == RN_MATH_FAST;
+  const int gm = oc ? oc->gradient_mode : RN_GRAD_AUTO;
+  const bool adjoint = (gm == RN_GRAD_ADJOINT) || !m->rir_has_gradient;
+  const int history = oc && oc->history > 0 ? oc->history : 5;
+  if (history > 64) return fail(RN_E_INVALID, "L-BFGS history too long");
+  auto key = std::make_tuple(adjoint, fast, history);
+  auto it = m->opt_kernels.find(key);
+  if (it != m->opt_kernels.end()) {
+    *out = it->second.get();
+    return RN_OK;
+  }
+  const Program* P = nullptr;
+  int rc = get_program(m, adjoint, fast, &P);
+  if (rc) return rc;
+  // the whole optimisation state of a start is thread-local: x, g, diag and the 2m-vector history
+  if ((uint64_t)P->n_params * (2 * (uint64_t)history + 4) > 4096)
+    return fail(RN_E_UNSUPPORTED, "rn_optimize keeps n*(2m+4) doubles per start in thread-local memory; model too large");
+  std::unique_ptr<rn_model::OptKernel> K(new rn_model::OptKernel());
+  EmitOptions eo;
+  eo.backend = 0;
+  eo.fast_math = fast;
+  eo.target_base = m->target_base;
+  K->source = emit_optimizer_source(*P, eo, history);
+  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+  opts.push_back(fast ? "--fmad=true" : "--fmad=false");
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, K->source.c_str(), "rainier_optimizer.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    return fail(RN_E_COMPILE, "nvrtcCreateProgram failed");
+  nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    return fail(RN_E_COMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log);
+  }
+  size_t n = 0;
+  nvrtcGetCUBINSize(prog, &n);
+  K->cubin.resize(n);
+  nvrtcGetCUBIN(prog, K->cubin.data());
+  nvrtcDestroyProgram(&prog);
+  *out = K.get();
+  m->opt_kernels.emplace(key, std::move(K));
+  return RN_OK;
+}
+
+extern "C" {
+
+void rn_optimize_config_default(rn_optimize_config* c) {  // Optimizer.scala:12-13
+  std::memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(*c);
+  c->history = 5;
+  c->eps = 0.1;
+  c->max_evaluations = 10000;
+  c->math_mode = RN_MATH_PARITY;
+  c->gradient_mode = RN_GRAD_AUTO;
+}
+
+int rn_optimize_emit_source(rn_model* m, const rn_optimize_config* oc, char* buf, size_t cap, size_t* needed) {
+  if (!m) return fail(RN_E_INVALID, "null model");
+  rn_model::OptKernel* K = nullptr;
+  int rc = get_opt_kernel(m, oc, &K);
+  if (rc) return rc;
+  if (needed) *needed = K->source.size() + 1;
+  if (buf && cap) {
+    size_t n = std::min(cap - 1, K->source.size());
+    std::memcpy(buf, K->source.data(), n);
+    buf[n] = 0;
+  }
+  return RN_OK;
+}
+
+int rn_optimize_emit_cubin(rn_model* m, const rn_optimize_config* oc, void* buf, size_t cap, size_t* needed) {
+  if (!m) return fail(RN_E_INVALID, "null model");
+  rn_model::OptKernel* K = nullptr;
+  int rc = get_opt_kernel(m, oc, &K);
+  if (rc) return rc;
+  if (needed) *needed = K->cubin.size();
+  if (buf && cap) std::memcpy(buf, K->cubin.data(), std::min(cap, K->cubin.size()));
+  return RN_OK;
+}
+
+int rn_optimize(rn_model* m, const rn_optimize_config* oc, const double* x0, int starts, double* x, double* f, int32_t* info,
+                int32_t* evaluations) {
+  if (!m || !x || starts <= 0) return fail(RN_E_INVALID, "bad argument");
+  if (m->device < 0) return fail(RN_E_CUDA, "model was created without a device (no CPU fallback)");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  rn_model::OptKernel* K = nullptr;
+  int rc = get_opt_kernel(m, oc, &K);
+  if (rc) return rc;
+  rc = make_current(A, m);
+  if (rc) return rc;
+  if (!K->mod) {
+    CU(A->cuModuleLoadData(&K->mod, K->cubin.data()));
+    CU(A->cuModuleGetFunction(&K->k_lbfgs, K->mod, "rn_k_lbfgs"));
+  }
+  const size_t n = m->n_params, S = (size_t)starts;
+  // one allocation: x0 | x | f | info | evals
+  const size_t off_x = n * S * 8, off_f = 2 * n * S * 8, off_info = off_f + S * 8, off_ev = off_info + S * 4;
+  const size_t total = off_ev + S * 4;
+  CUdeviceptr d = 0;
+  struct Free {
+    const Api* A;
+    CUdeviceptr* p;
+    ~Free() {
+      if (*p) A->cuMemFree(*p);
+    }
+  } guard{A, &d};
+  CU(A->cuMemAlloc(&d, total + 16));
+  std::vector<double> t(n * S);
+  if (x0) {
+    for (size_t c = 0; c < S; c++)
+      for (size_t i = 0; i < n; i++) t[i * S + c] = x0[c * n + i];
+    CU(A->cuMemcpyHtoD(d, t.data(), n * S * 8));
+  }
+  RnOptArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.x0 = x0 ? (const double*)(uintptr_t)d : nullptr;
+  a.x = (double*)(uintptr_t)(d + off_x);
+  a.f = (double*)(uintptr_t)(d + off_f);
+  a.info = (int*)(uintptr_t)(d + off_info);
+  a.evals = (int*)(uintptr_t)(d + off_ev);
+  a.data = (const double*)(uintptr_t)m->d_data;
+  a.eps = oc ? oc->eps : 0.1;
+  a.starts = starts;
+  a.max_evals = oc && oc->max_evaluations > 0 ? oc->max_evaluations : 10000;
+  void* params[] = {&a};
+  // small CTAs spread few starts over all SMs; starts diverge (different trajectory lengths), so warps are the unit
+  const unsigned block = starts >= 148 * 128 ? 128 : 32;
+  CU(A->cuLaunchKernel(K->k_lbfgs, (unsigned)((S + block - 1) / block), 1, 1, block, 1, 1, 0, nullptr, params, nullptr));
+  CU(A->cuMemcpyDtoH(t.data(), d + off_x, n * S * 8));
+  for (size_t c = 0; c < S; c++)
+    for (size_t i = 0; i < n; i++) x[c * n + i] = t[i * S + c];
+  if (f) CU(A->cuMemcpyDtoH(f, d + off_f, S * 8));
+  std::vector<int32_t> inf(S);
+  CU(A->cuMemcpyDtoH(inf.data(), d + off_info, S * 4));
+  if (info) std::memcpy(info, inf.data(), S * 4);
+  if (evaluations) CU(A->cuMemcpyDtoH(evaluations, d + off_ev, S * 4));
+  for (size_t c = 0; c < S; c++)
+    if (inf[c] & 4) return fail(RN_E_LOOKUP, "lookup index out of range");
+  return RN_OK;
 }
 
 }  // extern "C"

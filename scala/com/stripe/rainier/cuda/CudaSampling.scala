@@ -156,4 +156,17 @@ object CudaSampling {
       } finally Native.functionDestroy(h)
     }
   }
+
+  /** `Model.optimize` (core/Model.scala:26-30): `Optimizer.lbfgs(density())` (optimizer/Optimizer.scala:6-24) fused into
+    * one kernel; the single reference start x = 0, m = 5, eps = 0.1.  `optimizeMultiStart` returns the best of several
+    * starts (an extension: the reference has one start). */
+  def optimize[T, U](model: Model, t: T, device: Int = 0)(implicit toGen: ToGenerator[T, U], rng: RNG): U = {
+    val cm = CudaCompiler.compileTargets(model.targetGroup, withGradient = false, device = device)
+    try {
+      val x = new Array[Double](cm.nVars); val info = new Array[Int](1)
+      Native.optimize(cm.handle, null, 1, 5, 0.1, 10000, x, info)
+      if ((info(0) & 2) != 0) throw new RuntimeException("dginit") // LBFGS.java:253-254
+      toGen(t).prepare(model.parameters).apply(x)
+    } finally cm.close()
+  }
 }

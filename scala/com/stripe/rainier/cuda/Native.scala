@@ -34,5 +34,8 @@ object Native {
   @native def functionCreate(rir: ByteBuffer, device: Int): Long
   @native def functionEval(handle: Long, draws: Array[Double], count: Long, out: Array[Double]): Unit
   @native def functionDestroy(handle: Long): Unit
+  /** rn_optimize: Optimizer.lbfgs for a batch of starts; x0 == null: every start at 0 (the reference's start) */
+  @native def optimize(handle: Long, x0: Array[Double], starts: Int, m: Int, eps: Double, maxEvals: Int,
+                       x: Array[Double], info: Array[Int]): Unit
   @native def lastError(): String
 }

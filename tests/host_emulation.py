@@ -137,6 +137,18 @@ extern "C" void emu_eval(const double* x, double* out, long long count, const lo
 """
 
 
+_OPTIMIZER_SHIM = r"""
+// Host emulation of one rn_k_lbfgs launch (rn_optimizer.cuh): one "thread" (start) at a time.
+extern "C" void emu_lbfgs(const double* x0, double* x, double* f, int* info, int* evals, const double* data, double eps,
+                          int starts, int max_evals) {
+  RnOptArgs a;
+  a.x0 = x0; a.x = x; a.f = f; a.info = info; a.evals = evals; a.data = data; a.eps = eps; a.starts = starts; a.max_evals = max_evals;
+  blockDim.x = 1; gridDim.x = (unsigned)starts; threadIdx.x = 0;
+  for (int c = 0; c < starts; c++) { blockIdx.x = (unsigned)c; rn_k_lbfgs(a); }
+}
+"""
+
+
 def compile_source(src, fast=False, opt="-O1"):
     d = os.path.join(tempfile.gettempdir(), "rn_emul")
     os.makedirs(d, exist_ok=True)
@@ -151,6 +163,8 @@ def compile_source(src, fast=False, opt="-O1"):
             launch_wpc = "    for (int k = 0; k < chains; k++) rn_emu_run_warp(k, chains, [&] { kern(a); });\n"
             if src.startswith("// generated by rainier_b200 (CUDA source emitter, function flavour)"):  # rn_function.cuh
                 f.write(src + _FUNCTION_SHIM)
+            elif src.startswith("// generated by rainier_b200 (CUDA source emitter, optimizer flavour)"):  # rn_optimizer.cuh
+                f.write(src + _OPTIMIZER_SHIM)
             else:
                 f.write(src + (_WPC_SHIM if wpc else _SHIM) + _SAMPLER_SHIM.replace("@LAUNCH@", launch_wpc if wpc else launch_tpc))
         flags = [opt, "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w", "-pthread"]
@@ -225,3 +239,23 @@ def eval_function(src, x, m, layout="rows", iterations=None, chains=None, grid=3
     L.emu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.POINTER(C.c_int), C.c_int]
     L.emu_eval(x.ctypes.data, out.ctypes.data, count, lay_a, C.byref(err), grid)
     return out, err.value
+
+
+def optimize(src, model, x0=None, starts=1, eps=0.1, max_evals=10000, fast=False):
+    """Runs the emitted optimizer source (CudaModel.emit_optimizer_source) on the host.  Returns dict like
+    CudaModel.optimize."""
+    L = compile_source(src, fast)
+    n = model.nVars
+    if x0 is not None:
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, n)
+        starts = x0.shape[0]
+        x0t = np.ascontiguousarray(x0.T)
+    x = np.zeros((n, starts))
+    f = np.zeros(starts)
+    info = np.zeros(starts, dtype=np.int32)
+    evals = np.zeros(starts, dtype=np.int32)
+    data = model.pack_columns()
+    L.emu_lbfgs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int]
+    L.emu_lbfgs(x0t.ctypes.data if x0 is not None else None, x.ctypes.data, f.ctypes.data, info.ctypes.data, evals.ctypes.data,
+                data.ctypes.data, eps, starts, max_evals)
+    return {"x": np.ascontiguousarray(x.T), "f": f, "info": info, "evals": evals}

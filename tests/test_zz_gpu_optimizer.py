@@ -1,0 +1,83 @@
+"""
+GPU parity of SURVEY.md 8f-4 (batched multi-start MAP: Model.optimize -> Optimizer.lbfgs -> LBFGS.java) through the C ABI
+(rn_optimize): every start bit-identical to the oracle's restatement of the reference's optimizer -- iterates, number of
+density evaluations, exit code.  (Named test_zz_* so that it runs after the files of the hot path proper.)
+"""
+import numpy as np
+import pytest
+
+from oracle.rainier_py import configs, sbc_models
+from oracle.rainier_py.binding import OracleModel
+from oracle.rainier_py.compute import Evaluator
+from oracle.rainier_py.optimizer import lbfgs
+from rainier_b200 import abi, api
+
+from test_optimizer_host import EGGS, _assert_identical, egg_model, fit_normal
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(model, x0, **kw):
+    rir, cols = model.compile(True)
+    om = OracleModel(rir, cols)
+    got = api.CudaModel(rir, cols).optimize(x0, **kw)
+    ref = [lbfgs(om.density_batch, om.n, x0=x, m=kw.get("m", 5), eps=kw.get("eps", 0.1), max_evals=kw.get("max_evals", 10000))
+           for x in np.asarray(x0, dtype=np.float64).reshape(-1, om.n)]
+    return got, ref
+
+
+def test_reference_start_and_multi_start_fit_normal():
+    """OptimizerTest.scala:8-13's model; start 0 is the reference's own run (x = 0, m = 5, eps = 0.1)"""
+    model, mu, sigma = fit_normal()
+    x0 = np.random.default_rng(0).normal(size=(300, 2)) * 2.0
+    x0[0] = 0.0
+    got, ref = _run(model, x0)
+    _assert_identical(got, ref)
+    assert np.all(got["info"] == 0)
+    rir, cols = model.compile(True)
+    z = api.CudaModel(rir, cols).optimize(starts=5)  # x0 = NULL: all starts at 0
+    assert np.array_equal(z["x"], np.repeat(got["x"][:1], 5, axis=0))
+    ev = Evaluator({p: v for p, v in zip(model.parameters, z["x"][0])})
+    assert abs(ev.toDouble(mu) - 2.0) < 0.05
+
+
+@pytest.mark.parametrize("name", ["funnel", "eight_schools"])
+def test_bit_identical_n10(name):
+    model = getattr(configs, name)()
+    x0 = np.random.default_rng(1).normal(size=(64, 10)) * 0.7
+    x0[0] = 0.0
+    got, ref = _run(model, x0, max_evals=400)
+    _assert_identical(got, ref)
+    got, ref = _run(model, x0[:8], m=3, eps=1e-6, max_evals=300)
+    _assert_identical(got, ref)
+
+
+def test_cap_non_finite_starts_and_closed_form():
+    model, lam = egg_model()
+    x0 = np.array([[0.0], [3.0], [800.0], [-800.0], [np.nan], [np.inf], [1e-300]])
+    got, ref = _run(model, x0, max_evals=60)
+    _assert_identical(got, ref)
+    got, ref = _run(model, x0[:2], eps=1e-300, max_evals=7)
+    _assert_identical(got, ref)
+    assert np.all(got["info"] == 1) and np.all(got["evals"] == 7)
+    # 20 000 starts spread over the prior's bulk all reach the closed-form mode (k + sum y) / (N + 1/theta)
+    rir, cols = model.compile(True)
+    big = api.CudaModel(rir, cols).optimize(np.linspace(-2.0, 6.0, 20000)[:, None], eps=1e-6, max_evals=500)
+    ok = big["info"] == 0
+    assert ok.mean() > 0.99
+    lam_hat = np.array([Evaluator({model.parameters[0]: float(x)}).toDouble(lam) for x in big["x"][ok][::500, 0]])
+    assert np.max(np.abs(lam_hat - (0.5 + sum(EGGS)) / (len(EGGS) + 0.01))) < 1e-5
+
+
+def test_streamed_rows_model_and_fast_math():
+    model, real, rng, _ = sbc_models.build("SBCLaplace")
+    got, ref = _run(model, np.array([[0.0], [0.5], [-1.0]]), max_evals=200)
+    _assert_identical(got, ref)
+    model2, _, _ = fit_normal()
+    rir, cols = model2.compile(True)
+    x0 = np.random.default_rng(3).normal(size=(50, 2))
+    a = api.CudaModel(rir, cols).optimize(x0, fast=True, eps=1e-7, max_evals=500)
+    b = api.CudaModel(rir, cols).optimize(x0, eps=1e-7, max_evals=500)
+    both = (a["info"] == 0) & (b["info"] == 0)
+    assert both.mean() > 0.9
+    np.testing.assert_allclose(a["x"][both], b["x"][both], rtol=1e-5, atol=1e-6)  # same optimum, different rounding paths
