@@ -29,6 +29,15 @@ for name, build in (("funnel10", lambda: configs.funnel(10)), ("eight_schools", 
     open(os.path.join(OUT, name + ".primal.rir"), "wb").write(rir)
     print(name, "ok")
 
+# a compiled function (RIR_FLAG_FUNCTION): the 12 derived quantities of eight schools as Generator.prepare would compile
+# them for Trace.predict -- __graft_entry__.build() assembles the function-flavour kernel (rn_k_eval) from it
+from oracle.rainier_py.compute import compile_function_rir  # noqa: E402
+
+model, mu, tau, thetas, _ = configs.eight_schools_parts()
+open(os.path.join(OUT, "eight_schools.derived.fn.rir"), "wb").write(
+    compile_function_rir(model.parameters, configs.eight_schools_derived(mu, tau, thetas)))
+print("eight_schools.derived.fn ok")
+
 # one small streamed model with its columns (logistic regression, 700 observations x 4 covariates, primal flavour):
 # __graft_entry__.build()/smoke() use it to assemble and run the warp-per-chain (TMA-tiled) kernel shape
 import numpy as np  # noqa: E402

@@ -71,8 +71,8 @@ def logreg(n=100000, d=50, seed=20260924):
     return Model.observe([int(y) for y in ys], Vec.from_([list(row) for row in X]).map(lambda x: Bernoulli(x.dot(betas).logistic())))
 
 
-def eight_schools():
-    """cfg 4: rainier-benchmark/.../bench/stan/EightSchools.scala:9-24 verbatim."""
+def eight_schools_parts():
+    """cfg 4: rainier-benchmark/.../bench/stan/EightSchools.scala:9-24 verbatim; returns (model, mu, tau, thetas, sigmas)."""
     ys = [28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0]
     sigmas = [15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0]
     mu = Normal(0, 5).latent()
@@ -81,7 +81,18 @@ def eight_schools():
     model = Model.empty
     for i, (y, s) in enumerate(zip(ys, sigmas)):
         model = model.merge(Model.observe(y, Normal(thetas.at(i), s)))
-    return model
+    return model, mu, tau, thetas, sigmas
+
+
+def eight_schools():
+    return eight_schools_parts()[0]
+
+
+def eight_schools_derived(mu, tau, thetas):
+    """12 derived quantities of eight schools used as posterior-predictive requirements (Trace.predict) in fixtures,
+    tests and scripts/bench_function.py: mu, tau, the 8 thetas, log|theta_0 - theta_1|, tau^mu."""
+    t = [thetas.at(i) for i in range(8)]
+    return [mu, tau] + t + [(t[0] - t[1]).abs().log(), tau.pow(mu)]
 
 
 def poisson_glm_data(groups=1000, n=1000000, seed=20260925):

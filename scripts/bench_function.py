@@ -23,7 +23,6 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
@@ -40,11 +39,11 @@ def main():
 
     from oracle.rainier_py.binding import OracleFunction
     from oracle.rainier_py.compute import compile_function_rir
+    from oracle.rainier_py import configs
     from rainier_b200 import api
-    from test_function_host import _derived, schools
 
-    model, mu, tau, thetas, _ = schools()
-    reals = _derived(mu, tau, thetas)[:12]
+    model, mu, tau, thetas, _ = configs.eight_schools_parts()
+    reals = configs.eight_schools_derived(mu, tau, thetas)
     frir = compile_function_rir(model.parameters, reals)
     rir, cols = model.compile(True)
     n, m = 10, len(reals)
@@ -61,7 +60,6 @@ def main():
     f = api.CudaFunction(frir, fast=args.fast)
     out = torch.empty((chains, iters, m), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    st = torch.cuda.ExternalStream(f.stream()) if f.stream() else None
     f.eval_device(d.data_ptr(), iters, chains, out.data_ptr())  # compiles + loads
     f.sync()
     st = torch.cuda.ExternalStream(f.stream())

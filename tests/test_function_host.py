@@ -17,7 +17,7 @@ import struct
 import numpy as np
 import pytest
 
-from oracle.rainier_py import sbc_models
+from oracle.rainier_py import configs, sbc_models
 from oracle.rainier_py.binding import OracleError, OracleFunction, OracleModel, ScalaRNG
 from oracle.rainier_py.compute import Real, compile_function_rir
 from oracle.rainier_py.core import Cauchy, Generator, Model, Normal, to_generator
@@ -30,15 +30,7 @@ GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sbc_gol
 
 def schools():
     """rainier-benchmark/.../bench/stan/EightSchools.scala:9-24, keeping the latent handles"""
-    ys = [28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0]
-    sigmas = [15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0]
-    mu = Normal(0, 5).latent()
-    tau = Cauchy(0, 5).latent().abs()
-    thetas = Normal(mu, tau).latentVec(8)
-    model = Model.empty
-    for i, (y, s) in enumerate(zip(ys, sigmas)):
-        model = model.merge(Model.observe(y, Normal(thetas.at(i), s)))
-    return model, mu, tau, thetas, sigmas
+    return configs.eight_schools_parts()
 
 
 @pytest.mark.parametrize("name", sbc_models.ENABLED)
@@ -62,7 +54,7 @@ def test_goldset_through_compiled_predict(name):
 
 def _derived(mu, tau, thetas):
     t = [thetas.at(i) for i in range(8)]
-    return [mu, tau] + t + [(t[0] - t[1]).abs().log(), tau.pow(mu), Real.sum(t) / 8.0, (t[2] * t[3]).exp(), mu, Real.zero + 3.5]
+    return configs.eight_schools_derived(mu, tau, thetas) + [Real.sum(t) / 8.0, (t[2] * t[3]).exp(), mu, Real.zero + 3.5]
 
 
 def test_emitted_function_bit_identical_to_oracle_both_layouts():
