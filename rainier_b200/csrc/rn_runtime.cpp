@@ -1962,6 +1962,7 @@ static int function_load(const Api* A, rn_function* f) {
   CU(A->cuStreamCreate(&f->stream, 1 /*CU_STREAM_NON_BLOCKING*/));
   CU(A->cuMemAlloc(&f->d_err, 8));
   CU(A->cuMemsetD8Async(f->d_err, 0, 8, f->stream));
+  CU(A->cuStreamSynchronize(f->stream));  // evaluations may be enqueued on a caller's stream
   CUdevice dev;
   int sms = 0;
   if (A->cuDeviceGet(&dev, f->device) == 0 && A->cuDeviceGetAttribute(&sms, 16 /*MULTIPROCESSOR_COUNT*/, dev) == 0 && sms > 0)
@@ -2087,6 +2088,7 @@ int rn_function_sync(rn_function* f) {
   CU(A->cuMemcpyDtoH(&err, f->d_err, 4));
   if (err) {
     CU(A->cuMemsetD8Async(f->d_err, 0, 8, f->stream));
+    CU(A->cuStreamSynchronize(f->stream));
     if (err & 1) return fail(RN_E_LOOKUP, "lookup index out of range");
   }
   return RN_OK;
