@@ -252,6 +252,13 @@ int rn_function_emit_source(rn_function* f, char* buf, size_t cap, size_t* neede
 int rn_function_emit_cubin(rn_function* f, void* buf, size_t cap, size_t* needed);
 int rn_function_op_counts(const rn_function* f, double out[2]);
 void rn_function_destroy(rn_function* f);
+/* rn_sample_predict   <- object Model.sample(t, config): List[U] = model.sample(config).predict(gen)
+ *                         (rainier-core/.../core/Model.scala:56-63): sampling and the requirement values of predict in one
+ * call; the draws stay on the device and only chains*iterations*m doubles come back.  f: the generator's requirements over
+ * the model's parameters.  predictions: host [chains][iterations][m] (Trace.predict's order).  mass, stats, cfg->diagnostics,
+ * cfg->stats_rings as in rn_sample. */
+int rn_sample_predict(rn_model* m, const rn_config* cfg, rn_function* f, const int64_t* seeds, int chains, double* predictions,
+                      double* mass, rn_chain_stats* stats);
 
 /* ---- MAP optimisation: batched multi-start L-BFGS ------------------------------------------ */
 /* rn_optimize          <- Optimizer.lbfgs(df: DensityFunction): Array[Double]

@@ -100,6 +100,8 @@ def lib():
         L.rn_function_emit_cubin.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.rn_function_op_counts.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.rn_function_destroy.argtypes = [C.c_void_p]
+        L.rn_sample_predict.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
         sizes = (C.c_int32 * 4)()
         L.rn_abi_sizes(sizes)
         if sizes[0] != C.sizeof(Config) or sizes[1] != C.sizeof(ChainStats) or sizes[2] != C.sizeof(RngState):
@@ -514,6 +516,27 @@ class CudaModel:
                 return self._out[index + 1]
 
         return _DF()
+
+    # -- object Model.sample(t, config) = sample + predict (core/Model.scala:56-63) --
+    def sample_predict(self, function, config=None, nChains=4, seeds=None, out=None):
+        """model.sample(config).predict(gen) in one call: returns (predictions [chains][iterations][m], Trace without
+        chains).  The draws stay on the device; only the requirement values cross PCIe."""
+        config = config or SamplerConfig()
+        cfg, keep = lower_config(config)
+        if seeds is None:
+            seeds = np.arange(nChains, dtype=np.int64) + 1
+        seeds_a = np.ascontiguousarray(seeds, dtype=np.int64)
+        nChains = len(seeds_a)
+        n = self.nVars
+        dense = cfg.mass_tuner == abi.RN_MASS_DENSE or (cfg.mass_tuner == abi.RN_MASS_STATIC and cfg.static_matrix == abi.RN_MATRIX_DENSE)
+        pred = out if out is not None else np.empty((nChains, cfg.iterations, function.nOutputs), dtype=np.float64)
+        mass = np.empty((nChains, n * n if dense else n), dtype=np.float64)
+        stats = (ChainStats * nChains)()
+        rings = np.zeros((nChains, 3, cfg.stats_window), dtype=np.float64)
+        cfg.stats_rings = rings.ctypes.data_as(C.POINTER(C.c_double))
+        _check(lib().rn_sample_predict(self.h, C.byref(cfg), function.h, seeds_a.ctypes.data, nChains, pred.ctypes.data,
+                                       mass.ctypes.data, C.cast(stats, C.c_void_p)))
+        return pred, Trace(None, mass, [Stats(stats[c], rings[c]) for c in range(nChains)])
 
     # -- Model.optimize / Optimizer.lbfgs, batched over starts --
     @staticmethod

@@ -2303,3 +2303,62 @@ int rn_optimize(rn_model* m, const rn_optimize_config* oc, const double* x0, int
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// rn_sample_predict: `Model.sample(t, config)` (rainier-core/.../core/Model.scala:56-63) = model.sample(config).predict(gen)
+// in one call.  The draws never leave the device: the chains are sampled into a resident [iterations][n][chains] block,
+// rn_k_eval turns it into the generator's requirement values in Trace.predict's order, and only those
+// chains*iterations*m doubles cross PCIe (m/n of what rn_sample ships; a single predicted Real of the funnel: 10x less).
+// Built from the staged entry points (rn_sampler_*, rn_function_eval_device); rn_sample itself is untouched.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int rn_sample_predict(rn_model* m, const rn_config* cfg, rn_function* f, const int64_t* seeds, int chains,
+                                 double* predictions, double* mass, rn_chain_stats* stats) {
+  if (!m || !cfg || !f || chains <= 0 || cfg->iterations < 0) return fail(RN_E_INVALID, "bad argument");
+  if (!predictions && cfg->iterations > 0) return fail(RN_E_INVALID, "null predictions buffer");
+  if (m->device < 0 || f->device < 0) return fail(RN_E_CUDA, "model/function was created without a device (no CPU fallback)");
+  if (m->device != f->device) return fail(RN_E_INVALID, "model and function live on different devices");
+  if (f->prog.n_params != m->n_params) return fail(RN_E_INVALID, "the function's inputs are not the model's parameters");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  rn_sampler* s = nullptr;
+  int rc = rn_sampler_create(m, cfg, seeds, chains, &s);
+  if (rc) return rc;
+  struct Guard {
+    rn_sampler* s;
+    ~Guard() { rn_sampler_destroy(s); }
+  } g{s};
+  rc = rn_sampler_warmup(s, -1);
+  if (rc) return rc;
+  rc = rn_sampler_run(s, 0, nullptr);  // lf.resetStats() after warmup even when no iteration follows (Driver.scala:31)
+  if (rc) return rc;
+  const size_t C = (size_t)chains, n = m->n_params, I = (size_t)cfg->iterations, mo = f->prog.fn_outputs.size();
+  if (I > 0) {
+    const size_t want[2] = {I * n * C * 8 /* draws [I][n][C] */, C * I * mo * 8 /* predictions [C][I][m] */};
+    for (int k = 0; k < 2; k++)
+      if (m->pool_bytes[k] < want[k]) {
+        if (m->pool[k]) A->cuMemFree(m->pool[k]);
+        m->pool[k] = 0;
+        m->pool_bytes[k] = 0;
+        CU(A->cuMemAlloc(&m->pool[k], want[k]));
+        m->pool_bytes[k] = want[k];
+      }
+    rc = rn_sampler_run(s, (int)I, (double*)(uintptr_t)m->pool[0]);
+    if (rc) return rc;
+    rc = function_load(A, f);  // same primary context as the model's
+    if (rc) return rc;
+    // on the sampler's stream: ordered after the last rn_k_iter launch, no event needed
+    rc = rn_function_eval_device(f, (const double*)(uintptr_t)m->pool[0], RN_LAYOUT_SAMPLER, (int64_t)I, (int64_t)C,
+                                 (double*)(uintptr_t)m->pool[1], (void*)s->stream);
+    if (rc) return rc;
+    rc = drain_to_host(A, s->stream, m->pool[1], predictions, want[1], /*sync=*/true);
+    if (rc) return rc;
+    if (cfg->diagnostics) {
+      rc = rn_sampler_diagnostics(s, (const double*)(uintptr_t)m->pool[0], (int)I, 0, cfg->diagnostics);
+      if (rc) return rc;
+    }
+    rc = rn_function_sync(f);  // lookup errors of the evaluation
+    if (rc) return rc;
+  }
+  return rn_sampler_stats(s, stats, mass, cfg->stats_rings);
+}

@@ -91,6 +91,13 @@ def main():
         t0 = time.perf_counter()
         f(hx)
         t_e2e.append(time.perf_counter() - t0)
+    # one call for sample + predict (object Model.sample(t, config)): only the m requirement values cross PCIe
+    pb = api.PinnedBuffer((chains, iters, m))
+    t_sp = []
+    for k in range(3):
+        t0 = time.perf_counter()
+        cm.sample_predict(f, cfg, seeds=np.arange(chains) + 1000, out=pb.array)
+        t_sp.append(time.perf_counter() - t0)
     # cpu baseline: bounded sample on one core
     sample = hx[: min(count, 2_000_000)]
     of = OracleFunction(frir)
@@ -108,7 +115,11 @@ def main():
                      "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
                      "bytes_per_draw": (n + m) * 8.0, "peak_source": src},
         "e2e": {"value": count / min(t_e2e), "unit": "draws/s", "h2d_bytes_per_step": count * n * 8, "d2h_bytes_per_step": count * m * 8,
-                "api": "rn_function_eval (C ABI), pageable host buffers"},
+                "api": "rn_function_eval (C ABI), pageable host buffers",
+                "sample_predict_ms_per_call": min(t_sp) * 1e3,
+                "sample_predict_note": "rn_sample_predict: 50 warmup + %d sampling iterations of HMC(5) for %d chains, predictions "
+                                       "[chains][iterations][m] into a page-locked buffer (%d MB instead of %d MB of draws)"
+                                       % (iters, chains, count * m * 8 >> 20, count * n * 8 >> 20)},
         "cpu_baseline": {"value": len(sample) / t_cpu, "unit": "draws/s", "cores": 1, "kind": "port",
                          "sample": "%d draws through rno_function_eval" % len(sample)},
     }))

@@ -143,6 +143,9 @@ def test_function_container_validation_and_no_cpu_fallback():
     with pytest.raises(api.RainierCudaError) as e:  # no device: emit/compile only, evaluation fails loudly
         f(np.zeros((1, 10)))
     assert e.value.code == abi.RN_E_CUDA
+    with pytest.raises(api.RainierCudaError) as e:  # sample + predict in one call: same rule
+        api.CudaModel(*model.compile(True), device=-1).sample_predict(f, api.SamplerConfig(iterations=2, warmupIterations=2), seeds=[1])
+    assert e.value.code == abi.RN_E_CUDA
     # a model container is not a function container and vice versa
     mrir, cols = model.compile(True)
     with pytest.raises(api.RainierCudaError) as e:

@@ -115,3 +115,27 @@ def test_function_lookup_error_and_fast_math():
     rir2 = compile_function_rir(model.parameters, reals)
     x = np.random.default_rng(4).normal(size=(1000, 10))
     np.testing.assert_allclose(api.CudaFunction(rir2, fast=True)(x), OracleFunction(rir2)(x), rtol=1e-9, atol=1e-12)  # north_star's 1e-9 relative; FMA contraction moves last bits of cancelling sums
+
+
+def test_sample_predict_in_one_call():
+    """object Model.sample(t, config) (core/Model.scala:56-63) = model.sample(config).predict(gen): rn_sample_predict keeps
+    the draws on the device and returns only the requirement values -- identical to rn_sample followed by rn_function_eval."""
+    model, mu, tau, thetas, _ = schools()
+    reals = _derived(mu, tau, thetas)
+    rir, cols = model.compile(True)
+    cm = api.CudaModel(rir, cols)
+    f = api.CudaFunction(compile_function_rir(model.parameters, reals))
+    cfg = api.SamplerConfig(iterations=41, warmupIterations=150)
+    seeds = np.arange(777) + 11
+    pred, tr = cm.sample_predict(f, cfg, seeds=seeds)
+    full = cm.sample(cfg, seeds=seeds)
+    assert pred.shape == (777, 41, len(reals))
+    assert np.array_equal(pred.reshape(-1, len(reals)), full.requirements(f))
+    assert np.array_equal(pred, OracleFunction(f._rir)(full.chains.reshape(-1, cm.nVars)).reshape(pred.shape))
+    assert [s.gradientEvaluations for s in tr.stats] == [s.gradientEvaluations for s in full.stats]
+    assert np.array_equal(tr.mass, full.mass)
+    # page-locked destination: one DMA
+    buf = api.PinnedBuffer((777, 41, len(reals)))
+    pred2, _ = cm.sample_predict(f, cfg, seeds=seeds, out=buf.array)
+    assert np.array_equal(pred2, pred)
+    buf.close()
