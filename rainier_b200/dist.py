@@ -64,3 +64,25 @@ def gather_samples(local, total_chains, group=None):
     out = np.concatenate(pieces, axis=0)
     assert out.shape[0] == total_chains
     return out
+
+
+def best_start(x, f, info=None, group=None):
+    """multi-start MAP over ranks (rn_optimize): every rank optimises its block of starts
+    (`chain_block(total_starts, rank, world)`); the job's answer is the converged start with the smallest f = -density.
+    x: [starts_r][n], f: [starts_r], info: [starts_r] exit codes (0 = converged) -> (x_best [n], f_best, owner_rank) on
+    every rank.  One small all-gather of (f, x) per rank; ties and NaNs resolve to the lowest (rank, index), so the
+    result does not depend on the rank layout."""
+    import torch.distributed as dist
+    x, f = np.asarray(x, dtype=np.float64), np.asarray(f, dtype=np.float64).copy()
+    if info is not None:
+        f[np.asarray(info) != 0] = np.inf
+    f[np.isnan(f)] = np.inf
+    k = int(np.argmin(f)) if len(f) else -1
+    mine = (float(f[k]), x[k].copy()) if k >= 0 else (np.inf, None)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return mine[1], mine[0], 0
+    world = dist.get_world_size(group)
+    pieces = [None] * world
+    dist.all_gather_object(pieces, mine, group=group)
+    owner = min(range(world), key=lambda r: (pieces[r][0], r))
+    return pieces[owner][1], pieces[owner][0], owner

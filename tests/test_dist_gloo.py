@@ -46,6 +46,16 @@ def _worker(rank, world, port, total, out_dir):
     stats = torch.tensor(np.concatenate([[q.shape[0]], q.sum(axis=0), (q * q).sum(axis=0)]), dtype=torch.float64)
     rdist.allreduce_window_stats(stats)
     tmax = rdist.max_over_ranks(1.0 + rank)
+    # multi-start MAP: starts sharded like chains, the best converged start is the job's answer on every rank
+    from oracle.rainier_py.optimizer import lbfgs
+    srir = open(os.path.join(ROOT, "rainier_b200", "models", "eight_schools.rir"), "rb").read()
+    om = OracleModel(srir, [])
+    starts = np.random.default_rng(5).normal(size=(total, 10)) * 0.7
+    lo, hi = rdist.chain_block(total, rank, world)
+    res = [lbfgs(om.density_batch, 10, x0=x, max_evals=300) for x in starts[lo:hi]]
+    xb, fb, owner = rdist.best_start([r["x"] for r in res], [r["f"] for r in res], [r["info"] for r in res])
+    if rank == 0:
+        np.save(os.path.join(out_dir, "best.npy"), np.concatenate([xb, [fb, owner]]))
     if rank == 0:
         np.save(os.path.join(out_dir, "full.npy"), full)
         np.save(os.path.join(out_dir, "stats.npy"), stats.numpy())
@@ -87,3 +97,13 @@ def test_two_ranks_gloo(tmp_path):
     var = rdist.pooled_variance(stats[0], stats[1:11], stats[11:])
     assert np.allclose(var, q.var(axis=0), rtol=1e-9)
     assert np.load(tmp_path / "tmax.npy")[0] == 2.0
+    # multi-start MAP over 2 ranks == the same starts in one process
+    from oracle.rainier_py.optimizer import lbfgs
+    om = OracleModel(open(os.path.join(ROOT, "rainier_b200", "models", "eight_schools.rir"), "rb").read(), [])
+    starts = np.random.default_rng(5).normal(size=(total, 10)) * 0.7
+    res = [lbfgs(om.density_batch, 10, x0=x, max_evals=300) for x in starts]
+    xb, fb, _ = rdist.best_start([r["x"] for r in res], [r["f"] for r in res], [r["info"] for r in res])
+    best = np.load(tmp_path / "best.npy")
+    assert np.array_equal(best[:10], xb) and best[10] == fb
+    lo, hi = rdist.chain_block(total, int(best[11]), world)
+    assert any(np.array_equal(r["x"], xb) for r in res[lo:hi])
