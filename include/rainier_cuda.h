@@ -267,7 +267,8 @@ int rn_sample_predict(rn_model* m, const rn_config* cfg, rn_function* f, const i
  *                         the body of Model.optimize (rainier-core/.../core/Model.scala:26-30)
  * The reference optimises from the single start x = 0.  Here every start of a batch is one GPU thread that runs the whole
  * optimisation (density + gradient + line search + history) inside one kernel; start c with x0 = NULL (or a zero row) is
- * bit-identical to the reference's run.  Thread-per-chain models only (n*(2*history+4) <= 4096 doubles per start). */
+ * bit-identical to the reference's run (thread-per-start shape: n*(2*history+4) <= 4096 doubles per start).  Streamed models
+ * and large n use one warp per start (rows across lanes, L-BFGS history in shared memory). */
 typedef struct rn_optimize_config {
   int32_t struct_size;
   int32_t history;          /* m of new LBFGS(x, m, eps); Optimizer.scala:12 uses 5 */
@@ -275,7 +276,9 @@ typedef struct rn_optimize_config {
   int32_t max_evaluations;  /* per start; the reference loops without a cap -- a kernel needs one (default 10000) */
   int32_t math_mode;        /* RN_MATH_* */
   int32_t gradient_mode;    /* RN_GRAD_* */
-  int32_t reserved;
+  int32_t backend;          /* RN_BACKEND_AUTO | RN_BACKEND_THREAD (one thread per start: bit-identical to the reference's
+                               run) | RN_BACKEND_WARP (one warp per start: streamed models, history in shared memory; sums in
+                               tree order -> agreement to rounding) */
 } rn_optimize_config;
 void rn_optimize_config_default(rn_optimize_config* cfg);
 /* x0: host [starts][n] or NULL (all starts at 0).  x: host [starts][n].  f: host [starts] = -density at x (what LBFGS

@@ -82,4 +82,4 @@ class ChainStats(C.Structure):
 
 class OptimizeConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("history", C.c_int32), ("eps", C.c_double), ("max_evaluations", C.c_int32),
-                ("math_mode", C.c_int32), ("gradient_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("math_mode", C.c_int32), ("gradient_mode", C.c_int32), ("backend", C.c_int32)]

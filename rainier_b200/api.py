@@ -540,12 +540,13 @@ class CudaModel:
 
     # -- Model.optimize / Optimizer.lbfgs, batched over starts --
     @staticmethod
-    def _optimize_config(m=5, eps=0.1, max_evals=10000, fast=False, gradient_mode=abi.RN_GRAD_AUTO):
+    def _optimize_config(m=5, eps=0.1, max_evals=10000, fast=False, gradient_mode=abi.RN_GRAD_AUTO, backend=abi.RN_BACKEND_AUTO):
         oc = abi.OptimizeConfig()
         lib().rn_optimize_config_default(C.byref(oc))
         oc.history, oc.eps, oc.max_evaluations = int(m), float(eps), int(max_evals)
         oc.math_mode = abi.RN_MATH_FAST if fast else abi.RN_MATH_PARITY
         oc.gradient_mode = gradient_mode
+        oc.backend = backend
         return oc
 
     def optimize(self, x0=None, starts=1, **kw):

@@ -579,12 +579,19 @@ std::string emit_optimizer_source(const Program& P, const EmitOptions& opt, int 
   os << "// generated by rainier_b200 (CUDA source emitter, optimizer flavour) -- do not edit\n";
   os << "#define RN_N " << P.n_params << "\n";
   os << "#define RN_NSLOTS " << P.n_slots << "\n";
-  os << "#define RN_BACKEND 0\n";
+  os << "#define RN_BACKEND " << (opt.backend == 1 ? 1 : 0) << "\n";
   os << "#define RN_LBFGS_M " << history << "\n";
   if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
-  os << kPreludeSource << "\n";
   EmitOptions eo = opt;
-  eo.backend = 0;
+  if (opt.backend == 1) {  // one warp per start, independent per-warp row loads (no CTA-shared tiles: starts diverge)
+    eo.wpc_k = 1;
+    eo.tma_stages = 0;
+    eo.enable_ehmc = false;
+    os << "#define RN_WPC_K 1\n#define RN_TMA_STAGES 0\n#define RN_TMA_TILE_DOUBLES 0\n";
+  } else {
+    eo.backend = 0;
+  }
+  os << kPreludeSource << "\n";
   os << emit_density(P, eo) << "\n" << kOptimizerSource << "\n";
   return os.str();
 }

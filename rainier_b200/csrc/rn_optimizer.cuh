@@ -1,4 +1,4 @@
-// rn_optimizer.cuh -- hand-written: batched multi-start MAP optimisation, one thread per start.
+// rn_optimizer.cuh -- hand-written: batched multi-start MAP optimisation, one thread (or one warp) per start.
 //
 // Replaces the loop of Optimizer.lbfgs (rainier-sampler/.../optimizer/Optimizer.scala:6-24) -- `df.update(x)`; negate
 // density and gradient; `complete = lb(f, g)` -- together with the reverse-communication L-BFGS it drives
@@ -15,9 +15,29 @@
 #ifndef RN_OPTIMIZER_CUH
 #define RN_OPTIMIZER_CUH
 
+// Two shapes share this source (like the samplers):
+//   RN_BACKEND 0, one THREAD per start: vectors in thread-local memory, every sum sequential -> bit-identical to the oracle.
+//   RN_BACKEND 1, one WARP per start (streamed models / many parameters): the start's vectors (x, g, diag and the 2m-vector
+//     history) live in the warp's shared-memory slice and are updated lane-strided; dot products are per-lane partial sums
+//     + a shuffle butterfly (all lanes hold the same total), scalars and the whole line-search logic are replicated and
+//     identical in all lanes, so control flow stays warp-uniform.  Sums become trees -> agreement with the oracle to
+//     rounding (and the emitted rn_density() itself sums rows in tree order there), not bit for bit.
+//   A lane only ever re-reads vector elements it wrote itself (same striding everywhere); the one cross-lane hand-off is
+//   x -> rn_density(), fenced by RN_LB_SYNC().
 #ifndef RN_LBFGS_M
 #define RN_LBFGS_M 5  // Optimizer.scala:12
 #endif
+#if RN_BACKEND == 1
+#define RN_LB_LANE ((int)(threadIdx.x % RN_G))
+#define RN_LB_FOR_N(i, count) for (int i = RN_LB_LANE; i < (count); i += RN_G)
+#define RN_LB_REDUCE(s) rn_warp_sum(s)
+#define RN_LB_SYNC() RN_SYNC()
+#else
+#define RN_LB_FOR_N(i, count) for (int i = 0; i < (count); i++)
+#define RN_LB_REDUCE(s) (s)
+#define RN_LB_SYNC()
+#endif
+#define RN_LB_FOR(i) RN_LB_FOR_N(i, RN_N)
 #define RN_LB_W (RN_N * (2 * RN_LBFGS_M + 1) + 2 * RN_LBFGS_M)
 #define RN_LB_ISPT (RN_N + 2 * RN_LBFGS_M)
 #define RN_LB_IYPT (RN_LB_ISPT + RN_N * RN_LBFGS_M)
@@ -37,7 +57,7 @@ RN_DEVICE double rn_jmax(double a, double b) {
 RN_DEVICE double rn_max3(double a, double b, double c) { return a < b ? (b < c ? c : b) : (a < c ? c : a); }
 
 struct RnLbfgs {
-  double x[RN_N], diag[RN_N], w[RN_LB_W];
+  double *x, *diag, *w;  // [RN_N], [RN_N], [RN_LB_W]: thread-local arrays (backend 0) or the warp's shared-memory slice
   double eps, stp, stp1, ys, yy;
   int iter, point, npt, info, nfev, bound;
   // line-search state
@@ -45,20 +65,23 @@ struct RnLbfgs {
   int infoc, brackt, stage1;
 };
 
-RN_DEVICE double rn_lb_dot(const double* a, const double* b) {  // ddot with unit strides: a sequential sum
+RN_DEVICE double rn_lb_dot(const double* a, const double* b) {  // ddot with unit strides: a sequential sum (backend 0)
   double s = 0.0;
-  for (int i = 0; i < RN_N; i++) s = s + a[i] * b[i];
-  return s;
+  RN_LB_FOR(i) s = s + a[i] * b[i];
+  return RN_LB_REDUCE(s);
 }
 RN_DEVICE void rn_lb_axpy(double da, const double* a, double* y) {  // daxpy; a zero factor leaves y untouched
   if (da == 0.0) return;
-  for (int i = 0; i < RN_N; i++) y[i] = y[i] + da * a[i];
+  RN_LB_FOR(i) y[i] = y[i] + da * a[i];
 }
 
-RN_DEVICE void rn_lb_init(RnLbfgs& S, double eps) {
+RN_DEVICE void rn_lb_init(RnLbfgs& S, double* x, double* diag, double* w, double eps) {
+  S.x = x;
+  S.diag = diag;
+  S.w = w;
   S.eps = eps;
-  for (int i = 0; i < RN_LB_W; i++) S.w[i] = 0.0;
-  for (int i = 0; i < RN_N; i++) S.diag[i] = 1.0;
+  RN_LB_FOR_N(i, RN_LB_W) S.w[i] = 0.0;
+  RN_LB_FOR(i) S.diag[i] = 1.0;
   S.iter = S.point = S.npt = S.info = S.nfev = S.bound = 0;
   S.stp = S.stp1 = S.ys = S.yy = 0.0;
   S.dginit = S.dgtest = S.finit = S.stmin = S.stmax = S.width = S.width1 = 0.0;
@@ -183,8 +206,7 @@ RN_DEVICE bool rn_lb_search(RnLbfgs& S, const double f, const double* g) {
   const double* dir = S.w + RN_LB_ISPT + S.point * RN_N;
   if (S.info != -1) {
     S.infoc = 1;
-    S.dginit = 0;
-    for (int j = 0; j < RN_N; j++) S.dginit = S.dginit + g[j] * dir[j];
+    S.dginit = rn_lb_dot(g, dir);
     if (S.dginit >= 0) return false;
     S.brackt = 0;
     S.stage1 = 1;
@@ -193,7 +215,7 @@ RN_DEVICE bool rn_lb_search(RnLbfgs& S, const double f, const double* g) {
     S.dgtest = FTOL * S.dginit;
     S.width = STPMAX - STPMIN;
     S.width1 = S.width / P5;
-    for (int j = 0; j < RN_N; j++) S.diag[j] = S.x[j];
+    RN_LB_FOR(j) S.diag[j] = S.x[j];
     S.stx = 0;
     S.fx = S.finit;
     S.dgx = S.dginit;
@@ -215,14 +237,13 @@ RN_DEVICE bool rn_lb_search(RnLbfgs& S, const double f, const double* g) {
       if ((S.brackt && (S.stp <= S.stmin || S.stp >= S.stmax)) || S.nfev >= MAXFEV - 1 || S.infoc == 0 ||
           (S.brackt && S.stmax - S.stmin <= XTOL * S.stmax))
         S.stp = S.stx;
-      for (int j = 0; j < RN_N; j++) S.x[j] = S.diag[j] + S.stp * dir[j];
+      RN_LB_FOR(j) S.x[j] = S.diag[j] + S.stp * dir[j];
       S.info = -1;
       return true;
     }
     S.info = 0;
     S.nfev = S.nfev + 1;
-    double dg = 0;
-    for (int j = 0; j < RN_N; j++) dg = dg + g[j] * dir[j];
+    const double dg = rn_lb_dot(g, dir);
     const double ftest1 = S.finit + S.stp * S.dgtest;
     if ((S.brackt && (S.stp <= S.stmin || S.stp >= S.stmax)) || S.infoc == 0) S.info = 6;
     if (S.stp == STPMAX && f <= ftest1 && dg <= S.dgtest) S.info = 5;
@@ -260,7 +281,7 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
   double* w = S.w;
   bool whole = false;
   if (S.iter == 0) {
-    for (int i = 0; i < RN_N; i++) w[RN_LB_ISPT + i] = -g[i] * S.diag[i];
+    RN_LB_FOR(i) w[RN_LB_ISPT + i] = -g[i] * S.diag[i];
     const double gnorm = sqrt(rn_lb_dot(g, g));
     S.stp1 = 1 / gnorm;
     whole = true;
@@ -275,11 +296,11 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
         S.ys = rn_lb_dot(w + RN_LB_IYPT + S.npt, w + RN_LB_ISPT + S.npt);
         S.yy = rn_lb_dot(w + RN_LB_IYPT + S.npt, w + RN_LB_IYPT + S.npt);
         const double h0 = S.ys / S.yy;
-        for (int i = 0; i < RN_N; i++) S.diag[i] = h0;
+        RN_LB_FOR(i) S.diag[i] = h0;
         int cp = S.point;
         if (S.point == 0) cp = RN_LBFGS_M;
         w[RN_N + cp - 1] = 1 / S.ys;
-        for (int i = 0; i < RN_N; i++) w[i] = -g[i];
+        RN_LB_FOR(i) w[i] = -g[i];
         cp = S.point;
         for (int k = 0; k < S.bound; k++) {  // backward pass over the history
           cp = cp - 1;
@@ -289,7 +310,7 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
           w[inmc] = w[RN_N + cp] * sq;
           rn_lb_axpy(-w[inmc], w + RN_LB_IYPT + cp * RN_N, w);
         }
-        for (int i = 0; i < RN_N; i++) w[i] = S.diag[i] * w[i];
+        RN_LB_FOR(i) w[i] = S.diag[i] * w[i];
         for (int k = 0; k < S.bound; k++) {  // forward pass
           const double yr = rn_lb_dot(w + RN_LB_IYPT + cp * RN_N, w);
           double beta = w[RN_N + cp] * yr;
@@ -298,17 +319,17 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
           cp = cp + 1;
           if (cp == RN_LBFGS_M) cp = 0;
         }
-        for (int i = 0; i < RN_N; i++) w[RN_LB_ISPT + S.point * RN_N + i] = w[i];
+        RN_LB_FOR(i) w[RN_LB_ISPT + S.point * RN_N + i] = w[i];
       }
       S.nfev = 0;
       S.stp = 1;
       if (S.iter == 1) S.stp = S.stp1;
-      for (int i = 0; i < RN_N; i++) w[i] = g[i];
+      RN_LB_FOR(i) w[i] = g[i];
     }
     if (!rn_lb_search(S, f, g)) return 2;
     if (S.info == -1) return 0;
     S.npt = S.point * RN_N;
-    for (int i = 0; i < RN_N; i++) {
+    RN_LB_FOR(i) {
       w[RN_LB_ISPT + S.npt + i] = S.stp * w[RN_LB_ISPT + S.npt + i];
       w[RN_LB_IYPT + S.npt + i] = g[i] - w[i];
     }
@@ -322,28 +343,59 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
   }
 }
 
+#define S_X_ARRAY(a) (*reinterpret_cast<double (*)[RN_N]>(a))  // the thread-per-chain density takes array references
 // =============================================================================================================
 // rn_k_lbfgs: x0 [N][starts] (NULL: all starts at 0, the reference's only start) -> x [N][starts], f [starts] = -density
 // at x, info [starts] (bit 0 evaluation cap reached, bit 1 "dginit", bit 2 lookup error), evals [starts]
 // =============================================================================================================
+#if RN_BACKEND == 1
+// shared-memory slice of one start: x | gradient | g = -gradient | diag | w | scratch of the emitted density
+#define RN_OPT_SMEM_DOUBLES (4 * RN_N + RN_LB_W + RN_WPC_SCRATCH)
+#ifdef RN_HOST_EMULATION
+static double rn_smem[1 << 17];  // one emulated start at a time
+#else
+extern __shared__ __align__(128) double rn_smem[];
+#endif
+#endif
+
 RN_GLOBAL void rn_k_lbfgs(const RnOptArgs A) {
+#if RN_BACKEND == 1
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) / RN_G);
+  if (c >= A.starts) return;  // the whole warp leaves together
+  double* base = rn_smem + (size_t)RN_GROUP * RN_OPT_SMEM_DOUBLES;
+  double *x = base, *grad = base + RN_N, *g = base + 2 * RN_N, *diag = base + 3 * RN_N, *w = base + 4 * RN_N;
+  double* scr = base + 4 * RN_N + RN_LB_W;
+  RnTma tma;  // the CTA-shared tile pipeline stays off: starts take different numbers of evaluations
+  tma.on = 0;
+  tma.seq = 0;
+  tma.nthreads = 0;
+  tma.stage = nullptr;
+  tma.full = nullptr;
+#else
   const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= A.starts) return;
+  double x[RN_N], grad[RN_N], g[RN_N], diag[RN_N], w[RN_LB_W];
+#endif
   RnLbfgs S;
-  rn_lb_init(S, A.eps);
-  for (int i = 0; i < RN_N; i++) S.x[i] = A.x0 ? A.x0[(size_t)i * A.starts + c] : 0.0;
+  rn_lb_init(S, x, diag, w, A.eps);
+  RN_LB_FOR(i) x[i] = A.x0 ? A.x0[(size_t)i * A.starts + c] : 0.0;
   int evals = 0, info = 0, err = 0;
-  double f = RN_NAN, g[RN_N], grad[RN_N];
+  double f = RN_NAN;
   for (;;) {
     if (evals >= A.max_evals) {
       info = 1;
       break;
     }
     double dens;
-    rn_density(S.x, dens, grad, A.data, err);  // df.update(x), Optimizer.scala:15
+    RN_LB_SYNC();  // x was written lane-strided; the density reads all of it in every lane
+#if RN_BACKEND == 1
+    rn_density(x, dens, grad, scr, A.data, err, tma);  // df.update(x), Optimizer.scala:15 (ends with a group barrier)
+#else
+    rn_density(S_X_ARRAY(x), dens, S_X_ARRAY(grad), A.data, err);  // df.update(x), Optimizer.scala:15
+#endif
     evals++;
     f = dens * -1;
-    for (int i = 0; i < RN_N; i++) g[i] = grad[i] * -1;
+    RN_LB_FOR(i) g[i] = grad[i] * -1;
     const int r = rn_lb_apply(S, f, g);
     if (r == 1) break;
     if (r == 2) {
@@ -352,7 +404,10 @@ RN_GLOBAL void rn_k_lbfgs(const RnOptArgs A) {
     }
   }
   if (err & 1) info |= 4;
-  for (int i = 0; i < RN_N; i++) A.x[(size_t)i * A.starts + c] = S.x[i];
+  RN_LB_FOR(i) A.x[(size_t)i * A.starts + c] = x[i];
+#if RN_BACKEND == 1
+  if (RN_LB_LANE != 0) return;
+#endif
   A.f[c] = f;
   A.info[c] = info;
   A.evals[c] = evals;

@@ -201,8 +201,11 @@ struct rn_model {
     std::vector<char> cubin;
     CUmodule mod = nullptr;
     CUfunction k_lbfgs = nullptr;
+    int backend = 0;           // 0 one thread per start, 1 one warp per start
+    int smem_doubles = 0;      // backend 1: shared-memory slice of one start
+    int starts_per_cta = 1;    // backend 1
   };
-  std::map<std::tuple<bool, bool, int>, std::unique_ptr<OptKernel>> opt_kernels;
+  std::map<std::tuple<bool, bool, int, int>, std::unique_ptr<OptKernel>> opt_kernels;
 };
 
 static int make_current(const Api* A, rn_model* m) {
@@ -2161,7 +2164,12 @@ static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::O
   const bool adjoint = (gm == RN_GRAD_ADJOINT) || !m->rir_has_gradient;
   const int history = oc && oc->history > 0 ? oc->history : 5;
   if (history > 64) return fail(RN_E_INVALID, "L-BFGS history too long");
-  auto key = std::make_tuple(adjoint, fast, history);
+  // shape: like the samplers -- a warp per start when rows are streamed in earnest or the state is large
+  int want = oc ? oc->backend : RN_BACKEND_AUTO;
+  if (const char* e = getenv("RN_BACKEND")) want = atoi(e);
+  if (want == RN_BACKEND_AUTO) want = key_for(m, nullptr).backend == 1 ? RN_BACKEND_WARP : RN_BACKEND_THREAD;
+  const int backend = want == RN_BACKEND_WARP ? 1 : 0;
+  auto key = std::make_tuple(adjoint, fast, history, backend);
   auto it = m->opt_kernels.find(key);
   if (it != m->opt_kernels.end()) {
     *out = it->second.get();
@@ -2170,14 +2178,30 @@ static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::O
   const Program* P = nullptr;
   int rc = get_program(m, adjoint, fast, &P);
   if (rc) return rc;
-  // the whole optimisation state of a start is thread-local: x, g, diag and the 2m-vector history
-  if ((uint64_t)P->n_params * (2 * (uint64_t)history + 4) > 4096)
-    return fail(RN_E_UNSUPPORTED, "rn_optimize keeps n*(2m+4) doubles per start in thread-local memory; model too large");
   std::unique_ptr<rn_model::OptKernel> K(new rn_model::OptKernel());
+  K->backend = backend;
   EmitOptions eo;
-  eo.backend = 0;
+  eo.backend = backend;
   eo.fast_math = fast;
   eo.target_base = m->target_base;
+  const uint64_t lb_w = (uint64_t)P->n_params * (2 * (uint64_t)history + 1) + 2 * (uint64_t)history;
+  if (backend == 0) {
+    // the whole optimisation state of a start is thread-local: x, g, diag and the 2m-vector history
+    if ((uint64_t)P->n_params * (2 * (uint64_t)history + 4) > 4096)
+      return fail(RN_E_UNSUPPORTED, "rn_optimize (thread per start) keeps n*(2m+4) doubles per start in thread-local memory; use RN_BACKEND_WARP");
+  } else {
+    if (P->symbolic && P->n_params > 96)
+      return fail(RN_E_UNSUPPORTED, "warp-per-start with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
+    eo.wpc_k = 1;
+    eo.tma_stages = 0;
+    eo.enable_ehmc = false;
+    const WpcSizes z = wpc_sizes(*P, eo);  // 4n (x, gradient, g, diag reuse the sampler's q/p/g/m slots) + density scratch
+    const uint64_t per_start = (uint64_t)z.per_warp_doubles + lb_w;
+    const uint64_t cap = (227 * 1024 - 2048) / 8;
+    if (per_start > cap) return fail(RN_E_UNSUPPORTED, "rn_optimize: the L-BFGS history of one start does not fit shared memory");
+    K->smem_doubles = (int)per_start;
+    K->starts_per_cta = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, cap / per_start));
+  }
   K->source = emit_optimizer_source(*P, eo, history);
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(fast ? "--fmad=true" : "--fmad=false");
@@ -2213,6 +2237,7 @@ void rn_optimize_config_default(rn_optimize_config* c) {  // Optimizer.scala:12-
   c->max_evaluations = 10000;
   c->math_mode = RN_MATH_PARITY;
   c->gradient_mode = RN_GRAD_AUTO;
+  c->backend = RN_BACKEND_AUTO;
 }
 
 int rn_optimize_emit_source(rn_model* m, const rn_optimize_config* oc, char* buf, size_t cap, size_t* needed) {
@@ -2254,6 +2279,8 @@ int rn_optimize(rn_model* m, const rn_optimize_config* oc, const double* x0, int
   if (!K->mod) {
     CU(A->cuModuleLoadData(&K->mod, K->cubin.data()));
     CU(A->cuModuleGetFunction(&K->k_lbfgs, K->mod, "rn_k_lbfgs"));
+    if (K->backend == 1)
+      CU(A->cuFuncSetAttribute(K->k_lbfgs, 8 /*MAX_DYNAMIC_SHARED_SIZE_BYTES*/, K->starts_per_cta * K->smem_doubles * 8));
   }
   const size_t n = m->n_params, S = (size_t)starts;
   // one allocation: x0 | x | f | info | evals
@@ -2286,9 +2313,15 @@ int rn_optimize(rn_model* m, const rn_optimize_config* oc, const double* x0, int
   a.starts = starts;
   a.max_evals = oc && oc->max_evaluations > 0 ? oc->max_evaluations : 10000;
   void* params[] = {&a};
-  // small CTAs spread few starts over all SMs; starts diverge (different trajectory lengths), so warps are the unit
-  const unsigned block = starts >= 148 * 128 ? 128 : 32;
-  CU(A->cuLaunchKernel(K->k_lbfgs, (unsigned)((S + block - 1) / block), 1, 1, block, 1, 1, 0, nullptr, params, nullptr));
+  if (K->backend == 1) {
+    const unsigned spc = (unsigned)K->starts_per_cta;
+    CU(A->cuLaunchKernel(K->k_lbfgs, (unsigned)((S + spc - 1) / spc), 1, 1, spc * 32, 1, 1, spc * (unsigned)K->smem_doubles * 8, nullptr,
+                         params, nullptr));
+  } else {
+    // small CTAs spread few starts over all SMs; starts diverge (different trajectory lengths), so warps are the unit
+    const unsigned block = starts >= 148 * 128 ? 128 : 32;
+    CU(A->cuLaunchKernel(K->k_lbfgs, (unsigned)((S + block - 1) / block), 1, 1, block, 1, 1, 0, nullptr, params, nullptr));
+  }
   CU(A->cuMemcpyDtoH(t.data(), d + off_x, n * S * 8));
   for (size_t c = 0; c < S; c++)
     for (size_t i = 0; i < n; i++) x[c * n + i] = t[i * S + c];

@@ -88,7 +88,7 @@ extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, c
 }
 """
 
-_WPC_SHIM = r"""
+_WPC_RUNNER = r"""
 #include <thread>
 #include <vector>
 #include <functional>
@@ -109,6 +109,9 @@ static void rn_emu_run_warp(int block, int nblocks, const std::function<void()>&
   pthread_barrier_destroy(&g.bar);
   for (int k = 0; k < RN_WPC_K; k++) pthread_barrier_destroy(&g.warp[k].bar);
 }
+"""
+
+_WPC_SHIM = _WPC_RUNNER + r"""
 extern "C" void emu_density(const double* q, int chains, double* out, const double* data, int* err) {
   for (int c = 0; c < chains; c++) rn_emu_run_warp(c, chains, [&] { rn_k_density(q, out, data, err, chains); });
 }
@@ -149,6 +152,17 @@ extern "C" void emu_lbfgs(const double* x0, double* x, double* f, int* info, int
 """
 
 
+_OPTIMIZER_SHIM_WPC = r"""
+// one emulated start = one warp of 32 host threads (see _WPC_RUNNER)
+extern "C" void emu_lbfgs(const double* x0, double* x, double* f, int* info, int* evals, const double* data, double eps,
+                          int starts, int max_evals) {
+  RnOptArgs a;
+  a.x0 = x0; a.x = x; a.f = f; a.info = info; a.evals = evals; a.data = data; a.eps = eps; a.starts = starts; a.max_evals = max_evals;
+  for (int c = 0; c < starts; c++) rn_emu_run_warp(c, starts, [&] { rn_k_lbfgs(a); });
+}
+"""
+
+
 def compile_source(src, fast=False, opt="-O1"):
     d = os.path.join(tempfile.gettempdir(), "rn_emul")
     os.makedirs(d, exist_ok=True)
@@ -164,7 +178,7 @@ def compile_source(src, fast=False, opt="-O1"):
             if src.startswith("// generated by rainier_b200 (CUDA source emitter, function flavour)"):  # rn_function.cuh
                 f.write(src + _FUNCTION_SHIM)
             elif src.startswith("// generated by rainier_b200 (CUDA source emitter, optimizer flavour)"):  # rn_optimizer.cuh
-                f.write(src + _OPTIMIZER_SHIM)
+                f.write(src + (_WPC_RUNNER + _OPTIMIZER_SHIM_WPC if wpc else _OPTIMIZER_SHIM))
             else:
                 f.write(src + (_WPC_SHIM if wpc else _SHIM) + _SAMPLER_SHIM.replace("@LAUNCH@", launch_wpc if wpc else launch_tpc))
         flags = [opt, "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w", "-pthread"]

@@ -43,7 +43,8 @@ def _both(model, x0, **kw):
     rir, cols = model.compile(True)
     om = OracleModel(rir, cols)
     cm = api.CudaModel(rir, cols, device=-1)
-    emu = he.optimize(cm.emit_optimizer_source(m=kw.get("m", 5)), cm, x0, eps=kw.get("eps", 0.1), max_evals=kw.get("max_evals", 10000))
+    # thread per start: the bit-identical shape (AUTO picks the warp shape for streamed models)
+    emu = he.optimize(cm.emit_optimizer_source(m=kw.get("m", 5), backend=abi.RN_BACKEND_THREAD), cm, x0, eps=kw.get("eps", 0.1), max_evals=kw.get("max_evals", 10000))
     ref = [lbfgs(om.density_batch, om.n, x0=x, m=kw.get("m", 5), eps=kw.get("eps", 0.1), max_evals=kw.get("max_evals", 10000))
            for x in np.asarray(x0, dtype=np.float64).reshape(-1, om.n)]
     return emu, ref, om
@@ -95,7 +96,7 @@ def test_kernel_source_bit_identical_fit_normal():
     # x0 = NULL means every start at 0
     rir, cols = model.compile(True)
     cm = api.CudaModel(rir, cols, device=-1)
-    z = he.optimize(cm.emit_optimizer_source(), cm, None, starts=3)
+    z = he.optimize(cm.emit_optimizer_source(backend=abi.RN_BACKEND_THREAD), cm, None, starts=3)
     assert np.array_equal(z["x"], np.repeat(emu["x"][:1], 3, axis=0)) and np.all(z["evals"] == emu["evals"][0])
 
 
@@ -147,3 +148,31 @@ def test_abi_errors_and_nvrtc():
     oc = abi.OptimizeConfig()
     api.lib().rn_optimize_config_default(oc)
     assert (oc.history, oc.eps) == (5, 0.1)  # Optimizer.scala:12-13
+
+
+def test_warp_per_start_shape_streamed_models():
+    """RN_BACKEND_WARP: one warp per start, rows across lanes, history in shared memory (emulated: 32 host threads around a
+    barrier).  Sums are trees there, so agreement with the oracle is to rounding, not bit for bit; the number of evaluations
+    and the exit codes still match on a smooth objective."""
+    for (nobs, d, seed) in ((700, 4, 0), (160, 37, 1)):  # 37 parameters: lane striding with a ragged second pass
+        rir, cols = configs.logreg(nobs, d).compile(True)
+        om = OracleModel(rir, cols)
+        cm = api.CudaModel(rir, cols, device=-1)
+        x0 = np.random.default_rng(seed).normal(size=(3, d)) * 0.3
+        x0[0] = 0.0
+        src = cm.emit_optimizer_source(backend=abi.RN_BACKEND_WARP)
+        assert "#define RN_BACKEND 1" in src and "rn_warp_sum" in src
+        got = he.optimize(src, cm, x0, eps=1e-5, max_evals=300)
+        ref = [lbfgs(om.density_batch, d, x0=x, eps=1e-5, max_evals=300) for x in x0]
+        for c, r in enumerate(ref):
+            assert got["info"][c] == r["info"] == 0 and got["evals"][c] == r["evals"]
+            np.testing.assert_allclose(got["x"][c], r["x"], rtol=1e-9, atol=1e-11)
+            assert abs(got["f"][c] - r["f"]) <= 1e-11 * abs(r["f"])
+    # the emitter-derived (adjoint) gradient of a primal-only container through the same shape
+    rirp, colsp = configs.logreg(700, 4).compile(False)
+    cmp_ = api.CudaModel(rirp, colsp, device=-1)
+    rir, cols = configs.logreg(700, 4).compile(True)
+    ref = lbfgs(OracleModel(rir, cols).density_batch, 4, eps=1e-5, max_evals=300)
+    got = he.optimize(cmp_.emit_optimizer_source(backend=abi.RN_BACKEND_WARP), cmp_, None, starts=2, eps=1e-5, max_evals=300)
+    np.testing.assert_allclose(got["x"][1], ref["x"], rtol=1e-8, atol=1e-10)
+    assert cmp_.emit_optimizer_cubin(backend=abi.RN_BACKEND_WARP)[:4] == b"\x7fELF"
