@@ -583,11 +583,11 @@ std::string emit_optimizer_source(const Program& P, const EmitOptions& opt, int 
   os << "#define RN_LBFGS_M " << history << "\n";
   if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
   EmitOptions eo = opt;
-  if (opt.backend == 1) {  // one warp per start, independent per-warp row loads (no CTA-shared tiles: starts diverge)
-    eo.wpc_k = 1;
+  if (opt.backend == 1) {  // K warps per start, independent per-warp row loads (no CTA-shared tiles: starts diverge)
+    eo.wpc_k = std::max(1, opt.wpc_k);
     eo.tma_stages = 0;
     eo.enable_ehmc = false;
-    os << "#define RN_WPC_K 1\n#define RN_TMA_STAGES 0\n#define RN_TMA_TILE_DOUBLES 0\n";
+    os << "#define RN_WPC_K " << eo.wpc_k << "\n#define RN_TMA_STAGES 0\n#define RN_TMA_TILE_DOUBLES 0\n";
   } else {
     eo.backend = 0;
   }

@@ -30,17 +30,36 @@
 #if RN_BACKEND == 1
 #define RN_LB_LANE ((int)(threadIdx.x % RN_G))
 #define RN_LB_FOR_N(i, count) for (int i = RN_LB_LANE; i < (count); i += RN_G)
-#define RN_LB_REDUCE(s) rn_warp_sum(s)
+#define RN_LB_REDUCE(s, red) rn_lb_group_sum(s, red)
 #define RN_LB_SYNC() RN_SYNC()
 #else
 #define RN_LB_FOR_N(i, count) for (int i = 0; i < (count); i++)
-#define RN_LB_REDUCE(s) (s)
+#define RN_LB_REDUCE(s, red) (s)
 #define RN_LB_SYNC()
 #endif
 #define RN_LB_FOR(i) RN_LB_FOR_N(i, RN_N)
 #define RN_LB_W (RN_N * (2 * RN_LBFGS_M + 1) + 2 * RN_LBFGS_M)
 #define RN_LB_ISPT (RN_N + 2 * RN_LBFGS_M)
 #define RN_LB_IYPT (RN_LB_ISPT + RN_N * RN_LBFGS_M)
+
+#if RN_BACKEND == 1
+// Sum over the RN_G = 32*RN_WPC_K threads that own a start; every thread receives the same total.  One warp: shuffle
+// butterfly.  K warps (a start whose state is so large that one warp per start would leave the SM nearly empty): the warps'
+// totals meet in K doubles of the start's shared-memory slice and are added in one fixed order by every thread.
+RN_DEVICE double rn_lb_group_sum(double x, double* red) {
+  x = rn_warp_sum(x);
+#if RN_WPC_K > 1
+  if ((threadIdx.x & 31) == 0) red[(threadIdx.x % RN_G) >> 5] = x;
+  RN_SYNC();
+  x = red[0];
+  for (int k = 1; k < RN_WPC_K; k++) x = x + red[k];
+  RN_SYNC();
+#else
+  (void)red;
+#endif
+  return x;
+}
+#endif
 
 RN_DEVICE double rn_jmin(double a, double b) {  // java.lang.Math.min: NaN wins, -0.0 < 0.0
   if (a != a) return a;
@@ -57,7 +76,8 @@ RN_DEVICE double rn_jmax(double a, double b) {
 RN_DEVICE double rn_max3(double a, double b, double c) { return a < b ? (b < c ? c : b) : (a < c ? c : a); }
 
 struct RnLbfgs {
-  double *x, *diag, *w;  // [RN_N], [RN_N], [RN_LB_W]: thread-local arrays (backend 0) or the warp's shared-memory slice
+  double *x, *diag, *w;  // [RN_N], [RN_N], [RN_LB_W]: thread-local arrays (backend 0) or the start's shared-memory slice
+  double* red;           // backend 1 with K warps per start: K doubles of cross-warp reduction scratch
   double eps, stp, stp1, ys, yy;
   int iter, point, npt, info, nfev, bound;
   // line-search state
@@ -65,17 +85,19 @@ struct RnLbfgs {
   int infoc, brackt, stage1;
 };
 
-RN_DEVICE double rn_lb_dot(const double* a, const double* b) {  // ddot with unit strides: a sequential sum (backend 0)
+RN_DEVICE double rn_lb_dot(const RnLbfgs& S, const double* a, const double* b) {  // ddot, unit strides: a sequential sum (backend 0)
   double s = 0.0;
   RN_LB_FOR(i) s = s + a[i] * b[i];
-  return RN_LB_REDUCE(s);
+  (void)S;
+  return RN_LB_REDUCE(s, S.red);
 }
 RN_DEVICE void rn_lb_axpy(double da, const double* a, double* y) {  // daxpy; a zero factor leaves y untouched
   if (da == 0.0) return;
   RN_LB_FOR(i) y[i] = y[i] + da * a[i];
 }
 
-RN_DEVICE void rn_lb_init(RnLbfgs& S, double* x, double* diag, double* w, double eps) {
+RN_DEVICE void rn_lb_init(RnLbfgs& S, double* x, double* diag, double* w, double* red, double eps) {
+  S.red = red;
   S.x = x;
   S.diag = diag;
   S.w = w;
@@ -206,7 +228,7 @@ RN_DEVICE bool rn_lb_search(RnLbfgs& S, const double f, const double* g) {
   const double* dir = S.w + RN_LB_ISPT + S.point * RN_N;
   if (S.info != -1) {
     S.infoc = 1;
-    S.dginit = rn_lb_dot(g, dir);
+    S.dginit = rn_lb_dot(S, g, dir);
     if (S.dginit >= 0) return false;
     S.brackt = 0;
     S.stage1 = 1;
@@ -243,7 +265,7 @@ RN_DEVICE bool rn_lb_search(RnLbfgs& S, const double f, const double* g) {
     }
     S.info = 0;
     S.nfev = S.nfev + 1;
-    const double dg = rn_lb_dot(g, dir);
+    const double dg = rn_lb_dot(S, g, dir);
     const double ftest1 = S.finit + S.stp * S.dgtest;
     if ((S.brackt && (S.stp <= S.stmin || S.stp >= S.stmax)) || S.infoc == 0) S.info = 6;
     if (S.stp == STPMAX && f <= ftest1 && dg <= S.dgtest) S.info = 5;
@@ -282,7 +304,7 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
   bool whole = false;
   if (S.iter == 0) {
     RN_LB_FOR(i) w[RN_LB_ISPT + i] = -g[i] * S.diag[i];
-    const double gnorm = sqrt(rn_lb_dot(g, g));
+    const double gnorm = sqrt(rn_lb_dot(S, g, g));
     S.stp1 = 1 / gnorm;
     whole = true;
   }
@@ -293,8 +315,8 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
       S.bound = S.iter - 1;
       if (S.iter != 1) {
         if (S.iter > RN_LBFGS_M) S.bound = RN_LBFGS_M;
-        S.ys = rn_lb_dot(w + RN_LB_IYPT + S.npt, w + RN_LB_ISPT + S.npt);
-        S.yy = rn_lb_dot(w + RN_LB_IYPT + S.npt, w + RN_LB_IYPT + S.npt);
+        S.ys = rn_lb_dot(S, w + RN_LB_IYPT + S.npt, w + RN_LB_ISPT + S.npt);
+        S.yy = rn_lb_dot(S, w + RN_LB_IYPT + S.npt, w + RN_LB_IYPT + S.npt);
         const double h0 = S.ys / S.yy;
         RN_LB_FOR(i) S.diag[i] = h0;
         int cp = S.point;
@@ -305,14 +327,14 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
         for (int k = 0; k < S.bound; k++) {  // backward pass over the history
           cp = cp - 1;
           if (cp == -1) cp = RN_LBFGS_M - 1;
-          const double sq = rn_lb_dot(w + RN_LB_ISPT + cp * RN_N, w);
+          const double sq = rn_lb_dot(S, w + RN_LB_ISPT + cp * RN_N, w);
           const int inmc = RN_N + RN_LBFGS_M + cp;
           w[inmc] = w[RN_N + cp] * sq;
           rn_lb_axpy(-w[inmc], w + RN_LB_IYPT + cp * RN_N, w);
         }
         RN_LB_FOR(i) w[i] = S.diag[i] * w[i];
         for (int k = 0; k < S.bound; k++) {  // forward pass
-          const double yr = rn_lb_dot(w + RN_LB_IYPT + cp * RN_N, w);
+          const double yr = rn_lb_dot(S, w + RN_LB_IYPT + cp * RN_N, w);
           double beta = w[RN_N + cp] * yr;
           beta = w[RN_N + RN_LBFGS_M + cp] - beta;
           rn_lb_axpy(beta, w + RN_LB_ISPT + cp * RN_N, w);
@@ -335,8 +357,8 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
     }
     S.point = S.point + 1;
     if (S.point == RN_LBFGS_M) S.point = 0;
-    const double gnorm = sqrt(rn_lb_dot(g, g));
-    double xnorm = sqrt(rn_lb_dot(S.x, S.x));
+    const double gnorm = sqrt(rn_lb_dot(S, g, g));
+    double xnorm = sqrt(rn_lb_dot(S, S.x, S.x));
     xnorm = rn_jmax(1.0, xnorm);
     if (gnorm / xnorm <= S.eps) return 1;
     whole = true;
@@ -349,8 +371,8 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
 // at x, info [starts] (bit 0 evaluation cap reached, bit 1 "dginit", bit 2 lookup error), evals [starts]
 // =============================================================================================================
 #if RN_BACKEND == 1
-// shared-memory slice of one start: x | gradient | g = -gradient | diag | w | scratch of the emitted density
-#define RN_OPT_SMEM_DOUBLES (4 * RN_N + RN_LB_W + RN_WPC_SCRATCH)
+// shared-memory slice of one start: x | gradient | g = -gradient | diag | w | scratch of the emitted density | K reduction slots
+#define RN_OPT_SMEM_DOUBLES (4 * RN_N + RN_LB_W + RN_WPC_SCRATCH + RN_WPC_K)
 #ifdef RN_HOST_EMULATION
 static double rn_smem[1 << 17];  // one emulated start at a time
 #else
@@ -361,10 +383,11 @@ extern __shared__ __align__(128) double rn_smem[];
 RN_GLOBAL void rn_k_lbfgs(const RnOptArgs A) {
 #if RN_BACKEND == 1
   const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) / RN_G);
-  if (c >= A.starts) return;  // the whole warp leaves together
+  if (c >= A.starts) return;  // the whole group leaves together
   double* base = rn_smem + (size_t)RN_GROUP * RN_OPT_SMEM_DOUBLES;
   double *x = base, *grad = base + RN_N, *g = base + 2 * RN_N, *diag = base + 3 * RN_N, *w = base + 4 * RN_N;
   double* scr = base + 4 * RN_N + RN_LB_W;
+  double* red = scr + RN_WPC_SCRATCH;
   RnTma tma;  // the CTA-shared tile pipeline stays off: starts take different numbers of evaluations
   tma.on = 0;
   tma.seq = 0;
@@ -375,9 +398,10 @@ RN_GLOBAL void rn_k_lbfgs(const RnOptArgs A) {
   const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= A.starts) return;
   double x[RN_N], grad[RN_N], g[RN_N], diag[RN_N], w[RN_LB_W];
+  double* red = nullptr;
 #endif
   RnLbfgs S;
-  rn_lb_init(S, x, diag, w, A.eps);
+  rn_lb_init(S, x, diag, w, red, A.eps);
   RN_LB_FOR(i) x[i] = A.x0 ? A.x0[(size_t)i * A.starts + c] : 0.0;
   int evals = 0, info = 0, err = 0;
   double f = RN_NAN;

@@ -204,6 +204,7 @@ struct rn_model {
     int backend = 0;           // 0 one thread per start, 1 one warp per start
     int smem_doubles = 0;      // backend 1: shared-memory slice of one start
     int starts_per_cta = 1;    // backend 1
+    int wpc_k = 1;             // backend 1: warps per start
   };
   std::map<std::tuple<bool, bool, int, int>, std::unique_ptr<OptKernel>> opt_kernels;
 };
@@ -2192,15 +2193,29 @@ static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::O
   } else {
     if (P->symbolic && P->n_params > 96)
       return fail(RN_E_UNSUPPORTED, "warp-per-start with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
-    eo.wpc_k = 1;
     eo.tma_stages = 0;
     eo.enable_ehmc = false;
-    const WpcSizes z = wpc_sizes(*P, eo);  // 4n (x, gradient, g, diag reuse the sampler's q/p/g/m slots) + density scratch
-    const uint64_t per_start = (uint64_t)z.per_warp_doubles + lb_w;
     const uint64_t cap = (227 * 1024 - 2048) / 8;
+    // warps per start: one, unless the start's shared-memory state is so large that fewer than 16 starts fit an SM (same
+    // rule as the samplers, rn_runtime.cpp:get_kernel)
+    int k = 1;
+    {
+      eo.wpc_k = 1;
+      const uint64_t one = (uint64_t)wpc_sizes(*P, eo).per_warp_doubles + lb_w + 1;
+      if (one > cap) return fail(RN_E_UNSUPPORTED, "rn_optimize: the L-BFGS history of one start does not fit shared memory");
+      const uint64_t fit = std::max<uint64_t>(1, cap / one);
+      while (k < 8 && fit * (uint64_t)k < 16) k *= 2;
+      if (const char* e = getenv("RN_WPC_K")) k = std::max(1, std::min(8, atoi(e)));
+      if (k != 1 && k != 2 && k != 4 && k != 8) k = 1;
+    }
+    eo.wpc_k = k;
+    const WpcSizes z = wpc_sizes(*P, eo);  // 4n (x, gradient, g, diag take the sampler's q/p/g/m slots) + density scratch
+    const uint64_t per_start = (uint64_t)z.per_warp_doubles + lb_w + (uint64_t)k;
     if (per_start > cap) return fail(RN_E_UNSUPPORTED, "rn_optimize: the L-BFGS history of one start does not fit shared memory");
+    K->wpc_k = k;
     K->smem_doubles = (int)per_start;
-    K->starts_per_cta = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, cap / per_start));
+    // at most 256 threads per CTA (255 registers each fit the register file); named barriers 2..15 when K > 1
+    K->starts_per_cta = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)(8 / k), cap / per_start));
   }
   K->source = emit_optimizer_source(*P, eo, history);
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
@@ -2315,8 +2330,8 @@ int rn_optimize(rn_model* m, const rn_optimize_config* oc, const double* x0, int
   void* params[] = {&a};
   if (K->backend == 1) {
     const unsigned spc = (unsigned)K->starts_per_cta;
-    CU(A->cuLaunchKernel(K->k_lbfgs, (unsigned)((S + spc - 1) / spc), 1, 1, spc * 32, 1, 1, spc * (unsigned)K->smem_doubles * 8, nullptr,
-                         params, nullptr));
+    CU(A->cuLaunchKernel(K->k_lbfgs, (unsigned)((S + spc - 1) / spc), 1, 1, spc * 32 * (unsigned)K->wpc_k, 1, 1,
+                         spc * (unsigned)K->smem_doubles * 8, nullptr, params, nullptr));
   } else {
     // small CTAs spread few starts over all SMs; starts diverge (different trajectory lengths), so warps are the unit
     const unsigned block = starts >= 148 * 128 ? 128 : 32;

@@ -12,3 +12,6 @@ echo "== ncu rn_k_eval"; timeout 600 ncu --set full --clock-control none --impor
 echo "== ncu rn_k_lbfgs"; timeout 600 ncu --set full --clock-control none --import-source on -k rn_k_lbfgs -c 1 -o gpurun_out/ncu_rn_k_lbfgs python scripts/bench_optimize.py --steps 1 --warmup 0 --starts 37888 > gpurun_out/ncu_lbfgs.log 2>&1; tail -3 gpurun_out/ncu_lbfgs.log
 echo "== full pytest -m gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
 echo "== bench"; timeout 600 python bench.py | tee gpurun_out/bench_parity.json | cut -c1-400
+echo "== compute-sanitizer memcheck / racecheck on the new kernels"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_function.py -q -m gpu -k "bit_identical and not 300000" 2>&1 | tail -4
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_optimizer.py -q -m gpu -k "warp_per_start" 2>&1 | tail -4

@@ -176,3 +176,38 @@ def test_warp_per_start_shape_streamed_models():
     got = he.optimize(cmp_.emit_optimizer_source(backend=abi.RN_BACKEND_WARP), cmp_, None, starts=2, eps=1e-5, max_evals=300)
     np.testing.assert_allclose(got["x"][1], ref["x"], rtol=1e-8, atol=1e-10)
     assert cmp_.emit_optimizer_cubin(backend=abi.RN_BACKEND_WARP)[:4] == b"\x7fELF"
+
+
+def test_k_warps_per_start():
+    """A start whose state is large gets K warps (same rule as the samplers: aim at 16 warps per SM): 130 parameters ->
+    K = 2 by itself; RN_WPC_K forces it on a small model.  Emulated as 32*K host threads per start around group/warp barriers."""
+    import os
+    import re
+    d, nobs = 130, 96
+    rirp, colsp = configs.logreg(nobs, d).compile(False)  # primal container: emitter-derived gradient (n > 96)
+    rir, cols = configs.logreg(nobs, d).compile(True)
+    cm = api.CudaModel(rirp, colsp, device=-1)
+    src = cm.emit_optimizer_source(backend=abi.RN_BACKEND_WARP)
+    assert re.findall(r"#define RN_WPC_K (\d+)", src) == ["2"]
+    got = he.optimize(src, cm, np.zeros((1, d)), eps=1e-4, max_evals=300)
+    ref = lbfgs(OracleModel(rir, cols).density_batch, d, eps=1e-4, max_evals=300)
+    assert got["info"][0] == ref["info"] == 0 and got["evals"][0] == ref["evals"]
+    np.testing.assert_allclose(got["x"][0], ref["x"], rtol=1e-9, atol=1e-11)
+    with pytest.raises(api.RainierCudaError) as e:  # the symbolic gradient keeps n+1 accumulators per lane
+        api.CudaModel(rir, cols, device=-1).emit_optimizer_source(backend=abi.RN_BACKEND_WARP, gradient_mode=abi.RN_GRAD_SYMBOLIC)
+    assert e.value.code == abi.RN_E_UNSUPPORTED
+    rir4, cols4 = configs.logreg(160, 37).compile(True)
+    x0 = np.random.default_rng(1).normal(size=(2, 37)) * 0.3
+    ref4 = [lbfgs(OracleModel(rir4, cols4).density_batch, 37, x0=x, eps=1e-5, max_evals=300) for x in x0]
+    os.environ["RN_WPC_K"] = "4"
+    try:
+        cm4 = api.CudaModel(rir4, cols4, device=-1)
+        src4 = cm4.emit_optimizer_source(backend=abi.RN_BACKEND_WARP)
+        assert "#define RN_WPC_K 4" in src4
+        got4 = he.optimize(src4, cm4, x0, eps=1e-5, max_evals=300)
+        assert cm4.emit_optimizer_cubin(backend=abi.RN_BACKEND_WARP)[:4] == b"\x7fELF"  # named barriers assemble
+    finally:
+        del os.environ["RN_WPC_K"]
+    for c, r in enumerate(ref4):
+        assert got4["evals"][c] == r["evals"] and got4["info"][c] == 0
+        np.testing.assert_allclose(got4["x"][c], r["x"], rtol=1e-9, atol=1e-11)

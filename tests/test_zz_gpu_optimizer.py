@@ -103,3 +103,19 @@ def test_warp_per_start_logistic_regression():
     many = api.CudaModel(rirp, colsp).optimize(np.random.default_rng(7).normal(size=(2000, 4)) * 0.5, eps=1e-5, max_evals=300)
     assert np.all(many["info"] == 0)
     assert np.max(np.abs(many["x"] - many["x"][0])) < 1e-4 and np.ptp(many["f"]) < 1e-6
+
+
+def test_k_warps_per_start_large_state():
+    """130 parameters: the runtime gives every start 2 warps (group barrier + cross-warp reduction of the dot products)"""
+    d, nobs = 130, 96
+    rirp, colsp = configs.logreg(nobs, d).compile(False)
+    rir, cols = configs.logreg(nobs, d).compile(True)
+    x0 = np.random.default_rng(2).normal(size=(40, d)) * 0.1
+    x0[0] = 0.0
+    got = api.CudaModel(rirp, colsp).optimize(x0, eps=1e-4, max_evals=300, backend=abi.RN_BACKEND_WARP)
+    om = OracleModel(rir, cols)
+    for c in range(4):
+        ref = lbfgs(om.density_batch, d, x0=x0[c], eps=1e-4, max_evals=300)
+        assert got["info"][c] == ref["info"] == 0 and got["evals"][c] == ref["evals"]
+        np.testing.assert_allclose(got["x"][c], ref["x"], rtol=1e-8, atol=1e-10)
+    assert np.all(got["info"] == 0) and np.ptp(got["f"]) < 1e-3 * abs(got["f"][0])
