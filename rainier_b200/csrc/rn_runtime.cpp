@@ -1925,6 +1925,7 @@ struct rn_function {
   CUmodule mod = nullptr;
   CUfunction k_eval = nullptr;
   CUstream stream = nullptr;
+  CUstream stream2 = nullptr;  // second staging slot of rn_function_eval (host buffers)
   CUdeviceptr d_err = 0;
   CUdeviceptr scratch = 0;  // grow-only staging of rn_function_eval (host buffers)
   size_t scratch_bytes = 0;
@@ -2109,11 +2110,15 @@ int rn_function_eval(rn_function* f, const double* x, int64_t count, double* out
   int rc = function_load(A, f);
   if (rc) return rc;
   if (count == 0) return RN_OK;
-  // chunks of at most 256 MB of staging; [chunk][n] in, [chunk][m] out
+  // Two staging slots, each with its own stream: chunk i is copied in, evaluated and copied out on stream i&1, so the
+  // host->device copy of one chunk overlaps the device->host copy of the previous one (PCIe is full duplex) and the
+  // kernel hides under both.  In-order streams make slot reuse safe without events.  [chunk][n] in, [chunk][m] out.
   const size_t per_point = (n + m) * 8;
-  const int64_t chunk_max = std::max<int64_t>(1, (int64_t)((size_t)256 << 20) / (int64_t)per_point);
+  const int64_t chunk_max = std::max<int64_t>(1, (int64_t)((size_t)32 << 20) / (int64_t)per_point);
   const int64_t chunk = std::min<int64_t>(count, chunk_max);
-  const size_t need = (size_t)chunk * per_point + 16;
+  const size_t x_bytes = ((size_t)chunk * n * 8 + 255) & ~(size_t)255, slot_bytes = x_bytes + (((size_t)chunk * m * 8 + 255) & ~(size_t)255);
+  const int slots = count > chunk ? 2 : 1;
+  const size_t need = slot_bytes * (size_t)slots;
   if (f->scratch_bytes < need) {
     if (f->scratch) A->cuMemFree(f->scratch);
     f->scratch = 0;
@@ -2121,15 +2126,18 @@ int rn_function_eval(rn_function* f, const double* x, int64_t count, double* out
     CU(A->cuMemAlloc(&f->scratch, need));
     f->scratch_bytes = need;
   }
-  const CUdeviceptr d_x = f->scratch, d_out = f->scratch + (((size_t)chunk * n * 8 + 15) & ~(size_t)15);
-  for (int64_t p0 = 0; p0 < count; p0 += chunk) {
+  if (slots == 2 && !f->stream2) CU(A->cuStreamCreate(&f->stream2, 1 /*CU_STREAM_NON_BLOCKING*/));
+  int64_t i = 0;
+  for (int64_t p0 = 0; p0 < count; p0 += chunk, i++) {
     const int64_t c = std::min<int64_t>(chunk, count - p0);
-    if (n > 0) CU(A->cuMemcpyHtoDAsync(d_x, x + (size_t)p0 * n, (size_t)c * n * 8, f->stream));
-    rc = rn_function_eval_device(f, (const double*)(uintptr_t)d_x, RN_LAYOUT_ROWS, 1, c, (double*)(uintptr_t)d_out, nullptr);
+    const CUstream st = (i & 1) ? f->stream2 : f->stream;
+    const CUdeviceptr d_x = f->scratch + (size_t)(i & 1) * slot_bytes, d_out = d_x + x_bytes;
+    if (n > 0) CU(A->cuMemcpyHtoDAsync(d_x, x + (size_t)p0 * n, (size_t)c * n * 8, st));
+    rc = rn_function_eval_device(f, (const double*)(uintptr_t)d_x, RN_LAYOUT_ROWS, 1, c, (double*)(uintptr_t)d_out, (void*)st);
     if (rc) return rc;
-    CU(A->cuMemcpyDtoHAsync(out + (size_t)p0 * m, d_out, (size_t)c * m * 8, f->stream));
-    CU(A->cuStreamSynchronize(f->stream));
+    CU(A->cuMemcpyDtoHAsync(out + (size_t)p0 * m, d_out, (size_t)c * m * 8, st));
   }
+  if (f->stream2) CU(A->cuStreamSynchronize(f->stream2));
   return rn_function_sync(f);
 }
 
@@ -2142,6 +2150,10 @@ void rn_function_destroy(rn_function* f) {
     if (f->stream) {
       A->cuStreamSynchronize(f->stream);
       A->cuStreamDestroy(f->stream);
+    }
+    if (f->stream2) {
+      A->cuStreamSynchronize(f->stream2);
+      A->cuStreamDestroy(f->stream2);
     }
     if (f->mod) A->cuModuleUnload(f->mod);
     if (f->d_err) A->cuMemFree(f->d_err);
