@@ -13,7 +13,7 @@ transcendental ones) per draw.  One launch of rn_k_eval per step.
   e2e      : the same through rn_function_eval with HOST buffers ([count][n] in, [count][m] out; H2D + D2H inside)
   cpu_baseline : the oracle's rno_function_eval on one host core (the reference's per-draw CompiledFunction.output loop is
              single-threaded too, core/Generator.scala:76-93), bounded sample
-Prints one JSON line.  Not part of the product; needs oracle/rainier_py to build the model (the reference's Scala front end).
+Prints one JSON line.  Not part of the product; models come from the committed fixtures, oracle/ is used as checker and CPU baseline only.
 """
 import argparse
 import json
@@ -37,16 +37,13 @@ def main():
     args = ap.parse_args()
     import torch
 
-    from oracle.rainier_py.binding import OracleFunction
-    from oracle.rainier_py.compute import compile_function_rir
-    from oracle.rainier_py import configs
     from rainier_b200 import api
 
-    model, mu, tau, thetas, _ = configs.eight_schools_parts()
-    reals = configs.eight_schools_derived(mu, tau, thetas)
-    frir = compile_function_rir(model.parameters, reals)
-    rir, cols = model.compile(True)
-    n, m = 10, len(reals)
+    # committed fixtures (oracle/make_fixtures.py): the frozen DAG of eight schools and its 12 derived quantities as a function
+    mdir = os.path.join(ROOT, "rainier_b200", "models")
+    rir, cols = open(os.path.join(mdir, "eight_schools.rir"), "rb").read(), []
+    frir = open(os.path.join(mdir, "eight_schools.derived.fn.rir"), "rb").read()
+    n, m = 10, 12
     chains, iters = args.chains, args.iterations
     count = chains * iters
     cm = api.CudaModel(rir, cols)
@@ -80,7 +77,8 @@ def main():
         peak, src = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
     except Exception:
         peak, src = 6650.0, "fallback"
-    # parity spot check against the oracle (first chain block)
+    # parity spot check against the oracle (first chain block) -- the oracle is the checker / CPU baseline only
+    from oracle.rainier_py.binding import OracleFunction
     draws = d[:, :, :64].permute(2, 0, 1).contiguous().cpu().numpy().reshape(-1, n)
     ref = OracleFunction(frir)(draws).reshape(64, iters, m)
     same = bool(np.array_equal(out[:64].cpu().numpy(), ref)) if not args.fast else None
