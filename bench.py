@@ -368,6 +368,13 @@ def main():
                      "ncu_source": "profiles/r1_ncu_funnel_parity_v5.csv, profiles/r1_ncu_funnel_fast_v2.csv "
                                    "(sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active)"},
         }
+        try:  # the end-to-end call is bound by the device->host link, not by the kernel: say how close to it the call runs
+            gbs = C_ * I_ * N_DIM * 8 / (float(e2e_ms["median"]) * 1e-3) / 1e9
+            line["e2e"]["pcie"] = {"achieved_gbs": gbs, "measured_d2h_gbs": 56.7, "frac": gbs / 56.7,
+                                   "source": "profiles/r1_pcie_probe.txt (page-locked cuMemcpyDtoH on a B200 box of this pool)",
+                                   "note": "per rank; whole rn_sample call (create, kernels, drain, stats) over the sample bytes"}
+        except Exception:
+            pass
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line))
