@@ -567,7 +567,8 @@ WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
   WpcSizes z;
   Emitter E(P, opt);
   E.density_wpc();
-  z.per_warp_doubles = (opt.enable_ehmc ? 7 : 4) * (int)P.n_params + E.tab_doubles + E.n_smem_acc + E.red_doubles;
+  // chain vectors (q, p, gradient, mass [+ EHMC snapshot]) [+ 2 scratch vectors of the dense mass matrix code] + density scratch
+  z.per_warp_doubles = ((opt.enable_ehmc ? 7 : 4) + (opt.mass_max == 2 ? 2 : 0)) * (int)P.n_params + E.tab_doubles + E.n_smem_acc + E.red_doubles;
   for (const TargetInfo& T : P.targets)
     if (T.streamed() && T.n_rows >= 32ull * (uint64_t)std::max(1, opt.wpc_k))
       z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * 32 * std::max(1, opt.wpc_k));
@@ -628,7 +629,7 @@ std::string emit_source(const Program& P, const EmitOptions& opt) {
   os << kPreludeSource << "\n";
   os << emit_density(P, opt) << "\n";
   if (opt.backend == 1) {
-    os << "#define RN_WPC_SMEM_DOUBLES (" << (opt.enable_ehmc ? 7 : 4) << " * RN_N + RN_WPC_SCRATCH)\n";
+    os << "#define RN_WPC_SMEM_DOUBLES (" << ((opt.enable_ehmc ? 7 : 4) + (opt.mass_max == 2 ? 2 : 0)) << " * RN_N + RN_WPC_SCRATCH)\n";
     os << kSamplerWpcSource << "\n";
   } else {
     os << kSamplerSource << "\n";

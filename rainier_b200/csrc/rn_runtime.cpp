@@ -250,7 +250,8 @@ static KernelKey key_for(const rn_model* m, const rn_config* cfg) {
       for (const TargetInfo& T : it->second->targets)
         if (T.streamed()) row_work += T.n_rows * (uint64_t)(T.row_fwd.size() + T.row_bwd.size() + 1);
     want = (row_work >= 16384 || m->n_params > 48) ? RN_BACKEND_WARP : RN_BACKEND_THREAD;
-    if (k.mass_max == 2) want = RN_BACKEND_THREAD;  // dense mass lives in the thread-per-chain kernels
+    if (k.mass_max == 2) want = RN_BACKEND_THREAD;  // AUTO keeps dense mass on the thread-per-chain kernels (the shape measured on
+                                                    // the GPU); the warp-per-chain kernels take it when asked for explicitly
   }
   k.backend = want == RN_BACKEND_WARP ? 1 : 0;
   return k;
@@ -280,7 +281,6 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
   eo.mass_max = key.mass_max;
   eo.enable_ehmc = key.ehmc;
   eo.target_base = m->target_base;
-  if (eo.backend == 1 && eo.mass_max == 2) return fail(RN_E_UNSUPPORTED, "dense mass matrices need the thread-per-chain backend");
   if (eo.backend == 1 && P->symbolic && P->n_params > 96)
     return fail(RN_E_UNSUPPORTED, "warp-per-chain with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
   K->backend = eo.backend;

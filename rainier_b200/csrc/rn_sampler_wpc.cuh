@@ -10,8 +10,13 @@
 // keep their left-to-right order; only the row sum of the density changes order (tree instead of sequential),
 // which moves results in the last ~3 digits.
 //
-// Supported here: HMC / EHMC, DualAvg / static step size, identity / diagonal mass (adaptive or static).  Dense
-// mass matrices use the thread-per-chain backend.
+// Supported here: HMC / EHMC, DualAvg / static step size, identity / diagonal / dense mass (adaptive or static).
+// Dense mass (RN_MASS_MAX == 2; opt-in for this shape, AUTO keeps dense configurations on the thread-per-chain kernels):
+// the n x n matrix, its packed Cholesky factor and the covariance estimator stay in the chain's global-memory state --
+// for the streamed models this shape serves, n^2 loads per leapfrog step are noise beside rows x columns per gradient --
+// row i of every mat-vec belongs to lane i % RN_G and is summed left to right like DenseMassMatrix.squareMultiply
+// (MassMatrix.scala:35-51); the back-substitution of the momentum draw and the Cholesky factorisation at a window end are
+// sequential by nature and run on one lane, in the reference's order.
 #ifndef RN_SAMPLER_WPC_CUH
 #define RN_SAMPLER_WPC_CUH
 
@@ -45,6 +50,13 @@ struct RnW {
   double* sp;
   double* sg;
   double* scr;  // emitted density scratch (lookup tables, scatter accumulators)
+#if RN_MASS_MAX >= 2
+  double* v;    // dense mass: velocity M^-1 p / oldDiff of the covariance estimator
+  double* v2;   //             newDiff
+  const double* M;     // [N*N][chains] (this chain's column of the SoA array)
+  const double* chol;  // packed upper Cholesky factor [N(N+1)/2][chains]
+  size_t ld;           // chains
+#endif
   double U;     // potential of pqBuf (replicated in registers)
   int mass_kind;
   RnTma tma;    // shared data-tile pipeline of the CTA (off unless the kernel enables it)
@@ -69,7 +81,24 @@ RN_DEVICE void rn_w_setup(RnW& w, double* base) {
   w.sq = w.sp = w.sg = base;
   w.scr = base + 4 * RN_N;
 #endif
+#if RN_MASS_MAX >= 2
+  w.v = w.scr;  // the slice is [vectors | v | v2 | density scratch] when dense mass is compiled in
+  w.v2 = w.scr + RN_N;
+  w.scr = w.scr + 2 * RN_N;
+  w.M = nullptr;
+  w.chol = nullptr;
+  w.ld = 0;
+#endif
 }
+
+#if RN_MASS_MAX >= 2
+// (M^-1 p)_i for the rows of this lane, left to right over j (DenseMassMatrix.squareMultiply, MassMatrix.scala:35-51)
+RN_DEVICE double rn_dense_row(const RnW& w, const double* p, int i) {
+  double y = 0.0;
+  for (int j = 0; j < RN_N; j++) y += p[j] * w.M[(size_t)(i * RN_N + j) * w.ld];
+  return y;
+}
+#endif
 
 // OR over the chain's RN_G threads (red: RN_WPC_K doubles of the group's reduction scratch)
 RN_DEVICE unsigned rn_group_or(unsigned x, double* red) {
@@ -97,6 +126,15 @@ RN_DEVICE void rn_ring_add(const RnArgs& A, int c, RnStats& S, int which, double
 // energy = potential + dot(velocity, p)/2, sequential order (LeapFrog.scala:134-139,205-231)
 RN_DEVICE double rn_energy(const RnW& w, const double* p, double U) {
   double k = 0.0;
+#if RN_MASS_MAX >= 2
+  if (w.mass_kind == 2) {  // velocity rows across the lanes, then the dot product in every lane, in index order
+    RN_SYNC();             // (w.v may still be read by the previous caller)
+    RN_FOR_LANES(i) w.v[i] = rn_dense_row(w, p, i);
+    RN_SYNC();
+    for (int i = 0; i < RN_N; i++) k += (w.v[i] * p[i]);
+    return U + k / 2.0;
+  }
+#endif
   if (w.mass_kind == 1) {
     for (int i = 0; i < RN_N; i++) k += ((p[i] * w.m[i]) * p[i]);
   } else {
@@ -124,6 +162,13 @@ RN_DEVICE void rn_full_ps(RnW& w, double stepSize, RnStats& S) {  // LeapFrog.sc
   RN_SYNC();
 }
 RN_DEVICE void rn_new_qs(RnW& w, double stepSize) {  // LeapFrog.scala:147-154
+#if RN_MASS_MAX >= 2
+  if (w.mass_kind == 2) {
+    RN_FOR_LANES(i) w.q[i] += (stepSize * rn_dense_row(w, w.p, i));
+    RN_SYNC();
+    return;
+  }
+#endif
   if (w.mass_kind == 1) {
     RN_FOR_LANES(i) w.q[i] += (stepSize * (w.p[i] * w.m[i]));
   } else {
@@ -154,6 +199,27 @@ RN_DEVICE void rn_initialize_ps(const RnW& w, RnRng& rng, double* dst) {
     if ((i % RN_G) == RN_LANE) dst[i] = (w.mass_kind == 1) ? z / sqrt(w.m[i]) : z;
   }
   RN_SYNC();
+#if RN_MASS_MAX >= 2
+  if (w.mass_kind == 2) {  // DenseMassMatrix.upperTriangularSolve (MassMatrix.scala:55-72), in place: dst holds z on entry
+    if (RN_LANE == 0) {
+      int i = RN_N - 1;
+      int m = ((i + 1) * (i + 2)) / 2 - 1;
+      while (i >= 0) {
+        int j = RN_N - 1;
+        double dot = 0.0;
+        while (j > i) {
+          dot += dst[j] * w.chol[(size_t)m * w.ld];
+          j -= 1;
+          m -= 1;
+        }
+        dst[i] = (dst[i] - dot) / w.chol[(size_t)m * w.ld];
+        i -= 1;
+        m -= 1;
+      }
+    }
+    RN_SYNC();
+  }
+#endif
 }
 
 RN_DEVICE void rn_load_stats(const RnArgs& A, int c, RnStats& S) {
@@ -309,6 +375,11 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     RN_FOR_LANES(i) w.m[i] = RN_AT(A.mass, i, c);
     RN_SYNC();
   }
+#if RN_MASS_MAX >= 2
+  w.M = A.mass + c;
+  w.chol = A.chol + c;
+  w.ld = (size_t)A.chains;
+#endif
   double stepSize = RN_AT(A.da, 0, c);
   double logStepSize = 0, logStepSizeBar = 0, avgError = 0, shrinkageTarget = 0;
   int daIter = 0;
@@ -449,6 +520,89 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
         logStepSizeBar = (stepSizeMultiplier * logStepSize + (1.0 - stepSizeMultiplier) * logStepSizeBar);
         stepSize = rn_exp(logStepSize);
       }
+#if RN_MASS_MAX >= 2
+      if (A.mass_tuner == 2) {  // DenseMassMatrixTuner: WindowedMassMatrixTuner (MassMatrix.scala:147-164) over CovarianceEstimator
+        win_j += 1;
+        if (!(win_j < A.skip_first || (A.total_warmup - win_j) < A.skip_last)) {
+          win_i += 1;
+          est_samples += 1;
+          RN_SYNC();
+          RN_FOR_LANES(i) {  // VarianceEstimator.update (MassMatrixEstimator.scala:69-83), diffs kept for the outer product
+            double mean = RN_AT(A.est_mean, i, c);
+            const double oldDiff = w.q[i] - mean;
+            mean += (oldDiff / (double)est_samples);
+            const double newDiff = w.q[i] - mean;
+            RN_AT(A.est_mean, i, c) = mean;
+            RN_AT(A.est_raw, i, c) += oldDiff * newDiff;
+            w.v[i] = oldDiff;
+            w.v2[i] = newDiff;
+          }
+          RN_SYNC();
+          for (int e = RN_LANE; e < RN_N * RN_N; e += RN_G)  // CovarianceEstimator.update, :28-41
+            RN_AT(A.est_cov, e, c) += w.v2[e / RN_N] * w.v[e % RN_N];
+          if (win_i == win_size) {
+            win_i = 0;
+            win_size = rn_d2i(win_size * A.win_expansion);
+            const double z = (double)(est_samples - 1);
+            for (int e = RN_LANE; e < RN_N * RN_N; e += RN_G) {  // DenseMassMatrix(covariance()), :43-50
+              const double v = RN_AT(A.est_cov, e, c) / z;
+              if (v == 0.0) S.err |= 2;  // require(!elements.contains(0.0)), MassMatrix.scala:16
+              RN_AT(A.mass, e, c) = v;
+              RN_AT(A.est_cov, e, c) = 0.0;
+            }
+            RN_FOR_LANES(i) {  // reset(): mean/raw only, NOT samples (:60-67)
+              RN_AT(A.est_mean, i, c) = 0.0;
+              RN_AT(A.est_raw, i, c) = 0.0;
+            }
+            S.err |= (int)rn_group_or((unsigned)(S.err & 2), w.scr + RN_WPC_RED_OFF);
+            RN_SYNC();
+#ifndef RN_HOST_EMULATION
+            __threadfence_block();  // the matrix written lane-strided above is read by lane 0 below
+#endif
+            if (RN_LANE == 0) {  // choleskyUpperTriangular (MassMatrix.scala:76-117); `lower` borrows the estimator's
+              double* lower = A.est_cov + c;  // covariance block, which was just reset and is zeroed again below
+              const size_t ld = (size_t)A.chains;
+              int l = 0;
+              for (int i = 0; i < RN_N; i++)
+                for (int k = 0; k <= i; k++) {
+                  double sum = 0.0;
+                  for (int j = 0; j < k; j++) sum += lower[(size_t)((i * (i + 1)) / 2 + j) * ld] * lower[(size_t)((k * (k + 1)) / 2 + j) * ld];
+                  const double x = RN_AT(A.mass, i * RN_N + k, c) - sum;
+                  if (i == k)
+                    lower[(size_t)l * ld] = sqrt(x);
+                  else {
+                    const double diag = lower[(size_t)(((k + 1) * (k + 2)) / 2 - 1) * ld];
+                    lower[(size_t)l * ld] = (1.0 / diag * x);
+                  }
+                  l += 1;
+                }
+              l = 0;
+              for (int i = 0; i < RN_N; i++)
+                for (int k = 0; k < (RN_N - i); k++) {
+                  RN_AT(A.chol, l, c) = lower[(size_t)(((k + i) * (k + i + 1)) / 2 + i) * ld];
+                  l += 1;
+                }
+              for (int e = 0; e < (RN_N * (RN_N + 1)) / 2; e++) lower[(size_t)e * ld] = 0.0;
+            }
+#ifndef RN_HOST_EMULATION
+            __threadfence_block();
+#endif
+            RN_SYNC();
+            w.mass_kind = 2;
+            if (A.step_tuner == 0) {  // stepSizeTuner.reset(), DualAvg.scala:17-21
+              const double ss = rn_exp(logStepSizeBar);
+              logStepSize = rn_log(ss);
+              logStepSizeBar = 0.0;
+              avgError = 0.0;
+              daIter = 0;
+              shrinkageTarget = rn_log(10 * ss);
+              stepSize = ss;
+            }
+          }
+          RN_SYNC();
+        }
+      }
+#endif
       if (A.mass_tuner == 1) {  // DiagonalMassMatrixTuner, MassMatrix.scala:147-164
         win_j += 1;
         if (A.adaptation == 1) {  // pooled extension: window sums only (see rn_k_pool_reduce / rn_k_pool_apply)

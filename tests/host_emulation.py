@@ -166,7 +166,7 @@ extern "C" void emu_lbfgs(const double* x0, double* x, double* f, int* info, int
 def compile_source(src, fast=False, opt="-O1"):
     d = os.path.join(tempfile.gettempdir(), "rn_emul")
     os.makedirs(d, exist_ok=True)
-    key = hashlib.sha1((src + str(fast) + opt).encode()).hexdigest()[:16]
+    key = hashlib.sha1((src + str(fast) + opt + os.environ.get("RN_EMU_ASAN", "")).encode()).hexdigest()[:16]
     so = os.path.join(d, key + ".so")
     if not os.path.exists(so):
         cpp = os.path.join(d, key + ".cpp")
@@ -181,7 +181,7 @@ def compile_source(src, fast=False, opt="-O1"):
                 f.write(src + (_WPC_RUNNER + _OPTIMIZER_SHIM_WPC if wpc else _OPTIMIZER_SHIM))
             else:
                 f.write(src + (_WPC_SHIM if wpc else _SHIM) + _SAMPLER_SHIM.replace("@LAUNCH@", launch_wpc if wpc else launch_tpc))
-        flags = [opt, "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w", "-pthread"]
+        flags = [opt, "-std=c++17", "-fPIC", "-shared", "-DRN_HOST_EMULATION", "-w", "-pthread"] + (["-g", "-fsanitize=address"] if os.environ.get("RN_EMU_ASAN") else [])
         flags.append("-ffp-contract=fast" if fast else "-ffp-contract=off")
         subprocess.run(["g++"] + flags + [cpp, "-o", so], check=True)
     return C.CDLL(so)

@@ -76,10 +76,13 @@ def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None, tma="0", k=
     ref_d = om.density_batch(q)
     assert err == 0 and np.max(np.abs(d - ref_d) / np.maximum(np.abs(ref_d), 1e-9)) < tol
     got = he.sample(src, cfg, seeds, cm)
-    ref = om.sample(cfg, seeds=seeds, trace=True)
+    dense = cfg.mass_tuner == abi.RN_MASS_DENSE or (cfg.mass_tuner == abi.RN_MASS_STATIC and cfg.static_matrix == abi.RN_MATRIX_DENSE)
+    ref = om.sample(cfg, seeds=seeds, trace=True, dense_mass=dense)
     assert np.array_equal(got["trace"][:, :, 1], ref["trace"][:, :, 1]), "accept decisions differ"
     assert np.array_equal(got["trace"][:, :, 3], ref["trace"][:, :, 3]), "leapfrog step counts differ"
     assert np.max(np.abs(got["samples"] - ref["samples"]) / np.maximum(np.abs(ref["samples"]), 1e-9)) < tol
+    if cfg.mass_tuner == abi.RN_MASS_DENSE and got["mass_kind"] == 2:  # the adapted covariance matrix itself
+        assert np.max(np.abs(got["mass"] - ref["mass"]) / np.maximum(np.abs(ref["mass"]), 1e-9)) < max(tol, 1e-300)
     for k, o in enumerate(ref["stats"]):
         assert got["stats"][k, 0] == o.gradient_evaluations and got["stats"][k, 3] == o.rng.seed48
 
@@ -127,3 +130,20 @@ def test_reference_leapfrog_test_standard_normal_on_host():
     x = got["samples"][0, :, 0]
     assert abs(x.mean()) < 0.2
     assert abs(((x - 0.0) ** 2).sum() / (len(x) - 1) - 1.0) < 0.2
+
+
+def test_wpc_dense_mass_matrix_on_host():
+    """DenseMassMatrixTuner on the warp-per-chain kernels (opt-in: AUTO keeps dense configurations on the thread-per-chain
+    kernels): mat-vec rows across the lanes, back-substitution and Cholesky on one lane, all in the reference's summation
+    order -> bit-exact on a data-free model, adapted covariance matrix included (MassMatrix.scala:35-117,
+    MassMatrixEstimator.scala:9-50); streamed rows within 1e-9 with equal accept decisions.  (Static dense matrices: GPU
+    test only -- the host emulation shim has no static-matrix upload.)"""
+    # short trajectories: every emulated barrier is a pthread barrier over 32 host threads
+    cfg = api.make_config(iterations=4, warmupIterations=65, sampler=api.EHMCSampler(16, 1, 10, 0.1), stepSizeTuner=api.DualAvgTuner(0.8),
+                          massMatrixTuner=api.DenseMassMatrixTuner(20, 1.5, 10, 10))  # windows end at iterations 30 and 60
+    _run_wpc(configs.eight_schools(), cfg, np.arange(1) + 3, tol=1e-300)
+    model = configs.logreg(300, 3)
+    prir, pcols = model.compile(False)
+    cfg = api.make_config(iterations=4, warmupIterations=40, sampler=api.HMCSampler(3), stepSizeTuner=api.DualAvgTuner(0.8),
+                          massMatrixTuner=api.DenseMassMatrixTuner(15, 1.5, 5, 5))
+    _run_wpc(model, cfg, np.arange(1) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2")
