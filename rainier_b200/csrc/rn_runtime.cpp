@@ -875,8 +875,14 @@ int check_config(const rn_model* m, const rn_config* c, int chains) {
   if (c->mass_tuner < RN_MASS_IDENTITY || c->mass_tuner > RN_MASS_STATIC) return fail(RN_E_UNSUPPORTED, "unknown mass matrix tuner");
   if (c->mass_tuner == RN_MASS_STATIC && c->static_matrix != RN_MATRIX_IDENTITY && !c->static_matrix_elements)
     return fail(RN_E_INVALID, "static mass matrix without elements");
-  if ((c->mass_tuner == RN_MASS_DENSE || (c->mass_tuner == RN_MASS_STATIC && c->static_matrix == RN_MATRIX_DENSE)) && m->n_params > 64)
-    return fail(RN_E_UNSUPPORTED, "dense mass matrix supported for n <= 64");
+  if (c->mass_tuner == RN_MASS_DENSE || (c->mass_tuner == RN_MASS_STATIC && c->static_matrix == RN_MATRIX_DENSE)) {
+    // thread per chain: the Cholesky scratch is thread-local; warp per chain: matrix, factor and estimator live in the
+    // chain's global-memory state (n^2 doubles each)
+    const bool warp = c->backend == RN_BACKEND_WARP;
+    if (!warp && m->n_params > 64)
+      return fail(RN_E_UNSUPPORTED, "dense mass matrix on the thread-per-chain kernels is supported for n <= 64 (use RN_BACKEND_WARP)");
+    if (warp && m->n_params > 512) return fail(RN_E_UNSUPPORTED, "dense mass matrix supported for n <= 512");
+  }
   if (c->adaptation == RN_ADAPT_POOLED && c->mass_tuner != RN_MASS_DIAGONAL)
     return fail(RN_E_UNSUPPORTED, "pooled adaptation is implemented for the diagonal mass-matrix tuner");
   return RN_OK;

@@ -147,3 +147,16 @@ def test_wpc_dense_mass_matrix_on_host():
     cfg = api.make_config(iterations=4, warmupIterations=40, sampler=api.HMCSampler(3), stepSizeTuner=api.DualAvgTuner(0.8),
                           massMatrixTuner=api.DenseMassMatrixTuner(15, 1.5, 5, 5))
     _run_wpc(model, cfg, np.arange(1) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2")
+
+
+def test_wpc_dense_mass_matrix_beyond_the_thread_shape_limit():
+    """70 parameters: more than the thread-per-chain kernels keep in thread-local Cholesky scratch (n <= 64) -- the
+    warp-per-chain shape holds matrix, factor and estimator in the chain's global state; still bit-exact on a data-free model"""
+    model = configs.funnel(70)
+    cfg = api.make_config(iterations=2, warmupIterations=34, sampler=api.HMCSampler(2), stepSizeTuner=api.DualAvgTuner(0.8),
+                          massMatrixTuner=api.DenseMassMatrixTuner(12, 1.5, 4, 4))
+    _run_wpc(model, cfg, np.arange(1) + 3, tol=1e-300)
+    cfg.backend = abi.RN_BACKEND_THREAD
+    with pytest.raises(api.RainierCudaError) as e:
+        api.CudaModel(*model.compile(True), device=-1).sample(cfg, seeds=[1])
+    assert e.value.code == abi.RN_E_UNSUPPORTED
