@@ -1,10 +1,10 @@
 #!/bin/bash
 # Session O (first session of round 2): GPU confirmation + measurement of the rows added CPU-only at the end of round 1
-# (8f-2 rn_function_*, 8f-4 rn_optimize), then the standing evidence (tests, bench, launch list).
+# (8f-2 rn_function_*, 8f-4 rn_optimize, dense mass on the warp-per-chain kernels), then the standing evidence (tests, bench, launch list).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export RN_KERNEL_CACHE=$PWD/build/kcache
-echo "== pytest -m gpu (new rows first)"; timeout 900 python -m pytest tests/test_zz_gpu_function.py tests/test_zz_gpu_optimizer.py -q -m gpu 2>&1 | tail -15
+echo "== pytest -m gpu (new rows first)"; timeout 900 python -m pytest tests/test_zz_gpu_function.py tests/test_zz_gpu_optimizer.py tests/test_zz_gpu_wpc_dense.py -q -m gpu 2>&1 | tail -15
 echo "== bench_function parity"; timeout 300 python scripts/bench_function.py | tee gpurun_out/bench_function_parity.json | cut -c1-1500
 echo "== bench_function fast"; timeout 300 python scripts/bench_function.py --fast | tee gpurun_out/bench_function_fast.json | cut -c1-600
 echo "== bench_optimize parity"; timeout 300 python scripts/bench_optimize.py | tee gpurun_out/bench_optimize_parity.json | cut -c1-1500
