@@ -25,6 +25,8 @@ struct EmuCfg {
   int mass_tuner, initial_window, skip_first, skip_last;
   double win_expansion;
   int stats_window, warmup, iterations;
+  int static_kind;              // StaticMassMatrix: 0 identity, 1 diagonal, 2 dense (mass_tuner == 3)
+  const double* static_elements;  // n or n*n
 };
 extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, const double* data, double* samples,
                           double* trace, long long* out_stats, double* mass_out, int* mass_kind_out) {
@@ -54,10 +56,32 @@ extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, c
   auto launch = [&](void (*kern)(const RnArgs)) {
 @LAUNCH@  };
   a.mass_kind = 0;
-  launch(rn_k_init);
+  launch(rn_k_init);  // LeapFrog.initialize draws with the identity matrix (Driver.scala:22) also under a StaticMassMatrix
   int win_size = c->initial_window, win_i = 0, win_j = 0, est = 0, mass_kind = 0;
+  if (c->mass_tuner == 3 && c->static_kind != 0) {  // what rn_sampler_create uploads: the matrix replicated per chain and,
+    mass_kind = c->static_kind;                     // for a dense one, choleskyUpperTriangular (MassMatrix.scala:76-117)
+    const size_t ne = c->static_kind == 2 ? n * n : n;
+    for (size_t e = 0; e < ne; e++)
+      for (size_t k = 0; k < C; k++) mass[e * C + k] = c->static_elements[e];
+    if (c->static_kind == 2) {
+      auto tri = [](size_t k) { return (k * (k + 1)) / 2; };
+      std::vector<double> lower(tri(n), 0.0);
+      size_t l = 0;
+      for (size_t i = 0; i < n; i++)
+        for (size_t k = 0; k <= i; k++) {
+          double sum = 0.0;
+          for (size_t j = 0; j < k; j++) sum += lower[tri(i) + j] * lower[tri(k) + j];
+          const double x = c->static_elements[i * n + k] - sum;
+          lower[l++] = (i == k) ? std::sqrt(x) : (1.0 / lower[tri(k + 1) - 1] * x);
+        }
+      l = 0;
+      for (size_t i = 0; i < n; i++)
+        for (size_t k = 0; k < n - i; k++, l++)
+          for (size_t ch = 0; ch < C; ch++) chol[l * C + ch] = lower[tri(k + i) + i];
+    }
+  }
   if (c->warmup > 0) {
-    a.phase = 0; a.n_iter = c->warmup; a.mass_kind = 0; a.win_size = win_size; a.win_i = 0; a.win_j = 0; a.est_samples = 0;
+    a.phase = 0; a.n_iter = c->warmup; a.mass_kind = mass_kind; a.win_size = win_size; a.win_i = 0; a.win_j = 0; a.est_samples = 0;
     a.trace = trace;
     launch(rn_k_iter);
     if (c->mass_tuner == 1 || c->mass_tuner == 2)  // host mirror of WindowedMassMatrixTuner.update (rn_runtime.cpp: advance_window)
@@ -205,7 +229,8 @@ class EmuCfg(C.Structure):
     _fields_ = [("sampler", C.c_int), ("n_steps", C.c_int), ("max_steps", C.c_int), ("min_steps", C.c_int), ("buf_size", C.c_int),
                 ("step_tuner", C.c_int), ("p_count", C.c_double), ("delta", C.c_double), ("static_step", C.c_double),
                 ("mass_tuner", C.c_int), ("initial_window", C.c_int), ("skip_first", C.c_int), ("skip_last", C.c_int),
-                ("win_expansion", C.c_double), ("stats_window", C.c_int), ("warmup", C.c_int), ("iterations", C.c_int)]
+                ("win_expansion", C.c_double), ("stats_window", C.c_int), ("warmup", C.c_int), ("iterations", C.c_int),
+                ("static_kind", C.c_int), ("static_elements", C.POINTER(C.c_double))]
 
 
 def sample(src, cfg, seeds, model):
@@ -216,7 +241,8 @@ def sample(src, cfg, seeds, model):
     chains, n = len(seeds), model.nVars
     e = EmuCfg(cfg.sampler, cfg.n_steps, cfg.max_steps, cfg.min_steps, cfg.buf_size, cfg.step_size_tuner, cfg.p_count, cfg.delta,
                cfg.static_step_size, cfg.mass_tuner, cfg.initial_window_size, cfg.skip_first, cfg.skip_last, cfg.window_expansion,
-               cfg.stats_window, cfg.warmup_iterations, cfg.iterations)
+               cfg.stats_window, cfg.warmup_iterations, cfg.iterations,
+               cfg.static_matrix if cfg.mass_tuner == 3 else 0, cfg.static_matrix_elements if cfg.mass_tuner == 3 else None)
     it, tot = cfg.iterations, cfg.warmup_iterations + cfg.iterations
     samples = np.zeros((max(it, 1), n, chains))
     trace = np.zeros((max(tot, 1), 4, chains))

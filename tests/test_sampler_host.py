@@ -160,3 +160,20 @@ def test_wpc_dense_mass_matrix_beyond_the_thread_shape_limit():
     with pytest.raises(api.RainierCudaError) as e:
         api.CudaModel(*model.compile(True), device=-1).sample(cfg, seeds=[1])
     assert e.value.code == abi.RN_E_UNSUPPORTED
+
+
+def test_static_mass_matrices_on_host_both_shapes():
+    """StaticMassMatrix(DiagonalMassMatrix / DenseMassMatrix) (Sampler.scala:47-50, MassMatrix.scala:3-32): velocity,
+    momentum draw through the packed Cholesky factor, energy -- on the thread-per-chain source and on the warp-per-chain
+    source, bit-exact on a data-free model (the reference's LeapFrogTest uses a static DiagonalMassMatrix, :70-78)."""
+    n = 10
+    diag = api.DiagonalMassMatrix(np.linspace(0.5, 2.0, n))
+    A = np.random.default_rng(3).normal(size=(n, n)) * 0.2 + np.eye(n) * 1.5
+    dense = api.DenseMassMatrix((A @ A.T).reshape(-1))
+    for mass in (diag, dense):
+        cfg = _cfg(6, 25, api.HMCSampler(3), api.DualAvgTuner(0.8), api.StaticMassMatrix(mass))
+        got = _run(configs.funnel(), cfg, np.arange(3) + 1, dense=mass is dense)  # thread per chain; compared with the oracle inside _run
+        assert got["mass_kind"] == (1 if mass is diag else 2)
+        cfgw = api.make_config(iterations=4, warmupIterations=20, sampler=api.EHMCSampler(8, 1, 6, 0.2), stepSizeTuner=api.DualAvgTuner(0.8),
+                               massMatrixTuner=api.StaticMassMatrix(mass))
+        _run_wpc(configs.funnel(), cfgw, np.arange(1) + 5, tol=1e-300)
