@@ -27,6 +27,7 @@ struct EmuCfg {
   int stats_window, warmup, iterations;
   int static_kind;              // StaticMassMatrix: 0 identity, 1 diagonal, 2 dense (mass_tuner == 3)
   const double* static_elements;  // n or n*n
+  int chains_per_cta;           // warp-per-chain source: chains of one emulated CTA (1 = one chain at a time)
 };
 extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, const double* data, double* samples,
                           double* trace, long long* out_stats, double* mass_out, int* mass_kind_out) {
@@ -117,22 +118,35 @@ _WPC_RUNNER = r"""
 #include <vector>
 #include <functional>
 // one emulated chain = RN_G = 32*K host threads: a barrier per warp and one for the group (rn_prelude.cuh,
-// RN_HOST_EMULATION && RN_BACKEND == 1)
-static void rn_emu_run_warp(int block, int nblocks, const std::function<void()>& body) {
-  RnEmuGroup g;
-  pthread_barrier_init(&g.bar, nullptr, RN_G);
-  for (int k = 0; k < RN_WPC_K; k++) pthread_barrier_init(&g.warp[k].bar, nullptr, 32);
-  rn_emu_group = &g;
+// RN_HOST_EMULATION && RN_BACKEND == 1).  A CTA holds `slots` chains (`active` of them own a chain; the others leave at
+// once, like the idle warps of the last CTA of a launch); with slots > 1 the CTA-level barriers are real.
+static void rn_emu_run_cta(int block, int nblocks, int slots, int active, const std::function<void()>& body) {
+  std::vector<RnEmuGroup> groups(slots);
+  for (auto& g : groups) {
+    pthread_barrier_init(&g.bar, nullptr, RN_G);
+    for (int k = 0; k < RN_WPC_K; k++) pthread_barrier_init(&g.warp[k].bar, nullptr, 32);
+  }
+  RnEmuCta cta;
+  pthread_barrier_init(&cta.all, nullptr, slots * RN_G);
+  pthread_barrier_init(&cta.active, nullptr, active * RN_G);
+  rn_emu_cta = slots > 1 ? &cta : nullptr;
   std::vector<std::thread> th;
-  for (int tid = 0; tid < RN_G; tid++)
+  for (int tid = 0; tid < slots * RN_G; tid++)
     th.emplace_back([&, tid] {
-      blockDim.x = RN_G; gridDim.x = (unsigned)nblocks; blockIdx.x = (unsigned)block; threadIdx.x = (unsigned)tid;
+      rn_emu_group = &groups[tid / RN_G];
+      blockDim.x = (unsigned)(slots * RN_G); gridDim.x = (unsigned)nblocks; blockIdx.x = (unsigned)block; threadIdx.x = (unsigned)tid;
       body();
     });
   for (auto& t : th) t.join();
-  pthread_barrier_destroy(&g.bar);
-  for (int k = 0; k < RN_WPC_K; k++) pthread_barrier_destroy(&g.warp[k].bar);
+  rn_emu_cta = nullptr;
+  pthread_barrier_destroy(&cta.all);
+  pthread_barrier_destroy(&cta.active);
+  for (auto& g : groups) {
+    pthread_barrier_destroy(&g.bar);
+    for (int k = 0; k < RN_WPC_K; k++) pthread_barrier_destroy(&g.warp[k].bar);
+  }
 }
+static void rn_emu_run_warp(int block, int nblocks, const std::function<void()>& body) { rn_emu_run_cta(block, nblocks, 1, 1, body); }
 """
 
 _WPC_SHIM = _WPC_RUNNER + r"""
@@ -198,7 +212,9 @@ def compile_source(src, fast=False, opt="-O1"):
             wpc = "#define RN_BACKEND 1" in src
             launch_tpc = ("    blockDim.x = 1; gridDim.x = (unsigned)chains; threadIdx.x = 0;\n"
                           "    for (int k = 0; k < chains; k++) { blockIdx.x = (unsigned)k; kern(a); }\n")
-            launch_wpc = "    for (int k = 0; k < chains; k++) rn_emu_run_warp(k, chains, [&] { kern(a); });\n"
+            launch_wpc = ("    const int spc = c->chains_per_cta > 0 ? c->chains_per_cta : 1, nb = (chains + spc - 1) / spc;\n"
+                          "    for (int b = 0; b < nb; b++)\n"
+                          "      rn_emu_run_cta(b, nb, spc, (chains - b * spc) < spc ? (chains - b * spc) : spc, [&] { kern(a); });\n")
             if src.startswith("// generated by rainier_b200 (CUDA source emitter, function flavour)"):  # rn_function.cuh
                 f.write(src + _FUNCTION_SHIM)
             elif src.startswith("// generated by rainier_b200 (CUDA source emitter, optimizer flavour)"):  # rn_optimizer.cuh
@@ -230,10 +246,10 @@ class EmuCfg(C.Structure):
                 ("step_tuner", C.c_int), ("p_count", C.c_double), ("delta", C.c_double), ("static_step", C.c_double),
                 ("mass_tuner", C.c_int), ("initial_window", C.c_int), ("skip_first", C.c_int), ("skip_last", C.c_int),
                 ("win_expansion", C.c_double), ("stats_window", C.c_int), ("warmup", C.c_int), ("iterations", C.c_int),
-                ("static_kind", C.c_int), ("static_elements", C.POINTER(C.c_double))]
+                ("static_kind", C.c_int), ("static_elements", C.POINTER(C.c_double)), ("chains_per_cta", C.c_int)]
 
 
-def sample(src, cfg, seeds, model):
+def sample(src, cfg, seeds, model, chains_per_cta=1):
     """Runs the emitted thread-per-chain sampler kernels on the host.  cfg: lowered rn_config (abi.Config).
     Returns dict(samples [chains][iters][n], trace [chains][warm+iters][4], stats [chains][5], mass, mass_kind)."""
     L = compile_source(src)
@@ -242,7 +258,8 @@ def sample(src, cfg, seeds, model):
     e = EmuCfg(cfg.sampler, cfg.n_steps, cfg.max_steps, cfg.min_steps, cfg.buf_size, cfg.step_size_tuner, cfg.p_count, cfg.delta,
                cfg.static_step_size, cfg.mass_tuner, cfg.initial_window_size, cfg.skip_first, cfg.skip_last, cfg.window_expansion,
                cfg.stats_window, cfg.warmup_iterations, cfg.iterations,
-               cfg.static_matrix if cfg.mass_tuner == 3 else 0, cfg.static_matrix_elements if cfg.mass_tuner == 3 else None)
+               cfg.static_matrix if cfg.mass_tuner == 3 else 0, cfg.static_matrix_elements if cfg.mass_tuner == 3 else None,
+               int(chains_per_cta))
     it, tot = cfg.iterations, cfg.warmup_iterations + cfg.iterations
     samples = np.zeros((max(it, 1), n, chains))
     trace = np.zeros((max(tot, 1), 4, chains))

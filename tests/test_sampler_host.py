@@ -57,7 +57,7 @@ def test_streamed_rows_on_host():
 # ---------------------------------------------------------------------------------------------------------------
 # warp-per-chain source (rn_sampler_wpc.cuh + the emitted rows-across-lanes density) on 32 host threads per chain
 # ---------------------------------------------------------------------------------------------------------------
-def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None, tma="0", k="1"):
+def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None, tma="0", k="1", chains_per_cta=1):
     import os
     rir, cols = model.compile(True)
     config.backend = abi.RN_BACKEND_WARP
@@ -75,7 +75,7 @@ def _run_wpc(model, config, seeds, tol, rir_gpu=None, cols_gpu=None, tma="0", k=
     d, err = he.density(src, q, None, cm)
     ref_d = om.density_batch(q)
     assert err == 0 and np.max(np.abs(d - ref_d) / np.maximum(np.abs(ref_d), 1e-9)) < tol
-    got = he.sample(src, cfg, seeds, cm)
+    got = he.sample(src, cfg, seeds, cm, chains_per_cta=chains_per_cta)
     dense = cfg.mass_tuner == abi.RN_MASS_DENSE or (cfg.mass_tuner == abi.RN_MASS_STATIC and cfg.static_matrix == abi.RN_MATRIX_DENSE)
     ref = om.sample(cfg, seeds=seeds, trace=True, dense_mass=dense)
     assert np.array_equal(got["trace"][:, :, 1], ref["trace"][:, :, 1]), "accept decisions differ"
@@ -177,3 +177,20 @@ def test_static_mass_matrices_on_host_both_shapes():
         cfgw = api.make_config(iterations=4, warmupIterations=20, sampler=api.EHMCSampler(8, 1, 6, 0.2), stepSizeTuner=api.DualAvgTuner(0.8),
                                massMatrixTuner=api.StaticMassMatrix(mass))
         _run_wpc(configs.funnel(), cfgw, np.arange(1) + 5, tol=1e-300)
+
+
+def test_wpc_several_chains_per_cta_share_the_data_tiles_on_host():
+    """The lockstep protocol of the CTA-shared data tiles (rn_sampler_wpc.cuh / emitted tile loop): 3 chains per emulated CTA
+    (96 host threads; the second CTA of the launch has one chain and two idle slots), thread 0 of the CTA issues every
+    "bulk copy", all chain-owning warps consume the same staged tile between the tile barrier pair; 2 stages; then the same
+    with 2 warps per chain.  HMC (every chain evaluates the density equally often), streamed logistic regression."""
+    model = configs.logreg(300, 3)
+    prir, pcols = model.compile(False)
+    cfg = api.make_config(iterations=4, warmupIterations=12, sampler=api.HMCSampler(3), stepSizeTuner=api.DualAvgTuner(0.8),
+                          massMatrixTuner=api.IdentityMassMatrixTuner())
+    _run_wpc(model, cfg, np.arange(4) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2", chains_per_cta=3)
+    model = configs.logreg(600, 3)
+    prir, pcols = model.compile(False)
+    cfg = api.make_config(iterations=3, warmupIterations=0, sampler=api.HMCSampler(2), stepSizeTuner=api.StaticStepSize(0.02),
+                          massMatrixTuner=api.IdentityMassMatrixTuner())
+    _run_wpc(model, cfg, np.arange(3) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2", k="2", chains_per_cta=2)
