@@ -166,6 +166,11 @@ int rn_emit_source(rn_model* m, const rn_config* cfg, char* buf, size_t cap, siz
  * tile-major block [tile][column][32 rows] (one tile = one contiguous chunk = one TMA bulk copy).  cols as in
  * rn_model_create; *needed receives the size in doubles; image may be NULL to query it. */
 int rn_model_pack_columns(const rn_model* m, const double* const* cols, double* image, size_t cap_doubles, size_t* needed);
+/* debug/analysis: where the frozen DAG "really is a dense mat-vec" -- maximal sums of parameter x column products in the
+ * streamed row bodies (the Translator's fold of a `Line` with column coefficients, compute/Translator.scala:91-125).
+ * out = [dot products per gradient evaluation (summed over rows), their multiply-adds per gradient, terms of the longest
+ * dot, distinct dots in the emitted row bodies]. */
+int rn_model_dot_structure(rn_model* m, const rn_config* cfg, double out[4]);
 /* debug: the compiled cubin of the same kernel (for cuobjdump -sass). */
 int rn_emit_cubin(rn_model* m, const rn_config* cfg, void* buf, size_t cap, size_t* needed);
 void rn_model_destroy(rn_model* m);

@@ -476,6 +476,55 @@ std::string build_program(const void* rir, size_t len, bool want_adjoint, bool f
     for (int i = 0; i < n; i++) P.grad_nodes[i] = param_adj[i].empty() ? B.cst(0.0) : B.sum(param_adj[i]);
   }
 
+  // ---- dense structure: maximal left-folded sums of parameter x column products in every streamed row body ----
+  for (TargetInfo& T : P.targets) {
+    if (!T.streamed()) continue;
+    auto term = [&](int id, int& param, int& col) {  // MUL(parameter input, column input), either order
+      const Node& m = P.nodes[id];
+      if (m.kind != K_BINARY || m.op != RIR_B_MUL) return false;
+      const Node &x = P.nodes[m.a], &y = P.nodes[m.b];
+      if (x.kind != K_INPUT || y.kind != K_INPUT) return false;
+      const bool xp = (uint32_t)x.a < P.n_params, yp = (uint32_t)y.a < P.n_params;
+      if (xp == yp) return false;
+      param = xp ? x.a : y.a;
+      col = xp ? y.a : x.a;
+      return true;
+    };
+    std::vector<char> inner(P.nodes.size(), 0);  // ADD nodes that are the left operand of a longer fold
+    std::vector<DotInfo> found;
+    for (int id : T.row_fwd) {
+      const Node& n = P.nodes[id];
+      if (n.kind != K_BINARY || n.op != RIR_B_ADD) continue;
+      DotInfo d;
+      d.node = id;
+      int cur = id;
+      std::vector<std::pair<int, int>> rev;  // terms from the last to the first
+      for (;;) {
+        const Node& a = P.nodes[cur];
+        int p = 0, c = 0;
+        if (a.kind == K_BINARY && a.op == RIR_B_ADD && term(a.b, p, c)) {
+          rev.push_back({p, c});
+          if (cur != id) inner[cur] = 1;
+          cur = a.a;
+          continue;
+        }
+        if (term(cur, p, c))
+          rev.push_back({p, c});
+        else
+          d.base = cur;
+        break;
+      }
+      if (rev.size() < 2) continue;
+      for (auto it = rev.rbegin(); it != rev.rend(); ++it) {
+        d.params.push_back(it->first);
+        d.columns.push_back(it->second);
+      }
+      found.push_back(std::move(d));
+    }
+    for (DotInfo& d : found)
+      if (!inner[d.node]) T.dots.push_back(std::move(d));
+  }
+
   // ---- op counts ----
   P.counts.flops_row.assign(P.targets.size(), 0.0);
   P.counts.special_row.assign(P.targets.size(), 0.0);

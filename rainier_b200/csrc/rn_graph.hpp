@@ -59,6 +59,17 @@ struct ScatterStmt {
   int32_t node;
 };
 
+// A row-variant dot product `base + sum_j q[param_j] * column_j` -- the Translator's left fold of a `Line` whose
+// coefficients are observation columns (compute/Translator.scala:91-125), e.g. x.dot(betas) of a regression.  These are
+// the places where the frozen DAG "really is a dense mat-vec" (over all rows: X*beta; over all chains: a GEMM), the
+// candidates of the chain-batched DMMA contraction.  Found by find_dots(); analysis only so far.
+struct DotInfo {
+  int32_t node = -1;                 // the ADD node holding the complete sum
+  int32_t base = -1;                 // first operand of the fold when it is not itself a param*column product, else -1
+  std::vector<int32_t> params;       // parameter index of every term, in fold order
+  std::vector<int32_t> columns;      // column input index of every term
+};
+
 struct TargetInfo {
   uint64_t n_rows = 0;
   uint32_t first_input = 0, n_cols = 0;
@@ -67,6 +78,7 @@ struct TargetInfo {
   std::vector<int32_t> row_bwd;        // ROW_BWD nodes, emission order
   std::vector<AccStmt> row_acc;        // per-row accumulations
   std::vector<ScatterStmt> row_scatter;
+  std::vector<DotInfo> dots;           // maximal param x column dot products of the row body (>= 2 terms)
   bool streamed() const { return n_cols > 0 && n_rows > 0; }
 };
 

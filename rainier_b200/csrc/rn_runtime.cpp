@@ -646,6 +646,25 @@ int rn_model_op_counts(rn_model* m, const rn_config* cfg, double out[4]) {
   return RN_OK;
 }
 
+// dense structure of the streamed row bodies (DotInfo, rn_graph.hpp): out = [dot products per gradient evaluation summed
+// over rows, their multiply-adds per gradient (forward only), longest dot, number of distinct dots in the emitted code]
+int rn_model_dot_structure(rn_model* m, const rn_config* cfg, double out[4]) {
+  if (!m || !out) return fail(RN_E_INVALID, "null argument");
+  KernelKey key = key_for(m, cfg);
+  const Program* P = nullptr;
+  int rc = get_program(m, key.adjoint, key.fast, &P);
+  if (rc) return rc;
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (const TargetInfo& T : P->targets)
+    for (const DotInfo& d : T.dots) {
+      out[0] += (double)T.n_rows;
+      out[1] += (double)T.n_rows * (double)d.params.size();
+      out[2] = std::max(out[2], (double)d.params.size());
+      out[3] += 1;
+    }
+  return RN_OK;
+}
+
 int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
   if (!m || !q || !out || chains <= 0) return fail(RN_E_INVALID, "bad argument");
   if (m->device < 0) return fail(RN_E_CUDA, "model was created without a device (no CPU fallback)");

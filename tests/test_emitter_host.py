@@ -79,3 +79,21 @@ def test_warp_per_chain_source_shape():
     assert "#define RN_WPC_K 2" in src2 and "double* red = scr +" in src2
     cub = api.CudaModel(rir, cols, device=-1).emit_cubin(cfg)  # NVRTC accepts it for sm_100a
     assert cub[:4] == b"\x7fELF"
+
+
+def test_dense_structure_recognition():
+    """rn_model_dot_structure: the parameter x column dot products of the streamed row bodies (the Translator's fold of a
+    `Line` with column coefficients, compute/Translator.scala:91-125) -- one per observation, d terms each, for a
+    regression on d covariates; none in a data-free model or where coefficients are not columns.  Groundwork of the
+    chain-batched DMMA contraction: this is the detector of "where the DAG really is a dense mat-vec"."""
+    for nobs, d in ((700, 4), (160, 37)):
+        for with_gradient in (True, False):
+            rir, cols = configs.logreg(nobs, d).compile(with_gradient)
+            st = api.CudaModel(rir, cols, device=-1).dot_structure()
+            assert st["dots_per_gradient"] == nobs and st["dot_fmas_per_gradient"] == nobs * d
+            assert st["longest_dot"] == d and st["distinct_dots"] == 9  # 8 unrolled splits (Model.scala:98-132) + the init block
+    rir, cols = configs.eight_schools().compile(True)
+    assert api.CudaModel(rir, cols, device=-1).dot_structure()["distinct_dots"] == 0
+    model, real, rng, _ = sbc_models.build("SBCLaplace")  # streamed, but no parameter x column products
+    rir, cols = model.compile(True)
+    assert len(cols) > 0 and api.CudaModel(rir, cols, device=-1).dot_structure()["dots_per_gradient"] == 0
