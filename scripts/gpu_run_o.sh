@@ -15,3 +15,4 @@ echo "== bench"; timeout 600 python bench.py | tee gpurun_out/bench_parity.json 
 echo "== compute-sanitizer memcheck / racecheck on the new kernels"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_function.py -q -m gpu -k "bit_identical and not 300000" 2>&1 | tail -4
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_optimizer.py -q -m gpu -k "warp_per_start" 2>&1 | tail -4
+echo "== DMMA probe (fragment mapping + fp64 tensor-core rate at cfg 3's shape)"; timeout 300 python scripts/probe_dmma.py | tee gpurun_out/probe_dmma.json | cut -c1-800
