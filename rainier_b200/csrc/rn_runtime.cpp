@@ -1958,12 +1958,12 @@ struct rn_function {
   int64_t launches = 0;
 };
 
-static int function_compile(rn_function* f) {
-  if (!f->cubin.empty()) return RN_OK;
+// NVRTC: source -> sm_100a cubin (the function and optimizer flavours; get_kernel keeps its own copy with the cubin cache)
+static int nvrtc_to_cubin(const std::string& source, const char* name, bool fast, std::vector<char>& cubin) {
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-  opts.push_back(f->fast ? "--fmad=true" : "--fmad=false");
+  opts.push_back(fast ? "--fmad=true" : "--fmad=false");
   nvrtcProgram prog;
-  if (nvrtcCreateProgram(&prog, f->source.c_str(), "rainier_function.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+  if (nvrtcCreateProgram(&prog, source.c_str(), name, 0, nullptr, nullptr) != NVRTC_SUCCESS)
     return fail(RN_E_COMPILE, "nvrtcCreateProgram failed");
   nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   if (r != NVRTC_SUCCESS) {
@@ -1976,10 +1976,15 @@ static int function_compile(rn_function* f) {
   }
   size_t n = 0;
   nvrtcGetCUBINSize(prog, &n);
-  f->cubin.resize(n);
-  nvrtcGetCUBIN(prog, f->cubin.data());
+  cubin.resize(n);
+  nvrtcGetCUBIN(prog, cubin.data());
   nvrtcDestroyProgram(&prog);
   return RN_OK;
+}
+
+static int function_compile(rn_function* f) {
+  if (!f->cubin.empty()) return RN_OK;
+  return nvrtc_to_cubin(f->source, "rainier_function.cu", f->fast, f->cubin);
 }
 
 static int function_load(const Api* A, rn_function* f) {
@@ -2255,25 +2260,8 @@ static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::O
     K->starts_per_cta = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)(8 / k), cap / per_start));
   }
   K->source = emit_optimizer_source(*P, eo, history);
-  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-  opts.push_back(fast ? "--fmad=true" : "--fmad=false");
-  nvrtcProgram prog;
-  if (nvrtcCreateProgram(&prog, K->source.c_str(), "rainier_optimizer.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
-    return fail(RN_E_COMPILE, "nvrtcCreateProgram failed");
-  nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
-  if (r != NVRTC_SUCCESS) {
-    size_t n = 0;
-    nvrtcGetProgramLogSize(prog, &n);
-    std::string log(n, '\0');
-    nvrtcGetProgramLog(prog, &log[0]);
-    nvrtcDestroyProgram(&prog);
-    return fail(RN_E_COMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log);
-  }
-  size_t n = 0;
-  nvrtcGetCUBINSize(prog, &n);
-  K->cubin.resize(n);
-  nvrtcGetCUBIN(prog, K->cubin.data());
-  nvrtcDestroyProgram(&prog);
+  rc = nvrtc_to_cubin(K->source, "rainier_optimizer.cu", fast, K->cubin);
+  if (rc) return rc;
   *out = K.get();
   m->opt_kernels.emplace(key, std::move(K));
   return RN_OK;
