@@ -171,6 +171,11 @@ int rn_model_pack_columns(const rn_model* m, const double* const* cols, double* 
  * out = [dot products per gradient evaluation (summed over rows), their multiply-adds per gradient, terms of the longest
  * dot, distinct dots in the emitted row bodies]. */
 int rn_model_dot_structure(rn_model* m, const rn_config* cfg, double out[4]);
+/* debug/analysis: which streamed targets are separable -- their row sum is sum_k S_k * p_k(parameters) with S_k a row sum of
+ * products of column-only values, the shape the reference's inliner folds into constants on the JVM
+ * (compute/Target.scala:136-207, compute/PartialEvaluator.scala:86-97).  out = [streamed targets, separable among them,
+ * atoms S_k, rows no longer streamed per gradient evaluation].  Analysis only. */
+int rn_model_separable_structure(rn_model* m, double out[4]);
 /* debug: the compiled cubin of the same kernel (for cuobjdump -sass). */
 int rn_emit_cubin(rn_model* m, const rn_config* cfg, void* buf, size_t cap, size_t* needed);
 void rn_model_destroy(rn_model* m);

@@ -55,6 +55,7 @@ def lib():
         L.rn_model_pack_columns.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.rn_model_destroy.argtypes = [C.c_void_p]
         L.rn_model_op_counts.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(C.c_double)]
+        L.rn_model_separable_structure.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.rn_model_dot_structure.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(C.c_double)]
         L.rn_density_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.rn_emit_source.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -492,6 +493,12 @@ class CudaModel:
         out = (C.c_double * 4)()
         _check(lib().rn_model_op_counts(self.h, C.byref(cfg) if cfg else None, out))
         return {"flops_invariant": out[0], "special_invariant": out[1], "flops_rows": out[2], "special_rows": out[3]}
+
+    def separable_structure(self):
+        """which streamed targets a device-side inliner could fold into constants (sufficient statistics)"""
+        out = (C.c_double * 4)()
+        _check(lib().rn_model_separable_structure(self.h, out))
+        return {"streamed_targets": int(out[0]), "separable_targets": int(out[1]), "atoms": int(out[2]), "rows_removed": int(out[3])}
 
     def dot_structure(self, config=None):
         """where the DAG is a dense mat-vec: parameter x column dot products of the streamed row bodies"""

@@ -3,7 +3,10 @@
 
 #include <cmath>
 #include <cstring>
+#include <algorithm>
+#include <functional>
 #include <map>
+#include <set>
 
 namespace rn {
 
@@ -646,6 +649,108 @@ std::string build_function(const void* rir, size_t len, Program& P) {
       count_node(P.nodes[i], P.counts.flops_inv, P.counts.special_inv);
     }
   return "";
+}
+
+SeparableInfo analyze_separable(const Program& P, int max_degree, int max_atoms) {
+  SeparableInfo R;
+  const int N = (int)P.nodes.size();
+  // parameter / column dependence of every node
+  std::vector<char> pdep(N, 0), cdep(N, 0);
+  for (int i = 0; i < N; i++) {
+    const Node& n = P.nodes[i];
+    auto dep = [&](int x) {
+      pdep[i] |= pdep[x];
+      cdep[i] |= cdep[x];
+    };
+    switch (n.kind) {
+      case K_INPUT: ((uint32_t)n.a < P.n_params ? pdep[i] : cdep[i]) = 1; break;
+      case K_UNARY: dep(n.a); break;
+      case K_BINARY: dep(n.a); dep(n.b); break;
+      case K_LOOKUP:
+        dep(n.a);
+        for (int k = 0; k < n.c; k++) dep(P.lookup_refs[n.b + k]);
+        break;
+      case K_SELEQ: dep(n.a); dep(n.b); dep(n.c); break;
+      default: break;
+    }
+  }
+  typedef std::vector<int32_t> Mono;  // sorted ids of column-only atoms; empty = parameter-only term
+  typedef std::set<Mono> Poly;
+  for (const TargetInfo& T : P.targets) {
+    if (!T.streamed()) continue;
+    R.streamed_targets++;
+    std::map<int, Poly> form;
+    bool ok = true;
+    std::function<const Poly*(int)> get = [&](int id) -> const Poly* {
+      auto it = form.find(id);
+      if (it != form.end()) return &it->second;
+      Poly p;
+      if (!cdep[id])
+        p.insert(Mono());  // parameter-only or constant: a coefficient
+      else if (!pdep[id])
+        p.insert(Mono(1, id));  // column-only: an atom, however complicated
+      else {
+        const Node& n = P.nodes[id];
+        auto mul = [&](const Poly& a, const Poly& b, Poly& out) {
+          for (const Mono& x : a)
+            for (const Mono& y : b) {
+              Mono m(x);
+              m.insert(m.end(), y.begin(), y.end());
+              std::sort(m.begin(), m.end());
+              if ((int)m.size() > max_degree) return false;
+              out.insert(std::move(m));
+              if ((int)out.size() > max_atoms) return false;
+            }
+          return true;
+        };
+        bool good = false;
+        if (n.kind == K_BINARY && (n.op == RIR_B_ADD || n.op == RIR_B_SUB)) {
+          const Poly *a = get(n.a), *b = ok ? get(n.b) : nullptr;
+          if (a && b) {
+            p = *a;
+            p.insert(b->begin(), b->end());
+            good = (int)p.size() <= max_atoms;
+          }
+        } else if (n.kind == K_BINARY && n.op == RIR_B_MUL) {
+          const Poly *a = get(n.a), *b = ok ? get(n.b) : nullptr;
+          good = a && b && mul(*a, *b, p);
+        } else if (n.kind == K_BINARY && n.op == RIR_B_DIV && !pdep[n.b]) {  // division by a column-only value: times an atom
+          const Poly* a = get(n.a);
+          Poly inv;
+          inv.insert(Mono(1, id));  // stands for 1 / val[n.b]; a distinct atom per node is a safe over-count
+          good = a && mul(*a, inv, p);
+        } else if (n.kind == K_BINARY && n.op == RIR_B_DIV && !cdep[n.b]) {  // division by a parameter-only value: scales
+          const Poly* a = get(n.a);
+          if (a) {
+            p = *a;
+            good = true;
+          }
+        } else if (n.kind == K_BINARY && n.op == RIR_B_POW && P.nodes[n.b].kind == K_CONST && P.nodes[n.b].value == 2.0) {
+          const Poly* a = get(n.a);
+          good = a && mul(*a, *a, p);
+        } else if (n.kind == K_UNARY && (n.op == RIR_U_NOOP || n.op == U_NEG)) {
+          const Poly* a = get(n.a);
+          if (a) {
+            p = *a;
+            good = true;
+          }
+        }
+        if (!good) {  // a nonlinear operation on a node that mixes parameters and columns
+          ok = false;
+          return nullptr;
+        }
+      }
+      return &form.emplace(id, std::move(p)).first->second;
+    };
+    const Poly* out = T.outputs.empty() ? nullptr : get(T.outputs[0]);
+    if (ok && out) {
+      R.separable_targets++;
+      for (const Mono& m : *out)
+        if (!m.empty()) R.atoms++;
+      R.rows_removed += (int64_t)T.n_rows;
+    }
+  }
+  return R;
 }
 
 }  // namespace rn

@@ -111,6 +111,23 @@ struct Program {
 // returns empty string on success, else an error message
 std::string build_program(const void* rir, size_t len, bool want_adjoint, bool fast_math, Program& out);
 
+// Separability analysis of the streamed targets (analysis only): can the row sum of a
+// target's primal output be written as sum_k S_k * p_k(parameters) with S_k = sum over rows of a product of at most
+// `max_degree` column-only sub-expressions ("atoms")?  That is the shape the reference's inliner folds into constants on the
+// JVM (compute/Target.scala:136-207 decides, compute/PartialEvaluator.scala:86-97 folds) -- here decided on the SSA form by
+// carrying a polynomial over column-only atoms through ADD / SUB / MUL / constant powers and refusing any other operation on
+// a node that mixes parameters and columns (the reference's `nonlinearOp` on a `combination`).  More general than the
+// reference's rule: squares are expanded regardless of the number of terms (the reference stops at 5 additive terms,
+// compute/LogLineOps.scala:43-66), so a Gaussian regression on any number of covariates is separable: its atoms are the
+// entries of X^T X, X^T y and y^T y.
+struct SeparableInfo {
+  int streamed_targets = 0;
+  int separable_targets = 0;
+  int64_t atoms = 0;          // distinct products of column-only nodes over the separable targets (the S_k to reduce)
+  int64_t rows_removed = 0;   // rows that would no longer be streamed per gradient evaluation
+};
+SeparableInfo analyze_separable(const Program& P, int max_degree = 2, int max_atoms = 4096);
+
 // RIR_FLAG_FUNCTION containers: Compiler.compile(inputs, outputs): CompiledFunction (compute/Compiler.scala:22-30) --
 // m named outputs over n_params inputs, forward evaluation only (Generator.prepare's "requirements",
 // core/Generator.scala:59-94).  Fills nodes / lookup_refs / inv_fwd (nodes some output needs, topological) /

@@ -665,6 +665,21 @@ int rn_model_dot_structure(rn_model* m, const rn_config* cfg, double out[4]) {
   return RN_OK;
 }
 
+// separability of the streamed targets (SeparableInfo, rn_graph.hpp): out = [streamed targets, separable among them, atoms
+// (row sums a device-side inliner would have to reduce), rows no longer streamed per gradient evaluation]
+int rn_model_separable_structure(rn_model* m, double out[4]) {
+  if (!m || !out) return fail(RN_E_INVALID, "null argument");
+  const Program* P = nullptr;
+  int rc = get_program(m, true, false, &P);  // the primal outputs decide (adjoint-mode program: one output per target)
+  if (rc) return rc;
+  const SeparableInfo s = analyze_separable(*P);
+  out[0] = s.streamed_targets;
+  out[1] = s.separable_targets;
+  out[2] = (double)s.atoms;
+  out[3] = (double)s.rows_removed;
+  return RN_OK;
+}
+
 int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
   if (!m || !q || !out || chains <= 0) return fail(RN_E_INVALID, "bad argument");
   if (m->device < 0) return fail(RN_E_CUDA, "model was created without a device (no CPU fallback)");

@@ -97,3 +97,25 @@ def test_dense_structure_recognition():
     model, real, rng, _ = sbc_models.build("SBCLaplace")  # streamed, but no parameter x column products
     rir, cols = model.compile(True)
     assert len(cols) > 0 and api.CudaModel(rir, cols, device=-1).dot_structure()["dots_per_gradient"] == 0
+
+
+def test_separability_analysis():
+    """rn_model_separable_structure: which streamed targets have a row sum of the form sum_k S_k * p_k(parameters) -- what
+    the reference's inliner folds into constants on the JVM (compute/Target.scala:136-207).  A Gaussian regression on 5
+    covariates is NOT inlined by the reference (6 additive terms: 21 >= 20, compute/LogLineOps.scala:43-66) and streams
+    its rows, yet it is separable (its atoms are the entries of X^T X, X^T y, y^T y per unrolled split); a logistic
+    regression and a Laplace likelihood are not (exp / abs of a parameter x column mix).  Groundwork of the device-side
+    inliner."""
+    rir, cols = configs.linreg(400, covariates=3).compile(False)
+    assert not cols  # the reference inlines this one itself: nothing is streamed
+    assert api.CudaModel(rir, cols, device=-1).separable_structure()["streamed_targets"] == 0
+    for with_gradient in (True, False):
+        rir, cols = configs.linreg(400, covariates=5).compile(with_gradient)
+        st = api.CudaModel(rir, cols, device=-1).separable_structure()
+        assert st["streamed_targets"] == 2 and st["separable_targets"] == 2 and st["rows_removed"] == 49 + 8
+        assert 8 * 28 <= st["atoms"] <= 9 * 28  # (5 covariates + y + 1)(..+1)/2 = 28 products per unrolled observation
+        rir, cols = configs.logreg(700, 4).compile(with_gradient)
+        st = api.CudaModel(rir, cols, device=-1).separable_structure()
+        assert st["streamed_targets"] == 2 and st["separable_targets"] == 0
+    model, real, rng, _ = sbc_models.build("SBCLaplace")
+    assert api.CudaModel(*model.compile(True), device=-1).separable_structure()["separable_targets"] == 0
