@@ -14,8 +14,7 @@ from rainier_b200 import abi, api
 
 from test_optimizer_host import EGGS, _assert_identical, egg_model, fit_normal
 
-PENDING = ("written when the round's GPU budget was all but spent: verified on CPU (host-emulated kernel sources) and by the correctness-only scripts/mini_check2.py run on a B200 (profiles/r1_mini_check2.txt); the first full GPU run of this file is round 2's first session (scripts/gpu_run_o.sh) -- non-strict, so a pass is reported as XPASS and a failure cannot stop `pytest -x` before the reports of the hot path's own files are complete")
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason=PENDING)]
+pytestmark = pytest.mark.gpu
 
 
 def _run(model, x0, **kw):
