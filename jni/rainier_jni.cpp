@@ -1,5 +1,5 @@
 // jni/rainier_jni.cpp -- the thin JNI shim between Rainier's Scala host code and the C ABI of librainier_cuda.so
-// (include/rainier_cuda.h).  Binds the native methods of scala/com/stripe/rainier/cuda/Native.scala.
+// (include/rainier_cuda.h).  Binds the static native methods of scala/com/stripe/rainier/cuda/Native.java.
 //
 // NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no JDK (no <jni.h>, no javac/scalac).  It is written
 // against the JNI specification and guarded by __has_include so that `make -C jni` is a no-op where <jni.h> is
@@ -7,8 +7,13 @@
 //   g++ -O2 -std=c++17 -fPIC -shared -I$JAVA_HOME/include -I$JAVA_HOME/include/linux jni/rainier_jni.cpp \
 //       -Lrainier_b200 -lrainier_cuda -Wl,-rpath,'$ORIGIN' -o librainier_jni.so
 //
-// Every function is a 1:1 forward; arrays are pinned with Get/ReleasePrimitiveArrayCritical (no copies on HotSpot),
-// the RIR container and the rn_config POD travel as direct ByteBuffers filled by the Scala side
+// Every function is a 1:1 forward.  The natives are the STATIC methods of the Java class
+// scala/com/stripe/rainier/cuda/Native.java (hence the `jclass` receiver and the unmangled `..._Native_<method>` names).
+// Java arrays cross by REGION COPIES (Get/Set<Type>ArrayRegion) around the native call: rn_sample / rn_density_batch /
+// rn_function_eval / rn_optimize can run for seconds to minutes (NVRTC compile, warmup, a blocking stream sync, worker
+// threads), and JNI forbids blocking inside a Get/ReleasePrimitiveArrayCritical region (it would also stall the GC of
+// every JVM thread).  The bulk path (`sampleDirect`) takes a direct, page-locked ByteBuffer and copies nothing.
+// The RIR container and the rn_config POD travel as direct ByteBuffers filled by the Scala side
 // (scala/com/stripe/rainier/cuda/RIR.scala, CudaConfig.scala).  A non-zero return code becomes a RuntimeException
 // carrying rn_last_error() -- mirroring the reference, where failures on this path are exceptions thrown from
 // generated code (ir/MethodGenerator.scala:164-167).
@@ -21,6 +26,8 @@
 #ifdef RN_HAVE_JNI
 #include <jni.h>
 
+#include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "../include/rainier_cuda.h"
@@ -30,16 +37,21 @@ void throw_last(JNIEnv* env) {
   jclass c = env->FindClass("java/lang/RuntimeException");
   if (c) env->ThrowNew(c, rn_last_error());
 }
-struct Crit {  // RAII for Get/ReleasePrimitiveArrayCritical
-  JNIEnv* env;
-  jarray arr;
-  void* p;
-  jint mode;
-  Crit(JNIEnv* e, jarray a, jint m = 0) : env(e), arr(a), p(a ? e->GetPrimitiveArrayCritical(a, nullptr) : nullptr), mode(m) {}
-  ~Crit() {
-    if (p) env->ReleasePrimitiveArrayCritical(arr, p, mode);
-  }
-};
+// region copies: Java array -> native vector before the call, native vector -> Java array after it
+std::vector<double> in_doubles(JNIEnv* env, jdoubleArray a) {
+  std::vector<double> v(a ? (size_t)env->GetArrayLength(a) : 0);
+  if (!v.empty()) env->GetDoubleArrayRegion(a, 0, (jsize)v.size(), v.data());
+  return v;
+}
+std::vector<int64_t> in_longs(JNIEnv* env, jlongArray a) {
+  static_assert(sizeof(jlong) == sizeof(int64_t), "jlong is 64 bits");
+  std::vector<int64_t> v(a ? (size_t)env->GetArrayLength(a) : 0);
+  if (!v.empty()) env->GetLongArrayRegion(a, 0, (jsize)v.size(), (jlong*)v.data());
+  return v;
+}
+void out_doubles(JNIEnv* env, jdoubleArray a, const double* src, size_t n) {
+  if (a && n) env->SetDoubleArrayRegion(a, 0, (jsize)n, src);
+}
 }  // namespace
 
 extern "C" {
@@ -76,12 +88,11 @@ JNIEXPORT jint JNICALL Java_com_stripe_rainier_cuda_Native_nvars(JNIEnv*, jclass
 // def densityBatch(h: Long, q: Array[Double], chains: Int, out: Array[Double]): Unit
 JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_densityBatch(JNIEnv* env, jclass, jlong h, jdoubleArray q,
                                                                        jint chains, jdoubleArray out) {
-  int rc;
-  {
-    Crit cq(env, q, JNI_ABORT), co(env, out);
-    rc = rn_density_batch((rn_model*)(intptr_t)h, (const double*)cq.p, chains, (double*)co.p);
-  }
-  if (rc != RN_OK) throw_last(env);
+  const std::vector<double> vq = in_doubles(env, q);
+  std::vector<double> vo((size_t)env->GetArrayLength(out));
+  const int rc = rn_density_batch((rn_model*)(intptr_t)h, vq.data(), chains, vo.data());
+  if (rc != RN_OK) return throw_last(env);
+  out_doubles(env, out, vo.data(), vo.size());
 }
 
 // def sample(h: Long, config: ByteBuffer, seeds: Array[Long], samples: Array[Double], mass: Array[Double],
@@ -91,13 +102,14 @@ JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_sample(JNIEnv* env, j
                                                                  jobject stats) {
   const rn_config* cfg = (const rn_config*)env->GetDirectBufferAddress(config);
   rn_chain_stats* st = stats ? (rn_chain_stats*)env->GetDirectBufferAddress(stats) : nullptr;
-  const jint chains = env->GetArrayLength(seeds);
-  int rc;
-  {
-    Crit cs(env, seeds, JNI_ABORT), co(env, samples), cm(env, mass);
-    rc = rn_sample((rn_model*)(intptr_t)h, cfg, (const int64_t*)cs.p, chains, (double*)co.p, (double*)cm.p, st);
-  }
-  if (rc != RN_OK) throw_last(env);
+  const std::vector<int64_t> vs = in_longs(env, seeds);
+  const size_t ns = samples ? (size_t)env->GetArrayLength(samples) : 0, nm = mass ? (size_t)env->GetArrayLength(mass) : 0;
+  std::unique_ptr<double[]> vo(ns ? new double[ns] : nullptr);  // uninitialised: rn_sample writes every element
+  std::vector<double> vm(nm);
+  const int rc = rn_sample((rn_model*)(intptr_t)h, cfg, vs.data(), (int)vs.size(), vo.get(), nm ? vm.data() : nullptr, st);
+  if (rc != RN_OK) return throw_last(env);
+  out_doubles(env, samples, vo.get(), ns);
+  out_doubles(env, mass, vm.data(), nm);
 }
 
 // def hostAlloc(device: Int, bytes: Long): ByteBuffer   -- page-locked memory as a direct buffer (rn_host_alloc)
@@ -122,13 +134,11 @@ JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_sampleDirect(JNIEnv* 
   const rn_config* cfg = (const rn_config*)env->GetDirectBufferAddress(config);
   rn_chain_stats* st = stats ? (rn_chain_stats*)env->GetDirectBufferAddress(stats) : nullptr;
   double* out = (double*)env->GetDirectBufferAddress(samples);
-  const jint chains = env->GetArrayLength(seeds);
-  int rc;
-  {
-    Crit cs(env, seeds, JNI_ABORT), cm(env, mass);
-    rc = rn_sample((rn_model*)(intptr_t)h, cfg, (const int64_t*)cs.p, chains, out, (double*)cm.p, st);
-  }
-  if (rc != RN_OK) throw_last(env);
+  const std::vector<int64_t> vs = in_longs(env, seeds);
+  std::vector<double> vm(mass ? (size_t)env->GetArrayLength(mass) : 0);
+  const int rc = rn_sample((rn_model*)(intptr_t)h, cfg, vs.data(), (int)vs.size(), out, vm.empty() ? nullptr : vm.data(), st);
+  if (rc != RN_OK) return throw_last(env);
+  out_doubles(env, mass, vm.data(), vm.size());
 }
 
 JNIEXPORT jstring JNICALL Java_com_stripe_rainier_cuda_Native_emitSource(JNIEnv* env, jclass, jlong h, jobject config) {
@@ -164,12 +174,11 @@ JNIEXPORT jlong JNICALL Java_com_stripe_rainier_cuda_Native_functionCreate(JNIEn
 // def functionEval(handle: Long, draws: Array[Double], count: Long, out: Array[Double]): Unit   draws [count][n] -> out [count][m]
 JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_functionEval(JNIEnv* env, jclass, jlong h, jdoubleArray draws, jlong count,
                                                                         jdoubleArray out) {
-  int rc;
-  {
-    Crit cx(env, draws, JNI_ABORT), co(env, out);
-    rc = rn_function_eval((rn_function*)(intptr_t)h, (const double*)cx.p, (int64_t)count, (double*)co.p);
-  }
-  if (rc != RN_OK) throw_last(env);
+  const std::vector<double> vx = in_doubles(env, draws);
+  std::vector<double> vo((size_t)env->GetArrayLength(out));
+  const int rc = rn_function_eval((rn_function*)(intptr_t)h, vx.data(), (int64_t)count, vo.data());
+  if (rc != RN_OK) return throw_last(env);
+  out_doubles(env, out, vo.data(), vo.size());
 }
 JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_functionDestroy(JNIEnv*, jclass, jlong h) {
   rn_function_destroy((rn_function*)(intptr_t)h);
@@ -184,12 +193,13 @@ JNIEXPORT void JNICALL Java_com_stripe_rainier_cuda_Native_optimize(JNIEnv* env,
   oc.history = m;
   oc.eps = eps;
   oc.max_evaluations = maxEvals;
-  int rc;
-  {
-    Crit c0(env, x0, JNI_ABORT), cx(env, x), ci(env, info);
-    rc = rn_optimize((rn_model*)(intptr_t)h, &oc, (const double*)c0.p, starts, (double*)cx.p, nullptr, (int32_t*)ci.p, nullptr);
-  }
-  if (rc != RN_OK) throw_last(env);
+  const std::vector<double> v0 = in_doubles(env, x0);
+  std::vector<double> vx((size_t)env->GetArrayLength(x));
+  std::vector<int32_t> vi(info ? (size_t)env->GetArrayLength(info) : 0);
+  const int rc = rn_optimize((rn_model*)(intptr_t)h, &oc, x0 ? v0.data() : nullptr, starts, vx.data(), nullptr, vi.empty() ? nullptr : vi.data(), nullptr);
+  if (rc != RN_OK) return throw_last(env);
+  out_doubles(env, x, vx.data(), vx.size());
+  if (info) env->SetIntArrayRegion(info, 0, (jsize)vi.size(), (const jint*)vi.data());
 }
 JNIEXPORT jstring JNICALL Java_com_stripe_rainier_cuda_Native_lastError(JNIEnv* env, jclass) {
   return env->NewStringUTF(rn_last_error());

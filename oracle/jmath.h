@@ -23,6 +23,19 @@
 
 namespace rno {
 
+/*
+ * The three functions below (log, exp, pow) are transcriptions of FDLIBM 5.3 (e_log.c, e_exp.c, e_pow.c), the
+ * algorithm java.lang.StrictMath is specified to use.  FDLIBM's notice, preserved as its licence requires:
+ *
+ * ====================================================
+ * Copyright (C) 1993, 2004 by Sun Microsystems, Inc. All rights reserved.
+ *
+ * Developed at SunSoft, a Sun Microsystems, Inc. business.
+ * Permission to use, copy, modify, and distribute this
+ * software is freely granted, provided that this notice
+ * is preserved.
+ * ====================================================
+ */
 /* ---- fdlibm __ieee754_log (StrictMath.log) ---------------------------------------------------------- */
 static inline int32_t hi_word(double x) {
   uint64_t u;

@@ -159,7 +159,7 @@ struct Kernel {
   std::string source;
   std::vector<char> cubin;
   CUmodule mod = nullptr;
-  CUfunction k_init = nullptr, k_iter = nullptr, k_density = nullptr, k_transpose = nullptr, k_pool_reduce = nullptr,
+  CUfunction k_init = nullptr, k_iter = nullptr, k_warmup = nullptr, k_density = nullptr, k_transpose = nullptr, k_pool_reduce = nullptr,
              k_pool_apply = nullptr, k_diag_chain = nullptr, k_diag_reduce = nullptr;
   const Program* prog = nullptr;
   int backend = 0;            // 0 thread per chain, 1 warp per chain
@@ -168,6 +168,9 @@ struct Kernel {
   int wpc_k = 1;
   int tma_stages = 0;         // CTA-shared data-tile pipeline (backend 1): stages, doubles per stage
   int tile_doubles = 0;
+  // backend 0: bytes of dynamic shared memory per THREAD (rn_sampler.cuh: momentum, diagonal mass, EHMC snapshot momentum,
+  // Stats counters live there instead of in registers) -- must mirror RN_TS_DOUBLES / RN_TS_INTS
+  unsigned tpc_smem_per_thread = 0;
   unsigned smem_bytes() const {  // dynamic shared memory of one CTA: per-warp slices | 128B pad | stages | mbarriers
     size_t d = (size_t)warps_per_cta * wpc_smem_doubles;
     if (tma_stages > 0) d = ((d + 15) & ~(size_t)15) + (size_t)tma_stages * tile_doubles + (size_t)tma_stages;
@@ -284,6 +287,13 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
   if (eo.backend == 1 && P->symbolic && P->n_params > 96)
     return fail(RN_E_UNSUPPORTED, "warp-per-chain with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
   K->backend = eo.backend;
+  if (eo.backend == 0) {  // rn_sampler.cuh: RN_TS_DOUBLES * 8 + RN_TS_INTS * 4
+    const unsigned n = P->n_params;
+    const unsigned doubles = (n + 1) + (key.mass_max >= 1 ? n : 0) + (key.ehmc ? n : 0) + 5 + 4;
+    K->tpc_smem_per_thread = doubles * 8 + 10 * 4;
+    if ((size_t)K->tpc_smem_per_thread * 32 > 227 * 1024 - 1024)
+      return fail(RN_E_UNSUPPORTED, "thread-per-chain shape: the chain's shared-memory state does not fit; use RN_BACKEND_WARP");
+  }
   if (eo.backend == 1) {
     const size_t cap = 227 * 1024 - 2048;  // opt-in dynamic shared memory per CTA on sm_100, minus static/reserved
     int wmax = 8;
@@ -422,6 +432,10 @@ static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
   CU(A->cuModuleLoadData(&K->mod, K->cubin.data()));
   CU(A->cuModuleGetFunction(&K->k_init, K->mod, "rn_k_init"));
   CU(A->cuModuleGetFunction(&K->k_iter, K->mod, "rn_k_iter"));
+  if (K->backend == 0)  // thread per chain: the warmup phase is its own entry point (the sampling kernel carries no adaptation)
+    CU(A->cuModuleGetFunction(&K->k_warmup, K->mod, "rn_k_warmup"));
+  else
+    K->k_warmup = K->k_iter;
   CU(A->cuModuleGetFunction(&K->k_density, K->mod, "rn_k_density"));
   CU(A->cuModuleGetFunction(&K->k_transpose, K->mod, "rn_k_transpose"));
   CU(A->cuModuleGetFunction(&K->k_pool_reduce, K->mod, "rn_k_pool_reduce"));
@@ -432,6 +446,9 @@ static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
     const int bytes = (int)K->smem_bytes();
     for (CUfunction f : {K->k_init, K->k_iter, K->k_density})
       CU(A->cuFuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, bytes));
+  } else if (K->tpc_smem_per_thread * 128u > 48u * 1024u) {
+    for (CUfunction f : {K->k_init, K->k_iter, K->k_warmup})
+      CU(A->cuFuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)(K->tpc_smem_per_thread * 128u)));
   }
   return RN_OK;
 }
@@ -832,9 +849,9 @@ int launch(const Api* A, rn_sampler* s, CUfunction f, int count = -1) {
   // are spread over all 148 SMs with smaller CTAs instead of packing 64 SMs and idling the rest
   unsigned block = 128u;
   while (block > 32u && chains < (size_t)block * 148 * 2) block >>= 1;
-  if (const char* e = getenv("RN_BLOCK")) block = (unsigned)atoi(e);
+  if (const char* e = getenv("RN_BLOCK")) block = std::max(32u, std::min(128u, (unsigned)atoi(e) & ~31u));
   const unsigned grid = (unsigned)((chains + block - 1) / block);
-  CU(A->cuLaunchKernel(f, grid, 1, 1, block, 1, 1, 0, s->stream, params, nullptr));
+  CU(A->cuLaunchKernel(f, grid, 1, 1, block, 1, 1, s->K->tpc_smem_per_thread * block, s->stream, params, nullptr));
   s->launches++;
   return RN_OK;
 }
@@ -1147,7 +1164,7 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.est_samples = s->est_samples;
     a.samples = (phase == 1 && d_samples) ? d_samples + (size_t)done * s->m->n_params * (size_t)s->chains : nullptr;
     a.trace = s->d_trace ? (double*)(uintptr_t)(s->d_trace + s->trace_pos * 4 * (size_t)s->chains * 8) : nullptr;
-    int rc = launch(A, s, s->K->k_iter, chain_end - chain_begin);
+    int rc = launch(A, s, phase == 0 ? s->K->k_warmup : s->K->k_iter, chain_end - chain_begin);
     if (rc) return rc;
     if (phase == 0) {
       const int closed = advance_window(s, k);

@@ -25,61 +25,125 @@
 #define RN_LN2 0.6931471805599453
 #define RN_AT(ptr, field, c) (ptr)[(size_t)(field) * (size_t)A.chains + (size_t)(c)]
 
-struct RnStats {
-  rn_i64 grads, steps;
-  int iters, accepted, err;
-  double e_mean, e_raw, trans2;
-  int e_n;
-  int ring_i[3], ring_full[3];
+// ---- this thread's COLD state lives in shared memory -----------------------------------------------------------
+// The fused iteration is latency-bound on dependent fp64 chains (ncu, profiles/r1_ncu_funnel_parity_v5.csv: `wait`
+// stalls 45 % at 4 warps per scheduler), so what matters is how many warps fit the register file.  Everything a chain
+// does not touch inside the density evaluation is therefore kept out of registers: the momentum p (dead while the
+// density runs), the diagonal mass matrix, the EHMC snapshot's momentum and the Stats counters (touched once per
+// iteration) sit in dynamic shared memory as [slot][blockDim.x] -- conflict-free, one LDS/STS per access.  q, the
+// gradient and the density's temporaries keep the registers.  (Host emulation: blockDim.x == 1, a thread_local array.)
+#if RN_MASS_MAX >= 1
+#define RN_TS_NMASS RN_N
+#else
+#define RN_TS_NMASS 0
+#endif
+#if RN_ENABLE_EHMC
+#define RN_TS_NSNAP RN_N
+#else
+#define RN_TS_NSNAP 0
+#endif
+#define RN_TS_P 0                                        /* momentum, RN_N + 1 slots (+1: scratch of the polar method) */
+#define RN_TS_MASS (RN_N + 1)                            /* diagonal mass matrix (variances) */
+#define RN_TS_SNAP (RN_TS_MASS + RN_TS_NMASS)            /* momentum of the EHMC snapshot */
+#define RN_TS_STAT (RN_TS_SNAP + RN_TS_NSNAP)            /* e_mean, e_raw, trans2, grads (i64), steps (i64) */
+#define RN_TS_HOT (RN_TS_STAT + 5)                       /* rng.seed (i64), rng.nng, prevH, startH: parked across the leapfrog */
+#define RN_TS_DOUBLES (RN_TS_HOT + 4)
+#define RN_TS_INTS 10                                    /* iters, accepted, e_n, ring_i[3], ring_full[3], rng.have */
+struct RnTs {
+  double* d;
+  int* i;
+  unsigned bs;
+};
+#ifdef RN_HOST_EMULATION
+static thread_local double rn_ts_mem_d[RN_TS_DOUBLES];
+static thread_local int rn_ts_mem_i[RN_TS_INTS];
+RN_DEVICE RnTs rn_ts_get() { return RnTs{rn_ts_mem_d, rn_ts_mem_i, 1u}; }
+#define RN_STCS(ptr, v) (*(ptr) = (v))
+#else
+extern __shared__ double rn_ts_mem[];
+RN_DEVICE RnTs rn_ts_get() {
+  RnTs T;
+  T.bs = blockDim.x;
+  T.d = rn_ts_mem + threadIdx.x;
+  T.i = (int*)(rn_ts_mem + (size_t)RN_TS_DOUBLES * blockDim.x) + threadIdx.x;
+  return T;
+}
+#define RN_STCS(ptr, v) __stcs((ptr), (v))  /* streaming store: samples / rings / trace must not evict the L2-resident state */
+#endif
+#define RN_TSD(slot) T.d[(unsigned)(slot) * T.bs]
+#define RN_TSI(slot) T.i[(unsigned)(slot) * T.bs]
+#define RN_P(i) RN_TSD(RN_TS_P + (i))
+#define RN_MASSD(i) RN_TSD(RN_TS_MASS + (i))
+#define RN_SNAP_P(i) RN_TSD(RN_TS_SNAP + (i))
+#define RN_ST_E_MEAN RN_TSD(RN_TS_STAT + 0)
+#define RN_ST_E_RAW RN_TSD(RN_TS_STAT + 1)
+#define RN_ST_TRANS2 RN_TSD(RN_TS_STAT + 2)
+#define RN_ST_GRADS RN_TSD(RN_TS_STAT + 3) /* rn_i64 bit pattern */
+#define RN_ST_STEPS RN_TSD(RN_TS_STAT + 4) /* rn_i64 bit pattern */
+#define RN_ST_ITERS RN_TSI(0)
+#define RN_ST_ACCEPTED RN_TSI(1)
+#define RN_ST_E_N RN_TSI(2)
+#define RN_ST_RING_I(r) RN_TSI(3 + (r))
+#define RN_ST_RING_FULL(r) RN_TSI(6 + (r))
+#define RN_TS_PREV_H RN_TSD(RN_TS_HOT + 2)
+#define RN_TS_START_H RN_TSD(RN_TS_HOT + 3)
+
+// counters of the iteration in flight (registers; folded into the shared-memory Stats once per iteration)
+struct RnIt {
+  int grads, steps, err;
 };
 
-RN_DEVICE void rn_ring_add(const RnArgs& A, int c, RnStats& S, int which, double value) {  // Stats.scala:24-30
-  int i = S.ring_i[which] + 1;
-  if (i == A.stats_window) S.ring_full[which] = 1;
-  i = i % A.stats_window;
-  S.ring_i[which] = i;
-  RN_AT(A.st_rings, which * A.stats_window + i, c) = value;
+// the RNG is idle while the trajectory is integrated: its state waits in shared memory
+RN_DEVICE RnRng rn_rng_unpark(const RnTs& T) {
+  RnRng r;
+  r.seed = rn_d2ll(RN_TSD(RN_TS_HOT + 0));
+  r.nng = RN_TSD(RN_TS_HOT + 1);
+  r.have = RN_TSI(9);
+  return r;
+}
+RN_DEVICE void rn_rng_park(const RnTs& T, const RnRng& r) {
+  RN_TSD(RN_TS_HOT + 0) = rn_ll2d(r.seed);
+  RN_TSD(RN_TS_HOT + 1) = r.nng;
+  RN_TSI(9) = r.have;
 }
 
-struct RnMass {
-  int kind;
-#if RN_MASS_MAX >= 1
-  double m[RN_N];  // diagonal elements (variances)
-#endif
-};
+RN_DEVICE void rn_ring_add(const RnArgs& A, int c, const RnTs& T, int which, double value) {  // Stats.scala:24-30
+  int i = RN_ST_RING_I(which) + 1;
+  if (i == A.stats_window) RN_ST_RING_FULL(which) = 1;
+  i = i % A.stats_window;
+  RN_ST_RING_I(which) = i;
+  RN_STCS(&RN_AT(A.st_rings, which * A.stats_window + i, c), value);
+}
 
-// velocity = M^-1 p  (LeapFrog.scala:205-219)
-RN_DEVICE void rn_velocity(const RnArgs& A, int c, const RnMass& M, const double (&in)[RN_N], double (&out)[RN_N]) {
+// velocity_i = (M^-1 p)_i  (LeapFrog.scala:205-219); p is the shared-memory momentum
+RN_DEVICE double rn_velocity_i(const RnArgs& A, int c, const RnTs& T, int kind, int i) {
   (void)A;
   (void)c;
 #if RN_MASS_MAX >= 2
-  if (M.kind == 2) {  // DenseMassMatrix.squareMultiply, MassMatrix.scala:35-51
-    for (int i = 0; i < RN_N; i++) {
-      double y = 0.0;
-      for (int j = 0; j < RN_N; j++) y += in[j] * RN_AT(A.mass, i * RN_N + j, c);
-      out[i] = y;
-    }
-    return;
+  if (kind == 2) {  // DenseMassMatrix.squareMultiply, MassMatrix.scala:35-51
+    double y = 0.0;
+    for (int j = 0; j < RN_N; j++) y += RN_P(j) * RN_AT(A.mass, i * RN_N + j, c);
+    return y;
   }
 #endif
 #if RN_MASS_MAX >= 1
-  if (M.kind == 1) {
-    RN_UNROLL
-    for (int i = 0; i < RN_N; i++) out[i] = in[i] * M.m[i];
-    return;
-  }
+  if (kind == 1) return RN_P(i) * RN_MASSD(i);
 #endif
-  RN_UNROLL
-  for (int i = 0; i < RN_N; i++) out[i] = in[i];
+  (void)kind;
+  return RN_P(i);
 }
 
 // energy = potential + dot(velocity, p)/2  (LeapFrog.scala:134-139,221-231)
-RN_DEVICE double rn_energy(const RnArgs& A, int c, const RnMass& M, const double (&p)[RN_N], double U) {
-  double v[RN_N];
-  rn_velocity(A, c, M, p, v);
+RN_DEVICE double rn_energy(const RnArgs& A, int c, const RnTs& T, int kind, double U) {
   double k = 0.0;
+#if RN_MASS_MAX >= 2
+  if (kind == 2) {
+    for (int i = 0; i < RN_N; i++) k += (rn_velocity_i(A, c, T, 2, i) * RN_P(i));
+    return U + k / 2.0;
+  }
+#endif
   RN_UNROLL
-  for (int i = 0; i < RN_N; i++) k += (v[i] * p[i]);
+  for (int i = 0; i < RN_N; i++) k += (rn_velocity_i(A, c, T, kind, i) * RN_P(i));
   return U + k / 2.0;
 }
 
@@ -88,66 +152,110 @@ RN_DEVICE double rn_log_accept(double deltaH) {  // LeapFrog.scala:141-145
   return rn_jmin0(-deltaH);
 }
 
-struct RnPQ {  // pqBuf + the gradient at pqBuf.q
-  double p[RN_N], q[RN_N], g[RN_N];
+struct RnPQ {  // pqBuf's q and potential + the gradient at pqBuf.q  (pqBuf's p: RN_P, shared memory)
+  double q[RN_N], g[RN_N];
   double U;
 };
 
-RN_DEVICE void rn_update(const RnArgs& A, RnPQ& s, RnStats& S) {  // copyQsAndUpdateDensity + potential
+RN_DEVICE void rn_update(const RnArgs& A, RnPQ& s, RnIt& S) {  // copyQsAndUpdateDensity + potential
   double dens;
   rn_density(s.q, dens, s.g, A.data, S.err);
   s.U = dens * -1;
   S.grads += 1;
 }
-RN_DEVICE void rn_full_ps(RnPQ& s, double stepSize, RnStats& S) {  // LeapFrog.scala:168-176 (gradient reused)
+RN_DEVICE void rn_full_ps(const RnTs& T, RnPQ& s, double stepSize, RnIt& S) {  // LeapFrog.scala:168-176 (gradient reused)
   S.grads += 1;
   RN_UNROLL
-  for (int i = 0; i < RN_N; i++) s.p[i] += stepSize * s.g[i];
+  for (int i = 0; i < RN_N; i++) RN_P(i) += stepSize * s.g[i];
 }
-RN_DEVICE void rn_new_qs(const RnArgs& A, int c, const RnMass& M, RnPQ& s, double stepSize) {  // :147-154
-  double v[RN_N];
-  rn_velocity(A, c, M, s.p, v);
+RN_DEVICE void rn_new_qs(const RnArgs& A, int c, const RnTs& T, int kind, RnPQ& s, double stepSize) {  // :147-154
+#if RN_MASS_MAX >= 2
+  if (kind == 2) {
+    for (int i = 0; i < RN_N; i++) s.q[i] += (stepSize * rn_velocity_i(A, c, T, 2, i));
+    return;
+  }
+#endif
   RN_UNROLL
-  for (int i = 0; i < RN_N; i++) s.q[i] += (stepSize * v[i]);
+  for (int i = 0; i < RN_N; i++) s.q[i] += (stepSize * rn_velocity_i(A, c, T, kind, i));
 }
 // initialHalfThenFullStep + (l-1) twoFullSteps + finalHalfStep, LeapFrog.scala:24-33,156-191.
 // `g` must hold the gradient at s.q on entry (true for params and for every state this kernel produces).
-RN_DEVICE void rn_leapfrog(const RnArgs& A, int c, const RnMass& M, RnPQ& s, int l, double stepSize, RnStats& S) {
+RN_DEVICE void rn_leapfrog(const RnArgs& A, int c, const RnTs& T, int kind, RnPQ& s, int l, double stepSize, RnIt& S) {
   // (one rn_update call site: the emitted density is inlined exactly once per use of rn_leapfrog)
-  rn_full_ps(s, stepSize / 2.0, S);
+  rn_full_ps(T, s, stepSize / 2.0, S);
   for (int i = 0;;) {
-    rn_new_qs(A, c, M, s, stepSize);
+    rn_new_qs(A, c, T, kind, s, stepSize);
     rn_update(A, s, S);
     if (++i >= l) break;
-    rn_full_ps(s, stepSize, S);
+    rn_full_ps(T, s, stepSize, S);
   }
-  rn_full_ps(s, stepSize / 2.0, S);
+  rn_full_ps(T, s, stepSize / 2.0, S);
 }
-RN_DEVICE void rn_take_steps(const RnArgs& A, int c, const RnMass& M, RnPQ& s, int l, double stepSize, RnStats& S) {
-  rn_ring_add(A, c, S, 0, stepSize);  // stats.stepSizes.add, LeapFrog.scala:25
-  rn_leapfrog(A, c, M, s, l, stepSize, S);
+RN_DEVICE void rn_take_steps(const RnArgs& A, int c, const RnTs& T, int kind, RnPQ& s, int l, double stepSize, RnIt& S) {
+  rn_ring_add(A, c, T, 0, stepSize);  // stats.stepSizes.add, LeapFrog.scala:25
+  rn_leapfrog(A, c, T, kind, s, l, stepSize, S);
   S.steps += l;
 }
 
-// momentum draw, LeapFrog.scala:233-255
-RN_DEVICE void rn_initialize_ps(const RnArgs& A, int c, const RnMass& M, RnRng& rng, double (&p)[RN_N]) {
+// RN_N standard normals into RN_P(0..RN_N-1), consuming java.util.Random exactly like RN_N calls of nextGaussian
+// (RNG.scala:23-25: cached second variate first, then polar pairs).  The rejection loop of the polar method diverges
+// inside a warp, so it is kept as small as possible: ONE flat loop over all pairs that only draws (v1, v2) and parks
+// the accepted ones in the slots their variates will occupy (a lane that is done with pair k goes on to pair k+1 while
+// its neighbours retry; a warp then runs max-over-lanes of the TOTAL number of attempts instead of the sum over pairs
+// of the per-pair maxima), and a second, convergent pass applies sqrt(-2 log(s)/s).  s is recomputed there from the
+// parked v1, v2 by the same two products and one sum -> the same bits.
+RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
+  int i0 = 0;
+  if (rng.have) {
+    rng.have = 0;
+    RN_P(0) = rng.nng;
+    i0 = 1;
+  }
+  const int npairs = (RN_N - i0 + 1) / 2;  // the last pair's second variate may be left over (-> rng.nng); slot RN_N is scratch
+  for (int k = 0; k < npairs;) {
+    const double v1 = 2 * rn_uniform(rng) - 1;
+    const double v2 = 2 * rn_uniform(rng) - 1;
+    const double s = v1 * v1 + v2 * v2;
+    if (!(s >= 1 || s == 0)) {
+      RN_P(i0 + 2 * k) = v1;
+      RN_P(i0 + 2 * k + 1) = v2;
+      k += 1;
+    }
+  }
+  for (int k = 0; k < npairs; k++) {
+    const int i = i0 + 2 * k;
+    const double v1 = RN_P(i), v2 = RN_P(i + 1);
+    const double s = v1 * v1 + v2 * v2;
+    const double multiplier = sqrt(-2 * rn_strict_log(s) / s);
+    RN_P(i) = v1 * multiplier;
+    if (i + 1 < RN_N) {
+      RN_P(i + 1) = v2 * multiplier;
+    } else {
+      rng.nng = v2 * multiplier;
+      rng.have = 1;
+    }
+  }
+}
+
+// momentum draw, LeapFrog.scala:233-255  (result in RN_P)
+RN_DEVICE void rn_initialize_ps(const RnArgs& A, int c, const RnTs& T, int kind, RnRng& rng) {
   (void)A;
   (void)c;
-  double z[RN_N];
-  for (int i = 0; i < RN_N; i++) z[i] = rn_normal(rng);
+  (void)kind;
+  rn_draw_normals(T, rng);  // buf(i) = rng.standardNormal
 #if RN_MASS_MAX >= 2
-  if (M.kind == 2) {  // DenseMassMatrix.upperTriangularSolve, MassMatrix.scala:55-72
-    int i = RN_N - 1;
+  if (kind == 2) {  // DenseMassMatrix.upperTriangularSolve, MassMatrix.scala:55-72; in place: slot i holds z_i until p_i
+    int i = RN_N - 1;  // replaces it, and p_i only reads z_i and the p_j, j > i, already in place
     int m = ((i + 1) * (i + 2)) / 2 - 1;
     while (i >= 0) {
       int j = RN_N - 1;
       double dot = 0.0;
       while (j > i) {
-        dot += p[j] * RN_AT(A.chol, m, c);
+        dot += RN_P(j) * RN_AT(A.chol, m, c);
         j -= 1;
         m -= 1;
       }
-      p[i] = (z[i] - dot) / RN_AT(A.chol, m, c);
+      RN_P(i) = (RN_P(i) - dot) / RN_AT(A.chol, m, c);
       i -= 1;
       m -= 1;
     }
@@ -155,56 +263,62 @@ RN_DEVICE void rn_initialize_ps(const RnArgs& A, int c, const RnMass& M, RnRng& 
   }
 #endif
 #if RN_MASS_MAX >= 1
-  if (M.kind == 1) {
+  if (kind == 1) {
     RN_UNROLL
-    for (int i = 0; i < RN_N; i++) p[i] = z[i] / sqrt(M.m[i]);  // buf(i) / stdDevs(i), stdDevs = sqrt(elements)
+    for (int i = 0; i < RN_N; i++) RN_P(i) = RN_P(i) / sqrt(RN_MASSD(i));  // buf(i) / stdDevs(i), stdDevs = sqrt(elements)
     return;
   }
 #endif
-  RN_UNROLL
-  for (int i = 0; i < RN_N; i++) p[i] = z[i];
 }
 
-RN_DEVICE void rn_load_mass(const RnArgs& A, int c, RnMass& M) {
+RN_DEVICE void rn_load_mass(const RnArgs& A, int c, const RnTs& T, int kind) {
   (void)A;
   (void)c;
+  (void)T;
+  (void)kind;
 #if RN_MASS_MAX >= 1
-  if (M.kind == 1) {
+  if (kind == 1) {
     RN_UNROLL
-    for (int i = 0; i < RN_N; i++) M.m[i] = RN_AT(A.mass, i, c);
+    for (int i = 0; i < RN_N; i++) RN_MASSD(i) = RN_AT(A.mass, i, c);
   }
 #endif
 }
 
-RN_DEVICE void rn_load_stats(const RnArgs& A, int c, RnStats& S) {
-  S.grads = A.st_grads[c];
-  S.steps = A.st_steps[c];
-  S.iters = A.st_iters[c];
-  S.accepted = A.st_accepted[c];
-  S.err = A.st_err[c];
-  S.e_mean = RN_AT(A.st_energy, 0, c);
-  S.e_raw = RN_AT(A.st_energy, 1, c);
-  S.trans2 = RN_AT(A.st_energy, 2, c);
-  S.e_n = A.st_energy_n[c];
+RN_DEVICE void rn_load_stats(const RnArgs& A, int c, const RnTs& T) {
+  RN_ST_GRADS = rn_ll2d(A.st_grads[c]);
+  RN_ST_STEPS = rn_ll2d(A.st_steps[c]);
+  RN_ST_ITERS = A.st_iters[c];
+  RN_ST_ACCEPTED = A.st_accepted[c];
+  RN_ST_E_MEAN = RN_AT(A.st_energy, 0, c);
+  RN_ST_E_RAW = RN_AT(A.st_energy, 1, c);
+  RN_ST_TRANS2 = RN_AT(A.st_energy, 2, c);
+  RN_ST_E_N = A.st_energy_n[c];
   for (int r = 0; r < 3; r++) {
-    S.ring_i[r] = RN_AT(A.st_ring_i, r, c);
-    S.ring_full[r] = RN_AT(A.st_ring_full, r, c);
+    RN_ST_RING_I(r) = RN_AT(A.st_ring_i, r, c);
+    RN_ST_RING_FULL(r) = RN_AT(A.st_ring_full, r, c);
   }
 }
-RN_DEVICE void rn_store_stats(const RnArgs& A, int c, const RnStats& S) {
-  A.st_grads[c] = S.grads;
-  A.st_steps[c] = S.steps;
-  A.st_iters[c] = S.iters;
-  A.st_accepted[c] = S.accepted;
-  A.st_err[c] = S.err;
-  RN_AT(A.st_energy, 0, c) = S.e_mean;
-  RN_AT(A.st_energy, 1, c) = S.e_raw;
-  RN_AT(A.st_energy, 2, c) = S.trans2;
-  A.st_energy_n[c] = S.e_n;
+RN_DEVICE void rn_store_stats(const RnArgs& A, int c, const RnTs& T, int err) {
+  A.st_grads[c] = rn_d2ll(RN_ST_GRADS);
+  A.st_steps[c] = rn_d2ll(RN_ST_STEPS);
+  A.st_iters[c] = RN_ST_ITERS;
+  A.st_accepted[c] = RN_ST_ACCEPTED;
+  if (err) A.st_err[c] |= err;
+  RN_AT(A.st_energy, 0, c) = RN_ST_E_MEAN;
+  RN_AT(A.st_energy, 1, c) = RN_ST_E_RAW;
+  RN_AT(A.st_energy, 2, c) = RN_ST_TRANS2;
+  A.st_energy_n[c] = RN_ST_E_N;
   for (int r = 0; r < 3; r++) {
-    RN_AT(A.st_ring_i, r, c) = S.ring_i[r];
-    RN_AT(A.st_ring_full, r, c) = S.ring_full[r];
+    RN_AT(A.st_ring_i, r, c) = RN_ST_RING_I(r);
+    RN_AT(A.st_ring_full, r, c) = RN_ST_RING_FULL(r);
   }
+}
+// fold the counters of the finished leapfrog calls into the shared-memory Stats
+RN_DEVICE void rn_fold(const RnTs& T, RnIt& S) {
+  RN_ST_GRADS = rn_ll2d(rn_d2ll(RN_ST_GRADS) + (rn_i64)S.grads);
+  RN_ST_STEPS = rn_ll2d(rn_d2ll(RN_ST_STEPS) + (rn_i64)S.steps);
+  S.grads = 0;
+  S.steps = 0;
 }
 
 // =============================================================================================================
@@ -213,53 +327,55 @@ RN_DEVICE void rn_store_stats(const RnArgs& A, int c, const RnStats& S) {
 RN_GLOBAL void rn_k_init(const RnArgs A) {
   const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= A.chains) return;
+  const RnTs T = rn_ts_get();
   RnRng rng;
   rng.seed = A.rng_seed[c];
   rng.nng = A.rng_nng[c];
   rng.have = A.rng_have[c];
-  RnStats S;
-  rn_load_stats(A, c, S);
-  RnMass M;
-  M.kind = 0;
+  rn_load_stats(A, c, T);
+  RnIt S;
+  S.grads = 0;
+  S.steps = 0;
+  S.err = 0;
 
   // LeapFrog.initialize, LeapFrog.scala:102-116
   RnPQ s;
-  for (int i = 0; i < RN_N; i++) {
-    s.p[i] = 0.0;
-    s.q[i] = rn_normal(rng);
-  }
+  rn_draw_normals(T, rng);  // pqBuf(i) = rng.standardNormal, i in nVars until 2 nVars
+  RN_UNROLL
+  for (int i = 0; i < RN_N; i++) s.q[i] = RN_P(i);
   rn_update(A, s, S);
-  double cq[RN_N], cg[RN_N], cp[RN_N];
-  double cU = s.U;
+  double cq[RN_N], cg[RN_N];
+  const double cU = s.U;
   RN_UNROLL
   for (int i = 0; i < RN_N; i++) {
     cq[i] = s.q[i];
     cg[i] = s.g[i];
   }
-  rn_initialize_ps(A, c, M, rng, cp);
+  rn_initialize_ps(A, c, T, 0, rng);
+  RN_UNROLL
+  for (int i = 0; i < RN_N; i++) RN_AT(A.params, i, c) = RN_P(i);  // params.p = the drawn momentum
 
   // stepSizeTuner.initialize
   double stepSize;
   if (A.step_tuner == 0) {  // DualAvgTuner.findReasonableStepSize, DualAvg.scala:27-41 (IdentityMassMatrix)
-    const double H0 = rn_energy(A, c, M, cp, cU);
+    const double H0 = rn_energy(A, c, T, 0, cU);
     stepSize = 1.0;
     double lap;
-    {
-      RN_UNROLL
-      for (int i = 0; i < RN_N; i++) { s.p[i] = cp[i]; s.q[i] = cq[i]; s.g[i] = cg[i]; }
-      s.U = cU;
-      rn_leapfrog(A, c, M, s, 1, stepSize, S);  // tryStepping, LeapFrog.scala:14-22
-      lap = rn_log_accept(rn_energy(A, c, M, s.p, s.U) - H0);
-    }
+    rn_leapfrog(A, c, T, 0, s, 1, stepSize, S);  // tryStepping, LeapFrog.scala:14-22 (s still equals params here)
+    lap = rn_log_accept(rn_energy(A, c, T, 0, s.U) - H0);
     const double exponent = (lap > -RN_LN2) ? 1.0 : -1.0;
     const double doubleOrHalf = (exponent > 0) ? 2.0 : 0.5;
     while (stepSize != 0.0 && (exponent * lap > -exponent * RN_LN2)) {
       stepSize *= doubleOrHalf;
       RN_UNROLL
-      for (int i = 0; i < RN_N; i++) { s.p[i] = cp[i]; s.q[i] = cq[i]; s.g[i] = cg[i]; }
+      for (int i = 0; i < RN_N; i++) {
+        RN_P(i) = RN_AT(A.params, i, c);
+        s.q[i] = cq[i];
+        s.g[i] = cg[i];
+      }
       s.U = cU;
-      rn_leapfrog(A, c, M, s, 1, stepSize, S);
-      lap = rn_log_accept(rn_energy(A, c, M, s.p, s.U) - H0);
+      rn_leapfrog(A, c, T, 0, s, 1, stepSize, S);
+      lap = rn_log_accept(rn_energy(A, c, T, 0, s.U) - H0);
     }
     // DualAvg.apply, DualAvg.scala:80-90
     RN_AT(A.da, 1, c) = rn_log(stepSize);
@@ -274,7 +390,6 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
 
   RN_UNROLL
   for (int i = 0; i < RN_N; i++) {
-    RN_AT(A.params, i, c) = cp[i];
     RN_AT(A.params, RN_N + i, c) = cq[i];
     RN_AT(A.grad, i, c) = cg[i];
   }
@@ -282,39 +397,40 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
   A.rng_seed[c] = rng.seed;
   A.rng_nng[c] = rng.nng;
   A.rng_have[c] = rng.have;
-  rn_store_stats(A, c, S);
+  rn_fold(T, S);
+  rn_store_stats(A, c, T, S.err);
 }
 
 // =============================================================================================================
-// rn_k_iter: A.n_iter iterations of Driver.warmup's loop (phase 0, Driver.scala:67-88) or of
-// Driver.collectSamples (phase 1, Driver.scala:102-117)
+// rn_k_warmup / rn_k_iter: A.n_iter iterations of Driver.warmup's loop (PHASE 0, Driver.scala:67-88) or of
+// Driver.collectSamples (PHASE 1, Driver.scala:102-117).  Two entry points of one body so that the sampling kernel
+// carries neither the code nor the registers of the adaptation.
 // =============================================================================================================
-RN_GLOBAL void rn_k_iter(const RnArgs A) {
+template <int PHASE>
+RN_DEVICE void rn_iterate(const RnArgs& A) {
   const int c = A.chain_begin + (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= A.chain_end) return;
-  RnRng rng;
-  rng.seed = A.rng_seed[c];
-  rng.nng = A.rng_nng[c];
-  rng.have = A.rng_have[c];
-  RnStats S;
-  rn_load_stats(A, c, S);
-  RnMass M;
-  M.kind = A.mass_kind;
-  rn_load_mass(A, c, M);
+  const RnTs T = rn_ts_get();
+  {
+    RnRng rng;
+    rng.seed = A.rng_seed[c];
+    rng.nng = A.rng_nng[c];
+    rng.have = A.rng_have[c];
+    rn_rng_park(T, rng);
+  }
+  rn_load_stats(A, c, T);
+  RnIt S;
+  S.grads = 0;
+  S.steps = 0;
+  S.err = 0;
+  int kind = A.mass_kind;
+  rn_load_mass(A, c, T, kind);
 
   // step size in force: warmup uses the tuner's running value; sampling uses stepSizeTuner.stepSize
-  // (= rn_exp(logStepSizeBar) for DualAvg, Driver.scala:37 / DualAvg.scala:23-25)
+  // (= rn_exp(logStepSizeBar) for DualAvg, Driver.scala:37 / DualAvg.scala:23-25).  The rest of the DualAvg state is
+  // touched once per warmup iteration and stays in (L1/L2-resident) global memory.
   double stepSize = RN_AT(A.da, 0, c);
-  double logStepSize = 0, logStepSizeBar = 0, avgError = 0, shrinkageTarget = 0;
-  int daIter = 0;
-  if (A.step_tuner == 0) {
-    logStepSize = RN_AT(A.da, 1, c);
-    logStepSizeBar = RN_AT(A.da, 2, c);
-    avgError = RN_AT(A.da, 3, c);
-    shrinkageTarget = RN_AT(A.da, 4, c);
-    daIter = A.da_iter[c];
-    if (A.phase == 1) stepSize = rn_exp(logStepSizeBar);
-  }
+  if (PHASE == 1 && A.step_tuner == 0) stepSize = rn_exp(RN_AT(A.da, 2, c));
   int win_size = A.win_size, win_i = A.win_i, win_j = A.win_j, est_samples = A.est_samples;
 #if RN_ENABLE_EHMC
   int ring_i = 0, ring_full = 0;
@@ -323,52 +439,71 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     ring_full = A.ring_full[c];
   }
 #endif
+  // prevH = energy(params) at startIteration (LeapFrog.scala:54) is, by construction, the energy finishIteration of the
+  // previous iteration filed under energyVariance (same function of the same numbers, :62-75) -- unless the mass matrix
+  // was replaced in between.  It is carried in a register and recomputed only then (and at the start of a launch).
+  bool havePrevH = false;
 
   for (int it = 0; it < A.n_iter; it++) {
     // ---------------- lf.startIteration, LeapFrog.scala:52-59 ----------------
     RnPQ s;
-    RN_UNROLL
-    for (int i = 0; i < RN_N; i++) s.p[i] = RN_AT(A.params, i, c);  // old momentum, for prevH
     const double cU = RN_AT(A.params, 2 * RN_N, c);
-    const double prevH = rn_energy(A, c, M, s.p, cU);
-    rn_initialize_ps(A, c, M, rng, s.p);
+    if (!havePrevH) {
+      RN_UNROLL
+      for (int i = 0; i < RN_N; i++) RN_P(i) = RN_AT(A.params, i, c);  // old momentum
+      RN_TS_PREV_H = rn_energy(A, c, T, kind, cU);
+    }
+    {
+      RnRng rng = rn_rng_unpark(T);
+      rn_initialize_ps(A, c, T, kind, rng);
+      rn_rng_park(T, rng);
+    }
     RN_UNROLL
     for (int i = 0; i < RN_N; i++) {
-      RN_AT(A.params, i, c) = s.p[i];  // initializePs writes into params (LeapFrog.scala:55); kept on reject
+      RN_AT(A.params, i, c) = RN_P(i);  // initializePs writes into params (LeapFrog.scala:55); kept on reject
       s.q[i] = RN_AT(A.params, RN_N + i, c);
       s.g[i] = RN_AT(A.grad, i, c);
     }
     s.U = cU;
-    const double startH = rn_energy(A, c, M, s.p, cU);  // finishIteration's energy(params), :62
-    const rn_i64 iterationStartGrads = S.grads;
-    const rn_i64 steps0 = S.steps;
+    RN_TS_START_H = rn_energy(A, c, T, kind, cU);  // finishIteration's energy(params), :62
     const double usedStep = stepSize;
 
     // ---------------- sampler.warmup / sampler.run ----------------
     if (A.sampler == 0) {  // HMCSampler, HMC.scala:6-23
-      rn_take_steps(A, c, M, s, A.n_steps, stepSize, S);
+      rn_take_steps(A, c, T, kind, s, A.n_steps, stepSize, S);
     }
 #if RN_ENABLE_EHMC
     else {  // EHMCSampler, EHMC.scala:15-61
       bool count = false;
-      if (A.phase == 0) count = (!ring_full) || (rn_uniform(rng) < A.p_count);  // shouldCountSteps, :29-30
+      if (PHASE == 0 && !ring_full) count = true;  // shouldCountSteps, :29-30 (|| short-circuits: no draw while the ring fills)
+      else if (PHASE == 0) {
+        RnRng rng = rn_rng_unpark(T);
+        count = rn_uniform(rng) < A.p_count;
+        rn_rng_park(T, rng);
+      }
       if (count) {  // countSteps, :32-50
         RnPQ snap;
         int l = 0;
         for (;;) {
           double out = 0.0;  // lf.isUTurn(params), LeapFrog.scala:35-47
           RN_UNROLL
-          for (int i = 0; i < RN_N; i++) out += (s.q[i] - RN_AT(A.params, RN_N + i, c)) * s.p[i];
+          for (int i = 0; i < RN_N; i++) out += (s.q[i] - RN_AT(A.params, RN_N + i, c)) * RN_P(i);
           const bool uturn = (out != out) ? true : (out < 0);
           if (uturn || !(l < A.max_steps)) break;
           l += 1;
-          rn_take_steps(A, c, M, s, 1, stepSize, S);
-          if (l == A.min_steps) snap = s;
+          rn_take_steps(A, c, T, kind, s, 1, stepSize, S);
+          if (l == A.min_steps) {
+            snap = s;
+            RN_UNROLL
+            for (int i = 0; i < RN_N; i++) RN_SNAP_P(i) = RN_P(i);
+          }
         }
         if (l < A.min_steps) {
-          rn_take_steps(A, c, M, s, A.min_steps - l, stepSize, S);
+          rn_take_steps(A, c, T, kind, s, A.min_steps - l, stepSize, S);
         } else {
           s = snap;
+          RN_UNROLL
+          for (int i = 0; i < RN_N; i++) RN_P(i) = RN_SNAP_P(i);
         }
         // steps.add(l), Stats.scala:24-30
         ring_i += 1;
@@ -376,65 +511,82 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
         ring_i = ring_i % A.buf_size;
         RN_AT(A.ring, ring_i, c) = (double)l;
       } else {  // steps.sample().toInt, Stats.scala:40-45
+        RnRng rng = rn_rng_unpark(T);
         const int idx = ring_full ? rn_rng_int(rng, A.buf_size) : rn_rng_int(rng, ring_i + 1);
+        rn_rng_park(T, rng);
         const int nsteps = rn_d2i(RN_AT(A.ring, idx, c));
-        rn_take_steps(A, c, M, s, nsteps, stepSize, S);
+        rn_take_steps(A, c, T, kind, s, nsteps, stepSize, S);
       }
     }
 #endif
 
     // ---------------- lf.finishIteration, LeapFrog.scala:61-82 ----------------
-    const double endH = rn_energy(A, c, M, s.p, s.U);
+    const double endH = rn_energy(A, c, T, kind, s.U);
+    const double startH = RN_TS_START_H;
     const double deltaH = endH - startH;
     const double a = rn_log_accept(deltaH);
-    const bool accept = a > rn_log(rn_uniform(rng));
+    bool accept;
+    {
+      RnRng rng = rn_rng_unpark(T);
+      accept = a > rn_log(rn_uniform(rng));
+      rn_rng_park(T, rng);
+    }
     double eH;
     if (accept) {
       RN_UNROLL
       for (int i = 0; i < RN_N; i++) {
-        RN_AT(A.params, i, c) = s.p[i];
+        RN_AT(A.params, i, c) = RN_P(i);
         RN_AT(A.params, RN_N + i, c) = s.q[i];
         RN_AT(A.grad, i, c) = s.g[i];
       }
       RN_AT(A.params, 2 * RN_N, c) = s.U;
       eH = endH;
-      S.accepted += 1;
+      RN_ST_ACCEPTED += 1;
     } else {
       RN_UNROLL
       for (int i = 0; i < RN_N; i++) s.q[i] = RN_AT(A.params, RN_N + i, c);  // s.q := current position either way
       eH = startH;
     }
     {  // stats.energyVariance.update(eH); energyTransitions2 += pow(eH - prevH, 2)
-      S.e_n += 1;
-      const double oldDiff = eH - S.e_mean;
-      S.e_mean += (oldDiff / (double)S.e_n);
-      const double newDiff = eH - S.e_mean;
-      S.e_raw += oldDiff * newDiff;
-      const double d = eH - prevH;
-      S.trans2 += d * d;
+      const int e_n = RN_ST_E_N + 1;
+      RN_ST_E_N = e_n;
+      double e_mean = RN_ST_E_MEAN;
+      const double oldDiff = eH - e_mean;
+      e_mean += (oldDiff / (double)e_n);
+      RN_ST_E_MEAN = e_mean;
+      const double newDiff = eH - e_mean;
+      RN_ST_E_RAW += oldDiff * newDiff;
+      const double d = eH - RN_TS_PREV_H;
+      RN_ST_TRANS2 += d * d;
     }
-    S.iters += 1;
-    rn_ring_add(A, c, S, 1, rn_exp(a));
-    rn_ring_add(A, c, S, 2, (double)(S.grads - iterationStartGrads));
+    RN_TS_PREV_H = eH;
+    havePrevH = true;
+    RN_ST_ITERS += 1;
+    rn_ring_add(A, c, T, 1, rn_exp(a));
+    rn_ring_add(A, c, T, 2, (double)S.grads);  // stats.gradientEvaluations - iterationStartGrads
 
     if (A.trace) {
       double* tr = A.trace + (size_t)it * 4 * (size_t)A.chains;
       tr[0 * (size_t)A.chains + c] = a;
       tr[1 * (size_t)A.chains + c] = accept ? 1.0 : 0.0;
       tr[2 * (size_t)A.chains + c] = usedStep;
-      tr[3 * (size_t)A.chains + c] = (double)(S.steps - steps0);
+      tr[3 * (size_t)A.chains + c] = (double)S.steps;
     }
+    rn_fold(T, S);
 
-    if (A.phase == 0) {
+    if (PHASE == 0) {
       // ---------------- stepSizeTuner.update, Driver.scala:69 / DualAvg.scala:58-77 ----------------
       if (A.step_tuner == 0) {
         const double newAcceptanceProb = rn_exp(a);
-        daIter = daIter + 1;
+        const int daIter = A.da_iter[c] + 1;
+        A.da_iter[c] = daIter;
         const double avgErrorMultiplier = 1.0 / ((double)daIter + 10);
         const double stepSizeMultiplier = rn_pow((double)daIter, -0.75);
-        avgError = ((1.0 - avgErrorMultiplier) * avgError + (avgErrorMultiplier * (A.delta - newAcceptanceProb)));
-        logStepSize = (shrinkageTarget - (avgError * sqrt((double)daIter) / 0.05));
-        logStepSizeBar = (stepSizeMultiplier * logStepSize + (1.0 - stepSizeMultiplier) * logStepSizeBar);
+        const double avgError = ((1.0 - avgErrorMultiplier) * RN_AT(A.da, 3, c) + (avgErrorMultiplier * (A.delta - newAcceptanceProb)));
+        RN_AT(A.da, 3, c) = avgError;
+        const double logStepSize = (RN_AT(A.da, 4, c) - (avgError * sqrt((double)daIter) / 0.05));
+        RN_AT(A.da, 1, c) = logStepSize;
+        RN_AT(A.da, 2, c) = (stepSizeMultiplier * logStepSize + (1.0 - stepSizeMultiplier) * RN_AT(A.da, 2, c));
         stepSize = rn_exp(logStepSize);
       }
       // ---------------- massMatrixTuner.update(sample), Driver.scala:74-80 / MassMatrix.scala:147-164 -------
@@ -459,15 +611,21 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
         } else if (!(win_j < A.skip_first || (A.total_warmup - win_j) < A.skip_last)) {
           win_i += 1;
           est_samples += 1;  // VarianceEstimator.update, MassMatrixEstimator.scala:69-83
+#if RN_MASS_MAX >= 2
           double oldDiff[RN_N], newDiff[RN_N];
+#endif
           RN_UNROLL
           for (int i = 0; i < RN_N; i++) {
             double mean = RN_AT(A.est_mean, i, c);
-            oldDiff[i] = s.q[i] - mean;
-            mean += (oldDiff[i] / (double)est_samples);
-            newDiff[i] = s.q[i] - mean;
+            const double od = s.q[i] - mean;
+            mean += (od / (double)est_samples);
+            const double nd = s.q[i] - mean;
             RN_AT(A.est_mean, i, c) = mean;
-            RN_AT(A.est_raw, i, c) += oldDiff[i] * newDiff[i];
+            RN_AT(A.est_raw, i, c) += od * nd;
+#if RN_MASS_MAX >= 2
+            oldDiff[i] = od;
+            newDiff[i] = nd;
+#endif
           }
 #if RN_MASS_MAX >= 2
           if (A.mass_tuner == 2) {  // CovarianceEstimator.update, :28-41
@@ -478,13 +636,14 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
           if (win_i == win_size) {
             win_i = 0;
             win_size = rn_d2i(win_size * A.win_expansion);
+            havePrevH = false;  // the next startIteration measures params with the NEW matrix
             if (A.mass_tuner == 1) {  // DiagonalMassMatrix(variance()), :92-103
-              M.kind = 1;
+              kind = 1;
               RN_UNROLL
               for (int i = 0; i < RN_N; i++) {
                 const double v = RN_AT(A.est_raw, i, c) / (double)est_samples;
                 if (v == 0.0) S.err |= 2;  // require(!elements.contains(0.0)), MassMatrix.scala:8
-                M.m[i] = v;
+                RN_MASSD(i) = v;
                 RN_AT(A.mass, i, c) = v;
                 RN_AT(A.est_mean, i, c) = 0.0;  // reset(): mean/raw only, NOT samples (:60-67)
                 RN_AT(A.est_raw, i, c) = 0.0;
@@ -492,7 +651,7 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
             }
 #if RN_MASS_MAX >= 2
             else {  // DenseMassMatrix(covariance()), :43-50 + Cholesky MassMatrix.scala:76-117
-              M.kind = 2;
+              kind = 2;
               const double z = (double)(est_samples - 1);
               for (int i = 0; i < RN_N * RN_N; i++) {
                 const double v = RN_AT(A.est_cov, i, c) / z;
@@ -529,12 +688,12 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
 #endif
             // stepSize = stepSizeTuner.reset(), Driver.scala:78 / DualAvg.scala:17-21
             if (A.step_tuner == 0) {
-              const double ss = rn_exp(logStepSizeBar);
-              logStepSize = rn_log(ss);
-              logStepSizeBar = 0.0;
-              avgError = 0.0;
-              daIter = 0;
-              shrinkageTarget = rn_log(10 * ss);
+              const double ss = rn_exp(RN_AT(A.da, 2, c));
+              RN_AT(A.da, 1, c) = rn_log(ss);
+              RN_AT(A.da, 2, c) = 0.0;
+              RN_AT(A.da, 3, c) = 0.0;
+              A.da_iter[c] = 0;
+              RN_AT(A.da, 4, c) = rn_log(10 * ss);
               stepSize = ss;
             }
           }
@@ -544,31 +703,28 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
     } else if (A.samples) {  // lf.variables(params, output), Driver.scala:105-107
       double* out = A.samples + (size_t)it * RN_N * (size_t)A.chains;
       RN_UNROLL
-      for (int i = 0; i < RN_N; i++) out[(size_t)i * (size_t)A.chains + c] = s.q[i];
+      for (int i = 0; i < RN_N; i++) RN_STCS(&out[(size_t)i * (size_t)A.chains + c], s.q[i]);
     }
   }
 
-  if (A.phase == 0) {
-    RN_AT(A.da, 0, c) = stepSize;
-    if (A.step_tuner == 0) {
-      RN_AT(A.da, 1, c) = logStepSize;
-      RN_AT(A.da, 2, c) = logStepSizeBar;
-      RN_AT(A.da, 3, c) = avgError;
-      RN_AT(A.da, 4, c) = shrinkageTarget;
-      A.da_iter[c] = daIter;
-    }
-  }
+  if (PHASE == 0) RN_AT(A.da, 0, c) = stepSize;
 #if RN_ENABLE_EHMC
   if (A.sampler == 1) {
     A.ring_i[c] = ring_i;
     A.ring_full[c] = ring_full;
   }
 #endif
-  A.rng_seed[c] = rng.seed;
-  A.rng_nng[c] = rng.nng;
-  A.rng_have[c] = rng.have;
-  rn_store_stats(A, c, S);
+  {
+    const RnRng rng = rn_rng_unpark(T);
+    A.rng_seed[c] = rng.seed;
+    A.rng_nng[c] = rng.nng;
+    A.rng_have[c] = rng.have;
+  }
+  rn_store_stats(A, c, T, S.err);
 }
+RN_GLOBAL void rn_k_warmup(const RnArgs A) { rn_iterate<0>(A); }
+RN_GLOBAL void rn_k_iter(const RnArgs A) { rn_iterate<1>(A); }
+#define RN_K_WARMUP rn_k_warmup
 
 // =============================================================================================================
 // rn_k_density: DensityFunction.update/density/gradient for a batch of positions (Model.scala:38-50).

@@ -334,6 +334,7 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
 }
 
 // =============================================================================================================
+#define RN_K_WARMUP rn_k_iter  /* one entry point for both phases on this shape (rn_sampler.cuh has two) */
 RN_GLOBAL void rn_k_iter(const RnArgs A) {
   const int c = A.chain_begin + (int)((blockIdx.x * blockDim.x + threadIdx.x) / RN_G);
 #if RN_TMA_STAGES > 0

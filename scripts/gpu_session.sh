@@ -18,7 +18,9 @@ for step in "$@"; do
     configs)   timeout 1500 python scripts/bench_configs.py > $log 2>&1; tail -12 $log | cut -c1-600 ;;
     dmma)      timeout 300 python scripts/probe_dmma.py > $log 2>&1; tail -3 $log | cut -c1-1200 ;;
     launches)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 > $log 2>&1; tail -2 $log | cut -c1-300 ;;
-    ncufunnel) timeout 900 ncu --set full --clock-control none --import-source on -k rn_k_iter -c 1 -o gpurun_out/${TAG}_ncu_funnel python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $log 2>&1; tail -2 $log | cut -c1-300 ;;
+    ncufunnel) timeout 900 ncu --set full --clock-control none --import-source on -k regex:rn_k_iter -c 1 -o gpurun_out/${TAG}_ncu_funnel python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $log 2>&1; tail -2 $log | cut -c1-300 ;;
+    sweep)     timeout 1200 python scripts/r2/sweep_iter.py > $log 2>&1; cat $log | cut -c1-300 ;;
+    diagdense) timeout 900 python scripts/r2/diag_wpc_dense.py > $log 2>&1; tail -120 $log ;;
     *)         if [ -f "$step" ]; then timeout 1800 bash "$step" > gpurun_out/${TAG}_$(basename $step).log 2>&1; tail -30 gpurun_out/${TAG}_$(basename $step).log; else echo "unknown step $step"; fi ;;
   esac
 done

@@ -84,7 +84,7 @@ extern "C" int emu_sample(const EmuCfg* c, const long long* seeds, int chains, c
   if (c->warmup > 0) {
     a.phase = 0; a.n_iter = c->warmup; a.mass_kind = mass_kind; a.win_size = win_size; a.win_i = 0; a.win_j = 0; a.est_samples = 0;
     a.trace = trace;
-    launch(rn_k_iter);
+    launch(RN_K_WARMUP);
     if (c->mass_tuner == 1 || c->mass_tuner == 2)  // host mirror of WindowedMassMatrixTuner.update (rn_runtime.cpp: advance_window)
       for (int k = 0; k < c->warmup; k++) {
         win_j += 1;
