@@ -117,17 +117,31 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+CPU_NOTE = ("C++ restatement of the reference's LeapFrog/HMC (oracle/) over the model's DataFunction COMPILED to straight-line "
+            "C++ (g++ -O2 -ffp-contract=off; bit-identical to the oracle's interpreter, tests/test_oracle_compiled.py) -- the "
+            "stand-in for the JVM `asm` path after JIT compilation, which cannot run in this image; one chain per host "
+            "thread, threads pinned, cores = affinity mask capped by the cgroup CPU quota")
+
+
+def _oracle_arm():
+    """the CPU arm's model, config and core count (shared by --impl reference and the cpu_baseline leg)"""
+    from oracle.rainier_py.binding import OracleModel, default_config, lib
+    rir = open(os.path.join(ROOT, "rainier_b200", "models", "funnel10.rir"), "rb").read()
+    om = OracleModel(rir, []).compile_density()
+    L = lib()
+    cores = L.rno_hardware_threads()
+    L.rno_set_threads(cores)
+    L.rno_set_pinning(1)
+    return om, default_config(), cores, L.rno_machine_threads()
+
+
 def run_reference(args):
     """--impl reference: the CPU oracle (stand-in for the JVM `asm` path, which cannot run here) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.rainier_py.binding import OracleModel, default_config, lib
     from rainier_b200 import abi
-    rir = open(os.path.join(ROOT, "rainier_b200", "models", "funnel10.rir"), "rb").read()
-    om = OracleModel(rir, [])
-    cores = lib().rno_hardware_threads()
-    cfg = default_config()
+    om, cfg, cores, machine = _oracle_arm()
     cfg.sampler, cfg.n_steps = abi.RN_SAMPLER_HMC, N_STEPS
     cfg.step_size_tuner, cfg.static_step_size = abi.RN_STEP_STATIC, STEP_SIZE
     cfg.mass_tuner = abi.RN_MASS_IDENTITY
@@ -155,21 +169,16 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "neals_funnel_10d_hmc_nsteps5", "sampler": "HMC(nSteps=5)", "step_size": STEP_SIZE,
                    "chains": chains, "iterations_per_step": cfg.iterations},
-        "cpu_baseline": {"value": value, "unit": "leapfrog-steps*chains/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "C++ restatement of the reference's LeapFrog/HMC + DataFunction interpreter (oracle/), "
-                                 "stand-in for the JVM asm path which cannot run in this image"},
+        "cpu_baseline": {"value": value, "unit": "leapfrog-steps*chains/s", "cores": cores, "machine_threads": machine,
+                         "per_core": value / cores, "kind": "port", "sample": sample, "note": CPU_NOTE},
         "e2e": {"value": value, "unit": "leapfrog-steps*chains/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 def cpu_baseline_leg():
-    from oracle.rainier_py.binding import OracleModel, default_config, lib
     from rainier_b200 import abi
-    rir = open(os.path.join(ROOT, "rainier_b200", "models", "funnel10.rir"), "rb").read()
-    om = OracleModel(rir, [])
-    cores = lib().rno_hardware_threads()
-    cfg = default_config()
+    om, cfg, cores, machine = _oracle_arm()
     cfg.sampler, cfg.n_steps = abi.RN_SAMPLER_HMC, N_STEPS
     cfg.step_size_tuner, cfg.static_step_size = abi.RN_STEP_STATIC, STEP_SIZE
     cfg.mass_tuner = abi.RN_MASS_IDENTITY
@@ -184,7 +193,9 @@ def cpu_baseline_leg():
     t = time.perf_counter()
     om.sample(cfg, seeds=np.arange(chains) + 1000)
     dt = time.perf_counter() - t
-    return {"value": chains * cfg.iterations * N_STEPS / dt, "unit": "leapfrog-steps*chains/s", "cores": cores, "kind": "port",
+    value = chains * cfg.iterations * N_STEPS / dt
+    return {"value": value, "unit": "leapfrog-steps*chains/s", "cores": cores, "machine_threads": machine, "per_core": value / cores,
+            "kind": "port", "note": CPU_NOTE,
             "sample": "%d chains x %d HMC iterations x %d leapfrog steps (%.1f s), one chain per host thread" % (
                 chains, cfg.iterations, N_STEPS, dt)}
 

@@ -142,6 +142,9 @@ typedef struct rn_chain_stats {
   double acceptance_rates_mean;
   double grads_per_iteration_mean;
   rn_rng_state rng;             /* RNG state after the last iteration */
+  double gradient_time_ns_mean;  /* gradientTimes.mean / iterationTimes.mean (Stats.scala:8-9), read by the notebook's   */
+  double iteration_time_ns_mean; /* HTMLProgress.scala:57,65: device time of the sampling launches / this chain's gradient */
+                                 /* evaluations, and / iterations of the batch (all chains advance together)              */
 } rn_chain_stats;
 
 typedef struct rn_model rn_model;

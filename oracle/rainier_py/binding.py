@@ -36,6 +36,8 @@ def lib():
         L.rno_model_destroy.argtypes = [C.c_void_p]
         L.rno_model_nvars.argtypes = [C.c_void_p]
         L.rno_density_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.rno_model_emit_cpp.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rno_model_use_compiled.argtypes = [C.c_void_p, C.c_char_p]
         L.rno_sample_traced.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
         L.rno_config_default.argtypes = [C.POINTER(Config)]
@@ -154,6 +156,43 @@ class OracleModel:
         if getattr(self, "h", None):
             lib().rno_model_destroy(self.h)
             self.h = None
+
+    def emit_cpp(self):
+        """C++ source of this model's DataFunction as straight-line code (rno_model_emit_cpp)"""
+        L = lib()
+        need = C.c_size_t()
+        L.rno_model_emit_cpp(self.h, None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        L.rno_model_emit_cpp(self.h, buf, need.value, C.byref(need))
+        return buf.value.decode()
+
+    def compile_density(self, enable=True):
+        """Switch the density to its COMPILED form: the node list as straight-line C++ built with the oracle's own flags
+        (g++ -O2 -ffp-contract=off) -- the stand-in for the JVM executing rainier-compute's generated bytecode after JIT
+        compilation, where the default form is a switch-per-node interpreter.  Bit-identical to the interpreter
+        (tests/test_oracle_compiled.py)."""
+        import hashlib
+        import tempfile
+        L = lib()
+        if not enable:
+            L.rno_model_use_compiled(self.h, None)
+            return self
+        src = self.emit_cpp()
+        d = os.path.join(tempfile.gettempdir(), "rno_compiled")
+        os.makedirs(d, exist_ok=True)
+        key = hashlib.sha1(src.encode()).hexdigest()[:16]
+        so = os.path.join(d, key + ".so")
+        if not os.path.exists(so):
+            cpp = os.path.join(d, key + ".cpp")
+            with open(cpp, "w") as f:
+                f.write(src)
+            tmp = so + ".tmp%d" % os.getpid()
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared", "-I", _ORACLE_DIR,
+                            cpp, "-o", tmp], check=True)
+            os.replace(tmp, so)
+        if L.rno_model_use_compiled(self.h, so.encode()) != 0:
+            raise OracleError(L.rno_last_error().decode())
+        return self
 
     def density_batch(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.n)

@@ -77,6 +77,8 @@ class ChainStats(C.Structure):
         ("acceptance_rates_mean", C.c_double),
         ("grads_per_iteration_mean", C.c_double),
         ("rng", RngState),
+        ("gradient_time_ns_mean", C.c_double),
+        ("iteration_time_ns_mean", C.c_double),
     ]
 
 

@@ -335,6 +335,8 @@ class Stats:
         self.stepSizesMean = st.step_sizes_mean
         self.acceptanceRatesMean = st.acceptance_rates_mean
         self.gradsPerIterationMean = st.grads_per_iteration_mean
+        self.gradientTimesMean = st.gradient_time_ns_mean    # Stats.gradientTimes.mean (ns), HTMLProgress.scala:65
+        self.iterationTimesMean = st.iteration_time_ns_mean  # Stats.iterationTimes.mean (ns), HTMLProgress.scala:57
         self.rings = rings
         self.rng = (st.rng.seed48, st.rng.next_gaussian, st.rng.have_next)
 

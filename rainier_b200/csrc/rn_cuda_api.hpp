@@ -71,6 +71,7 @@ struct Api {
   CUresult (*cuEventDestroy)(CUevent);
   CUresult (*cuEventRecord)(CUevent, CUstream);
   CUresult (*cuEventSynchronize)(CUevent);
+  CUresult (*cuEventElapsedTime)(float*, CUevent, CUevent);
   CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                              void**, void**);
   CUresult (*cuFuncGetAttribute)(int*, int, CUfunction);

@@ -101,6 +101,7 @@ const Api* api(std::string* why) {
       RN_SYM(cuEventDestroy, "cuEventDestroy_v2")
       RN_SYM(cuEventRecord, "cuEventRecord")
       RN_SYM(cuEventSynchronize, "cuEventSynchronize")
+      RN_SYM(cuEventElapsedTime, "cuEventElapsedTime")
       RN_SYM(cuLaunchKernel, "cuLaunchKernel")
       RN_SYM(cuFuncGetAttribute, "cuFuncGetAttribute")
       RN_SYM(cuFuncSetAttribute, "cuFuncSetAttribute")
@@ -822,6 +823,12 @@ struct rn_sampler {
   size_t trace_iters = 0, trace_pos = 0;
   rn_comm* comm = nullptr;
   CUdeviceptr d_pool = 0;  // [2n+1] pooled window statistics (RN_ADAPT_POOLED)
+  // device time of the sampling phase (Stats.gradientTimes / iterationTimes, Stats.scala:8-9): events bracket every
+  // batch of phase-1 launches; closed spans are summed when the stats are read
+  CUevent ev_run[2] = {nullptr, nullptr};
+  bool ev_open = false;
+  double sampling_ms = 0.0;
+  int64_t sampling_iterations = 0;
 };
 
 namespace {
@@ -1147,6 +1154,17 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
   const int per_launch = s->cfg.launch_iterations > 0 ? s->cfg.launch_iterations : 1000;
   const bool pooled = phase == 0 && s->cfg.adaptation == RN_ADAPT_POOLED && s->cfg.mass_tuner == RN_MASS_DIAGONAL;
   int done = 0;
+  if (phase == 1 && iterations > 0) {
+    if (!s->ev_run[0]) {
+      CU(A->cuEventCreate(&s->ev_run[0], 0));
+      CU(A->cuEventCreate(&s->ev_run[1], 0));
+    }
+    if (!s->ev_open) {
+      CU(A->cuEventRecord(s->ev_run[0], s->stream));
+      s->ev_open = true;
+    }
+    if (chain_begin == 0) s->sampling_iterations += iterations;  // rn_sample's chain blocks repeat the same iterations
+  }
   while (done < iterations) {
     int k = std::min(per_launch, iterations - done);
     if (pooled) k = iterations_to_window_end(s, k);  // launches end exactly at window ends
@@ -1176,6 +1194,7 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     if (s->d_trace) s->trace_pos += (size_t)k;
     done += k;
   }
+  if (phase == 1 && iterations > 0) CU(A->cuEventRecord(s->ev_run[1], s->stream));
   return RN_OK;
 }
 
@@ -1217,6 +1236,18 @@ int rn_sampler_run(rn_sampler* s, int iterations, double* d_samples) {
   return run_phase(A, s, 1, iterations, d_samples);
 }
 
+namespace {
+// fold the open event span of the sampling phase into sampling_ms (the stream must be idle)
+int close_sampling_span(const Api* A, rn_sampler* s) {
+  if (!s->ev_open) return RN_OK;
+  float ms = 0.f;
+  CU(A->cuEventElapsedTime(&ms, s->ev_run[0], s->ev_run[1]));
+  s->sampling_ms += (double)ms;
+  s->ev_open = false;
+  return RN_OK;
+}
+}  // namespace
+
 int rn_sampler_sync(rn_sampler* s) {
   std::string why;
   const Api* A = api(&why);
@@ -1249,6 +1280,10 @@ int rn_sampler_stats(rn_sampler* s, rn_chain_stats* stats, double* mass, double*
   if (!A) return fail(RN_E_CUDA, why);
   CU(A->cuCtxSetCurrent(s->m->ctx));
   CU(A->cuStreamSynchronize(s->stream));
+  {
+    int rc = close_sampling_span(A, s);
+    if (rc) return rc;
+  }
   const size_t C = (size_t)s->chains, n = s->m->n_params, W = (size_t)s->cfg.stats_window;
   const RnArgs& a = s->args;
   auto D = [](const void* p) { return (CUdeviceptr)(uintptr_t)p; };
@@ -1300,6 +1335,12 @@ int rn_sampler_stats(rn_sampler* s, rn_chain_stats* stats, double* mass, double*
       o.step_sizes_mean = means[0];
       o.acceptance_rates_mean = means[1];
       o.grads_per_iteration_mean = means[2];
+      // Stats.gradientTimes / iterationTimes (Stats.scala:8-9, LeapFrog.scala:57,77,196-198) hold per-call nanoseconds of
+      // ONE chain on a JVM thread; here all chains advance together, so the means are device time of the sampling
+      // launches / count: per iteration of the batch, and per gradient evaluation of this chain
+      const double ns = s->sampling_ms * 1e6;
+      o.iteration_time_ns_mean = s->sampling_iterations > 0 ? ns / (double)s->sampling_iterations : 0.0;
+      o.gradient_time_ns_mean = sg[c] > 0 ? ns / (double)sg[c] : 0.0;
       o.rng.seed48 = seed[c];
       o.rng.next_gaussian = nng[c];
       o.rng.have_next = have[c];
@@ -1440,6 +1481,8 @@ void rn_sampler_destroy(rn_sampler* s) {
       }
     }
     if (s->d_trace) A->cuMemFree(s->d_trace);
+    for (CUevent e : s->ev_run)
+      if (e) A->cuEventDestroy(e);
   }
   delete s;
 }

@@ -101,7 +101,9 @@ object CudaSampling {
     b.putInt(OffMassTuner, kind).putInt(OffInitWindow, t.initialWindowSize).putDouble(OffExpansion, t.windowExpansion)
       .putInt(OffSkipFirst, t.skipFirst).putInt(OffSkipLast, t.skipLast)
 
-  /** rn_chain_stats -> Stats (sampler/Stats.scala:3-17); timing ring buffers stay empty (kernel time is per batch). */
+  /** rn_chain_stats -> Stats (sampler/Stats.scala:3-17).  gradientTimes / iterationTimes (read by HTMLProgress.scala:57,65
+    * through `.mean`) receive one entry each: device time of the sampling launches / this chain's gradient evaluations,
+    * and / iterations of the batch -- all chains advance together, there is no per-call wall clock to record. */
   private def readStats(buf: ByteBuffer, c: Int, window: Int): Stats = {
     val o = c * Native.statsSize()
     val s = new Stats(window)
@@ -115,6 +117,8 @@ object CudaSampling {
     s.stepSizes.add(buf.getDouble(o + 96)) // means; full ring contents are available through rn_config.stats_rings
     s.acceptanceRates.add(buf.getDouble(o + 104))
     s.gradsPerIteration.add(buf.getDouble(o + 112))
+    s.gradientTimes.add(buf.getDouble(o + 144))
+    s.iterationTimes.add(buf.getDouble(o + 152))
     s
   }
 

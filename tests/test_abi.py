@@ -88,6 +88,7 @@ def test_scala_side_offsets():
     assert "configSize() == %d" % C.sizeof(abi.Config) in src
     for field, off in (("gradient_evaluations", 0), ("iterations", 16), ("divergences", 20), ("energy_mean", 40),
                        ("energy_raw", 48), ("energy_transitions2", 56), ("energy_samples", 64), ("step_sizes_mean", 96),
-                       ("acceptance_rates_mean", 104), ("grads_per_iteration_mean", 112)):
+                       ("acceptance_rates_mean", 104), ("grads_per_iteration_mean", 112), ("gradient_time_ns_mean", 144),
+                       ("iteration_time_ns_mean", 152)):
         assert getattr(abi.ChainStats, field).offset == off
         assert "o + %d" % off in src or off == 0
