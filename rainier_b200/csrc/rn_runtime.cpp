@@ -27,6 +27,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <tuple>
@@ -343,6 +344,13 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
   if (getenv("RN_LIBM_NOINLINE")) opts.push_back("-DRN_LIBM_NOINLINE=1");
+  std::vector<std::string> extra_defs;  // experiment switches of the device sources (RN_X_*): RN_NVRTC_DEFS="-DRN_X_P_REGS=1 ..."
+  if (const char* e = getenv("RN_NVRTC_DEFS")) {
+    std::istringstream is(e);
+    std::string tok;
+    while (is >> tok) extra_defs.push_back(tok);
+    for (const std::string& t : extra_defs) opts.push_back(t.c_str());
+  }
   std::string maxreg;
   {
     // registers/thread: the fused iteration kernel is latency-bound on dependent fp64 chains, so occupancy matters
@@ -447,9 +455,14 @@ static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
     const int bytes = (int)K->smem_bytes();
     for (CUfunction f : {K->k_init, K->k_iter, K->k_density})
       CU(A->cuFuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, bytes));
-  } else if (K->tpc_smem_per_thread * 128u > 48u * 1024u) {
-    for (CUfunction f : {K->k_init, K->k_iter, K->k_warmup})
-      CU(A->cuFuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)(K->tpc_smem_per_thread * 128u)));
+  } else {
+    for (CUfunction f : {K->k_init, K->k_iter, K->k_warmup}) {
+      if (K->tpc_smem_per_thread * 128u > 48u * 1024u)
+        CU(A->cuFuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)(K->tpc_smem_per_thread * 128u)));
+      // the chains' cold state lives in shared memory: ask for the largest carve-out, or the driver's default split
+      // (seen on B200: room for 5 CTAs of 25 KB) caps the occupancy below what the registers allow
+      CU(A->cuFuncSetAttribute(f, 9 /*CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT*/, 100));
+    }
   }
   return RN_OK;
 }

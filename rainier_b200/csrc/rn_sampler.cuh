@@ -72,7 +72,12 @@ RN_DEVICE RnTs rn_ts_get() {
 #endif
 #define RN_TSD(slot) T.d[(unsigned)(slot) * T.bs]
 #define RN_TSI(slot) T.i[(unsigned)(slot) * T.bs]
-#define RN_P(i) RN_TSD(RN_TS_P + (i))
+#define RN_Z(i) RN_TSD(RN_TS_P + (i)) /* scratch of the normal draws (aliases the shared-memory momentum) */
+#if defined(RN_X_P_REGS) && RN_X_P_REGS
+#define RN_P(i) s.p[i]                /* experiment switch: momentum in registers */
+#else
+#define RN_P(i) RN_TSD(RN_TS_P + (i)) /* momentum in shared memory */
+#endif
 #define RN_MASSD(i) RN_TSD(RN_TS_MASS + (i))
 #define RN_SNAP_P(i) RN_TSD(RN_TS_SNAP + (i))
 #define RN_ST_E_MEAN RN_TSD(RN_TS_STAT + 0)
@@ -115,8 +120,18 @@ RN_DEVICE void rn_ring_add(const RnArgs& A, int c, const RnTs& T, int which, dou
   RN_STCS(&RN_AT(A.st_rings, which * A.stats_window + i, c), value);
 }
 
+struct RnPQ {  // pqBuf's q and potential + the gradient at pqBuf.q  (pqBuf's p: RN_P, shared memory)
+  double q[RN_N], g[RN_N];
+  double U;
+#if defined(RN_X_P_REGS) && RN_X_P_REGS
+  double p[RN_N];
+#endif
+};
+
 // velocity_i = (M^-1 p)_i  (LeapFrog.scala:205-219); p is the shared-memory momentum
-RN_DEVICE double rn_velocity_i(const RnArgs& A, int c, const RnTs& T, int kind, int i) {
+RN_DEVICE double rn_velocity_i(const RnArgs& A, int c, const RnTs& T, const RnPQ& s, int kind, int i) {
+  (void)s;
+  (void)T;
   (void)A;
   (void)c;
 #if RN_MASS_MAX >= 2
@@ -134,16 +149,16 @@ RN_DEVICE double rn_velocity_i(const RnArgs& A, int c, const RnTs& T, int kind, 
 }
 
 // energy = potential + dot(velocity, p)/2  (LeapFrog.scala:134-139,221-231)
-RN_DEVICE double rn_energy(const RnArgs& A, int c, const RnTs& T, int kind, double U) {
+RN_DEVICE double rn_energy(const RnArgs& A, int c, const RnTs& T, const RnPQ& s, int kind, double U) {
   double k = 0.0;
 #if RN_MASS_MAX >= 2
   if (kind == 2) {
-    for (int i = 0; i < RN_N; i++) k += (rn_velocity_i(A, c, T, 2, i) * RN_P(i));
+    for (int i = 0; i < RN_N; i++) k += (rn_velocity_i(A, c, T, s, 2, i) * RN_P(i));
     return U + k / 2.0;
   }
 #endif
   RN_UNROLL
-  for (int i = 0; i < RN_N; i++) k += (rn_velocity_i(A, c, T, kind, i) * RN_P(i));
+  for (int i = 0; i < RN_N; i++) k += (rn_velocity_i(A, c, T, s, kind, i) * RN_P(i));
   return U + k / 2.0;
 }
 
@@ -152,10 +167,6 @@ RN_DEVICE double rn_log_accept(double deltaH) {  // LeapFrog.scala:141-145
   return rn_jmin0(-deltaH);
 }
 
-struct RnPQ {  // pqBuf's q and potential + the gradient at pqBuf.q  (pqBuf's p: RN_P, shared memory)
-  double q[RN_N], g[RN_N];
-  double U;
-};
 
 RN_DEVICE void rn_update(const RnArgs& A, RnPQ& s, RnIt& S) {  // copyQsAndUpdateDensity + potential
   double dens;
@@ -163,7 +174,8 @@ RN_DEVICE void rn_update(const RnArgs& A, RnPQ& s, RnIt& S) {  // copyQsAndUpdat
   s.U = dens * -1;
   S.grads += 1;
 }
-RN_DEVICE void rn_full_ps(const RnTs& T, RnPQ& s, double stepSize, RnIt& S) {  // LeapFrog.scala:168-176 (gradient reused)
+RN_DEVICE void rn_full_ps(const RnTs& T, RnPQ& s, double stepSize, RnIt& S) {
+  (void)T;  // LeapFrog.scala:168-176 (gradient reused)
   S.grads += 1;
   RN_UNROLL
   for (int i = 0; i < RN_N; i++) RN_P(i) += stepSize * s.g[i];
@@ -171,12 +183,12 @@ RN_DEVICE void rn_full_ps(const RnTs& T, RnPQ& s, double stepSize, RnIt& S) {  /
 RN_DEVICE void rn_new_qs(const RnArgs& A, int c, const RnTs& T, int kind, RnPQ& s, double stepSize) {  // :147-154
 #if RN_MASS_MAX >= 2
   if (kind == 2) {
-    for (int i = 0; i < RN_N; i++) s.q[i] += (stepSize * rn_velocity_i(A, c, T, 2, i));
+    for (int i = 0; i < RN_N; i++) s.q[i] += (stepSize * rn_velocity_i(A, c, T, s, 2, i));
     return;
   }
 #endif
   RN_UNROLL
-  for (int i = 0; i < RN_N; i++) s.q[i] += (stepSize * rn_velocity_i(A, c, T, kind, i));
+  for (int i = 0; i < RN_N; i++) s.q[i] += (stepSize * rn_velocity_i(A, c, T, s, kind, i));
 }
 // initialHalfThenFullStep + (l-1) twoFullSteps + finalHalfStep, LeapFrog.scala:24-33,156-191.
 // `g` must hold the gradient at s.q on entry (true for params and for every state this kernel produces).
@@ -205,10 +217,14 @@ RN_DEVICE void rn_take_steps(const RnArgs& A, int c, const RnTs& T, int kind, Rn
 // of the per-pair maxima), and a second, convergent pass applies sqrt(-2 log(s)/s).  s is recomputed there from the
 // parked v1, v2 by the same two products and one sum -> the same bits.
 RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
+#if defined(RN_X_NORMALS) && RN_X_NORMALS == 2
+  for (int i = 0; i < RN_N; i++) RN_Z(i) = rn_normal(rng);  // experiment switch: one nextGaussian at a time
+  return;
+#endif
   int i0 = 0;
   if (rng.have) {
     rng.have = 0;
-    RN_P(0) = rng.nng;
+    RN_Z(0) = rng.nng;
     i0 = 1;
   }
   const int npairs = (RN_N - i0 + 1) / 2;  // the last pair's second variate may be left over (-> rng.nng); slot RN_N is scratch
@@ -217,19 +233,22 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
     const double v2 = 2 * rn_uniform(rng) - 1;
     const double s = v1 * v1 + v2 * v2;
     if (!(s >= 1 || s == 0)) {
-      RN_P(i0 + 2 * k) = v1;
-      RN_P(i0 + 2 * k + 1) = v2;
+      RN_Z(i0 + 2 * k) = v1;
+      RN_Z(i0 + 2 * k + 1) = v2;
       k += 1;
     }
   }
+#if defined(RN_X_NORMALS) && RN_X_NORMALS == 1
+#pragma unroll 1
+#endif
   for (int k = 0; k < npairs; k++) {
     const int i = i0 + 2 * k;
-    const double v1 = RN_P(i), v2 = RN_P(i + 1);
+    const double v1 = RN_Z(i), v2 = RN_Z(i + 1);
     const double s = v1 * v1 + v2 * v2;
     const double multiplier = sqrt(-2 * rn_strict_log(s) / s);
-    RN_P(i) = v1 * multiplier;
+    RN_Z(i) = v1 * multiplier;
     if (i + 1 < RN_N) {
-      RN_P(i + 1) = v2 * multiplier;
+      RN_Z(i + 1) = v2 * multiplier;
     } else {
       rng.nng = v2 * multiplier;
       rng.have = 1;
@@ -238,11 +257,16 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
 }
 
 // momentum draw, LeapFrog.scala:233-255  (result in RN_P)
-RN_DEVICE void rn_initialize_ps(const RnArgs& A, int c, const RnTs& T, int kind, RnRng& rng) {
+RN_DEVICE void rn_initialize_ps(const RnArgs& A, int c, const RnTs& T, RnPQ& s, int kind, RnRng& rng) {
   (void)A;
   (void)c;
   (void)kind;
+  (void)s;
   rn_draw_normals(T, rng);  // buf(i) = rng.standardNormal
+#if defined(RN_X_P_REGS) && RN_X_P_REGS
+  RN_UNROLL
+  for (int i = 0; i < RN_N; i++) s.p[i] = RN_Z(i);
+#endif
 #if RN_MASS_MAX >= 2
   if (kind == 2) {  // DenseMassMatrix.upperTriangularSolve, MassMatrix.scala:55-72; in place: slot i holds z_i until p_i
     int i = RN_N - 1;  // replaces it, and p_i only reads z_i and the p_j, j > i, already in place
@@ -251,14 +275,17 @@ RN_DEVICE void rn_initialize_ps(const RnArgs& A, int c, const RnTs& T, int kind,
       int j = RN_N - 1;
       double dot = 0.0;
       while (j > i) {
-        dot += RN_P(j) * RN_AT(A.chol, m, c);
+        dot += RN_Z(j) * RN_AT(A.chol, m, c);
         j -= 1;
         m -= 1;
       }
-      RN_P(i) = (RN_P(i) - dot) / RN_AT(A.chol, m, c);
+      RN_Z(i) = (RN_Z(i) - dot) / RN_AT(A.chol, m, c);
       i -= 1;
       m -= 1;
     }
+#if defined(RN_X_P_REGS) && RN_X_P_REGS
+    for (int k = 0; k < RN_N; k++) s.p[k] = RN_Z(k);
+#endif
     return;
   }
 #endif
@@ -342,7 +369,7 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
   RnPQ s;
   rn_draw_normals(T, rng);  // pqBuf(i) = rng.standardNormal, i in nVars until 2 nVars
   RN_UNROLL
-  for (int i = 0; i < RN_N; i++) s.q[i] = RN_P(i);
+  for (int i = 0; i < RN_N; i++) s.q[i] = RN_Z(i);
   rn_update(A, s, S);
   double cq[RN_N], cg[RN_N];
   const double cU = s.U;
@@ -351,18 +378,18 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
     cq[i] = s.q[i];
     cg[i] = s.g[i];
   }
-  rn_initialize_ps(A, c, T, 0, rng);
+  rn_initialize_ps(A, c, T, s, 0, rng);
   RN_UNROLL
   for (int i = 0; i < RN_N; i++) RN_AT(A.params, i, c) = RN_P(i);  // params.p = the drawn momentum
 
   // stepSizeTuner.initialize
   double stepSize;
   if (A.step_tuner == 0) {  // DualAvgTuner.findReasonableStepSize, DualAvg.scala:27-41 (IdentityMassMatrix)
-    const double H0 = rn_energy(A, c, T, 0, cU);
+    const double H0 = rn_energy(A, c, T, s, 0, cU);
     stepSize = 1.0;
     double lap;
     rn_leapfrog(A, c, T, 0, s, 1, stepSize, S);  // tryStepping, LeapFrog.scala:14-22 (s still equals params here)
-    lap = rn_log_accept(rn_energy(A, c, T, 0, s.U) - H0);
+    lap = rn_log_accept(rn_energy(A, c, T, s, 0, s.U) - H0);
     const double exponent = (lap > -RN_LN2) ? 1.0 : -1.0;
     const double doubleOrHalf = (exponent > 0) ? 2.0 : 0.5;
     while (stepSize != 0.0 && (exponent * lap > -exponent * RN_LN2)) {
@@ -375,7 +402,7 @@ RN_GLOBAL void rn_k_init(const RnArgs A) {
       }
       s.U = cU;
       rn_leapfrog(A, c, T, 0, s, 1, stepSize, S);
-      lap = rn_log_accept(rn_energy(A, c, T, 0, s.U) - H0);
+      lap = rn_log_accept(rn_energy(A, c, T, s, 0, s.U) - H0);
     }
     // DualAvg.apply, DualAvg.scala:80-90
     RN_AT(A.da, 1, c) = rn_log(stepSize);
@@ -451,11 +478,11 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
     if (!havePrevH) {
       RN_UNROLL
       for (int i = 0; i < RN_N; i++) RN_P(i) = RN_AT(A.params, i, c);  // old momentum
-      RN_TS_PREV_H = rn_energy(A, c, T, kind, cU);
+      RN_TS_PREV_H = rn_energy(A, c, T, s, kind, cU);
     }
     {
       RnRng rng = rn_rng_unpark(T);
-      rn_initialize_ps(A, c, T, kind, rng);
+      rn_initialize_ps(A, c, T, s, kind, rng);
       rn_rng_park(T, rng);
     }
     RN_UNROLL
@@ -465,7 +492,7 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
       s.g[i] = RN_AT(A.grad, i, c);
     }
     s.U = cU;
-    RN_TS_START_H = rn_energy(A, c, T, kind, cU);  // finishIteration's energy(params), :62
+    RN_TS_START_H = rn_energy(A, c, T, s, kind, cU);  // finishIteration's energy(params), :62
     const double usedStep = stepSize;
 
     // ---------------- sampler.warmup / sampler.run ----------------
@@ -494,16 +521,20 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
           rn_take_steps(A, c, T, kind, s, 1, stepSize, S);
           if (l == A.min_steps) {
             snap = s;
+#if !(defined(RN_X_P_REGS) && RN_X_P_REGS)
             RN_UNROLL
             for (int i = 0; i < RN_N; i++) RN_SNAP_P(i) = RN_P(i);
+#endif
           }
         }
         if (l < A.min_steps) {
           rn_take_steps(A, c, T, kind, s, A.min_steps - l, stepSize, S);
         } else {
           s = snap;
+#if !(defined(RN_X_P_REGS) && RN_X_P_REGS)
           RN_UNROLL
           for (int i = 0; i < RN_N; i++) RN_P(i) = RN_SNAP_P(i);
+#endif
         }
         // steps.add(l), Stats.scala:24-30
         ring_i += 1;
@@ -521,7 +552,7 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
 #endif
 
     // ---------------- lf.finishIteration, LeapFrog.scala:61-82 ----------------
-    const double endH = rn_energy(A, c, T, kind, s.U);
+    const double endH = rn_energy(A, c, T, s, kind, s.U);
     const double startH = RN_TS_START_H;
     const double deltaH = endH - startH;
     const double a = rn_log_accept(deltaH);

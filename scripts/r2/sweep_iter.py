@@ -9,12 +9,16 @@ from rainier_b200 import abi, api
 ROOT = os.path.join(os.path.dirname(__file__), "..", "..")
 C_, I_ = 151552, 100
 rir = open(os.path.join(ROOT, "rainier_b200", "models", sys.argv[1] if len(sys.argv) > 1 else "funnel10.rir"), "rb").read()
-caps = [int(x) for x in os.environ.get("SWEEP_CAPS", "128,104,96,88,80,72,64").split(",")]
-blocks = [int(x) for x in os.environ.get("SWEEP_BLOCKS", "128,64").split(",")]
+caps = [int(x) for x in os.environ.get("SWEEP_CAPS", "128,96,80").split(",")]
+blocks = [int(x) for x in os.environ.get("SWEEP_BLOCKS", "128").split(",")]
+defsets = os.environ.get("SWEEP_DEFS", "|-DRN_X_P_REGS=1|-DRN_X_NORMALS=1|-DRN_X_NORMALS=2|-DRN_X_P_REGS=1 -DRN_X_NORMALS=1|"
+                         "-DRN_X_P_REGS=1 -DRN_X_NORMALS=2|-DRN_X_POW_NOINLINE=1|-DRN_X_NORMALS=1 -DRN_X_POW_NOINLINE=1").split("|")
 math = abi.RN_MATH_FAST if os.environ.get("SWEEP_FAST") else abi.RN_MATH_PARITY
 ref = None
-for cap in caps:
+for defs in defsets:
+  for cap in caps:
     for block in blocks:
+        os.environ["RN_NVRTC_DEFS"] = defs
         os.environ["RN_MAXRREGCOUNT"] = str(cap)
         os.environ["RN_BLOCK"] = str(block)
         model = api.CudaModel(rir, [], device=0)
@@ -35,6 +39,6 @@ for cap in caps:
             a.record(stream); smp.run(I_, d.data_ptr()); b.record(stream)
         smp.sync(); torch.cuda.synchronize()
         ms = sorted(a.elapsed_time(b) for a, b in ev)
-        print(json.dumps({"cap": cap, "block": block, "ms_min": ms[0], "ms_med": ms[2], "rate": C_ * I_ * 5 / (ms[2] * 1e-3),
+        print(json.dumps({"defs": defs, "cap": cap, "block": block, "ms_min": ms[0], "ms_med": ms[2], "rate": C_ * I_ * 5 / (ms[2] * 1e-3),
                           "same_bits": h == ref, "hash": h}), flush=True)
         smp.close(); model.close()
