@@ -26,12 +26,16 @@
 #define RN_AT(ptr, field, c) (ptr)[(size_t)(field) * (size_t)A.chains + (size_t)(c)]
 
 // ---- this thread's COLD state lives in shared memory -----------------------------------------------------------
-// The fused iteration is latency-bound on dependent fp64 chains (ncu, profiles/r1_ncu_funnel_parity_v5.csv: `wait`
-// stalls 45 % at 4 warps per scheduler), so what matters is how many warps fit the register file.  Everything a chain
-// does not touch inside the density evaluation is therefore kept out of registers: the momentum p (dead while the
-// density runs), the diagonal mass matrix, the EHMC snapshot's momentum and the Stats counters (touched once per
-// iteration) sit in dynamic shared memory as [slot][blockDim.x] -- conflict-free, one LDS/STS per access.  q, the
-// gradient and the density's temporaries keep the registers.  (Host emulation: blockDim.x == 1, a thread_local array.)
+// Everything a chain touches once per iteration is kept out of registers: the Stats counters, the RNG state, the energies
+// carried from startIteration to finishIteration, the diagonal mass matrix and the scratch of the normal draws sit in
+// dynamic shared memory as [slot][blockDim.x] -- conflict-free, one LDS/STS per access -- so that p, q, the gradient and
+// the density's temporaries fit 128 registers without spilling (round 1: 80 bytes of spill traffic in the leapfrog
+// loop).  Measured on B200 (profiles/r2_sweep_iter_v2_variants.jsonl): the kernel does NOT respond to occupancy (96 or
+// 80 registers per thread = 20 / 24 warps per SM are no faster than 128 = 16 warps: what the extra warps hide, the
+// tighter register allocation loses in instruction-level parallelism) but it does respond to CODE SIZE and instruction
+// count (stall `no_instruction` 12 % with the second pass of the normal draws unrolled, 3.68 -> 3.41 ms as a loop), which
+// is why the hot loops stay loops and the fdlibm functions run as one branch-free common path (rn_prelude.cuh).
+// (Host emulation: blockDim.x == 1, a thread_local array.)
 #if RN_MASS_MAX >= 1
 #define RN_TS_NMASS RN_N
 #else
@@ -72,8 +76,14 @@ RN_DEVICE RnTs rn_ts_get() {
 #endif
 #define RN_TSD(slot) T.d[(unsigned)(slot) * T.bs]
 #define RN_TSI(slot) T.i[(unsigned)(slot) * T.bs]
+#ifndef RN_X_P_REGS
+#define RN_X_P_REGS 1 /* momentum in registers: 3.25 ms vs 3.41 ms per launch at the headline size with it in shared memory */
+#endif
+#ifndef RN_X_NORMALS
+#define RN_X_NORMALS 1 /* flat rejection loop + second pass kept as a LOOP: the kernel is sensitive to code size (3.41 vs 3.68 ms unrolled) */
+#endif
 #define RN_Z(i) RN_TSD(RN_TS_P + (i)) /* scratch of the normal draws (aliases the shared-memory momentum) */
-#if defined(RN_X_P_REGS) && RN_X_P_REGS
+#if RN_X_P_REGS
 #define RN_P(i) s.p[i]                /* experiment switch: momentum in registers */
 #else
 #define RN_P(i) RN_TSD(RN_TS_P + (i)) /* momentum in shared memory */
@@ -123,7 +133,7 @@ RN_DEVICE void rn_ring_add(const RnArgs& A, int c, const RnTs& T, int which, dou
 struct RnPQ {  // pqBuf's q and potential + the gradient at pqBuf.q  (pqBuf's p: RN_P, shared memory)
   double q[RN_N], g[RN_N];
   double U;
-#if defined(RN_X_P_REGS) && RN_X_P_REGS
+#if RN_X_P_REGS
   double p[RN_N];
 #endif
 };
@@ -217,7 +227,7 @@ RN_DEVICE void rn_take_steps(const RnArgs& A, int c, const RnTs& T, int kind, Rn
 // of the per-pair maxima), and a second, convergent pass applies sqrt(-2 log(s)/s).  s is recomputed there from the
 // parked v1, v2 by the same two products and one sum -> the same bits.
 RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
-#if defined(RN_X_NORMALS) && RN_X_NORMALS == 2
+#if RN_X_NORMALS == 2
   for (int i = 0; i < RN_N; i++) RN_Z(i) = rn_normal(rng);  // experiment switch: one nextGaussian at a time
   return;
 #endif
@@ -238,7 +248,7 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
       k += 1;
     }
   }
-#if defined(RN_X_NORMALS) && RN_X_NORMALS == 1
+#if RN_X_NORMALS == 1
 #pragma unroll 1
 #endif
   for (int k = 0; k < npairs; k++) {
@@ -263,7 +273,7 @@ RN_DEVICE void rn_initialize_ps(const RnArgs& A, int c, const RnTs& T, RnPQ& s, 
   (void)kind;
   (void)s;
   rn_draw_normals(T, rng);  // buf(i) = rng.standardNormal
-#if defined(RN_X_P_REGS) && RN_X_P_REGS
+#if RN_X_P_REGS
   RN_UNROLL
   for (int i = 0; i < RN_N; i++) s.p[i] = RN_Z(i);
 #endif
@@ -283,7 +293,7 @@ RN_DEVICE void rn_initialize_ps(const RnArgs& A, int c, const RnTs& T, RnPQ& s, 
       i -= 1;
       m -= 1;
     }
-#if defined(RN_X_P_REGS) && RN_X_P_REGS
+#if RN_X_P_REGS
     for (int k = 0; k < RN_N; k++) s.p[k] = RN_Z(k);
 #endif
     return;
@@ -521,7 +531,7 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
           rn_take_steps(A, c, T, kind, s, 1, stepSize, S);
           if (l == A.min_steps) {
             snap = s;
-#if !(defined(RN_X_P_REGS) && RN_X_P_REGS)
+#if !(RN_X_P_REGS)
             RN_UNROLL
             for (int i = 0; i < RN_N; i++) RN_SNAP_P(i) = RN_P(i);
 #endif
@@ -531,7 +541,7 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
           rn_take_steps(A, c, T, kind, s, A.min_steps - l, stepSize, S);
         } else {
           s = snap;
-#if !(defined(RN_X_P_REGS) && RN_X_P_REGS)
+#if !(RN_X_P_REGS)
           RN_UNROLL
           for (int i = 0; i < RN_N; i++) RN_P(i) = RN_SNAP_P(i);
 #endif

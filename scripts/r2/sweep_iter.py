@@ -9,10 +9,9 @@ from rainier_b200 import abi, api
 ROOT = os.path.join(os.path.dirname(__file__), "..", "..")
 C_, I_ = 151552, 100
 rir = open(os.path.join(ROOT, "rainier_b200", "models", sys.argv[1] if len(sys.argv) > 1 else "funnel10.rir"), "rb").read()
-caps = [int(x) for x in os.environ.get("SWEEP_CAPS", "128,96,80").split(",")]
+caps = [int(x) for x in os.environ.get("SWEEP_CAPS", "128,96").split(",")]
 blocks = [int(x) for x in os.environ.get("SWEEP_BLOCKS", "128").split(",")]
-defsets = os.environ.get("SWEEP_DEFS", "|-DRN_X_P_REGS=1|-DRN_X_NORMALS=1|-DRN_X_NORMALS=2|-DRN_X_P_REGS=1 -DRN_X_NORMALS=1|"
-                         "-DRN_X_P_REGS=1 -DRN_X_NORMALS=2|-DRN_X_POW_NOINLINE=1|-DRN_X_NORMALS=1 -DRN_X_POW_NOINLINE=1").split("|")
+defsets = os.environ.get("SWEEP_DEFS", "|-DRN_X_LIBM_PLAIN=1 -DRN_X_LIBM_FULL_INLINE=1|-DRN_X_LIBM_FULL_INLINE=1|-DRN_X_P_REGS=0|-DRN_X_NORMALS=0|-DRN_X_NORMALS=2").split("|")
 math = abi.RN_MATH_FAST if os.environ.get("SWEEP_FAST") else abi.RN_MATH_PARITY
 ref = None
 for defs in defsets:
