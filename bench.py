@@ -104,10 +104,14 @@ class ClockSampler:
                 "reasons": [n for n in self.NAMES if n in self.reasons], "samples": len(self.sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE rn_k_iter launch at the default workload (151552 chains x 100
-# iterations), from `ncu --set full` (profiles/r1_ncu_funnel_parity_v5.csv, profiles/r1_ncu_funnel_fast_v2.csv): the 46 MB of chain state stays in
-# L2, so what reaches DRAM is the 1.2 GB sample stream plus write-allocate traffic -- below the algorithmic bytes.
-NCU_DRAM_BYTES_PER_LAUNCH = {"parity": 54746624 + 1809110000, "fast": 54043904 + 1686160000}
+def ncu_capture(math):
+    """dram__bytes_{read,write}.sum, fp64-pipe activity ... of ONE rn_k_iter launch at the default workload, from the most
+    recent `ncu --set full` capture of this kernel (scripts/ncu_summary.py writes profiles/ncu_funnel_<math>.json from the
+    .ncu-rep; the capture cannot run inside a timed bench).  None when no capture of the current kernel is committed."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_funnel_%s.json" % math)))
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -340,6 +344,8 @@ def main():
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
+        cap = ncu_capture(args.math)
+        have_cap = bool(cap) and (C_, I_) == (151552, 100)
         bps = bytes_per_leapfrog_step(N_DIM, N_STEPS)
         per_gpu_rate = value / world
         achieved = per_gpu_rate * bps / 1e9
@@ -368,16 +374,20 @@ def main():
                                          "note": "per rank; same rn_sample call with samples=NULL, rn_config.diagnostics set"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH[args.math] if (C_, I_) == (151552, 100) else None,
+                         "traffic": cap["dram_bytes"] if have_cap else None,
                          "traffic_unit": "bytes per rn_k_iter launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": cap["source"] if have_cap else None,
+                         # the same fraction computed from the bytes that actually crossed the HBM interface (state is L2-resident
+                         # across the 100 iterations of a launch, so this is well below the compulsory-traffic figure)
+                         "measured_traffic_frac": (cap["dram_bytes"] / (ms_max / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]) if have_cap else None,
                          "algorithmic_bytes_per_launch": bps * C_ * I_ * N_STEPS, "peak_source": peak_kind,
                          "bytes_per_leapfrog_step": bps,
-                         "note": "compulsory-traffic accounting (SURVEY.md 8d); the kernel is FP64-pipe bound, see fp64"},
+                         "note": "compulsory-traffic accounting (SURVEY.md 8d); the kernel is bound by the FP64 pipe / instruction issue, see fp64"},
             "fp64": {"flops_per_leapfrog_step": flops_step, "special_per_leapfrog_step": counts["special_invariant"] * evals_per_step,
                      "achieved_tflops": per_gpu_rate * flops_step / 1e12,
-                     "ncu_fp64_pipe_active_pct": {"parity": 46.3, "fast": 39.7}[args.math] if (C_, I_) == (151552, 100) else None,
-                     "ncu_source": "profiles/r1_ncu_funnel_parity_v5.csv, profiles/r1_ncu_funnel_fast_v2.csv "
-                                   "(sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active)"},
+                     "ncu_fp64_pipe_active_pct": cap.get("fp64_pipe_active_pct") if have_cap else None,
+                     "ncu_issue_active_pct": cap.get("issue_active_pct") if have_cap else None,
+                     "ncu_source": cap["source"] if have_cap else None},
         }
         try:  # the end-to-end call is bound by the device->host link, not by the kernel: say how close to it the call runs
             gbs = C_ * I_ * N_DIM * 8 / (float(e2e_ms["median"]) * 1e-3) / 1e9

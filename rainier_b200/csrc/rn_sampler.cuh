@@ -123,9 +123,11 @@ RN_DEVICE void rn_rng_park(const RnTs& T, const RnRng& r) {
 }
 
 RN_DEVICE void rn_ring_add(const RnArgs& A, int c, const RnTs& T, int which, double value) {  // Stats.scala:24-30
-  int i = RN_ST_RING_I(which) + 1;
-  if (i == A.stats_window) RN_ST_RING_FULL(which) = 1;
-  i = i % A.stats_window;
+  int i = RN_ST_RING_I(which) + 1;  // i <= stats_window: `i % size` is a compare, not a division
+  if (i == A.stats_window) {
+    RN_ST_RING_FULL(which) = 1;
+    i = 0;
+  }
   RN_ST_RING_I(which) = i;
   RN_STCS(&RN_AT(A.st_rings, which * A.stats_window + i, c), value);
 }
@@ -239,8 +241,8 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
   }
   const int npairs = (RN_N - i0 + 1) / 2;  // the last pair's second variate may be left over (-> rng.nng); slot RN_N is scratch
   for (int k = 0; k < npairs;) {
-    const double v1 = 2 * rn_uniform(rng) - 1;
-    const double v2 = 2 * rn_uniform(rng) - 1;
+    double v1, v2;
+    rn_polar_attempt(rng, v1, v2);
     const double s = v1 * v1 + v2 * v2;
     if (!(s >= 1 || s == 0)) {
       RN_Z(i0 + 2 * k) = v1;
