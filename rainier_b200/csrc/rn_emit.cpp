@@ -378,10 +378,11 @@ struct Emitter {
       os << "  // target " << t << (T.streamed() ? " (streamed)" : " (data-free)") << "\n";
       if (T.streamed()) {
         os << "  for (long long row = 0; row < " << (long long)T.n_rows << "LL; row++) {\n";
+        const int pitch = opt.pitch(t);
         os << "    const double* RN_RESTRICT rp = data + " << (unsigned long long)opt.target_base[t] << "ULL + (row >> 5) * "
-           << (unsigned long long)T.n_cols * 32 << "LL + (row & 31);\n";
+           << (unsigned long long)T.n_cols * pitch << "LL + (row & 31);\n";
         row_body(
-            T, "    ", [&](int k) { return "RN_LDG(rp + " + std::to_string(local_col(T, k) * 32) + ")"; },
+            T, "    ", [&](int k) { return "RN_LDG(rp + " + std::to_string(local_col(T, k) * pitch) + ")"; },
             [&](int slot) { return "acc[" + std::to_string(slot) + "]"; }, false, 0);
         os << "  }\n";
       } else {
@@ -424,6 +425,402 @@ struct Emitter {
     os << "}\n";
   }
 
+
+  // =============================================================================================================
+  // Chain-batched fp64 tensor-core path (DMMA, mma.sync.m8n8k4.f64) for streamed targets whose row body is
+  //     [dot products  z_d = base + sum_j q[p_j] * x_{d,j}]  ->  [elementwise code on z_d]  ->  sum over d
+  // -- the Translator's left fold of a `Line` with column coefficients (compute/Translator.scala:91-125), once per
+  // unrolled observation of Model.observe (core/Model.scala:98-132): logistic / Poisson / Gaussian regressions.
+  // Over the 8 chains of a CTA and the 32 rows of a tile the dots are Z^T[8 x 32] = B^T[8 x d] X^T[d x 32] and their
+  // adjoints G^T[8 x d] += W^T[8 x 32] X[32 x d]: warp w takes dot w (its own column block of every tile, fetched by its
+  // own single-stage TMA pipeline), computes both products for ALL 8 chains with DMMA -- one staged x_ij then serves 8
+  // chains instead of one (rows-across-lanes: one LDS.64 per DFMA, the shared-memory pipe was the busiest unit of round
+  // 1's kernel) -- and runs the emitted elementwise code on the C fragments (lane: chain = lane/4, row slots 2*(lane%4)+{0,1}).
+  // The per-warp partial sums meet in a CTA scratch and every chain's warp adds them in one fixed order (deterministic).
+  // Fragment maps (PTX ISA, mma.m8n8k4 .f64): A[m = lane/4][k = lane%4], B[k = lane%4][n = lane/4], C[m = lane/4][n = 2*(lane%4)+{0,1}].
+  //   forward   m = chain, k = term, n = row slot;   backward  m = chain, k = row slot (2*(lane%4)+h for k-step h), n = term.
+  // Row slot n of an 8-row group is physical row n ^ ((n >> 2) & 1): with a column pitch of 36 doubles both B-operand
+  // access patterns are then bank-conflict free per half-warp.
+  // =============================================================================================================
+  struct MmaDot {
+    int z = -1, w = -1, base = -1;
+    std::vector<int> cols;     // local column index of every term
+    std::vector<int> leaves;   // leaves of the output sum owned by this dot
+    std::vector<int> fwd, bwd; // row nodes its elementwise code needs, emission order
+    std::vector<AccStmt> acc;  // accumulations other than density / dot-term adjoints: (index into plan.other_slots, node)
+    int cmin = 0, cmax = 0;
+  };
+  struct MmaPlan {
+    bool ok = false;
+    std::vector<int> params;       // common term -> parameter map
+    std::vector<int> param_slot;   // accumulator slot of every term's parameter
+    std::vector<MmaDot> dots;
+    std::vector<int> other_slots;  // accumulator slots (besides 0 and the term parameters') the elementwise code adds to
+    int KS = 0, DT = 0, region_doubles = 0, redw = 0;
+  };
+  std::vector<MmaPlan> plans;
+  std::vector<int> mma_inv;        // invariant nodes some elementwise body reads (published per chain through shared memory)
+  int mma_inv_off = 0;
+  bool mma_all_ok = false;
+  int mma_shared_doubles = 0;
+  static constexpr int MMA_WARPS = 8;
+
+  static MmaPlan why(MmaPlan& pl, int line) {
+    if (getenv("RN_MMA_DEBUG")) fprintf(stderr, "[rn mma] target not eligible for the DMMA path: check %d\n", line);
+    return pl;
+  }
+  MmaPlan plan_mma(const TargetInfo& T, size_t t) {
+    MmaPlan pl;
+    const int pitch = opt.pitch(t);
+    if (P.symbolic || !T.streamed() || T.dots.empty() || !T.row_scatter.empty() || pitch < 36 || T.dots.size() > 64) return why(pl, 1);
+    pl.params = T.dots[0].params;
+    if (pl.params.size() < 4) return why(pl, 2);
+    for (const DotInfo& d : T.dots)
+      if (d.params != pl.params) return why(pl, 3);
+    std::set<int> rowset(T.row_fwd.begin(), T.row_fwd.end());
+    rowset.insert(T.row_bwd.begin(), T.row_bwd.end());
+    // dot internals: the term products and the partial sums of the fold
+    std::map<int, int> zdot;
+    std::set<int> internal;
+    for (size_t di = 0; di < T.dots.size(); di++) {
+      const DotInfo& d = T.dots[di];
+      zdot[d.node] = (int)di;
+      int cur = d.node;
+      for (size_t k = d.params.size(); k-- > 0;) {
+        const Node& a = P.nodes[cur];
+        if (k == 0 && d.base < 0) {
+          internal.insert(cur);  // the first term itself
+          break;
+        }
+        if (a.kind != K_BINARY || a.op != RIR_B_ADD) return why(pl, 4);
+        internal.insert(a.b);
+        if (cur != d.node) internal.insert(cur);
+        cur = a.a;
+      }
+    }
+    // which dots a row node depends on (through z_d); touching a dot internal any other way disqualifies
+    std::map<int, uint64_t> memo;
+    bool bad = false;
+    std::vector<int> ops;
+    std::function<uint64_t(int)> mask = [&](int id) -> uint64_t {
+      auto z = zdot.find(id);
+      if (z != zdot.end()) return 1ull << z->second;
+      if (internal.count(id)) {
+        bad = true;
+        return 0;
+      }
+      if (!rowset.count(id)) return 0;
+      auto it = memo.find(id);
+      if (it != memo.end()) return it->second;
+      std::vector<int> o;
+      operands(id, o);
+      uint64_t m = 0;
+      for (int x : o) m |= mask(x);
+      memo[id] = m;
+      return m;
+    };
+    auto single = [&](uint64_t m) { return m != 0 && (m & (m - 1)) == 0; };
+    auto owner = [&](uint64_t m) {
+      int d = 0;
+      while (m > 1) {
+        m >>= 1;
+        d++;
+      }
+      return d;
+    };
+    for (const DotInfo& d : T.dots)  // the fold's first operand (an intercept, the observation column of a residual) may be any
+      if (d.base >= 0 && (mask(d.base) != 0 || bad)) return why(pl, 5);  // value that does not itself hang on a dot
+    pl.dots.resize(T.dots.size());
+    for (size_t di = 0; di < T.dots.size(); di++) {
+      pl.dots[di].z = T.dots[di].node;
+      pl.dots[di].base = T.dots[di].base;
+      for (int c : T.dots[di].columns) pl.dots[di].cols.push_back(local_col(T, c - (int)P.n_params));  // DotInfo holds input indices
+    }
+    // output: a sum whose leaves depend on one dot each
+    std::function<bool(int)> leaves = [&](int id) -> bool {
+      const uint64_t m = mask(id);
+      if (bad) return false;
+      if (m == 0 || single(m)) {
+        pl.dots[m ? owner(m) : 0].leaves.push_back(id);
+        return true;
+      }
+      const Node& n = P.nodes[id];
+      if (n.kind != K_BINARY || n.op != RIR_B_ADD) return false;
+      return leaves(n.a) && leaves(n.b);
+    };
+    if (!leaves(T.outputs[0]) || bad) return why(pl, 6);
+    // accumulations
+    std::map<int, int> slot_of_param;
+    std::map<int, int> other_index;
+    for (const AccStmt& a : T.row_acc) {
+      if (a.slot == 0 && a.node == T.outputs[0]) continue;
+      const Node& c = P.nodes[a.node];
+      bool term_adj = false;
+      if (c.kind == K_BINARY && c.op == RIR_B_MUL && rowset.count(a.node)) {
+        // MUL(adjoint of z_d, column of term k) -> the DMMA's job
+        for (int swap = 0; swap < 2 && !term_adj; swap++) {
+          const int wn = swap ? c.b : c.a, cn = swap ? c.a : c.b;
+          const Node& col = P.nodes[cn];
+          if (col.kind != K_INPUT || (uint32_t)col.a < P.n_params) continue;
+          const int lc = local_col(T, col.a - (int)P.n_params);
+          for (size_t di = 0; di < pl.dots.size() && !term_adj; di++)
+            for (size_t k = 0; k < pl.dots[di].cols.size(); k++)
+              if (pl.dots[di].cols[k] == lc) {
+                if (pl.dots[di].w >= 0 && pl.dots[di].w != wn) return why(pl, 7);
+                auto sp = slot_of_param.find(pl.params[k]);
+                if (sp != slot_of_param.end() && sp->second != a.slot) return why(pl, 8);
+                slot_of_param[pl.params[k]] = a.slot;
+                pl.dots[di].w = wn;
+                term_adj = true;
+                break;
+              }
+        }
+      }
+      if (term_adj) continue;
+      const uint64_t m = mask(a.node);
+      if (bad || (m != 0 && !single(m))) return why(pl, 9);
+      if (a.slot == 0) return why(pl, 10);  // (density contributions come through the leaves only)
+      if (smem_slot[a.slot] >= 0) return why(pl, 11);
+      auto oi = other_index.find(a.slot);
+      if (oi == other_index.end()) {
+        oi = other_index.emplace(a.slot, (int)pl.other_slots.size()).first;
+        pl.other_slots.push_back(a.slot);
+      }
+      pl.dots[m ? owner(m) : 0].acc.push_back({oi->second, a.node});
+    }
+    for (size_t k = 0; k < pl.params.size(); k++) {
+      auto sp = slot_of_param.find(pl.params[k]);
+      if (sp == slot_of_param.end() || smem_slot[sp->second] >= 0) return why(pl, 12);
+      pl.param_slot.push_back(sp->second);
+    }
+    // needed nodes and column ranges per dot
+    for (size_t di = 0; di < pl.dots.size(); di++) {
+      MmaDot& d = pl.dots[di];
+      if (d.w < 0) return why(pl, 13);
+      std::set<int> need;
+      std::set<int> colset(d.cols.begin(), d.cols.end());
+      std::function<bool(int)> visit = [&](int id) -> bool {
+        if (id == d.z) {
+          need.insert(id);  // (keeps its place in the emission order; its operands are the DMMA's)
+          return true;
+        }
+        if (zdot.count(id) || internal.count(id)) return false;
+        const Node& n = P.nodes[id];
+        if (n.kind == K_CONST) return true;
+        if (n.kind == K_INPUT) {
+          if ((uint32_t)n.a >= P.n_params) colset.insert(local_col(T, n.a - (int)P.n_params));
+          return true;
+        }
+        if (!rowset.count(id)) {  // an invariant value of the chain
+          if (n.region != R_INV_FWD) return false;
+          if (std::find(mma_inv.begin(), mma_inv.end(), id) == mma_inv.end()) mma_inv.push_back(id);
+          return true;
+        }
+        if (tab_off.count(id)) return false;  // table lookups read the chain's own scratch
+        if (!need.insert(id).second) return true;
+        std::vector<int> o;
+        operands(id, o);
+        for (int x : o)
+          if (!visit(x)) return false;
+        return true;
+      };
+      for (int l : d.leaves)
+        if (!visit(l)) return why(pl, 14);
+      if (!visit(d.w)) return why(pl, 15);
+      for (const AccStmt& a : d.acc)
+        if (!visit(a.node)) return why(pl, 16);
+      if (d.base >= 0 && !visit(d.base)) return why(pl, 17);
+      for (int id : T.row_fwd)
+        if (need.count(id)) d.fwd.push_back(id);
+      for (int id : T.row_bwd)
+        if (need.count(id)) d.bwd.push_back(id);
+      d.cmin = *colset.begin();
+      d.cmax = *colset.rbegin();
+      pl.region_doubles = std::max(pl.region_doubles, (d.cmax - d.cmin + 1) * pitch);
+    }
+    pl.KS = ((int)pl.params.size() + 3) / 4;
+    pl.DT = ((int)pl.params.size() + 7) / 8;
+    pl.redw = pl.DT * 8 + 1 + (int)pl.other_slots.size();
+    pl.ok = true;
+    return pl;
+  }
+
+  // the elementwise code of one dot: one (row, chain) element
+  void mma_helper(const TargetInfo& T, size_t t, const MmaPlan& pl, size_t di) {
+    const MmaDot& d = pl.dots[di];
+    const int pitch = opt.pitch(t);
+    os << "RN_DEVICE void rn_mma_e" << t << "_" << di << "(const double zz, const RnSA rp, const double* RN_RESTRICT q, "
+          "const double* RN_RESTRICT xv, double& dens, double& wout, double* osum, int& err) {\n"
+       << "  (void)rp; (void)q; (void)xv; (void)osum; (void)err;\n";
+    for (size_t k = 0; k < mma_inv.size(); k++) os << "  const double v" << mma_inv[k] << " = xv[" << k << "]; (void)v" << mma_inv[k] << ";\n";
+    std::set<int> declared;
+    auto need_col = [&](int o) {
+      const Node& n = P.nodes[o];
+      if (n.kind != K_INPUT || (uint32_t)n.a < P.n_params) return;
+      const int k = n.a - (int)P.n_params;
+      if (declared.insert(k).second) os << "  const double c" << k << " = rn_lds(rp, " << (local_col(T, k) - d.cmin) * pitch << ");\n";
+    };
+    std::vector<int> o;
+    auto one = [&](int id) {
+      if (id == d.z) {  // the dot itself: the tensor core's sum, plus the fold's first operand
+        if (d.base >= 0) {
+          need_col(d.base);
+          os << "  const double v" << d.z << " = " << val(d.base) << " + zz;\n";
+        } else {
+          os << "  const double v" << d.z << " = zz;\n";
+        }
+        return;
+      }
+      operands(id, o);
+      for (int x : o) need_col(x);
+      stmt(id, "  ");
+    };
+    bool z_done = false;
+    for (int id : d.fwd) {
+      one(id);
+      if (id == d.z) z_done = true;
+    }
+    if (!z_done) one(d.z);
+    for (int l : d.leaves) {
+      need_col(l);
+      os << "  dens += " << val(l) << ";\n";
+    }
+    for (int id : d.bwd) one(id);
+    need_col(d.w);
+    os << "  wout = " << val(d.w) << ";\n";
+    for (const AccStmt& a : d.acc) {
+      need_col(a.node);
+      os << "  osum[" << a.slot << "] += " << val(a.node) << ";\n";
+    }
+    os << "}\n";
+  }
+
+  void mma_block(const TargetInfo& T, size_t t, const MmaPlan& pl, unsigned long long n_full) {
+    const int pitch = opt.pitch(t), NP = (int)pl.params.size(), KS = pl.KS, DT = pl.DT, NO = (int)pl.other_slots.size();
+    const unsigned long long base = (unsigned long long)opt.target_base[t], td = (unsigned long long)T.n_cols * pitch;
+    os << "    if (tma.on) {  // chain-batched DMMA over the CTA's 8 chains: warp w <-> dot w (see Emitter::mma_block)\n"
+       << "      const int wid = (int)(threadIdx.x >> 5), ln = (int)(threadIdx.x & 31), mc = ln >> 2, mk = ln & 3;\n";
+    if (!mma_inv.empty()) {
+      os << "      if (ln == 0) {\n";
+      for (size_t k = 0; k < mma_inv.size(); k++) os << "        scr[" << (mma_inv_off + (int)k) << "] = " << val(mma_inv[k]) << ";\n";
+      os << "      }\n";
+    }
+    os << "      rn_cta_bar(tma.nthreads);  // every chain's q (and invariants) are in its slice\n"
+       << "      const double* qo = q + (mc - wid) * RN_WPC_SMEM_DOUBLES;\n"
+       << "      const double* xo = scr + (mc - wid) * RN_WPC_SMEM_DOUBLES + " << mma_inv_off << ";\n"
+       << "      (void)xo;\n"
+       << "      double ar[" << KS << "];\n";
+    for (int ks = 0; ks < KS; ks++) {
+      // term ks*4 + mk: parameter index by lane
+      os << "      ar[" << ks << "] = ";
+      std::string e = "0.0";
+      for (int k = 3; k >= 0; k--) {
+        const int term = ks * 4 + k;
+        const std::string v = term < NP ? "qo[" + std::to_string(pl.params[term]) + "]" : "0.0";
+        e = k == 3 ? v : "(mk == " + std::to_string(k) + " ? " + v + " : " + e + ")";
+      }
+      os << e << ";\n";
+    }
+    os << "      double g[" << DT << "][2];\n      for (int i = 0; i < " << DT << "; i++) g[i][0] = g[i][1] = 0.0;\n"
+       << "      double dsum = 0.0, osum[" << std::max(1, NO) << "];\n      for (int i = 0; i < " << std::max(1, NO) << "; i++) osum[i] = 0.0;\n"
+       << "      double* const region = tma.stage + (size_t)wid * " << pl.region_doubles << ";\n"
+       << "      unsigned long long* const bar = tma.full + wid;\n"
+       << "      const double* RN_RESTRICT src = data + " << base << "ULL;\n";
+    for (size_t di = 0; di < pl.dots.size(); di++) {
+      const MmaDot& d = pl.dots[di];
+      const unsigned bytes = (unsigned)((d.cmax - d.cmin + 1) * pitch * 8);
+      // the B-operand addresses: per lane a base (term by lane, row slot by lane) plus compile-time offsets when the dot's
+      // columns are an arithmetic progression (the Translator folds a Vec.dot in column order); else per-lane offset tables
+      bool ap = true;
+      const int step = d.cols.size() > 1 ? d.cols[1] - d.cols[0] : 1;
+      for (size_t k = 1; k < d.cols.size(); k++)
+        if (d.cols[k] - d.cols[k - 1] != step) ap = false;
+      auto off = [&](int term) { return (d.cols[term < NP ? term : 0] - d.cmin) * pitch; };
+      auto by_lane = [&](const char* lane, int n, std::function<std::string(int)> f) {  // nested select over lane index 0..n-1
+        std::string e;
+        for (int k = n - 1; k >= 0; k--) e = k == n - 1 ? f(k) : "(" + std::string(lane) + " == " + std::to_string(k) + " ? " + f(k) + " : " + e + ")";
+        return e;
+      };
+      os << "      if (wid == " << (di % MMA_WARPS) << ") {  // dot " << di << ": columns " << d.cmin << ".." << d.cmax << " of the tile\n"
+         << "        const double* RN_RESTRICT s0 = src + " << (unsigned long long)d.cmin * pitch << "ULL;\n"
+         << "        if (ln == 0) rn_tma_load_raw(region, bar, s0, " << bytes << "u);\n";
+      // forward: B[k = mk][n = mc] = X[col(term ks*4+mk)][row slot mc]
+      os << "        const int pf = mc ^ ((mc >> 2) & 1), pb0 = (2 * mk) ^ ((mk >> 1) & 1), pb1 = (2 * mk + 1) ^ ((mk >> 1) & 1);\n";
+      if (ap) {
+        os << "        const RnSA bf = rn_sa(region + pf + (" << (d.cols[0] - d.cmin) << " + " << step << " * mk) * " << pitch << ");\n"
+           << "        const RnSA bb0 = rn_sa(region + pb0 + (" << (d.cols[0] - d.cmin) << " + " << step << " * mc) * " << pitch << ");\n"
+           << "        const RnSA bb1 = rn_sa(region + pb1 + (" << (d.cols[0] - d.cmin) << " + " << step << " * mc) * " << pitch << ");\n";
+      } else {
+        os << "        int fo[" << KS << "], bo[" << DT << "];\n";
+        for (int ks = 0; ks < KS; ks++)
+          os << "        fo[" << ks << "] = " << by_lane("mk", 4, [&](int k) { return std::to_string(off(ks * 4 + k)); }) << ";\n";
+        for (int dt = 0; dt < DT; dt++)
+          os << "        bo[" << dt << "] = " << by_lane("mc", 8, [&](int k) { return std::to_string(off(dt * 8 + k)); }) << ";\n";
+        os << "        const RnSA bf = rn_sa(region + pf), bb0 = rn_sa(region + pb0), bb1 = rn_sa(region + pb1);\n";
+      }
+      // padded terms (beyond the " << NP << " of the dot) multiply an operand of exact zeros; their B address must still be a
+      // finite number of the tile: the last group falls back to term 0's column
+      auto fwd_addr = [&](int ks) -> std::string {
+        if (!ap) return "fo[" + std::to_string(ks) + "]";
+        const int first = ks * 4;
+        if (first + 3 < NP) return std::to_string(4 * step * ks * pitch);
+        return "(mk < " + std::to_string(NP - first) + " ? " + std::to_string(4 * step * ks * pitch) + " : " + std::to_string(off(0)) + " - (" +
+               std::to_string(d.cols[0] - d.cmin) + " + " + std::to_string(step) + " * mk) * " + std::to_string(pitch) + ")";
+      };
+      auto bwd_addr = [&](int dt) -> std::string {
+        if (!ap) return "bo[" + std::to_string(dt) + "]";
+        const int first = dt * 8;
+        if (first + 7 < NP) return std::to_string(8 * step * dt * pitch);
+        return "(mc < " + std::to_string(NP - first) + " ? " + std::to_string(8 * step * dt * pitch) + " : " + std::to_string(off(0)) + " - (" +
+               std::to_string(d.cols[0] - d.cmin) + " + " + std::to_string(step) + " * mc) * " + std::to_string(pitch) + ")";
+      };
+      os << "        for (unsigned tile = 0; tile < " << n_full << "u; tile++) {\n"
+         << "          rn_mbar_wait_warp(bar, tma.seq & 1u);\n          tma.seq += 1;\n"
+         << "          double z[4][2], wv[4][2];\n"
+         << "          RN_UNROLL\n          for (int nt = 0; nt < 4; nt++) {\n"
+         << "            z[nt][0] = z[nt][1] = 0.0;\n";
+      for (int ks = 0; ks < KS; ks++) os << "            rn_dmma(z[nt][0], z[nt][1], ar[" << ks << "], rn_lds(bf, nt * 8 + " << fwd_addr(ks) << "));\n";
+      os << "          }\n"
+         << "          RN_UNROLL\n          for (int nt = 0; nt < 4; nt++) {\n"
+         << "            rn_mma_e" << t << "_" << di << "(z[nt][0], rn_sa(region + nt * 8 + pb0), qo, xo, dsum, wv[nt][0], osum, err);\n"
+         << "            rn_mma_e" << t << "_" << di << "(z[nt][1], rn_sa(region + nt * 8 + pb1), qo, xo, dsum, wv[nt][1], osum, err);\n"
+         << "          }\n"
+         << "          RN_UNROLL\n          for (int nt = 0; nt < 4; nt++) {\n";
+      for (int dt = 0; dt < DT; dt++)
+        os << "            rn_dmma(g[" << dt << "][0], g[" << dt << "][1], wv[nt][0], rn_lds(bb0, nt * 8 + " << bwd_addr(dt) << "));\n"
+           << "            rn_dmma(g[" << dt << "][0], g[" << dt << "][1], wv[nt][1], rn_lds(bb1, nt * 8 + " << bwd_addr(dt) << "));\n";
+      os << "          }\n"
+         << "          __syncwarp();\n"
+         << "          if (ln == 0 && tile + 1 < " << n_full << "u) rn_tma_load_raw(region, bar, s0 + (size_t)(tile + 1) * " << td << "ULL, " << bytes << "u);\n"
+         << "        }\n      }\n";
+    }
+    // per-warp partials -> CTA scratch [warp][chain][redw]; chain wid's warp totals them in warp order
+    const int NPAD = DT * 8;
+    os << "      double* const red = tma.stage + (size_t)" << MMA_WARPS << " * " << pl.region_doubles << ";\n"
+       << "      double* const mine = red + (size_t)(wid * 8 + mc) * " << pl.redw << ";\n";
+    for (int dt = 0; dt < DT; dt++)
+      os << "      mine[" << dt * 8 << " + 2 * mk] = g[" << dt << "][0];\n      mine[" << dt * 8 << " + 2 * mk + 1] = g[" << dt << "][1];\n";
+    os << "      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);\n      dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);\n"
+       << "      if (mk == 0) mine[" << NPAD << "] = dsum;\n";
+    for (int k = 0; k < NO; k++)
+      os << "      osum[" << k << "] += __shfl_xor_sync(0xffffffffu, osum[" << k << "], 1);\n      osum[" << k
+         << "] += __shfl_xor_sync(0xffffffffu, osum[" << k << "], 2);\n      if (mk == 0) mine[" << NPAD + 1 + k << "] = osum[" << k << "];\n";
+    os << "      rn_cta_bar(tma.nthreads);\n"
+       << "      double* const tot = red + (size_t)(wid * 8 + wid) * " << pl.redw << ";  // (read by this warp only)\n"
+       << "      for (int j = ln; j < " << pl.redw << "; j += 32) {\n"
+       << "        double s = 0.0;\n"
+       << "        for (int w8 = 0; w8 < " << std::min<int>(MMA_WARPS, (int)pl.dots.size()) << "; w8++) s += red[(size_t)(w8 * 8 + wid) * " << pl.redw << " + j];\n"
+       << "        tot[j] = s;\n      }\n"
+       << "      __syncwarp();\n"
+       << "      if (ln == 0) {\n"
+       << "        " << acc_ref(0) << " += tot[" << NPAD << "];\n";
+    for (int k = 0; k < NP; k++) os << "        " << acc_ref(pl.param_slot[k]) << " += tot[" << k << "];\n";
+    for (int k = 0; k < NO; k++) os << "        " << acc_ref(pl.other_slots[k]) << " += tot[" << NPAD + 1 + k << "];\n";
+    os << "      }\n"
+       << "      row0 += " << n_full * 32ull << "LL;\n"
+       << "    }\n";
+  }
+
   void density_wpc() {
     wpc = true;
     // which accumulator slots live in shared memory (targets of a scatter) and which in registers
@@ -449,18 +846,39 @@ struct Emitter {
     os << "// ---- emitted: log-density and gradient of the frozen DAG (" << (P.symbolic ? "symbolic" : "adjoint")
        << " gradient), warp-per-chain: rows across lanes ----\n";
     const int K = std::max(1, opt.wpc_k);
+    // chain-batched DMMA plans (analysis always; code only with opt.mma)
+    plans.assign(P.targets.size(), MmaPlan());
+    mma_all_ok = K == 1;
+    bool any_full = false;
+    for (size_t t = 0; t < P.targets.size(); t++) {
+      const TargetInfo& T = P.targets[t];
+      if (!T.streamed() || T.n_rows / 32 == 0) continue;
+      any_full = true;
+      plans[t] = plan_mma(T, t);
+      if (!plans[t].ok) mma_all_ok = false;
+      mma_shared_doubles = std::max(mma_shared_doubles, MMA_WARPS * plans[t].region_doubles + MMA_WARPS * 8 * plans[t].redw);
+    }
+    if (!any_full) mma_all_ok = false;
+    if (!mma_all_ok) mma_shared_doubles = 0;
+    const bool use_mma = opt.mma && mma_all_ok;
     int n_reg_acc = 0;
     for (int sl = 0; sl < P.n_slots; sl++)
       if (smem_slot[sl] < 0) n_reg_acc++;
     // cross-warp reduction scratch of the chain's group (K warps): [warp][register accumulators..., err]
     red_off = tab_doubles + n_smem_acc;
     red_doubles = K > 1 ? K * (n_reg_acc + 1) : 0;
-    os << "#define RN_WPC_SCRATCH " << (tab_doubles + n_smem_acc + red_doubles) << "\n";
+    mma_inv_off = tab_doubles + n_smem_acc + red_doubles;
+    os << "#define RN_WPC_SCRATCH " << (tab_doubles + n_smem_acc + red_doubles + (use_mma ? (int)mma_inv.size() : 0)) << "\n";
+    os << "#define RN_MMA_BARS " << (use_mma ? MMA_WARPS : 0) << "\n";
     os << "#define RN_WPC_RED_OFF " << red_off << "\n";
     os << "RN_DEVICE double rn_tab_lookup(const double* tab, int len, int low, double idx, int& err) {\n"
           "  const int k = rn_d2i(idx) - low;\n  if (k < 0 || k >= len) { err |= 1; return RN_NAN; }\n  return tab[k];\n}\n";
     os << "RN_DEVICE double rn_warp_sum(double x) {\n  RN_UNROLL\n  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);\n  return x;\n}\n";
     lookup_helpers();
+    if (use_mma)
+      for (size_t t = 0; t < P.targets.size(); t++)
+        if (plans[t].ok)
+          for (size_t di = 0; di < plans[t].dots.size(); di++) mma_helper(P.targets[t], t, plans[t], di);
     os << "RN_DEVICE void rn_density(const double* q, double& dens, double* grad, double* scr, "
           "const double* RN_RESTRICT data, int& err, RnTma& tma) {\n";
     os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x % RN_G);  // thread of the chain's group\n  (void)lane;\n";
@@ -477,11 +895,14 @@ struct Emitter {
       const TargetInfo& T = P.targets[t];
       os << "  // target " << t << (T.streamed() ? " (streamed, rows across the group's threads)" : " (data-free)") << "\n";
       if (T.streamed()) {
-        const unsigned long long base = (unsigned long long)opt.target_base[t], td = (unsigned long long)T.n_cols * 32;
+        const int pitch = opt.pitch(t);
+        const unsigned long long base = (unsigned long long)opt.target_base[t], td = (unsigned long long)T.n_cols * pitch;
         const unsigned long long rows_per_tile = 32ull * K;  // a "super-tile": K consecutive 32-row tiles, one per warp
         const unsigned long long n_full = T.n_rows / rows_per_tile;
         os << "  {\n    long long row0 = lane;\n";
-        if (opt.tma_stages > 0 && n_full > 0) {
+        if (use_mma && n_full > 0) {
+          mma_block(T, t, plans[t], n_full);
+        } else if (opt.tma_stages > 0 && n_full > 0) {
           // CTA lockstep over full tiles: tile t+S-1 in flight (one bulk copy) while all warps consume tile t from smem
           os << "    if (tma.on) {\n"
              << "      const unsigned n_full = " << n_full << "u, seq0 = tma.seq;\n"
@@ -498,7 +919,7 @@ struct Emitter {
              << "        const double* rp = tma.stage + (size_t)(seq % RN_TMA_STAGES) * RN_TMA_TILE_DOUBLES + (size_t)(lane >> 5) * " << td
              << " + (lane & 31);\n";
           row_body(
-              T, "        ", [&](int k) { return "rp[" + std::to_string(local_col(T, k) * 32) + "]"; },
+              T, "        ", [&](int k) { return "rp[" + std::to_string(local_col(T, k) * pitch) + "]"; },
               [&](int slot) { return acc_ref(slot); }, true, tab_doubles);
           os << "        rn_cta_bar(tma.nthreads);\n"
              << "      }\n"
@@ -509,7 +930,7 @@ struct Emitter {
         os << "    for (long long row = row0; row < " << (long long)T.n_rows << "LL; row += RN_G) {\n";
         os << "      const double* RN_RESTRICT rp = data + " << base << "ULL + (row >> 5) * " << td << "LL + (row & 31);\n";
         row_body(
-            T, "      ", [&](int k) { return "RN_LDG(rp + " + std::to_string(local_col(T, k) * 32) + ")"; },
+            T, "      ", [&](int k) { return "RN_LDG(rp + " + std::to_string(local_col(T, k) * pitch) + ")"; },
             [&](int slot) { return acc_ref(slot); }, true, tab_doubles);
         os << "    }\n  }\n";
       } else {
@@ -568,11 +989,21 @@ WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
   Emitter E(P, opt);
   E.density_wpc();
   // chain vectors (q, p, gradient, mass [+ EHMC snapshot]) [+ 2 scratch vectors of the dense mass matrix code] + density scratch
-  z.per_warp_doubles = ((opt.enable_ehmc ? 7 : 4) + (opt.mass_max == 2 ? 2 : 0)) * (int)P.n_params + E.tab_doubles + E.n_smem_acc + E.red_doubles;
+  z.per_warp_doubles = ((opt.enable_ehmc ? 7 : 4) + (opt.mass_max == 2 ? 2 : 0)) * (int)P.n_params + E.tab_doubles + E.n_smem_acc + E.red_doubles +
+                       ((opt.mma && E.mma_all_ok) ? (int)E.mma_inv.size() : 0);
   for (const TargetInfo& T : P.targets)
     if (T.streamed() && T.n_rows >= 32ull * (uint64_t)std::max(1, opt.wpc_k))
-      z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * 32 * std::max(1, opt.wpc_k));
+      z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * opt.pitch((size_t)(&T - &P.targets[0])) * std::max(1, opt.wpc_k));
+  z.mma_ok = E.mma_all_ok;
+  z.mma_shared_doubles = E.mma_shared_doubles;
   return z;
+}
+
+std::vector<int> default_pitches(const Program& P) {
+  std::vector<int> p(P.targets.size(), 32);
+  for (size_t t = 0; t < P.targets.size(); t++)
+    if (P.targets[t].streamed() && !P.targets[t].dots.empty() && P.targets[t].n_rows >= 64) p[t] = 36;
+  return p;
 }
 
 std::string emit_optimizer_source(const Program& P, const EmitOptions& opt, int history) {
@@ -624,12 +1055,16 @@ std::string emit_source(const Program& P, const EmitOptions& opt) {
   if (opt.backend == 1) {
     os << "#define RN_WPC_K " << std::max(1, opt.wpc_k) << "\n";
     os << "#define RN_TMA_STAGES " << opt.tma_stages << "\n";
-    os << "#define RN_TMA_TILE_DOUBLES " << wpc_sizes(P, opt).tile_doubles << "\n";
+    {
+      const WpcSizes z = wpc_sizes(P, opt);
+      os << "#define RN_TMA_TILE_DOUBLES " << ((opt.mma && z.mma_ok) ? z.mma_shared_doubles : z.tile_doubles) << "\n";
+    }
   }
   os << kPreludeSource << "\n";
+  if (opt.backend == 1)  // (RN_WPC_SCRATCH is defined by the emitted density; macros expand where they are used)
+    os << "#define RN_WPC_SMEM_DOUBLES (" << ((opt.enable_ehmc ? 7 : 4) + (opt.mass_max == 2 ? 2 : 0)) << " * RN_N + RN_WPC_SCRATCH)\n";
   os << emit_density(P, opt) << "\n";
   if (opt.backend == 1) {
-    os << "#define RN_WPC_SMEM_DOUBLES (" << ((opt.enable_ehmc ? 7 : 4) + (opt.mass_max == 2 ? 2 : 0)) << " * RN_N + RN_WPC_SCRATCH)\n";
     os << kSamplerWpcSource << "\n";
   } else {
     os << kSamplerSource << "\n";

@@ -15,8 +15,15 @@ struct EmitOptions {
   bool enable_ehmc = false;
   int tma_stages = 0;     // warp per chain: shared-memory stages of the CTA-shared data-tile pipeline (0 = off)
   int wpc_k = 1;          // warp per chain: warps owning one chain (1, 2, 4 or 8; > 1 for chains with a large state)
-  std::vector<uint64_t> target_base;  // per target: element offset of its tile-major [tile][column][32] block in the data buffer
+  std::vector<uint64_t> target_base;  // per target: element offset of its tile-major [tile][column][pitch] block in the data buffer
+  std::vector<int> target_pitch;      // per target: doubles between consecutive columns of a tile (32 rows + padding; empty = 32).
+                                      // 36 where the chain-batched DMMA path may run: X^T fragments are then bank-conflict free
+  bool mma = false;       // warp per chain: chain-batched fp64 tensor-core contraction of the row bodies' dot products (see
+                          // Emitter::mma_block); needs 8 chains (= 8 warps, wpc_k == 1) per CTA
+  int pitch(size_t t) const { return t < target_pitch.size() && target_pitch[t] > 0 ? target_pitch[t] : 32; }
 };
+// pitch a model should be packed with: 36 for streamed targets whose row body holds parameter x column dot products
+std::vector<int> default_pitches(const Program& P);
 
 // the generated rn_density() only
 std::string emit_density(const Program& P, const EmitOptions& opt);
@@ -33,6 +40,8 @@ std::string emit_optimizer_source(const Program& P, const EmitOptions& opt, int 
 struct WpcSizes {
   int per_warp_doubles = 0;  // per CHAIN (its wpc_k warps share the slice)
   int tile_doubles = 0;
+  bool mma_ok = false;       // every streamed target with full tiles can take the chain-batched DMMA path
+  int mma_shared_doubles = 0;  // CTA-shared doubles of that path: 8 per-warp column-block regions + the reduction scratch
 };
 WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt);
 

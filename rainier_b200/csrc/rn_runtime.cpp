@@ -170,12 +170,13 @@ struct Kernel {
   int wpc_k = 1;
   int tma_stages = 0;         // CTA-shared data-tile pipeline (backend 1): stages, doubles per stage
   int tile_doubles = 0;
+  bool mma = false;           // backend 1: chain-batched DMMA path compiled in (8 chains per CTA; tile_doubles = its shared doubles)
   // backend 0: bytes of dynamic shared memory per THREAD (rn_sampler.cuh: momentum, diagonal mass, EHMC snapshot momentum,
   // Stats counters live there instead of in registers) -- must mirror RN_TS_DOUBLES / RN_TS_INTS
   unsigned tpc_smem_per_thread = 0;
   unsigned smem_bytes() const {  // dynamic shared memory of one CTA: per-warp slices | 128B pad | stages | mbarriers
     size_t d = (size_t)warps_per_cta * wpc_smem_doubles;
-    if (tma_stages > 0) d = ((d + 15) & ~(size_t)15) + (size_t)tma_stages * tile_doubles + (size_t)tma_stages;
+    if (tma_stages > 0) d = ((d + 15) & ~(size_t)15) + (size_t)tma_stages * tile_doubles + (size_t)(mma ? 8 : tma_stages);
     return (unsigned)(d * 8);
   }
 };
@@ -188,6 +189,7 @@ struct rn_model {
   CUcontext ctx = nullptr;
   CUdeviceptr d_data = 0;
   std::vector<uint64_t> target_base;  // per target: element offset of its tile-major block in the data buffer
+  std::vector<int> target_pitch;      // per target: doubles between the columns of a tile (32, or 36 where the DMMA path may run)
   uint64_t data_doubles = 0;
   std::map<std::pair<bool, bool>, std::unique_ptr<Program>> programs;  // (adjoint, fast)
   std::map<KernelKey, std::unique_ptr<Kernel>> kernels;
@@ -286,6 +288,7 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
   eo.mass_max = key.mass_max;
   eo.enable_ehmc = key.ehmc;
   eo.target_base = m->target_base;
+  eo.target_pitch = m->target_pitch;
   if (eo.backend == 1 && P->symbolic && P->n_params > 96)
     return fail(RN_E_UNSUPPORTED, "warp-per-chain with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
   K->backend = eo.backend;
@@ -334,6 +337,25 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
     const size_t left = cap - (size_t)stages * tile - (stages ? 256 : 0);
     K->warps_per_cta = (int)std::max<size_t>(1, std::min<size_t>((size_t)wmax, left / std::max<size_t>(per_warp, 1)));
     eo.tma_stages = stages;
+    // chain-batched fp64 tensor-core path (rn_emit.cpp: Emitter::mma_block): HMC (every chain of a CTA evaluates the density
+    // equally often), not the dense-mass code, one warp per chain, 8 chains per CTA, and every streamed target eligible
+    bool want_mma = !key.ehmc && key.mass_max < 2 && eo.wpc_k == 1 && z.mma_ok && !P->symbolic;
+    if (const char* e = getenv("RN_MMA")) want_mma = want_mma && atoi(e) != 0;
+    if (want_mma) {
+      EmitOptions em = eo;
+      em.mma = true;
+      em.tma_stages = 1;
+      const WpcSizes zm = wpc_sizes(*P, em);
+      const size_t need = 8 * (size_t)zm.per_warp_doubles * 8 + 128 + (size_t)zm.mma_shared_doubles * 8 + 64;
+      if (zm.mma_ok && need <= cap) {
+        eo = em;
+        K->mma = true;
+        K->wpc_smem_doubles = zm.per_warp_doubles;
+        K->tile_doubles = zm.mma_shared_doubles;
+        K->tma_stages = 1;
+        K->warps_per_cta = 8;
+      }
+    }
   }
   K->source = emit_source(*P, eo);
   if (source_only) {
@@ -474,27 +496,30 @@ static int load_kernel(const Api* A, rn_model* m, Kernel* K) {
 // plain load of (column j, row r) is base + (r>>5)*n_cols*32 + j*32 + (r&31) -- still 256-byte coalesced across a warp.
 // (The reference keeps one JVM array per column, ir/DataFunction.scala:13-30, and gathers per row.)
 // ---------------------------------------------------------------------------------------------------------
-static uint64_t data_layout(const Program& P, std::vector<uint64_t>& target_base) {
+static uint64_t data_layout(const Program& P, std::vector<uint64_t>& target_base, std::vector<int>& target_pitch) {
   uint64_t off = 0;
   target_base.assign(P.targets.size(), 0);
+  target_pitch = default_pitches(P);
+  if (getenv("RN_PITCH32")) target_pitch.assign(P.targets.size(), 32);
   for (size_t t = 0; t < P.targets.size(); t++) {
     const TargetInfo& T = P.targets[t];
     if (!T.streamed()) continue;
     target_base[t] = off;
     const uint64_t tiles = (T.n_rows + 31) / 32;
-    off += tiles * (uint64_t)T.n_cols * 32;
+    off += tiles * (uint64_t)T.n_cols * (uint64_t)target_pitch[t];
     off = (off + 15) & ~15ull;
   }
   return off;
 }
-static void pack_columns(const Program& P, const std::vector<uint64_t>& target_base, const double* const* cols, double* image) {
+static void pack_columns(const Program& P, const std::vector<uint64_t>& target_base, const std::vector<int>& target_pitch,
+                         const double* const* cols, double* image) {
   for (size_t t = 0; t < P.targets.size(); t++) {
     const TargetInfo& T = P.targets[t];
     if (!T.streamed()) continue;
-    const uint64_t td = (uint64_t)T.n_cols * 32;
+    const uint64_t pitch = (uint64_t)target_pitch[t], td = (uint64_t)T.n_cols * pitch;
     for (uint32_t j = 0; j < T.n_cols; j++) {
       const double* src = cols[T.first_input - P.n_params + j];
-      double* dst = image + target_base[t] + (uint64_t)j * 32;
+      double* dst = image + target_base[t] + (uint64_t)j * pitch;
       for (uint64_t r = 0; r < T.n_rows; r++) dst[(r >> 5) * td + (r & 31)] = src[r];
     }
   }
@@ -575,7 +600,7 @@ int rn_model_create(const void* rir, size_t len, const double* const* cols, cons
     for (uint32_t j = 0; j < T.n_cols; j++)
       if ((uint64_t)col_rows[T.first_input - h.n_params + j] != T.n_rows)
         return fail(RN_E_INVALID, "column length does not match its target's row count");
-  m->data_doubles = data_layout(*P, m->target_base);
+  m->data_doubles = data_layout(*P, m->target_base, m->target_pitch);
   m->device = device;
   if (device >= 0) {
     std::string why;
@@ -589,7 +614,7 @@ int rn_model_create(const void* rir, size_t len, const double* const* cols, cons
     CU(A->cuCtxSetCurrent(m->ctx));
     if (m->data_doubles > 0) {
       std::vector<double> image(m->data_doubles, 0.0);
-      pack_columns(*P, m->target_base, cols, image.data());
+      pack_columns(*P, m->target_base, m->target_pitch, cols, image.data());
       CU(A->cuMemAlloc(&m->d_data, m->data_doubles * 8));
       CU(A->cuMemcpyHtoD(m->d_data, image.data(), m->data_doubles * 8));
     }
@@ -608,7 +633,7 @@ int rn_model_pack_columns(const rn_model* m, const double* const* cols, double* 
   auto it = m->programs.begin();
   if (it == m->programs.end()) return fail(RN_E_INVALID, "model has no program");
   std::memset(image, 0, (size_t)m->data_doubles * 8);
-  pack_columns(*it->second, m->target_base, cols, image);
+  pack_columns(*it->second, m->target_base, m->target_pitch, cols, image);
   return RN_OK;
 }
 
@@ -1186,6 +1211,7 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.n_iter = k;
     a.adaptation = s->cfg.adaptation == RN_ADAPT_POOLED ? 1 : 0;
     a.tma = s->K->tma_stages > 0 ? 1 : 0;
+    if (s->K->mma && ((chain_begin % 8) != 0 || ((chain_end - chain_begin) % 8) != 0)) a.tma = 0;  // the DMMA path wants full CTAs of 8 chains
     a.chain_begin = chain_begin;
     a.chain_end = chain_end;
     a.mass_kind = s->mass_kind;
@@ -2315,6 +2341,7 @@ static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::O
   eo.backend = backend;
   eo.fast_math = fast;
   eo.target_base = m->target_base;
+  eo.target_pitch = m->target_pitch;
   const uint64_t lb_w = (uint64_t)P->n_params * (2 * (uint64_t)history + 1) + 2 * (uint64_t)history;
   if (backend == 0) {
     // the whole optimisation state of a start is thread-local: x, g, diag and the 2m-vector history

@@ -344,7 +344,8 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
   const bool lockstep = (A.sampler == 0) && (A.tma != 0);  // HMC: every chain calls the density equally often
   if (lockstep) {
     if (threadIdx.x == 0) {
-      for (int s = 0; s < RN_TMA_STAGES; s++) rn_mbar_init(&bars[s], 1);
+      // RN_TMA_STAGES barriers of the CTA-shared tile pipeline, or one per warp of the chain-batched DMMA path
+      for (int s = 0; s < (RN_MMA_BARS > RN_TMA_STAGES ? RN_MMA_BARS : RN_TMA_STAGES); s++) rn_mbar_init(&bars[s], 1);
 #ifndef RN_HOST_EMULATION
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
