@@ -15,13 +15,13 @@ def rel_err(a, b, floor=1e-12):
     return float(np.nanmax(d)) if d.size else 0.0
 
 
-def run_both(rir, cols, config, seeds=None, rng_states=None, rir_gpu=None, device=0):
+def run_both(rir, cols, config, seeds=None, rng_states=None, rir_gpu=None, device=0, cols_gpu=None):
     """returns dict with gpu/oracle samples [chains][iters][n], traces [chains][iters_total][4], stats, mass"""
     cfg, keep = api.lower_config(config)
     dense = cfg.mass_tuner == 2 or (cfg.mass_tuner == 3 and cfg.static_matrix == 2)
     om = OracleModel(rir, cols)
     ref = om.sample(cfg, seeds=seeds, rng_states=rng_states, trace=True, dense_mass=dense)
-    gm = api.CudaModel(rir_gpu if rir_gpu is not None else rir, cols, device=device)
+    gm = api.CudaModel(rir_gpu if rir_gpu is not None else rir, cols_gpu if cols_gpu is not None else cols, device=device)
     s = api.CudaSampler(gm, config, seeds=seeds, rng_states=rng_states, trace=True)
     import torch
 

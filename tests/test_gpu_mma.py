@@ -33,7 +33,7 @@ def test_dmma_path_matches_the_oracle(name):
     cfg = _cfg(12, 0, api.HMCSampler(4), api.StaticStepSize(eps))
     src = api.CudaModel(prir, pcols, device=-1).emit_source(cfg)
     assert "rn_dmma(z" in src and "#define RN_MMA_BARS 8" in src, "the model should take the DMMA path"
-    r = parity.run_both(rir, cols, cfg, seeds=np.arange(64) + 3, rir_gpu=prir)
+    r = parity.run_both(rir, cols, cfg, seeds=np.arange(64) + 3, rir_gpu=prir, cols_gpu=pcols)
     parity.assert_parity(r, tol=1e-9, check_mass=False)
 
 
@@ -63,7 +63,7 @@ def test_dmma_with_adaptation_short_horizon():
     rir, cols = model.compile(True)
     prir, pcols = model.compile(False)
     cfg = _cfg(0, 10, api.HMCSampler(3), api.DualAvgTuner(0.8), api.DiagonalMassMatrixTuner(4, 1.5, 2, 2))
-    r = parity.run_both(rir, cols, cfg, seeds=np.arange(32) + 5, rir_gpu=prir)
+    r = parity.run_both(rir, cols, cfg, seeds=np.arange(32) + 5, rir_gpu=prir, cols_gpu=pcols)
     gt, rt = r["gpu_trace"], r["ref_trace"]
     assert np.array_equal(gt[:, :, 1], rt[:, :, 1]) and np.array_equal(gt[:, :, 3], rt[:, :, 3])
     assert parity.rel_err(gt[:, :, 2], rt[:, :, 2]) < 1e-6
