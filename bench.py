@@ -204,6 +204,148 @@ def cpu_baseline_leg():
                 chains, cfg.iterations, N_STEPS, dt)}
 
 
+
+def _load_npz_model(name):
+    """RIR + columns of a BASELINE configuration from build/models/<name>.npz -- written by __graft_entry__.build() with the
+    Python stand-in of the reference's Scala front end (the product side of the bench never imports oracle/)."""
+    f = os.path.join(ROOT, "build", "models", name + ".npz")
+    if not os.path.exists(f):
+        return None
+    z = np.load(f)
+    return z["rir"].tobytes(), [z["c%d" % i] for i in range(int(z["ncols"]))]
+
+
+def extra_configs(args, torch, dist, api, abi, rank, local_rank, world):
+    """BASELINE.json configs[2..4] next to the headline (device-resident, device-timed, max over ranks):
+      cfg3  logistic regression 50 x 100k, 2048 chains on ONE GPU (each rank runs the full config; value = one rank's rate)
+      cfg4  eight schools, DefaultConfig (EHMC + DualAvg + diagonal mass), 8192 chains SHARDED over the ranks, warmup with
+            the pooled mass-matrix statistics all-reduced over NCCL through the product's own communicator (rn_comm)
+      cfg5  Poisson GLM 1000 groups / 1M rows, 4096 chains SHARDED over the ranks (strong scaling)"""
+    out = {}
+    dev = torch.device("cuda", local_rank)
+
+    def device_rate(model, cfg, chains, iters, reps, seed0):
+        s = api.CudaSampler(model, cfg, seeds=np.arange(chains, dtype=np.int64) + seed0)
+        s.warmup(-1)
+        stream = torch.cuda.ExternalStream(s.stream, device=dev)
+        s.run(iters)
+        s.sync()
+        st0 = sum(x.leapfrogSteps for x in s.stats()[0])
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            s.run(iters)
+        e1.record(stream)
+        s.sync()
+        torch.cuda.synchronize()
+        stats = s.stats()[0]
+        steps = float(sum(x.leapfrogSteps for x in stats) - st0)
+        acc = float(np.mean([x.accepted / max(1, x.iterations) for x in stats]))
+        s.close()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+        n = torch.tensor([steps, acc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        return float(n[0]) / float(t[0]), float(t[0]), float(n[1]) / world
+
+    def static(eps, iters):
+        return api.make_config(iterations=iters, warmupIterations=0, sampler=api.HMCSampler(N_STEPS), stepSizeTuner=api.StaticStepSize(eps),
+                               massMatrixTuner=api.IdentityMassMatrixTuner(), launchIterations=iters)
+
+    # ---- cfg4: the one collective of the design ----
+    try:
+        rir = open(os.path.join(ROOT, "rainier_b200", "models", "eight_schools.rir"), "rb").read()
+        model = api.CudaModel(rir, [], device=local_rank)
+        total = 8192
+        per = total // world
+        seeds = np.arange(total, dtype=np.int64)[rank * per:(rank + 1) * per] + 1
+        comm = api.Comm.from_torch_distributed(local_rank) if world > 1 else None
+        res = {}
+        for mode in ("pooled", "per_chain"):
+            cfg = api.SamplerConfig(iterations=500, warmupIterations=500, adaptation=abi.RN_ADAPT_POOLED if mode == "pooled" else 0)
+            s = api.CudaSampler(model, cfg, seeds=seeds)
+            if mode == "pooled" and comm is not None:
+                s.set_comm(comm)
+            stream = torch.cuda.ExternalStream(s.stream, device=dev)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record(stream)
+            s.warmup(-1)
+            ev[1].record(stream)
+            s.run(500)
+            ev[2].record(stream)
+            s.sync()
+            torch.cuda.synchronize()
+            st, mass = s.stats()
+            calls, us = s.comm_stats()
+            steps = float(sum(x.leapfrogSteps for x in st))
+            t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), us], dtype=torch.float64, device=dev)
+            n = torch.tensor([steps], dtype=torch.float64, device=dev)
+            same = torch.tensor(np.asarray(mass[0], dtype=np.float64), device=dev)
+            lo, hi = same.clone(), same.clone()
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(n, op=dist.ReduceOp.SUM)
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            res[mode] = {"warmup_ms": float(t[0]), "sampling_ms": float(t[1]), "sampling_steps_x_chains_per_s": float(n[0]) / (float(t[1]) * 1e-3),
+                         "allreduce_calls": calls, "allreduce_us_total": float(t[2]),
+                         "mass_matrix_identical_on_all_ranks": bool(torch.equal(lo, hi)) if mode == "pooled" else None}
+            s.close()
+        if comm is not None:
+            comm.close()
+        model.close()
+        out["cfg4_eight_schools_8192_chains"] = dict(res, chains_total=total, chains_per_gpu=per, scaling="strong",
+                                                     config="DefaultConfig: EHMC(1024) + DualAvg(0.8) + DiagonalMassMatrixTuner; 500 warmup + 500 sampling iterations",
+                                                     collective="ncclAllReduce(sum, f64, 2n+1 = 21 doubles) per mass-matrix window through rn_comm (NCCL over NVLink)")
+    except Exception as e:  # a side measurement must not take the headline down
+        out["cfg4_eight_schools_8192_chains"] = {"error": str(e)[:300]}
+
+    # ---- cfg5: 4096 chains sharded ----
+    try:
+        mm = _load_npz_model("cfg5_primal")
+        if mm is None:
+            out["cfg5_poisson_glm_4096_chains"] = {"unavailable": "build/models/cfg5_primal.npz not built"}
+        else:
+            model = api.CudaModel(mm[0], mm[1], device=local_rank)
+            total = 4096
+            per = total // world
+            # the step size comes from 30 warmup iterations of DualAvg(0.8) (a fixed guess from a random start is rejected
+            # every time on a posterior this narrow); the timed part is the sampling phase with that adapted step
+            cfg5 = api.make_config(iterations=2, warmupIterations=30, sampler=api.HMCSampler(N_STEPS), stepSizeTuner=api.DualAvgTuner(0.8),
+                                   massMatrixTuner=api.IdentityMassMatrixTuner(), launchIterations=2)
+            rate, secs, acc = device_rate(model, cfg5, per, 2, 1, 1000 + rank * per)
+            out["cfg5_poisson_glm_4096_chains"] = {"steps_x_chains_per_s": rate, "seconds": secs, "accept_rate": acc, "chains_total": total,
+                                                   "chains_per_gpu": per, "scaling": "strong", "rows": 1000000, "groups": 1000,
+                                                   "config": "HMC(nSteps=5), step size from 30 DualAvg(0.8) warmup iterations, primal RIR + adjoint gradient (Lookup -> scatter)"}
+            model.close()
+    except Exception as e:
+        out["cfg5_poisson_glm_4096_chains"] = {"error": str(e)[:300]}
+
+    # ---- cfg3: 2048 chains on one GPU ----
+    try:
+        mm = _load_npz_model("cfg3_primal")
+        if mm is None:
+            out["cfg3_logreg_2048_chains"] = {"unavailable": "build/models/cfg3_primal.npz not built"}
+        else:
+            model = api.CudaModel(mm[0], mm[1], device=local_rank)
+            cfg = static(0.01, 2)
+            rate, secs, acc = device_rate(model, cfg, 2048, 2, 1, 1000)
+            src = model.emit_source(cfg)
+            out["cfg3_logreg_2048_chains"] = {"steps_x_chains_per_s_per_gpu": rate / world, "seconds": secs, "accept_rate": acc, "chains_per_gpu": 2048,
+                                              "rows": 100000, "covariates": 50, "config": "HMC(nSteps=5), static step 0.01, primal RIR + adjoint gradient",
+                                              "kernel": "chain-batched DMMA (mma.sync.m8n8k4.f64)" if "rn_dmma(z" in src else "rows across lanes"}
+            model.close()
+    except Exception as e:
+        out["cfg3_logreg_2048_chains"] = {"error": str(e)[:300]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,6 +358,7 @@ def main():
     ap.add_argument("--math", default="parity", choices=["parity", "fast"])
     ap.add_argument("--grad", default="auto", choices=["auto", "symbolic", "adjoint"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3/cfg4/cfg5 side measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -227,6 +370,8 @@ def main():
 
     from rainier_b200 import abi, api
 
+    if "RN_KERNEL_CACHE" not in os.environ and os.path.isdir(os.path.join(ROOT, "build", "kcache")):
+        os.environ["RN_KERNEL_CACHE"] = os.path.join(ROOT, "build", "kcache")  # NVRTC of the 1000-parameter model: ~35 s otherwise
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -342,6 +487,7 @@ def main():
     pin.close()
     seeds_pin.close()
 
+    extras = None if args.no_configs else extra_configs(args, torch, dist, api, abi, rank, local_rank, world)
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         cap = ncu_capture(args.math)
@@ -396,6 +542,8 @@ def main():
                                    "note": "per rank; whole rn_sample call (create, kernels, drain, stats) over the sample bytes"}
         except Exception:
             pass
+        if extras is not None:
+            line["configs"] = extras
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line))

@@ -224,6 +224,9 @@ void* rn_sampler_stream(rn_sampler* s);
 int64_t rn_sampler_launches(const rn_sampler* s);
 /* attach a communicator: pooled adaptation all-reduces over its ranks */
 int rn_sampler_set_comm(rn_sampler* s, rn_comm* comm);
+/* the collective of this path: ncclAllReduce calls issued by the pooled warmup so far and their summed device time in
+ * microseconds (event pairs on the sampler's stream; synchronises it) */
+int rn_sampler_comm_stats(rn_sampler* s, int64_t* calls, double* total_us);
 void rn_sampler_destroy(rn_sampler* s);
 
 /* ---- multi-GPU plumbing (one process per GPU; chains are sharded by the caller) ------------------------- */

@@ -76,6 +76,7 @@ def lib():
         L.rn_sampler_enable_trace.argtypes = [C.c_void_p]
         L.rn_sampler_read_trace.argtypes = [C.c_void_p, C.c_void_p]
         L.rn_sampler_set_comm.argtypes = [C.c_void_p, C.c_void_p]
+        L.rn_sampler_comm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.rn_comm_unique_id.argtypes = [C.c_char_p]
         L.rn_comm_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.rn_comm_destroy.argtypes = [C.c_void_p]
@@ -693,6 +694,12 @@ class CudaSampler:
     def set_comm(self, comm):
         self._comm = comm
         _check(lib().rn_sampler_set_comm(self.h, comm.h))
+
+    def comm_stats(self):
+        """(ncclAllReduce calls of the pooled warmup, their summed device time in microseconds)"""
+        calls, us = C.c_int64(0), C.c_double(0.0)
+        _check(lib().rn_sampler_comm_stats(self.h, C.byref(calls), C.byref(us)))
+        return int(calls.value), float(us.value)
 
     def warmup(self, iterations=-1):
         _check(lib().rn_sampler_warmup(self.h, int(iterations)))

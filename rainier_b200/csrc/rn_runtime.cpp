@@ -865,6 +865,9 @@ struct rn_sampler {
   // batch of phase-1 launches; closed spans are summed when the stats are read
   CUevent ev_run[2] = {nullptr, nullptr};
   bool ev_open = false;
+  // the warmup-phase all-reduce (RN_ADAPT_POOLED over rn_comm): calls issued, and event pairs around them (device time)
+  int64_t allreduce_calls = 0;
+  std::vector<std::pair<CUevent, CUevent>> allreduce_events;
   double sampling_ms = 0.0;
   int64_t sampling_iterations = 0;
 };
@@ -1173,9 +1176,20 @@ static int pool_window(const Api* A, rn_sampler* s, int window_len) {
     std::string why;
     const Nccl* N = nccl(&why);
     if (!N) return fail(RN_E_NCCL, why);
+    CUevent e0 = nullptr, e1 = nullptr;
+    if (s->allreduce_events.size() < 256) {
+      CU(A->cuEventCreate(&e0, 0));
+      CU(A->cuEventCreate(&e1, 0));
+      CU(A->cuEventRecord(e0, s->stream));
+    }
     int r = N->AllReduce((const void*)(uintptr_t)s->d_pool, (void*)(uintptr_t)s->d_pool, 2 * n + 1, 8 /*ncclFloat64*/,
                          0 /*ncclSum*/, s->comm->comm, (void*)s->stream);
+    if (e1) {
+      A->cuEventRecord(e1, s->stream);
+      s->allreduce_events.push_back({e0, e1});
+    }
     if (r != 0) return fail(RN_E_NCCL, std::string("ncclAllReduce: ") + (N->GetErrorString ? N->GetErrorString(r) : "?"));
+    s->allreduce_calls++;
   }
   {
     CUdeviceptr pool = s->d_pool;
@@ -1492,6 +1506,25 @@ int rn_sampler_diagnostics(rn_sampler* s, const double* d_samples, int iteration
   return RN_OK;
 }
 
+// number of ncclAllReduce calls of the pooled warmup so far and their summed device time (stream must be idle: syncs)
+int rn_sampler_comm_stats(rn_sampler* s, int64_t* calls, double* total_us) {
+  if (!s) return fail(RN_E_INVALID, "null sampler");
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  CU(A->cuCtxSetCurrent(s->m->ctx));
+  CU(A->cuStreamSynchronize(s->stream));
+  double us = 0.0;
+  for (auto& pr : s->allreduce_events) {
+    float ms = 0.f;
+    CU(A->cuEventElapsedTime(&ms, pr.first, pr.second));
+    us += (double)ms * 1e3;
+  }
+  if (calls) *calls = s->allreduce_calls;
+  if (total_us) *total_us = us;
+  return RN_OK;
+}
+
 int rn_sampler_set_comm(rn_sampler* s, rn_comm* comm) {
   s->comm = comm;
   return RN_OK;
@@ -1522,6 +1555,10 @@ void rn_sampler_destroy(rn_sampler* s) {
     if (s->d_trace) A->cuMemFree(s->d_trace);
     for (CUevent e : s->ev_run)
       if (e) A->cuEventDestroy(e);
+    for (auto& pr : s->allreduce_events) {
+      A->cuEventDestroy(pr.first);
+      A->cuEventDestroy(pr.second);
+    }
   }
   delete s;
 }
