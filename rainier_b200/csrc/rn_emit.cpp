@@ -457,6 +457,8 @@ struct Emitter {
     std::vector<MmaDot> dots;
     std::vector<int> other_slots;  // accumulator slots (besides 0 and the term parameters') the elementwise code adds to
     int KS = 0, DT = 0, region_doubles = 0, redw = 0;
+    bool uniform = false;  // every dot is the same code over its own column block (the unrolled observations of Model.observe):
+                           // ONE copy of the per-dot code serves all warps, only the block's first column differs
   };
   std::vector<MmaPlan> plans;
   std::vector<int> mma_inv;        // invariant nodes some elementwise body reads (published per chain through shared memory)
@@ -641,24 +643,87 @@ struct Emitter {
     pl.KS = ((int)pl.params.size() + 3) / 4;
     pl.DT = ((int)pl.params.size() + 7) / 8;
     pl.redw = pl.DT * 8 + 1 + (int)pl.other_slots.size();
+    pl.uniform = true;
+    {
+      const std::vector<std::string> s0 = mma_signature(T, pl, pl.dots[0]);
+      for (size_t di = 1; di < pl.dots.size() && pl.uniform; di++) {
+        const std::vector<std::string> sd = mma_signature(T, pl, pl.dots[di]);
+        if (sd != s0) {
+          pl.uniform = false;
+          if (getenv("RN_MMA_DEBUG")) {
+            fprintf(stderr, "[rn mma] dot %zu differs from dot 0 (%zu vs %zu statements)\n", di, sd.size(), s0.size());
+            for (size_t k = 0; k < std::min(sd.size(), s0.size()); k++)
+              if (sd[k] != s0[k]) {
+                fprintf(stderr, "  #%zu: %s  vs  %s\n", k, s0[k].c_str(), sd[k].c_str());
+                break;
+              }
+          }
+        }
+      }
+    }
     pl.ok = true;
     return pl;
+  }
+
+
+  // canonical form of one dot's elementwise code: node kinds / ops / constants, operands as positions in the dot's own
+  // statement list, columns relative to the block's first column -- equal signatures = the same code on another block
+  std::vector<std::string> mma_signature(const TargetInfo& T, const MmaPlan& pl, const MmaDot& d) const {
+    std::map<int, int> pos;
+    std::vector<int> order = d.fwd;
+    order.insert(order.end(), d.bwd.begin(), d.bwd.end());
+    for (size_t k = 0; k < order.size(); k++) pos[order[k]] = (int)k;
+    auto ref = [&](int id) -> std::string {
+      if (id == d.z) return "z";
+      auto it = pos.find(id);
+      if (it != pos.end()) return "n" + std::to_string(it->second);
+      const Node& n = P.nodes[id];
+      if (n.kind == K_CONST) return "k" + lit(n.value);
+      if (n.kind == K_INPUT) return (uint32_t)n.a < P.n_params ? "q" + std::to_string(n.a) : "c" + std::to_string(local_col(T, n.a - (int)P.n_params) - d.cmin);
+      return "i" + std::to_string(id);  // invariant node of the chain
+    };
+    std::vector<std::string> out;
+    std::vector<int> o;
+    for (int id : order) {
+      if (id == d.z) {
+        out.push_back("Z" + (d.base >= 0 ? ref(d.base) : std::string("-")));
+        continue;
+      }
+      const Node& n = P.nodes[id];
+      // constants of the node: op; Lookup: len, low (its entries are operands); SelEq: the compared index
+      std::string sg = std::to_string(n.kind) + ":" + std::to_string(n.op) + ":" + (n.kind == K_LOOKUP ? std::to_string(n.c) : std::string("-")) + ":" +
+                       ((n.kind == K_LOOKUP || n.kind == K_SELEQ) ? std::to_string(n.d) : std::string("-")) + ":" + std::to_string(n.region) +
+                       (tab_off.count(id) ? "T" : "");
+      operands(id, o);
+      for (int x : o) sg += "," + ref(x);
+      out.push_back(sg);
+    }
+    std::string tail = "L";
+    for (int l : d.leaves) tail += "," + ref(l);
+    tail += "|W" + ref(d.w) + "|A";
+    for (const AccStmt& a : d.acc) tail += "," + std::to_string(a.slot) + "=" + ref(a.node);
+    tail += "|C";
+    for (int c : d.cols) tail += "," + std::to_string(c - d.cmin);
+    tail += "|" + std::to_string(d.cmax - d.cmin);
+    out.push_back(tail);
+    (void)pl;
+    return out;
   }
 
   // the elementwise code of one dot: one (row, chain) element
   void mma_helper(const TargetInfo& T, size_t t, const MmaPlan& pl, size_t di) {
     const MmaDot& d = pl.dots[di];
     const int pitch = opt.pitch(t);
-    os << "RN_DEVICE void rn_mma_e" << t << "_" << di << "(const double zz, const RnSA rp, const double* RN_RESTRICT q, "
+    os << "RN_DEVICE void rn_mma_e" << t << "_" << di << "(const double zz, const RnSA rp, const int r8, const double* RN_RESTRICT q, "
           "const double* RN_RESTRICT xv, double& dens, double& wout, double* osum, int& err) {\n"
-       << "  (void)rp; (void)q; (void)xv; (void)osum; (void)err;\n";
+       << "  (void)rp; (void)r8; (void)q; (void)xv; (void)osum; (void)err;\n";
     for (size_t k = 0; k < mma_inv.size(); k++) os << "  const double v" << mma_inv[k] << " = xv[" << k << "]; (void)v" << mma_inv[k] << ";\n";
     std::set<int> declared;
     auto need_col = [&](int o) {
       const Node& n = P.nodes[o];
       if (n.kind != K_INPUT || (uint32_t)n.a < P.n_params) return;
       const int k = n.a - (int)P.n_params;
-      if (declared.insert(k).second) os << "  const double c" << k << " = rn_lds(rp, " << (local_col(T, k) - d.cmin) * pitch << ");\n";
+      if (declared.insert(k).second) os << "  const double c" << k << " = rn_lds(rp, r8 + " << (local_col(T, k) - d.cmin) * pitch << ");\n";
     };
     std::vector<int> o;
     auto one = [&](int id) {
@@ -726,8 +791,18 @@ struct Emitter {
        << "      double* const region = tma.stage + (size_t)wid * " << pl.region_doubles << ";\n"
        << "      unsigned long long* const bar = tma.full + wid;\n"
        << "      const double* RN_RESTRICT src = data + " << base << "ULL;\n";
-    for (size_t di = 0; di < pl.dots.size(); di++) {
-      const MmaDot& d = pl.dots[di];
+    // the per-dot code: once for all warps when the dots are the same code over their own column blocks (then only the
+    // block's first column differs -- a table indexed by the dot), else one copy per dot.  Kept SMALL on purpose: eight
+    // unrolled copies (170 KB of SASS) thrashed the instruction cache and ran 3x SLOWER than rows-across-lanes
+    // (profiles/r2_bench_mma_v1_icache_thrash.txt); the 8-row groups of a tile are a rolled loop for the same reason.
+    const size_t ncopies = pl.uniform ? 1 : pl.dots.size();
+    if (pl.uniform) {
+      os << "      static const int MMA_CMIN" << t << "[" << pl.dots.size() << "] = {";
+      for (size_t di = 0; di < pl.dots.size(); di++) os << (di ? ", " : "") << pl.dots[di].cmin;
+      os << "};\n";
+    }
+    for (size_t ci = 0; ci < ncopies; ci++) {
+      const MmaDot& d = pl.dots[ci];
       const unsigned bytes = (unsigned)((d.cmax - d.cmin + 1) * pitch * 8);
       // the B-operand addresses: per lane a base (term by lane, row slot by lane) plus compile-time offsets when the dot's
       // columns are an arithmetic progression (the Translator folds a Vec.dot in column order); else per-lane offset tables
@@ -741,11 +816,14 @@ struct Emitter {
         for (int k = n - 1; k >= 0; k--) e = k == n - 1 ? f(k) : "(" + std::string(lane) + " == " + std::to_string(k) + " ? " + f(k) + " : " + e + ")";
         return e;
       };
-      os << "      if (wid == " << (di % MMA_WARPS) << ") {  // dot " << di << ": columns " << d.cmin << ".." << d.cmax << " of the tile\n"
-         << "        const double* RN_RESTRICT s0 = src + " << (unsigned long long)d.cmin * pitch << "ULL;\n"
-         << "        if (ln == 0) rn_tma_load_raw(region, bar, s0, " << bytes << "u);\n";
-      // forward: B[k = mk][n = mc] = X[col(term ks*4+mk)][row slot mc]
-      os << "        const int pf = mc ^ ((mc >> 2) & 1), pb0 = (2 * mk) ^ ((mk >> 1) & 1), pb1 = (2 * mk + 1) ^ ((mk >> 1) & 1);\n";
+      if (pl.uniform)
+        os << "      for (int dot = wid; dot < " << pl.dots.size() << "; dot += " << MMA_WARPS << ") {  // this warp's dots (same code, other column block)\n"
+           << "        const double* RN_RESTRICT s0 = src + (size_t)MMA_CMIN" << t << "[dot] * " << pitch << ";\n";
+      else
+        os << "      if (wid == " << (ci % MMA_WARPS) << ") {  // dot " << ci << ": columns " << d.cmin << ".." << d.cmax << " of the tile\n"
+           << "        const double* RN_RESTRICT s0 = src + " << (unsigned long long)d.cmin * pitch << "ULL;\n";
+      os << "        if (ln == 0) rn_tma_load_raw(region, bar, s0, " << bytes << "u);\n"
+         << "        const int pf = mc ^ ((mc >> 2) & 1), pb0 = (2 * mk) ^ ((mk >> 1) & 1), pb1 = (2 * mk + 1) ^ ((mk >> 1) & 1);\n";
       if (ap) {
         os << "        const RnSA bf = rn_sa(region + pf + (" << (d.cols[0] - d.cmin) << " + " << step << " * mk) * " << pitch << ");\n"
            << "        const RnSA bb0 = rn_sa(region + pb0 + (" << (d.cols[0] - d.cmin) << " + " << step << " * mc) * " << pitch << ");\n"
@@ -758,8 +836,9 @@ struct Emitter {
           os << "        bo[" << dt << "] = " << by_lane("mc", 8, [&](int k) { return std::to_string(off(dt * 8 + k)); }) << ";\n";
         os << "        const RnSA bf = rn_sa(region + pf), bb0 = rn_sa(region + pb0), bb1 = rn_sa(region + pb1);\n";
       }
-      // padded terms (beyond the " << NP << " of the dot) multiply an operand of exact zeros; their B address must still be a
-      // finite number of the tile: the last group falls back to term 0's column
+      os << "        const RnSA e0 = rn_sa(region + pb0), e1 = rn_sa(region + pb1);\n";
+      // padded terms (beyond the NP of the dot) multiply an operand of exact zeros; their B address must still be a finite
+      // number of the tile: the last group falls back to term 0's column
       auto fwd_addr = [&](int ks) -> std::string {
         if (!ap) return "fo[" + std::to_string(ks) + "]";
         const int first = ks * 4;
@@ -776,19 +855,18 @@ struct Emitter {
       };
       os << "        for (unsigned tile = 0; tile < " << n_full << "u; tile++) {\n"
          << "          rn_mbar_wait_warp(bar, tma.seq & 1u);\n          tma.seq += 1;\n"
-         << "          double z[4][2], wv[4][2];\n"
-         << "          RN_UNROLL\n          for (int nt = 0; nt < 4; nt++) {\n"
-         << "            z[nt][0] = z[nt][1] = 0.0;\n";
-      for (int ks = 0; ks < KS; ks++) os << "            rn_dmma(z[nt][0], z[nt][1], ar[" << ks << "], rn_lds(bf, nt * 8 + " << fwd_addr(ks) << "));\n";
-      os << "          }\n"
-         << "          RN_UNROLL\n          for (int nt = 0; nt < 4; nt++) {\n"
-         << "            rn_mma_e" << t << "_" << di << "(z[nt][0], rn_sa(region + nt * 8 + pb0), qo, xo, dsum, wv[nt][0], osum, err);\n"
-         << "            rn_mma_e" << t << "_" << di << "(z[nt][1], rn_sa(region + nt * 8 + pb1), qo, xo, dsum, wv[nt][1], osum, err);\n"
-         << "          }\n"
-         << "          RN_UNROLL\n          for (int nt = 0; nt < 4; nt++) {\n";
+         << "#pragma unroll 1\n"
+         << "          for (int r8 = 0; r8 < 32; r8 += 8) {  // the tile's four 8-row groups\n"
+         << "            double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0, w0, w1;  // two accumulator chains: DMMA latency, not rate, bounds a chain\n";
+      for (int ks = 0; ks < KS; ks++)
+        os << "            rn_dmma(" << (ks % 2 ? "zb0, zb1" : "za0, za1") << ", ar[" << ks << "], rn_lds(bf, r8 + " << fwd_addr(ks) << "));\n";
+      os << "            za0 += zb0;\n            za1 += zb1;\n"
+         << "            rn_mma_e" << t << "_" << ci << "(za0, e0, r8, qo, xo, dsum, w0, osum, err);\n"
+         << "            rn_mma_e" << t << "_" << ci << "(za1, e1, r8, qo, xo, dsum, w1, osum, err);\n";
       for (int dt = 0; dt < DT; dt++)
-        os << "            rn_dmma(g[" << dt << "][0], g[" << dt << "][1], wv[nt][0], rn_lds(bb0, nt * 8 + " << bwd_addr(dt) << "));\n"
-           << "            rn_dmma(g[" << dt << "][0], g[" << dt << "][1], wv[nt][1], rn_lds(bb1, nt * 8 + " << bwd_addr(dt) << "));\n";
+        os << "            rn_dmma(g[" << dt << "][0], g[" << dt << "][1], w0, rn_lds(bb0, r8 + " << bwd_addr(dt) << "));\n";
+      for (int dt = 0; dt < DT; dt++)
+        os << "            rn_dmma(g[" << dt << "][0], g[" << dt << "][1], w1, rn_lds(bb1, r8 + " << bwd_addr(dt) << "));\n";
       os << "          }\n"
          << "          __syncwarp();\n"
          << "          if (ln == 0 && tile + 1 < " << n_full << "u) rn_tma_load_raw(region, bar, s0 + (size_t)(tile + 1) * " << td << "ULL, " << bytes << "u);\n"
@@ -878,7 +956,7 @@ struct Emitter {
     if (use_mma)
       for (size_t t = 0; t < P.targets.size(); t++)
         if (plans[t].ok)
-          for (size_t di = 0; di < plans[t].dots.size(); di++) mma_helper(P.targets[t], t, plans[t], di);
+          for (size_t di = 0; di < (plans[t].uniform ? 1 : plans[t].dots.size()); di++) mma_helper(P.targets[t], t, plans[t], di);
     os << "RN_DEVICE void rn_density(const double* q, double& dens, double* grad, double* scr, "
           "const double* RN_RESTRICT data, int& err, RnTma& tma) {\n";
     os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x % RN_G);  // thread of the chain's group\n  (void)lane;\n";
