@@ -42,6 +42,7 @@ struct Emitter {
   int red_off = 0, red_doubles = 0;       // cross-warp reduction scratch (K warps per chain)
   int n_smem_acc = 0, tab_doubles = 0;
   std::string col_suffix;                 // names of column values loaded in the current region of a row body
+  std::string node_suffix;                // appended to the names of row-body values (the DMMA path emits one body per element)
   Emitter(const Program& p, const EmitOptions& o) : P(p), opt(o) {}
 
   // The body of one row of a streamed target.  Keeps live ranges short, because a "row" of the reference's
@@ -256,6 +257,7 @@ struct Emitter {
       if ((uint32_t)n.a < P.n_params) return "q[" + std::to_string(n.a) + "]";
       return "c" + std::to_string(n.a - (int)P.n_params) + col_suffix;
     }
+    if (!node_suffix.empty() && (n.region == R_ROW_FWD || n.region == R_ROW_BWD)) return "v" + std::to_string(id) + node_suffix;
     return "v" + std::to_string(id);
   }
 
@@ -296,7 +298,7 @@ struct Emitter {
   void stmt(int id, const char* indent) {
     const Node& n = P.nodes[id];
     if (n.kind == K_CONST || n.kind == K_INPUT) return;
-    os << indent << "const double v" << id << " = ";
+    os << indent << "const double " << val(id) << " = ";
     switch (n.kind) {
       case K_UNARY: {
         const std::string x = val(n.a);
@@ -710,35 +712,43 @@ struct Emitter {
     return out;
   }
 
-  // the elementwise code of one dot: one (row, chain) element
+  // the elementwise code of one dot for the lane's EIGHT (row, chain) elements of a tile (element e = 2*nt + h: 8-row group
+  // nt, row slot 2*(lane%4)+h), statement by statement across the elements: eight independent dependency chains for the
+  // scheduler, like the interleaved observations of the rows-across-lanes body (one element at a time left a warp with a
+  // single serial chain of exp / log / divisions and the kernel latency-bound at 8 warps per SM)
   void mma_helper(const TargetInfo& T, size_t t, const MmaPlan& pl, size_t di) {
     const MmaDot& d = pl.dots[di];
     const int pitch = opt.pitch(t);
-    os << "RN_DEVICE void rn_mma_e" << t << "_" << di << "(const double zz, const RnSA rp, const int r8, const double* RN_RESTRICT q, "
-          "const double* RN_RESTRICT xv, double& dens, double& wout, double* osum, int& err) {\n"
-       << "  (void)rp; (void)r8; (void)q; (void)xv; (void)osum; (void)err;\n";
+    os << "RN_DEVICE void rn_mma_e" << t << "_" << di << "(const double (&zz)[8], const RnSA rp0, const RnSA rp1, const double* RN_RESTRICT q, "
+          "const double* RN_RESTRICT xv, double& dens, double (&wout)[8], double* osum, int& err) {\n"
+       << "  (void)rp0; (void)rp1; (void)q; (void)xv; (void)osum; (void)err;\n";
     for (size_t k = 0; k < mma_inv.size(); k++) os << "  const double v" << mma_inv[k] << " = xv[" << k << "]; (void)v" << mma_inv[k] << ";\n";
-    std::set<int> declared;
-    auto need_col = [&](int o) {
+    std::set<int> declared[8];
+    auto sfx = [&](int e) { return "_" + std::to_string(e); };
+    auto need_col = [&](int o, int e) {
       const Node& n = P.nodes[o];
       if (n.kind != K_INPUT || (uint32_t)n.a < P.n_params) return;
       const int k = n.a - (int)P.n_params;
-      if (declared.insert(k).second) os << "  const double c" << k << " = rn_lds(rp, r8 + " << (local_col(T, k) - d.cmin) * pitch << ");\n";
+      if (declared[e].insert(k).second)
+        os << "  const double c" << k << sfx(e) << " = rn_lds(" << (e & 1 ? "rp1" : "rp0") << ", " << (e >> 1) * 8 + (local_col(T, k) - d.cmin) * pitch << ");\n";
     };
     std::vector<int> o;
     auto one = [&](int id) {
-      if (id == d.z) {  // the dot itself: the tensor core's sum, plus the fold's first operand
-        if (d.base >= 0) {
-          need_col(d.base);
-          os << "  const double v" << d.z << " = " << val(d.base) << " + zz;\n";
-        } else {
-          os << "  const double v" << d.z << " = zz;\n";
+      for (int e = 0; e < 8; e++) {
+        node_suffix = col_suffix = sfx(e);
+        if (id == d.z) {  // the dot itself: the tensor core's sum, plus the fold's first operand
+          if (d.base >= 0) {
+            need_col(d.base, e);
+            os << "  const double " << val(d.z) << " = " << val(d.base) << " + zz[" << e << "];\n";
+          } else {
+            os << "  const double " << val(d.z) << " = zz[" << e << "];\n";
+          }
+          continue;
         }
-        return;
+        operands(id, o);
+        for (int x : o) need_col(x, e);
+        stmt(id, "  ");
       }
-      operands(id, o);
-      for (int x : o) need_col(x);
-      stmt(id, "  ");
     };
     bool z_done = false;
     for (int id : d.fwd) {
@@ -746,17 +756,24 @@ struct Emitter {
       if (id == d.z) z_done = true;
     }
     if (!z_done) one(d.z);
-    for (int l : d.leaves) {
-      need_col(l);
-      os << "  dens += " << val(l) << ";\n";
-    }
+    for (int l : d.leaves)
+      for (int e = 0; e < 8; e++) {
+        node_suffix = col_suffix = sfx(e);
+        need_col(l, e);
+        os << "  dens += " << val(l) << ";\n";
+      }
     for (int id : d.bwd) one(id);
-    need_col(d.w);
-    os << "  wout = " << val(d.w) << ";\n";
-    for (const AccStmt& a : d.acc) {
-      need_col(a.node);
-      os << "  osum[" << a.slot << "] += " << val(a.node) << ";\n";
+    for (int e = 0; e < 8; e++) {
+      node_suffix = col_suffix = sfx(e);
+      need_col(d.w, e);
+      os << "  wout[" << e << "] = " << val(d.w) << ";\n";
+      for (const AccStmt& a : d.acc) {
+        need_col(a.node, e);
+        os << "  osum[" << a.slot << "] += " << val(a.node) << ";\n";
+      }
     }
+    node_suffix.clear();
+    col_suffix.clear();
     os << "}\n";
   }
 
@@ -855,19 +872,18 @@ struct Emitter {
       };
       os << "        for (unsigned tile = 0; tile < " << n_full << "u; tile++) {\n"
          << "          rn_mbar_wait_warp(bar, tma.seq & 1u);\n          tma.seq += 1;\n"
-         << "#pragma unroll 1\n"
-         << "          for (int r8 = 0; r8 < 32; r8 += 8) {  // the tile's four 8-row groups\n"
-         << "            double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0, w0, w1;  // two accumulator chains: DMMA latency, not rate, bounds a chain\n";
-      for (int ks = 0; ks < KS; ks++)
-        os << "            rn_dmma(" << (ks % 2 ? "zb0, zb1" : "za0, za1") << ", ar[" << ks << "], rn_lds(bf, r8 + " << fwd_addr(ks) << "));\n";
-      os << "            za0 += zb0;\n            za1 += zb1;\n"
-         << "            rn_mma_e" << t << "_" << ci << "(za0, e0, r8, qo, xo, dsum, w0, osum, err);\n"
-         << "            rn_mma_e" << t << "_" << ci << "(za1, e1, r8, qo, xo, dsum, w1, osum, err);\n";
-      for (int dt = 0; dt < DT; dt++)
-        os << "            rn_dmma(g[" << dt << "][0], g[" << dt << "][1], w0, rn_lds(bb0, r8 + " << bwd_addr(dt) << "));\n";
-      for (int dt = 0; dt < DT; dt++)
-        os << "            rn_dmma(g[" << dt << "][0], g[" << dt << "][1], w1, rn_lds(bb1, r8 + " << bwd_addr(dt) << "));\n";
-      os << "          }\n"
+         << "          double z[8], wv[8];\n"
+         << "          RN_UNROLL\n          for (int e = 0; e < 8; e++) z[e] = 0.0;\n";
+      for (int ks = 0; ks < KS; ks++)  // term groups outermost: four independent accumulator chains (the tile's 8-row groups)
+        for (int nt = 0; nt < 4; nt++)
+          os << "          rn_dmma(z[" << 2 * nt << "], z[" << 2 * nt + 1 << "], ar[" << ks << "], rn_lds(bf, " << nt * 8 << " + " << fwd_addr(ks) << "));\n";
+      os << "          rn_mma_e" << t << "_" << ci << "(z, e0, e1, qo, xo, dsum, wv, osum, err);\n";
+      for (int nt = 0; nt < 4; nt++)
+        for (int h = 0; h < 2; h++)
+          for (int dt = 0; dt < DT; dt++)
+            os << "          rn_dmma(g[" << dt << "][0], g[" << dt << "][1], wv[" << 2 * nt + h << "], rn_lds(" << (h ? "bb1" : "bb0") << ", " << nt * 8 << " + "
+               << bwd_addr(dt) << "));\n";
+      os
          << "          __syncwarp();\n"
          << "          if (ln == 0 && tile + 1 < " << n_full << "u) rn_tma_load_raw(region, bar, s0 + (size_t)(tile + 1) * " << td << "ULL, " << bytes << "u);\n"
          << "        }\n      }\n";

@@ -1164,36 +1164,43 @@ int rn_sampler_read_trace(rn_sampler* s, double* out /*[chains][iters][4]*/) {
 static int pool_window(const Api* A, rn_sampler* s, int window_len) {
   const size_t n = s->m->n_params;
   CU(A->cuMemsetD8Async(s->d_pool, 0, (2 * n + 1) * 8, s->stream));
+  std::string why;
+  const Nccl* N = nullptr;
+  if (s->comm && s->comm->world > 1) {
+    N = nccl(&why);
+    if (!N) return fail(RN_E_NCCL, why);
+  }
+  // two passes (pooled mean, then Chan's combination of the chains' M2 around it), each a deterministic reduction over this
+  // GPU's chains followed by one small all-reduce over the ranks
+  for (int pass = 0; pass < 2; pass++) {
+    CUdeviceptr pool = s->d_pool;
+    int wl = window_len, ps = pass;
+    void* params[] = {&s->args, &pool, &wl, &ps};
+    CU(A->cuLaunchKernel(s->K->k_pool_reduce, (unsigned)n, 1, 1, 256, 1, 1, 0, s->stream, params, nullptr));
+    s->launches++;
+    if (N) {
+      CUevent e0 = nullptr, e1 = nullptr;
+      if (s->allreduce_events.size() < 256) {
+        CU(A->cuEventCreate(&e0, 0));
+        CU(A->cuEventCreate(&e1, 0));
+        CU(A->cuEventRecord(e0, s->stream));
+      }
+      const CUdeviceptr buf = pass ? s->d_pool + (1 + n) * 8 : s->d_pool;
+      const size_t count = pass ? n : n + 1;
+      int r = N->AllReduce((const void*)(uintptr_t)buf, (void*)(uintptr_t)buf, count, 8 /*ncclFloat64*/, 0 /*ncclSum*/, s->comm->comm,
+                           (void*)s->stream);
+      if (e1) {
+        A->cuEventRecord(e1, s->stream);
+        s->allreduce_events.push_back({e0, e1});
+      }
+      if (r != 0) return fail(RN_E_NCCL, std::string("ncclAllReduce: ") + (N->GetErrorString ? N->GetErrorString(r) : "?"));
+      s->allreduce_calls++;
+    }
+  }
   {
     CUdeviceptr pool = s->d_pool;
     int wl = window_len;
     void* params[] = {&s->args, &pool, &wl};
-    const unsigned grid = (unsigned)std::min<size_t>(296, ((size_t)s->chains + 255) / 256);
-    CU(A->cuLaunchKernel(s->K->k_pool_reduce, grid, 1, 1, 256, 1, 1, 0, s->stream, params, nullptr));
-    s->launches++;
-  }
-  if (s->comm && s->comm->world > 1) {
-    std::string why;
-    const Nccl* N = nccl(&why);
-    if (!N) return fail(RN_E_NCCL, why);
-    CUevent e0 = nullptr, e1 = nullptr;
-    if (s->allreduce_events.size() < 256) {
-      CU(A->cuEventCreate(&e0, 0));
-      CU(A->cuEventCreate(&e1, 0));
-      CU(A->cuEventRecord(e0, s->stream));
-    }
-    int r = N->AllReduce((const void*)(uintptr_t)s->d_pool, (void*)(uintptr_t)s->d_pool, 2 * n + 1, 8 /*ncclFloat64*/,
-                         0 /*ncclSum*/, s->comm->comm, (void*)s->stream);
-    if (e1) {
-      A->cuEventRecord(e1, s->stream);
-      s->allreduce_events.push_back({e0, e1});
-    }
-    if (r != 0) return fail(RN_E_NCCL, std::string("ncclAllReduce: ") + (N->GetErrorString ? N->GetErrorString(r) : "?"));
-    s->allreduce_calls++;
-  }
-  {
-    CUdeviceptr pool = s->d_pool;
-    void* params[] = {&s->args, &pool};
     CU(A->cuLaunchKernel(s->K->k_pool_apply, (unsigned)((s->chains + 127) / 128), 1, 1, 128, 1, 1, 0, s->stream, params, nullptr));
     s->launches++;
   }

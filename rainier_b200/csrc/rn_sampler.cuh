@@ -637,14 +637,17 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
       if (A.mass_tuner == 1 || A.mass_tuner == 2) {
         win_j += 1;
         if (A.adaptation == 1) {
-          // pooled extension: plain window sums per chain; the host reduces them over chains (and ranks) at the
-          // window end (rn_k_pool_reduce / rn_k_pool_apply) -- launches are cut at window ends in this mode
+          // pooled extension: per-chain Welford statistics of the window; combined over chains (and ranks) at the window
+          // end (rn_k_pool_reduce / rn_k_pool_apply) -- launches are cut at window ends in this mode
           if (!(win_j < A.skip_first || (A.total_warmup - win_j) < A.skip_last)) {
             win_i += 1;
             RN_UNROLL
-            for (int i = 0; i < RN_N; i++) {
-              RN_AT(A.est_mean, i, c) += s.q[i];
-              RN_AT(A.est_raw, i, c) += s.q[i] * s.q[i];
+            for (int i = 0; i < RN_N; i++) {  // the chain's Welford mean / M2 over this window
+              double mean = RN_AT(A.est_mean, i, c);
+              const double od = s.q[i] - mean;
+              mean += od / (double)win_i;
+              RN_AT(A.est_mean, i, c) = mean;
+              RN_AT(A.est_raw, i, c) += od * (s.q[i] - mean);
             }
             if (win_i == win_size) {
               win_i = 0;
@@ -815,36 +818,50 @@ RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT
 #endif
 
 // =============================================================================================================
-// Pooled mass-matrix adaptation (RN_ADAPT_POOLED; an extension, not reference semantics): at a window end the
-// per-chain window sums {sum q_i, sum q_i^2} are reduced over all chains of this GPU into pool[1..2n] (pool[0] =
-// number of draws), all-reduced over ranks by the host (NCCL) and applied to every chain: one shared diagonal
-// mass matrix, sums cleared, DualAvg restarted from each chain's averaged step size (Driver.scala:75-80).
+// Pooled mass-matrix adaptation (RN_ADAPT_POOLED; an extension, not reference semantics): at a window end the chains'
+// Welford statistics of the window (mean_c, M2_c over L draws) are combined over all chains of this GPU and, through two
+// small ncclAllReduce calls, over all ranks: first the means (-> pooled mean), then M2_c + L (mean_c - mean)^2 (Chan's
+// parallel variance: no s2/n - mean^2 cancellation).  Reductions run in a fixed order (no atomics): the shared diagonal
+// mass matrix is reproducible run to run.  It is applied to every chain, statistics cleared, DualAvg restarted from each
+// chain's averaged step size (Driver.scala:75-80).
 // =============================================================================================================
 #ifndef RN_HOST_EMULATION
-RN_GLOBAL void rn_k_pool_reduce(const RnArgs A, double* pool, int window_len) {
+RN_GLOBAL void rn_k_pool_reduce(const RnArgs A, double* pool, int window_len, int pass) {
+  // One block per parameter; thread t adds chains t, t + 256, ... in order, then a fixed tree: the result does not depend
+  // on scheduling (no atomics).  pass 0: pool[1 + i] = sum over chains of the chain's window mean, pool[0] = chains.
+  // pass 1 (after the all-reduce of pass 0): pool[1 + n + i] = sum over chains of [M2_c + L (mean_c - mean)^2] -- Chan's
+  // combination of the chains' Welford statistics around the POOLED mean (no s2/n - mean^2 cancellation).
   __shared__ double red[256];
-  for (int i = 0; i < 2 * RN_N; i++) {
-    const double* src = (i < RN_N) ? (A.est_mean + (size_t)i * A.chains) : (A.est_raw + (size_t)(i - RN_N) * A.chains);
-    double acc = 0.0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.chains; c += gridDim.x * blockDim.x) acc += src[c];
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
+  const int i = (int)blockIdx.x;
+  const double gmean = pass ? pool[1 + i] / pool[0] : 0.0;
+  const double* mean = A.est_mean + (size_t)i * A.chains;
+  const double* m2 = A.est_raw + (size_t)i * A.chains;
+  double acc = 0.0;
+  for (int c = (int)threadIdx.x; c < A.chains; c += (int)blockDim.x) {
+    if (pass) {
+      const double d = mean[c] - gmean;
+      acc += m2[c] + (double)window_len * d * d;
+    } else {
+      acc += mean[c];
     }
-    if (threadIdx.x == 0) atomicAdd(&pool[1 + i], red[0]);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = (int)blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&pool[0], (double)A.chains * (double)window_len);
+  if (threadIdx.x == 0) {
+    pool[1 + (pass ? RN_N : 0) + i] = red[0];
+    if (!pass && i == 0) pool[0] = (double)A.chains;
+  }
 }
-RN_GLOBAL void rn_k_pool_apply(const RnArgs A, const double* pool) {
+RN_GLOBAL void rn_k_pool_apply(const RnArgs A, const double* pool, int window_len) {
   const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= A.chains) return;
-  const double cnt = pool[0];
+  const double cnt = pool[0] * (double)window_len;  // draws of the window over all chains of all ranks
   for (int i = 0; i < RN_N; i++) {
-    const double mean = pool[1 + i] / cnt;
-    const double var = pool[1 + RN_N + i] / cnt - mean * mean;
+    const double var = pool[1 + RN_N + i] / cnt;
     if (!(var > 0.0)) A.st_err[c] |= 2;
     RN_AT(A.mass, i, c) = var;
     RN_AT(A.est_mean, i, c) = 0.0;

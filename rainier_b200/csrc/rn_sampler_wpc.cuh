@@ -607,12 +607,15 @@ RN_GLOBAL void rn_k_iter(const RnArgs A) {
 #endif
       if (A.mass_tuner == 1) {  // DiagonalMassMatrixTuner, MassMatrix.scala:147-164
         win_j += 1;
-        if (A.adaptation == 1) {  // pooled extension: window sums only (see rn_k_pool_reduce / rn_k_pool_apply)
+        if (A.adaptation == 1) {  // pooled extension: per-chain Welford statistics of the window (see rn_k_pool_reduce / rn_k_pool_apply)
           if (!(win_j < A.skip_first || (A.total_warmup - win_j) < A.skip_last)) {
             win_i += 1;
-            RN_FOR_LANES(i) {
-              RN_AT(A.est_mean, i, c) += w.q[i];
-              RN_AT(A.est_raw, i, c) += w.q[i] * w.q[i];
+            RN_FOR_LANES(i) {  // the chain's Welford mean / M2 over this window (combined over chains at the window end)
+              double mean = RN_AT(A.est_mean, i, c);
+              const double od = w.q[i] - mean;
+              mean += od / (double)win_i;
+              RN_AT(A.est_mean, i, c) = mean;
+              RN_AT(A.est_raw, i, c) += od * (w.q[i] - mean);
             }
             if (win_i == win_size) {
               win_i = 0;
@@ -727,30 +730,42 @@ RN_GLOBAL void rn_k_transpose(const double* RN_RESTRICT src, double* RN_RESTRICT
 // number of draws), all-reduced over ranks by the host (NCCL) and applied to every chain: one shared diagonal
 // mass matrix, sums cleared, DualAvg restarted from each chain's averaged step size (Driver.scala:75-80).
 // =============================================================================================================
-RN_GLOBAL void rn_k_pool_reduce(const RnArgs A, double* pool, int window_len) {
+RN_GLOBAL void rn_k_pool_reduce(const RnArgs A, double* pool, int window_len, int pass) {
+  // One block per parameter; thread t adds chains t, t + 256, ... in order, then a fixed tree: the result does not depend
+  // on scheduling (no atomics).  pass 0: pool[1 + i] = sum over chains of the chain's window mean, pool[0] = chains.
+  // pass 1 (after the all-reduce of pass 0): pool[1 + n + i] = sum over chains of [M2_c + L (mean_c - mean)^2] -- Chan's
+  // combination of the chains' Welford statistics around the POOLED mean (no s2/n - mean^2 cancellation).
   __shared__ double red[256];
-  for (int i = 0; i < 2 * RN_N; i++) {
-    const double* src = (i < RN_N) ? (A.est_mean + (size_t)i * A.chains) : (A.est_raw + (size_t)(i - RN_N) * A.chains);
-    double acc = 0.0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.chains; c += gridDim.x * blockDim.x) acc += src[c];
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
+  const int i = (int)blockIdx.x;
+  const double gmean = pass ? pool[1 + i] / pool[0] : 0.0;
+  const double* mean = A.est_mean + (size_t)i * A.chains;
+  const double* m2 = A.est_raw + (size_t)i * A.chains;
+  double acc = 0.0;
+  for (int c = (int)threadIdx.x; c < A.chains; c += (int)blockDim.x) {
+    if (pass) {
+      const double d = mean[c] - gmean;
+      acc += m2[c] + (double)window_len * d * d;
+    } else {
+      acc += mean[c];
     }
-    if (threadIdx.x == 0) atomicAdd(&pool[1 + i], red[0]);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = (int)blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&pool[0], (double)A.chains * (double)window_len);
+  if (threadIdx.x == 0) {
+    pool[1 + (pass ? RN_N : 0) + i] = red[0];
+    if (!pass && i == 0) pool[0] = (double)A.chains;
+  }
 }
-RN_GLOBAL void rn_k_pool_apply(const RnArgs A, const double* pool) {
+RN_GLOBAL void rn_k_pool_apply(const RnArgs A, const double* pool, int window_len) {
   const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= A.chains) return;
-  const double cnt = pool[0];
+  const double cnt = pool[0] * (double)window_len;  // draws of the window over all chains of all ranks
   for (int i = 0; i < RN_N; i++) {
-    const double mean = pool[1 + i] / cnt;
-    const double var = pool[1 + RN_N + i] / cnt - mean * mean;
+    const double var = pool[1 + RN_N + i] / cnt;
     if (!(var > 0.0)) A.st_err[c] |= 2;
     RN_AT(A.mass, i, c) = var;
     RN_AT(A.est_mean, i, c) = 0.0;

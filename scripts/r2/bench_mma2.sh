@@ -1,0 +1,6 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+export RN_KERNEL_CACHE=$PWD/build/kcache
+echo "== tests"; timeout 1500 python -m pytest tests/test_gpu_mma.py tests/test_gpu_full_size.py -q -m gpu -x 2>&1 | tail -15
+echo "== RN_MMA=1"; timeout 900 python scripts/bench_configs.py cfg3 --no-cpu --math=parity 2>&1 | cut -c1-400
+echo "== ncu cfg3"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:rn_k_iter -c 1 -o gpurun_out/r2h_ncu_cfg3 python scripts/bench_configs.py cfg3 --no-cpu --math=parity > gpurun_out/r2h_ncu_cfg3.log 2>&1; tail -2 gpurun_out/r2h_ncu_cfg3.log | cut -c1-200

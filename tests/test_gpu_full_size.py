@@ -24,15 +24,18 @@ def _static(it, nsteps, eps, **kw):
                            massMatrixTuner=api.IdentityMassMatrixTuner(), **kw)
 
 
-def _subset_matches(rir, cols, cfg, n_chains, pick, tol=1e-9, rir_gpu=None, cols_gpu=None, seed0=1000):
-    """full batch on the GPU; the picked chains re-run alone must be bit-identical; those are checked against the oracle"""
+def _subset_matches(rir, cols, cfg, n_chains, pick, tol=1e-9, rir_gpu=None, cols_gpu=None, seed0=1000, oracle_pick=None):
+    """full batch on the GPU; the picked chains re-run alone must be bit-identical; those (or `oracle_pick`, positions in
+    `pick`) are checked against the oracle.  (Models on the chain-batched DMMA path: pick whole groups of 8 consecutive chains
+    at multiples of 8 -- a CTA's 8 chains share the tensor-core tiles, a ragged batch takes the rows-across-lanes path.)"""
     seeds = np.arange(n_chains, dtype=np.int64) + seed0
     m = api.CudaModel(rir_gpu if rir_gpu is not None else rir, cols_gpu if cols_gpu is not None else cols)
     full = m.sample(cfg, seeds=seeds)
     small = m.sample(cfg, seeds=seeds[pick])
     assert np.array_equal(full.chains[pick], small.chains), "a chain's samples depend on the batch it ran in"
-    ref = OracleModel(rir, cols).sample(api.lower_config(cfg)[0], seeds=seeds[pick])
-    assert parity.rel_err(small.chains, ref["samples"], 1e-9) < tol
+    op = np.arange(len(pick)) if oracle_pick is None else np.asarray(oracle_pick)
+    ref = OracleModel(rir, cols).sample(api.lower_config(cfg)[0], seeds=seeds[pick][op], trace=True)
+    assert parity.rel_err(small.chains[op], ref["samples"], 1e-9) < tol
     return full
 
 
@@ -67,7 +70,33 @@ def test_cfg3_logistic_regression_100k_obs_50_covariates():
     assert parity.rel_err(got, ref, 1e-9) < 1e-9
     # short trajectories of 2048 chains (the BASELINE chain count); 2 chains re-run alone and against the oracle
     cfg = _static(2, 5, 0.01)
-    _subset_matches(rir, cols, cfg, 2048, np.array([0, 2047]), tol=1e-8, rir_gpu=prir, cols_gpu=pcols)
+    _subset_matches(rir, cols, cfg, 2048, np.r_[0:8, 2040:2048], tol=1e-8, rir_gpu=prir, cols_gpu=pcols, oracle_pick=[0, 15])
+
+
+def test_cfg3_longer_run_accept_decisions():
+    """cfg 3 over 25 iterations x 5 leapfrog steps ("checked for 2 iterations on 2 chains"): accept decisions, step
+    counts and samples of two chains of the DMMA batch against the oracle (its reverse-mode density on the primal RIR,
+    tests/test_oracle_adjoint.py)"""
+    prir, pcols = configs.logreg(100000, 50).compile(False)
+    cfg = _static(25, 5, 0.01)
+    seeds = np.arange(16, dtype=np.int64) + 1000
+    m = api.CudaModel(prir, pcols)
+    assert "rn_dmma(" in m.emit_source(cfg)
+    s = api.CudaSampler(m, cfg, seeds=seeds, trace=True)
+    import torch
+    d = torch.empty((25, 50, 16), dtype=torch.float64, device="cuda")
+    s.warmup(-1)
+    s.run(25, d.data_ptr())
+    s.sync()
+    got = d.permute(2, 0, 1).contiguous().cpu().numpy()
+    tr = s.read_trace()
+    s.close()
+    pick = np.array([0, 15])
+    ref = OracleModel(prir, pcols).sample(api.lower_config(cfg)[0], seeds=seeds[pick], trace=True)
+    assert np.array_equal(tr[pick][:, :, 1], ref["trace"][:, :, 1]), "accept decisions differ"
+    assert np.array_equal(tr[pick][:, :, 3], ref["trace"][:, :, 3])
+    assert parity.rel_err(got[pick], ref["samples"], 1e-9) < 1e-8
+    assert 0.5 < tr[:, :, 1].mean() <= 1.0
 
 
 def test_cfg4_eight_schools_default_config_8192_chains():
@@ -118,6 +147,34 @@ def test_cfg5_poisson_glm_reduced_oracle_and_additivity():
     beta = Normal(0, 10).latent()
     prior = api.CudaModel(*Model.track_([mu, sd] + alphas.toList() + [beta]).compile(False)).density_batch(q)
     assert parity.rel_err(a + b - prior, got, 1e-6) < 1e-9
+
+
+def test_cfg5_poisson_glm_full_size_1000_groups_1m_rows():
+    """BASELINE configs[4] at FULL size: density + gradient of all 1003 parameters at 4 positions, and the
+    samples / accept decisions of two chains out of the 4096-chain batch, against the oracle's reverse-mode density on the same
+    primal RIR -- the independent restatement of the reference's derivative rules (checked against the reference's own symbolic
+    gradient at 100 groups x 20000 rows: tests/test_oracle_adjoint.py, and the test above)."""
+    import os
+    f = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "models", "cfg5_primal.npz")
+    if not os.path.exists(f):
+        pytest.skip("build/models/cfg5_primal.npz not built (python __graft_entry__.py)")
+    z = np.load(f)
+    prir, pcols = z["rir"].tobytes(), [z["c%d" % i] for i in range(int(z["ncols"]))]
+    om = OracleModel(prir, pcols)
+    assert om.n == 1003 and len(pcols[0]) >= 124999
+    q = np.random.default_rng(3).normal(size=(4, 1003)) * 0.2
+    q[:, 1] = np.abs(q[:, 1])
+    m = api.CudaModel(prir, pcols)
+    assert parity.rel_err(m.density_batch(q), om.density_batch(q), 1e-9) < 1e-9
+    cfg = _static(2, 5, 1e-4)
+    seeds = np.arange(4096, dtype=np.int64) + 1000
+    full = m.sample(cfg, seeds=seeds)
+    pick = np.array([0, 4095])
+    small = m.sample(cfg, seeds=seeds[pick])
+    assert np.array_equal(full.chains[pick], small.chains)
+    ref = om.sample(api.lower_config(cfg)[0], seeds=seeds[pick], trace=True)
+    assert parity.rel_err(small.chains, ref["samples"], 1e-9) < 1e-8
+    assert [st.accepted for st in small.stats] == [st.accepted for st in ref["stats"]]
 
 
 def test_process_wide_staging_ring_outlives_a_model_handle():
