@@ -29,9 +29,20 @@ def seeds_for_rank(seeds, rank, world):
 
 def pooled_variance(count, s1, s2):
     """variance per parameter from pooled sums: count draws, s1 = sum q, s2 = sum q^2 (population variance, like
-    VarianceEstimator.variance = raw / samples, MassMatrixEstimator.scala:92-100)"""
+    VarianceEstimator.variance = raw / samples, MassMatrixEstimator.scala:92-100).  Textbook form, kept for reference: the
+    library itself combines Welford statistics (`combine_welford`), which does not cancel when |mean| >> sd."""
     mean = s1 / count
     return s2 / count - mean * mean
+
+
+def combine_welford(n, mean, m2):
+    """Host mirror of the library's pooled window reduction (rn_k_pool_reduce, two passes + two all-reduces): chains (or
+    ranks) each hold n draws with mean `mean[k]` and M2 `m2[k]` (sum of squared deviations from their own mean); the pooled
+    population variance is [sum_k m2[k] + n (mean[k] - mean)^2] / (K n) around the pooled mean (Chan et al.)."""
+    mean, m2 = np.asarray(mean, dtype=np.float64), np.asarray(m2, dtype=np.float64)
+    k = mean.shape[0]
+    g = mean.sum(axis=0) / k
+    return (m2 + n * (mean - g) ** 2).sum(axis=0) / (k * n)
 
 
 def allreduce_window_stats(stats, group=None):

@@ -96,6 +96,13 @@ def test_two_ranks_gloo(tmp_path):
     assert np.allclose(stats[1:11], q.sum(axis=0), rtol=1e-13) and np.allclose(stats[11:], (q * q).sum(axis=0), rtol=1e-13)
     var = rdist.pooled_variance(stats[0], stats[1:11], stats[11:])
     assert np.allclose(var, q.var(axis=0), rtol=1e-9)
+    # what the library does at a window end: per-chain Welford statistics combined around the pooled mean
+    draws = ref[:, -6:, :]  # a window of 6 draws per chain
+    w = rdist.combine_welford(6, draws.mean(axis=1), ((draws - draws.mean(axis=1, keepdims=True)) ** 2).sum(axis=1))
+    assert np.allclose(w, draws.reshape(-1, 10).var(axis=0), rtol=1e-12)
+    shifted = draws + 1e9  # |mean| >> sd: the sums-of-squares form loses everything, the combined form nothing
+    w2 = rdist.combine_welford(6, shifted.mean(axis=1), ((shifted - shifted.mean(axis=1, keepdims=True)) ** 2).sum(axis=1))
+    assert np.allclose(w2, w, rtol=1e-6)
     assert np.load(tmp_path / "tmax.npy")[0] == 2.0
     # multi-start MAP over 2 ranks == the same starts in one process
     from oracle.rainier_py.optimizer import lbfgs

@@ -61,7 +61,18 @@ def test_warp_per_chain_source_shape():
     m = api.CudaModel(rir, cols, device=-1)
     cfg = api.make_config(sampler=api.HMCSampler(2), backend=abi.RN_BACKEND_WARP)
     src = m.emit_source(cfg)
-    dens = src[src.index("// ---- emitted"):src.index("#define RN_WPC_SMEM_DOUBLES")]
+    dens = src[src.index("// ---- emitted"):src.index("// rn_sampler_wpc.cuh --")]
+    # logistic regression = dot products + elementwise code: the chain-batched DMMA path (per-warp TMA column blocks) ...
+    assert "rn_dmma(" in dens and "rn_tma_load_raw(" in dens and "rn_mbar_wait_warp(" in dens and "rn_cta_bar(" in dens
+    assert "#define RN_MMA_BARS 8" in src and dens.count("RN_DEVICE void rn_mma_e") == 1  # one copy serves the 8 unrolled observations
+    import os
+    os.environ["RN_MMA"] = "0"  # ... and, switched off, the CTA-shared tile pipeline of the rows-across-lanes body
+    try:
+        src = api.CudaModel(rir, cols, device=-1).emit_source(cfg)
+    finally:
+        del os.environ["RN_MMA"]
+    dens = src[src.index("// ---- emitted"):src.index("// rn_sampler_wpc.cuh --")]
+    assert "rn_dmma(" not in dens
     assert "rn_tma_load(" in dens and "rn_mbar_wait(" in dens and "rn_cta_bar(" in dens  # CTA-shared tiles
     assert "RN_LDG(rp +" in dens                                                          # independent per-warp path
     assert "rn_pow(" not in dens and "rn_pow_libm(" not in dens                           # d/dx x^-1 strength-reduced
@@ -69,8 +80,7 @@ def test_warp_per_chain_source_shape():
     assert " exp(" in rows and " log(" in rows and "rn_exp(" not in rows                  # libm in row regions only
     assert "RN_FENCE();" in rows                                                          # reverse sweep reloads columns
     assert "#define RN_TMA_STAGES" in src and "#define RN_WPC_K 1" in src
-    assert src == api.CudaModel(rir, cols, device=-1).emit_source(cfg)
-    import os
+    assert m.emit_source(cfg) == api.CudaModel(rir, cols, device=-1).emit_source(cfg)
     os.environ["RN_WPC_K"] = "2"
     try:
         src2 = api.CudaModel(rir, cols, device=-1).emit_source(cfg)
