@@ -467,7 +467,8 @@ struct Emitter {
   int mma_inv_off = 0;
   bool mma_all_ok = false;
   int mma_shared_doubles = 0;
-  static constexpr int MMA_WARPS = 8;
+  static constexpr int MMA_WARPS = 8;  // warps of one chain group = column-block regions / barriers per CTA
+  int mma_groups() const { return opt.mma_chains >= 16 ? 2 : 1; }
 
   static MmaPlan why(MmaPlan& pl, int line) {
     if (getenv("RN_MMA_DEBUG")) fprintf(stderr, "[rn mma] target not eligible for the DMMA path: check %d\n", line);
@@ -712,29 +713,30 @@ struct Emitter {
     return out;
   }
 
-  // the elementwise code of one dot for the lane's EIGHT (row, chain) elements of a tile (element e = 2*nt + h: 8-row group
-  // nt, row slot 2*(lane%4)+h), statement by statement across the elements: eight independent dependency chains for the
-  // scheduler, like the interleaved observations of the rows-across-lanes body (one element at a time left a warp with a
-  // single serial chain of exp / log / divisions and the kernel latency-bound at 8 warps per SM)
+  // the elementwise code of one dot for FOUR of the lane's eight (row, chain) elements of a tile (element e = 2*nt + h: 8-row
+  // group nt, row slot 2*(lane%4)+h; the call handles groups roff/8 and roff/8 + 1), statement by statement across the
+  // elements: four independent dependency chains for the scheduler, like the interleaved observations of the
+  // rows-across-lanes body (one element at a time left a warp with a single serial chain of exp / log / divisions; eight at
+  // a time spilled at 128 registers)
   void mma_helper(const TargetInfo& T, size_t t, const MmaPlan& pl, size_t di) {
     const MmaDot& d = pl.dots[di];
     const int pitch = opt.pitch(t);
-    os << "RN_DEVICE void rn_mma_e" << t << "_" << di << "(const double (&zz)[8], const RnSA rp0, const RnSA rp1, const double* RN_RESTRICT q, "
-          "const double* RN_RESTRICT xv, double& dens, double (&wout)[8], double* osum, int& err) {\n"
-       << "  (void)rp0; (void)rp1; (void)q; (void)xv; (void)osum; (void)err;\n";
+    os << "RN_DEVICE void rn_mma_e" << t << "_" << di << "(const double* zz, const RnSA rp0, const RnSA rp1, const int roff, const double* RN_RESTRICT q, "
+          "const double* RN_RESTRICT xv, double& dens, double* wout, double* osum, int& err) {\n"
+       << "  (void)rp0; (void)rp1; (void)roff; (void)q; (void)xv; (void)osum; (void)err;\n";
     for (size_t k = 0; k < mma_inv.size(); k++) os << "  const double v" << mma_inv[k] << " = xv[" << k << "]; (void)v" << mma_inv[k] << ";\n";
-    std::set<int> declared[8];
+    std::set<int> declared[4];
     auto sfx = [&](int e) { return "_" + std::to_string(e); };
     auto need_col = [&](int o, int e) {
       const Node& n = P.nodes[o];
       if (n.kind != K_INPUT || (uint32_t)n.a < P.n_params) return;
       const int k = n.a - (int)P.n_params;
       if (declared[e].insert(k).second)
-        os << "  const double c" << k << sfx(e) << " = rn_lds(" << (e & 1 ? "rp1" : "rp0") << ", " << (e >> 1) * 8 + (local_col(T, k) - d.cmin) * pitch << ");\n";
+        os << "  const double c" << k << sfx(e) << " = rn_lds(" << (e & 1 ? "rp1" : "rp0") << ", roff + " << (e >> 1) * 8 + (local_col(T, k) - d.cmin) * pitch << ");\n";
     };
     std::vector<int> o;
     auto one = [&](int id) {
-      for (int e = 0; e < 8; e++) {
+      for (int e = 0; e < 4; e++) {
         node_suffix = col_suffix = sfx(e);
         if (id == d.z) {  // the dot itself: the tensor core's sum, plus the fold's first operand
           if (d.base >= 0) {
@@ -757,13 +759,13 @@ struct Emitter {
     }
     if (!z_done) one(d.z);
     for (int l : d.leaves)
-      for (int e = 0; e < 8; e++) {
+      for (int e = 0; e < 4; e++) {
         node_suffix = col_suffix = sfx(e);
         need_col(l, e);
         os << "  dens += " << val(l) << ";\n";
       }
     for (int id : d.bwd) one(id);
-    for (int e = 0; e < 8; e++) {
+    for (int e = 0; e < 4; e++) {
       node_suffix = col_suffix = sfx(e);
       need_col(d.w, e);
       os << "  wout[" << e << "] = " << val(d.w) << ";\n";
@@ -780,16 +782,18 @@ struct Emitter {
   void mma_block(const TargetInfo& T, size_t t, const MmaPlan& pl, unsigned long long n_full) {
     const int pitch = opt.pitch(t), NP = (int)pl.params.size(), KS = pl.KS, DT = pl.DT, NO = (int)pl.other_slots.size();
     const unsigned long long base = (unsigned long long)opt.target_base[t], td = (unsigned long long)T.n_cols * pitch;
-    os << "    if (tma.on) {  // chain-batched DMMA over the CTA's 8 chains: warp w <-> dot w (see Emitter::mma_block)\n"
-       << "      const int wid = (int)(threadIdx.x >> 5), ln = (int)(threadIdx.x & 31), mc = ln >> 2, mk = ln & 3;\n";
+    const int NG = mma_groups();
+    os << "    if (tma.on) {  // chain-batched DMMA over the CTA's " << 8 * NG << " chains: warp w <-> dot w % 8 for chain group w / 8 (see Emitter::mma_block)\n"
+       << "      const int wfull = (int)(threadIdx.x >> 5), wid = wfull & 7, cg = wfull >> 3, ln = (int)(threadIdx.x & 31), mc = ln >> 2, mk = ln & 3;\n"
+       << "      (void)cg;\n";
     if (!mma_inv.empty()) {
       os << "      if (ln == 0) {\n";
       for (size_t k = 0; k < mma_inv.size(); k++) os << "        scr[" << (mma_inv_off + (int)k) << "] = " << val(mma_inv[k]) << ";\n";
       os << "      }\n";
     }
     os << "      rn_cta_bar(tma.nthreads);  // every chain's q (and invariants) are in its slice\n"
-       << "      const double* qo = q + (mc - wid) * RN_WPC_SMEM_DOUBLES;\n"
-       << "      const double* xo = scr + (mc - wid) * RN_WPC_SMEM_DOUBLES + " << mma_inv_off << ";\n"
+       << "      const double* qo = q + (cg * 8 + mc - wfull) * RN_WPC_SMEM_DOUBLES;\n"
+       << "      const double* xo = scr + (cg * 8 + mc - wfull) * RN_WPC_SMEM_DOUBLES + " << mma_inv_off << ";\n"
        << "      (void)xo;\n"
        << "      double ar[" << KS << "];\n";
     for (int ks = 0; ks < KS; ks++) {
@@ -839,7 +843,7 @@ struct Emitter {
       else
         os << "      if (wid == " << (ci % MMA_WARPS) << ") {  // dot " << ci << ": columns " << d.cmin << ".." << d.cmax << " of the tile\n"
            << "        const double* RN_RESTRICT s0 = src + " << (unsigned long long)d.cmin * pitch << "ULL;\n";
-      os << "        if (ln == 0) rn_tma_load_raw(region, bar, s0, " << bytes << "u);\n"
+      os << "        if (ln == 0 && cg == 0) rn_tma_load_raw(region, bar, s0, " << bytes << "u);\n"
          << "        const int pf = mc ^ ((mc >> 2) & 1), pb0 = (2 * mk) ^ ((mk >> 1) & 1), pb1 = (2 * mk + 1) ^ ((mk >> 1) & 1);\n";
       if (ap) {
         os << "        const RnSA bf = rn_sa(region + pf + (" << (d.cols[0] - d.cmin) << " + " << step << " * mk) * " << pitch << ");\n"
@@ -877,21 +881,22 @@ struct Emitter {
       for (int ks = 0; ks < KS; ks++)  // term groups outermost: four independent accumulator chains (the tile's 8-row groups)
         for (int nt = 0; nt < 4; nt++)
           os << "          rn_dmma(z[" << 2 * nt << "], z[" << 2 * nt + 1 << "], ar[" << ks << "], rn_lds(bf, " << nt * 8 << " + " << fwd_addr(ks) << "));\n";
-      os << "          rn_mma_e" << t << "_" << ci << "(z, e0, e1, qo, xo, dsum, wv, osum, err);\n";
+      os << "          rn_mma_e" << t << "_" << ci << "(z, e0, e1, 0, qo, xo, dsum, wv, osum, err);\n"
+         << "          rn_mma_e" << t << "_" << ci << "(z + 4, e0, e1, 16, qo, xo, dsum, wv + 4, osum, err);\n";
       for (int nt = 0; nt < 4; nt++)
         for (int h = 0; h < 2; h++)
           for (int dt = 0; dt < DT; dt++)
             os << "          rn_dmma(g[" << dt << "][0], g[" << dt << "][1], wv[" << 2 * nt + h << "], rn_lds(" << (h ? "bb1" : "bb0") << ", " << nt * 8 << " + "
                << bwd_addr(dt) << "));\n";
       os
-         << "          __syncwarp();\n"
-         << "          if (ln == 0 && tile + 1 < " << n_full << "u) rn_tma_load_raw(region, bar, s0 + (size_t)(tile + 1) * " << td << "ULL, " << bytes << "u);\n"
+         << "          " << (NG > 1 ? "rn_pair_bar(2 + wid, 64);  // both warps of the pair are done with the block" : "__syncwarp();") << "\n"
+         << "          if (ln == 0 && cg == 0 && tile + 1 < " << n_full << "u) rn_tma_load_raw(region, bar, s0 + (size_t)(tile + 1) * " << td << "ULL, " << bytes << "u);\n"
          << "        }\n      }\n";
     }
     // per-warp partials -> CTA scratch [warp][chain][redw]; chain wid's warp totals them in warp order
     const int NPAD = DT * 8;
     os << "      double* const red = tma.stage + (size_t)" << MMA_WARPS << " * " << pl.region_doubles << ";\n"
-       << "      double* const mine = red + (size_t)(wid * 8 + mc) * " << pl.redw << ";\n";
+       << "      double* const mine = red + (size_t)(wfull * 8 + mc) * " << pl.redw << ";\n";
     for (int dt = 0; dt < DT; dt++)
       os << "      mine[" << dt * 8 << " + 2 * mk] = g[" << dt << "][0];\n      mine[" << dt * 8 << " + 2 * mk + 1] = g[" << dt << "][1];\n";
     os << "      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);\n      dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);\n"
@@ -900,10 +905,10 @@ struct Emitter {
       os << "      osum[" << k << "] += __shfl_xor_sync(0xffffffffu, osum[" << k << "], 1);\n      osum[" << k
          << "] += __shfl_xor_sync(0xffffffffu, osum[" << k << "], 2);\n      if (mk == 0) mine[" << NPAD + 1 + k << "] = osum[" << k << "];\n";
     os << "      rn_cta_bar(tma.nthreads);\n"
-       << "      double* const tot = red + (size_t)(wid * 8 + wid) * " << pl.redw << ";  // (read by this warp only)\n"
+       << "      double* const tot = red + (size_t)(wfull * 8 + wid) * " << pl.redw << ";  // (read by this warp only)\n"
        << "      for (int j = ln; j < " << pl.redw << "; j += 32) {\n"
        << "        double s = 0.0;\n"
-       << "        for (int w8 = 0; w8 < " << std::min<int>(MMA_WARPS, (int)pl.dots.size()) << "; w8++) s += red[(size_t)(w8 * 8 + wid) * " << pl.redw << " + j];\n"
+       << "        for (int w8 = 0; w8 < " << std::min<int>(MMA_WARPS, (int)pl.dots.size()) << "; w8++) s += red[(size_t)((cg * 8 + w8) * 8 + wid) * " << pl.redw << " + j];\n"
        << "        tot[j] = s;\n      }\n"
        << "      __syncwarp();\n"
        << "      if (ln == 0) {\n"
@@ -950,7 +955,7 @@ struct Emitter {
       any_full = true;
       plans[t] = plan_mma(T, t);
       if (!plans[t].ok) mma_all_ok = false;
-      mma_shared_doubles = std::max(mma_shared_doubles, MMA_WARPS * plans[t].region_doubles + MMA_WARPS * 8 * plans[t].redw);
+      mma_shared_doubles = std::max(mma_shared_doubles, MMA_WARPS * plans[t].region_doubles + mma_groups() * MMA_WARPS * 8 * plans[t].redw);
     }
     if (!any_full) mma_all_ok = false;
     if (!mma_all_ok) mma_shared_doubles = 0;

@@ -170,7 +170,8 @@ struct Kernel {
   int wpc_k = 1;
   int tma_stages = 0;         // CTA-shared data-tile pipeline (backend 1): stages, doubles per stage
   int tile_doubles = 0;
-  bool mma = false;           // backend 1: chain-batched DMMA path compiled in (8 chains per CTA; tile_doubles = its shared doubles)
+  bool mma = false;           // backend 1: chain-batched DMMA path compiled in (tile_doubles = its shared doubles)
+  int mma_chains = 8;         //            chains per CTA on that path (8 or 16)
   // backend 0: bytes of dynamic shared memory per THREAD (rn_sampler.cuh: momentum, diagonal mass, EHMC snapshot momentum,
   // Stats counters live there instead of in registers) -- must mirror RN_TS_DOUBLES / RN_TS_INTS
   unsigned tpc_smem_per_thread = 0;
@@ -342,18 +343,26 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
     bool want_mma = !key.ehmc && key.mass_max < 2 && eo.wpc_k == 1 && z.mma_ok && !P->symbolic;
     if (const char* e = getenv("RN_MMA")) want_mma = want_mma && atoi(e) != 0;
     if (want_mma) {
-      EmitOptions em = eo;
-      em.mma = true;
-      em.tma_stages = 1;
-      const WpcSizes zm = wpc_sizes(*P, em);
-      const size_t need = 8 * (size_t)zm.per_warp_doubles * 8 + 128 + (size_t)zm.mma_shared_doubles * 8 + 64;
-      if (zm.mma_ok && need <= cap) {
-        eo = em;
-        K->mma = true;
-        K->wpc_smem_doubles = zm.per_warp_doubles;
-        K->tile_doubles = zm.mma_shared_doubles;
-        K->tma_stages = 1;
-        K->warps_per_cta = 8;
+      // 16 chains per CTA when they fit (two chain groups whose warps pair up on a dot's column block: twice the warps per
+      // SM -- the path is latency-bound at 8 -- for the same staged bytes), else 8
+      int want_chains = 16;
+      if (const char* e = getenv("RN_MMA_CHAINS")) want_chains = atoi(e) >= 16 ? 16 : 8;
+      for (int nc = want_chains; nc >= 8 && !K->mma; nc -= 8) {
+        EmitOptions em = eo;
+        em.mma = true;
+        em.mma_chains = nc;
+        em.tma_stages = 1;
+        const WpcSizes zm = wpc_sizes(*P, em);
+        const size_t need = (size_t)nc * (size_t)zm.per_warp_doubles * 8 + 128 + (size_t)zm.mma_shared_doubles * 8 + 64;
+        if (zm.mma_ok && need <= cap) {
+          eo = em;
+          K->mma = true;
+          K->mma_chains = nc;
+          K->wpc_smem_doubles = zm.per_warp_doubles;
+          K->tile_doubles = zm.mma_shared_doubles;
+          K->tma_stages = 1;
+          K->warps_per_cta = nc;
+        }
       }
     }
   }
@@ -1232,7 +1241,8 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.n_iter = k;
     a.adaptation = s->cfg.adaptation == RN_ADAPT_POOLED ? 1 : 0;
     a.tma = s->K->tma_stages > 0 ? 1 : 0;
-    if (s->K->mma && ((chain_begin % 8) != 0 || ((chain_end - chain_begin) % 8) != 0)) a.tma = 0;  // the DMMA path wants full CTAs of 8 chains
+    if (s->K->mma && ((chain_begin % s->K->mma_chains) != 0 || ((chain_end - chain_begin) % s->K->mma_chains) != 0))
+      a.tma = 0;  // the DMMA path wants full CTAs (8 or 16 chains); a ragged batch runs the per-warp path of the same kernel
     a.chain_begin = chain_begin;
     a.chain_end = chain_end;
     a.mass_kind = s->mass_kind;

@@ -97,16 +97,19 @@ def test_static_mass_matrices(funnel):
     parity.assert_parity(r, tol=1e-8)
 
 
-@pytest.mark.parametrize("name", ["SBCUniformNormal", "SBCBernoulli", "SBCExponential", "SBCLogNormal", "SBCBinomial"])
+@pytest.mark.parametrize("name", sbc_models.ENABLED)
 def test_reference_goldsets_on_gpu(name):
-    """The reference's own golden vectors (SBCModel.scala:46-267, 1e-10 as in SBCTest.scala:7-15), reproduced by the
-    CUDA path: same RNG stream, 10000 warmup iterations of HMCSampler(1)/DualAvgTuner(0.8), then predict."""
+    """The reference's own golden vectors -- all 11 of the enabled list (SBCTest.scala:20-34; SBCModel.scala:46-267, 1e-10 as
+    in SBCTest.scala:7-15), reproduced by the CUDA path: same RNG stream, 10000 warmup iterations of HMCSampler(1) /
+    DualAvgTuner(0.8), then predict.  Thread-per-chain shape throughout: it sums streamed rows (SBCLaplace) in the
+    reference's sequential order, which a 10000-iteration adaptive warmup needs to stay on the golden trajectory."""
     from oracle.rainier_py.compute import Evaluator
 
     gold = GOLD["models"][name]["goldset"]
     model, real, rng, _ = sbc_models.build(name)
     rir, cols = model.compile(True)
     cfg = _cfg(len(gold), 10000, api.HMCSampler(1), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner())
+    cfg.backend = abi.RN_BACKEND_THREAD
     tr = api.CudaModel(rir, cols).sample(cfg, rng_states=[rng.rand.state()])
     params = model.parameters
     for a, b in zip(tr.chains[0], gold):
@@ -134,6 +137,9 @@ def test_rn_sample_host_buffers(schools):
     assert parity.rel_err(tr.mass, ref["mass"]) < 1e-8
     for g, o in zip(tr.stats, ref["stats"]):
         assert g.gradientEvaluations == o.gradient_evaluations and g.accepted == o.accepted
+        # Stats.gradientTimes / iterationTimes (Stats.scala:8-9; read by the notebook's HTMLProgress): device time of the
+        # sampling launches / this chain's gradient evaluations and / iterations
+        assert 0 < g.gradientTimesMean < g.iterationTimesMean < 1e9
 
 
 def test_rn_sample_pinned_and_pageable_buffers_agree(funnel):
