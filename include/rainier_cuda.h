@@ -160,6 +160,18 @@ void rn_config_default(rn_config* cfg);
 int rn_model_create(const void* rir, size_t len, const double* const* cols, const int64_t* col_rows,
                     int n_cols, int device, rn_model** out);
 int rn_model_nvars(const rn_model* m);
+/* Device-side inlining (replaces TargetGroup.inlinable + PartialEvaluator.inline, compute/Target.scala:136-207,
+ * compute/PartialEvaluator.scala:86-97): rn_model_create folds every SEPARABLE streamed target of a primal container into a
+ * data-free polynomial -- the row sums of its column-only monomials are reduced on the device once -- so the caller sends the
+ * streamed form and never runs the reference's inliner (RN_INLINE=0 disables).  Returns the number of targets folded;
+ * *monomials / *rows (optional) = monomials summed and rows no longer streamed per gradient evaluation. */
+int rn_model_inlined(const rn_model* m, int64_t* monomials, int64_t* rows);
+/* tooling / tests (no device): the host halves of that step.  rn_inline_plan: number of separable targets of a primal
+ * container; for target k of them its index, the number of column-only monomials and the RIR_FLAG_FUNCTION container that
+ * evaluates them over the target's columns.  rn_inline_apply: the rewritten container given the monomials' row sums. */
+int rn_inline_plan(const void* rir, size_t len, int k, int* n_targets, int* target_index, int64_t* n_monomials, void* fn_rir, size_t cap,
+                   size_t* needed);
+int rn_inline_apply(const void* rir, size_t len, const double* sums, size_t n_sums, void* out, size_t cap, size_t* needed);
 /* q: host [chains][n];  out: host [chains][n+1] = density then gradient (Model.scala:48-49) */
 int rn_density_batch(rn_model* m, const double* q, int chains, double* out);
 /* debug: emitted CUDA source of the fused kernel for `cfg` (NUL-terminated).  Returns RN_OK and the needed

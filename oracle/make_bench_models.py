@@ -15,12 +15,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def streamed_primal(model):
+    """the model's primal container WITHOUT the reference's inlining step (rn_model_create inlines on the device)"""
+    from oracle.rainier_py import compute
+    keep = compute.inlinable
+    compute.inlinable = lambda real: False
+    try:
+        return model.compile(False)
+    finally:
+        compute.inlinable = keep
+
+
 def main(which=None):
     from oracle.rainier_py import configs
     d = os.path.join(ROOT, "build", "models")
     os.makedirs(d, exist_ok=True)
     builders = {
         "cfg2s": lambda: configs.linreg(10000, covariates=5).compile(True),
+        "cfg2s_primal": lambda: streamed_primal(configs.linreg(10000, covariates=5)),  # what the Scala side sends: no inlining, no gradient
         "cfg3_primal": lambda: configs.logreg(100000, 50).compile(False),
         "cfg4": lambda: configs.eight_schools().compile(True),
         "cfg5_primal": lambda: configs.poisson_glm(1000, 1000000).compile(False),

@@ -57,6 +57,10 @@ def lib():
         L.rn_model_op_counts.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(C.c_double)]
         L.rn_model_separable_structure.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.rn_model_dot_structure.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(C.c_double)]
+        L.rn_model_inlined.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.rn_inline_plan.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.c_void_p,
+                                     C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rn_inline_apply.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.rn_density_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.rn_emit_source.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.rn_emit_cubin.argtypes = [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -475,6 +479,12 @@ class CudaModel:
         return image
 
     # -- debug (the analogue of rainier-decompile) --
+    def inlined(self):
+        """(targets folded at create, monomials summed on the device, rows no longer streamed per gradient)"""
+        mono, rows = C.c_int64(0), C.c_int64(0)
+        n = lib().rn_model_inlined(self.h, C.byref(mono), C.byref(rows))
+        return int(n), int(mono.value), int(rows.value)
+
     def emit_source(self, config=None):
         cfg = lower_config(config)[0] if config is not None else None
         need = C.c_size_t()
@@ -637,6 +647,33 @@ class CudaModel:
         tr = Trace(samples if keep_samples else None, mass, [Stats(stats[c], rings[c]) for c in range(nChains)])
         tr.diagnostics = diag  # [n][2] = rHat, effectiveSampleSize (Trace.diagnostics), reduced on the device
         return tr
+
+
+def inline_plan(rir):
+    """host half of the device-side inlining (rn_inline_plan): [(target index, n monomials, function-flavour RIR bytes)] for the
+    separable streamed targets of a primal container"""
+    rir = bytes(rir)
+    nt = C.c_int(0)
+    _check(lib().rn_inline_plan(rir, len(rir), -1, C.byref(nt), None, None, None, 0, None))
+    out = []
+    for k in range(nt.value):
+        ti, nm, need = C.c_int(0), C.c_int64(0), C.c_size_t(0)
+        _check(lib().rn_inline_plan(rir, len(rir), k, None, C.byref(ti), C.byref(nm), None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().rn_inline_plan(rir, len(rir), k, None, None, None, buf, need.value, C.byref(need)))
+        out.append((ti.value, nm.value, buf.raw))
+    return out
+
+
+def inline_apply(rir, sums):
+    """the rewritten (data-free) container for the monomials' row sums (rn_inline_apply); sums: concatenated over targets"""
+    rir = bytes(rir)
+    s = np.ascontiguousarray(sums, dtype=np.float64)
+    need = C.c_size_t(0)
+    _check(lib().rn_inline_apply(rir, len(rir), s.ctypes.data, len(s), None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _check(lib().rn_inline_apply(rir, len(rir), s.ctypes.data, len(s), buf, need.value, C.byref(need)))
+    return buf.raw
 
 
 class Comm:

@@ -34,4 +34,25 @@ RN_GLOBAL void rn_k_eval(const RnEvalArgs A) {
 #endif
 }
 
+// Fixed-order row reduction of the values rn_k_eval wrote as [output][row]: sums[j] += sum over rows of vals[j][.] -- one block per
+// output, thread t adds rows t, t + 256, ... in order, then a fixed tree (no atomics: the same bits every run).  Used by the
+// device-side inlining of separable likelihoods (rn_inline.hpp), where the "outputs" are column-only monomials of a target.
+#ifndef RN_HOST_EMULATION
+RN_GLOBAL void rn_k_reduce_rows(const double* RN_RESTRICT vals, const long long rows, const int m, double* sums) {
+  __shared__ double red[256];
+  const int j = (int)blockIdx.x;
+  if (j >= m) return;
+  const double* v = vals + (size_t)j * (size_t)rows;
+  double acc = 0.0;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) acc += v[r];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = (int)blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[j] += red[0];
+}
+#endif
+
 #endif  // RN_FUNCTION_CUH

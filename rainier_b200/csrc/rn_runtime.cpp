@@ -37,6 +37,7 @@
 #include "rn_args.h"
 #include "rn_cuda_api.hpp"
 #include "rn_emit.hpp"
+#include "rn_inline.hpp"
 #include "rn_graph.hpp"
 
 using namespace rn;
@@ -191,6 +192,8 @@ struct rn_model {
   CUdeviceptr d_data = 0;
   std::vector<uint64_t> target_base;  // per target: element offset of its tile-major block in the data buffer
   std::vector<int> target_pitch;      // per target: doubles between the columns of a tile (32, or 36 where the DMMA path may run)
+  int inlined_targets = 0;            // streamed targets folded into data-free polynomials at create (rn_inline.hpp)
+  int64_t inlined_monomials = 0, inlined_rows = 0;
   uint64_t data_doubles = 0;
   std::map<std::pair<bool, bool>, std::unique_ptr<Program>> programs;  // (adjoint, fast)
   std::map<KernelKey, std::unique_ptr<Kernel>> kernels;
@@ -589,8 +592,10 @@ void rn_abi_sizes(int32_t out[4]) {
   out[3] = (int32_t)sizeof(RnArgs);
 }
 
-int rn_model_create(const void* rir, size_t len, const double* const* cols, const int64_t* col_rows, int n_cols,
-                    int device, rn_model** out) {
+static int device_inline(rn_model* streamed, const InlinePlan& plan, std::vector<uint8_t>& new_rir);
+
+static int model_create_impl(const void* rir, size_t len, const double* const* cols, const int64_t* col_rows, int n_cols,
+                             int device, rn_model** out) {
   if (!rir || !out) return fail(RN_E_INVALID, "null argument");
   std::unique_ptr<rn_model> m(new rn_model());
   m->rir.assign((const uint8_t*)rir, (const uint8_t*)rir + len);
@@ -607,7 +612,7 @@ int rn_model_create(const void* rir, size_t len, const double* const* cols, cons
   if (rc) return rc;
   for (const TargetInfo& T : P->targets)
     for (uint32_t j = 0; j < T.n_cols; j++)
-      if ((uint64_t)col_rows[T.first_input - h.n_params + j] != T.n_rows)
+      if (T.n_rows > 0 && (uint64_t)col_rows[T.first_input - h.n_params + j] != T.n_rows)  // (n_rows == 0: inlined, columns unread)
         return fail(RN_E_INVALID, "column length does not match its target's row count");
   m->data_doubles = data_layout(*P, m->target_base, m->target_pitch);
   m->device = device;
@@ -630,6 +635,80 @@ int rn_model_create(const void* rir, size_t len, const double* const* cols, cons
   }
   *out = m.release();
   return RN_OK;
+}
+
+// Model creation = the streamed container as sent, then device-side inlining of its separable targets (rn_inline.hpp): the
+// column-only monomials are summed over the rows ON THE DEVICE (data already in place), the target becomes a data-free
+// polynomial, and the model is rebuilt from the rewritten container.  RN_INLINE=0 keeps every target streamed.
+int rn_model_create(const void* rir, size_t len, const double* const* cols, const int64_t* col_rows, int n_cols,
+                    int device, rn_model** out) {
+  rn_model* m = nullptr;
+  int rc = model_create_impl(rir, len, cols, col_rows, n_cols, device, &m);
+  if (rc) return rc;
+  const char* e = getenv("RN_INLINE");
+  if (device >= 0 && !(e && atoi(e) == 0)) {
+    InlinePlan plan;
+    if (plan_inline(rir, len, plan).empty() && !plan.inl.empty()) {
+      std::vector<uint8_t> nr;
+      rc = device_inline(m, plan, nr);
+      rn_model* m2 = nullptr;
+      if (rc == RN_OK) rc = model_create_impl(nr.data(), nr.size(), cols, col_rows, n_cols, device, &m2);
+      if (rc) {
+        const std::string keep = rn_last_error();
+        rn_model_destroy(m);
+        return fail(rc, keep);
+      }
+      m2->inlined_targets = (int)plan.inl.size();
+      for (const InlineTarget& I : plan.inl) {
+        m2->inlined_monomials += (int64_t)I.monos.size();
+        m2->inlined_rows += (int64_t)plan.targets[I.target].t.n_rows;
+      }
+      rn_model_destroy(m);
+      m = m2;
+    }
+  }
+  *out = m;
+  return RN_OK;
+}
+// the two host halves of the inlining for tooling and tests (no device): which targets are separable and the function-flavour
+// program of target k's monomials; the rewritten container for given row sums
+int rn_inline_plan(const void* rir, size_t len, int k, int* n_targets, int* target_index, int64_t* n_monomials, void* fn_rir, size_t cap,
+                   size_t* needed) {
+  InlinePlan plan;
+  const std::string e = plan_inline(rir, len, plan);
+  if (!e.empty()) return fail(RN_E_INVALID, e);
+  if (n_targets) *n_targets = (int)plan.inl.size();
+  if (k < 0 || k >= (int)plan.inl.size()) return RN_OK;
+  if (target_index) *target_index = plan.inl[k].target;
+  if (n_monomials) *n_monomials = (int64_t)plan.inl[k].monos.size();
+  const std::vector<uint8_t> f = inline_function_rir(plan, (size_t)k);
+  if (needed) *needed = f.size();
+  if (fn_rir && cap >= f.size()) std::memcpy(fn_rir, f.data(), f.size());
+  return RN_OK;
+}
+int rn_inline_apply(const void* rir, size_t len, const double* sums /* all targets' monomials, concatenated */, size_t n_sums, void* out,
+                    size_t cap, size_t* needed) {
+  InlinePlan plan;
+  const std::string e = plan_inline(rir, len, plan);
+  if (!e.empty()) return fail(RN_E_INVALID, e);
+  std::vector<std::vector<double>> s(plan.inl.size());
+  size_t pos = 0;
+  for (size_t k = 0; k < plan.inl.size(); k++) {
+    if (pos + plan.inl[k].monos.size() > n_sums) return fail(RN_E_INVALID, "too few sums");
+    s[k].assign(sums + pos, sums + pos + plan.inl[k].monos.size());
+    pos += plan.inl[k].monos.size();
+  }
+  const std::vector<uint8_t> nr = apply_inline(plan, s);
+  if (needed) *needed = nr.size();
+  if (out && cap >= nr.size()) std::memcpy(out, nr.data(), nr.size());
+  return RN_OK;
+}
+// what create folded: streamed targets inlined, monomials summed, rows no longer streamed per gradient
+int rn_model_inlined(const rn_model* m, int64_t* monomials, int64_t* rows) {
+  if (!m) return 0;
+  if (monomials) *monomials = m->inlined_monomials;
+  if (rows) *rows = m->inlined_rows;
+  return m->inlined_targets;
 }
 
 // test/debug: the packed image of the data buffer exactly as rn_model_create uploads it (host emulation of the emitted
@@ -2116,7 +2195,7 @@ struct rn_function {
   std::string source;
   std::vector<char> cubin;
   CUmodule mod = nullptr;
-  CUfunction k_eval = nullptr;
+  CUfunction k_eval = nullptr, k_reduce = nullptr;
   CUstream stream = nullptr;
   CUstream stream2 = nullptr;  // second staging slot of rn_function_eval (host buffers)
   CUdeviceptr d_err = 0;
@@ -2162,6 +2241,7 @@ static int function_load(const Api* A, rn_function* f) {
   if (rc) return rc;
   CU(A->cuModuleLoadData(&f->mod, f->cubin.data()));
   CU(A->cuModuleGetFunction(&f->k_eval, f->mod, "rn_k_eval"));
+  CU(A->cuModuleGetFunction(&f->k_reduce, f->mod, "rn_k_reduce_rows"));
   CU(A->cuStreamCreate(&f->stream, 1 /*CU_STREAM_NON_BLOCKING*/));
   CU(A->cuMemAlloc(&f->d_err, 8));
   CU(A->cuMemsetD8Async(f->d_err, 0, 8, f->stream));
@@ -2183,6 +2263,67 @@ static int function_launch(const Api* A, rn_function* f, const RnEvalArgs& args,
   void* params[] = {&a};
   CU(A->cuLaunchKernel(f->k_eval, grid, 1, 1, 128, 1, 1, 0, st, params, nullptr));
   f->launches++;
+  return RN_OK;
+}
+
+// the row sums of an inlinable target's column-only monomials, on the device (rn_inline.hpp step 2): rn_k_eval over the
+// target's tile-major block in place (one thread per row; values written [monomial][row]) and rn_k_reduce_rows (one block
+// per monomial, fixed order), in chunks of rows
+static int device_inline(rn_model* M, const InlinePlan& plan, std::vector<uint8_t>& new_rir) {
+  std::string why;
+  const Api* A = api(&why);
+  if (!A) return fail(RN_E_CUDA, why);
+  std::vector<std::vector<double>> sums(plan.inl.size());
+  for (size_t k = 0; k < plan.inl.size(); k++) {
+    const InlineTarget& I = plan.inl[k];
+    const rir_target& T = plan.targets[I.target].t;
+    const size_t m = I.monos.size();
+    sums[k].assign(m, 0.0);
+    if (m == 0) continue;
+    const std::vector<uint8_t> frir = inline_function_rir(plan, k);
+    rn_function* f = nullptr;
+    int rc = rn_function_create(frir.data(), frir.size(), M->device, RN_MATH_PARITY, &f);
+    if (rc) return rc;
+    struct Done {
+      rn_function* f;
+      const Api* A;
+      CUdeviceptr a = 0, b = 0;
+      ~Done() {
+        if (a) A->cuMemFree(a);
+        if (b) A->cuMemFree(b);
+        rn_function_destroy(f);
+      }
+    } g{f, A};
+    rc = function_load(A, f);
+    if (rc) return rc;
+    const long long pitch = M->target_pitch[I.target], ncols = T.n_cols, rows = (long long)T.n_rows;
+    const long long chunk = std::min<long long>((rows + 31) / 32 * 32, std::max<long long>(32, (((long long)64 << 20) / (long long)(m * 8)) / 32 * 32));
+    CU(A->cuMemAlloc(&g.a, (size_t)chunk * m * 8));
+    CU(A->cuMemAlloc(&g.b, m * 8));
+    CU(A->cuMemsetD8Async(g.b, 0, m * 8, f->stream));
+    for (long long r0 = 0; r0 < rows; r0 += chunk) {
+      const long long cnt = std::min(chunk, rows - r0);
+      RnEvalArgs a;
+      std::memset(&a, 0, sizeof(a));
+      a.x = (const double*)(uintptr_t)(M->d_data + (M->target_base[I.target] + (uint64_t)(r0 / 32) * (uint64_t)(ncols * pitch)) * 8);
+      a.out = (double*)(uintptr_t)g.a;
+      a.count = cnt;
+      a.in_inner = 32, a.in_outer = ncols * pitch, a.in_pstride = 1, a.in_estride = pitch;  // row p of the tile-major block
+      a.out_inner = cnt, a.out_outer = 0, a.out_pstride = 1, a.out_estride = cnt;           // [monomial][row]
+      rc = function_launch(A, f, a, f->stream);
+      if (rc) return rc;
+      long long cn = cnt;
+      int mi = (int)m;
+      CUdeviceptr vals = g.a, sm = g.b;
+      void* params[] = {&vals, &cn, &mi, &sm};
+      CU(A->cuLaunchKernel(f->k_reduce, (unsigned)m, 1, 1, 256, 1, 1, 0, f->stream, params, nullptr));
+      f->launches++;
+    }
+    rc = rn_function_sync(f);
+    if (rc) return rc;
+    CU(A->cuMemcpyDtoH(sums[k].data(), g.b, m * 8));
+  }
+  new_rir = apply_inline(plan, sums);
   return RN_OK;
 }
 

@@ -94,6 +94,12 @@ for name in which:
         rir, cols = cached("cfg2s", lambda: configs.linreg(n_obs, covariates=5).compile(True))
         chains, iters, eps, label = 4096, 20, 0.002, "linreg 5 cov, %d obs (streamed), 4096 chains" % n_obs
         prir, pcols = rir, cols
+    elif name == "cfg2si":  # the same 5-covariate regression sent as the streamed PRIMAL container: inlined on the device at create
+        from oracle.make_bench_models import streamed_primal
+        n_obs = 2000 if small else 10000
+        prir, pcols = cached("cfg2s_primal", lambda: streamed_primal(configs.linreg(n_obs, covariates=5)))
+        rir, cols = None, None
+        chains, iters, eps, label = 4096, 200, 0.002, "linreg 5 cov, %d obs, streamed container inlined on the device, 4096 chains" % n_obs
     elif name == "cfg3":
         n_obs, d = (10000, 50) if small else (100000, 50)
         # GPU: primal RIR + the emitter's adjoint gradient (what CudaCompiler sends; 43 MB of columns, L2-resident).
