@@ -148,8 +148,14 @@ struct Builder {
             break;
           case RIR_B_POW:
             if (active[a]) {  // g * exponent * base.pow(exponent - 1)
-              int em1 = P.nodes[b].kind == K_CONST ? cst(P.nodes[b].value - 1.0) : bin(RIR_B_SUB, b, cst(1.0));
-              push(a, bin(RIR_B_MUL, bin(RIR_B_MUL, adj, b), bin(RIR_B_POW, a, em1)));
+              if (P.nodes[b].kind == K_CONST && P.nodes[b].value == -1.0) {
+                // y = 1/x: dy/dx = -1/x^2 = -(y*y) -- the node's own value, two multiplications instead of a division per
+                // observation (the logistic link 1/(1 + e^z) of every Bernoulli row)
+                push(a, bin(RIR_B_MUL, un(U_NEG, adj), bin(RIR_B_MUL, id, id)));
+              } else {
+                int em1 = P.nodes[b].kind == K_CONST ? cst(P.nodes[b].value - 1.0) : bin(RIR_B_SUB, b, cst(1.0));
+                push(a, bin(RIR_B_MUL, bin(RIR_B_MUL, adj, b), bin(RIR_B_POW, a, em1)));
+              }
             }
             if (active[b]) {  // g * child * log(eq(base,0,1,base))
               int cmp = bin(RIR_B_COMPARE, a, cst(0.0));
