@@ -23,7 +23,9 @@
  * rn_last_error() (thread-local).  NaN/inf are *values* and propagate exactly as in the reference
  * (LeapFrog.scala:43-46,138-142); only a lookup index outside its table -- a NullPointerException thrown from
  * generated code in the reference (ir/MethodGenerator.scala:164-167) -- is an error (RN_E_LOOKUP).
- * A handle is not thread-safe (one stream); distinct handles may be used from distinct threads.
+ * A handle is not thread-safe (one stream); distinct handles may be used from distinct threads -- handles derived from the
+ * same model handle -- samplers, rn_sample / rn_sample_predict / rn_optimize calls, diagnostics -- share its kernel and scratch
+ * caches and serialise on the model's internal lock where they touch them.
  *
  * The CPU oracle (oracle/, test infrastructure only) exports the same symbols with an `rno_` prefix so the
  * parity tests can diff the two call for call.

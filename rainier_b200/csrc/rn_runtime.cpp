@@ -184,6 +184,10 @@ struct Kernel {
 };
 
 struct rn_model {
+  // Handles derived from one model (samplers, rn_sample, rn_optimize, diagnostics) share its caches: compiled kernels, the
+  // spare arena / stream, the sample and diagnostics scratch pools.  Every entry point that touches them takes this lock,
+  // so distinct handles of one model may be used from distinct threads (they serialise where they share state).
+  std::recursive_mutex mu;
   std::vector<uint8_t> rir;
   uint32_t n_params = 0, n_inputs = 0;
   bool rir_has_gradient = false;
@@ -751,6 +755,7 @@ void rn_model_destroy(rn_model* m) {
 
 int rn_emit_source(rn_model* m, const rn_config* cfg, char* buf, size_t cap, size_t* needed) {
   if (!m) return fail(RN_E_INVALID, "null model");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   std::string src;
   int rc = get_kernel(m, cfg, nullptr, &src);
   if (rc) return rc;
@@ -765,6 +770,7 @@ int rn_emit_source(rn_model* m, const rn_config* cfg, char* buf, size_t cap, siz
 
 int rn_emit_cubin(rn_model* m, const rn_config* cfg, void* buf, size_t cap, size_t* needed) {
   if (!m) return fail(RN_E_INVALID, "null model");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   Kernel* K = nullptr;
   int rc = get_kernel(m, cfg, &K);
   if (rc) return rc;
@@ -776,6 +782,7 @@ int rn_emit_cubin(rn_model* m, const rn_config* cfg, void* buf, size_t cap, size
 // static op counts of one gradient evaluation: out = [flops_invariant, special_invariant, sum over streamed
 // targets of rows*flops_row, sum of rows*special_row]
 int rn_model_op_counts(rn_model* m, const rn_config* cfg, double out[4]) {
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   KernelKey key = key_for(m, cfg);
   const Program* P = nullptr;
   int rc = get_program(m, key.adjoint, key.fast, &P);
@@ -794,6 +801,7 @@ int rn_model_op_counts(rn_model* m, const rn_config* cfg, double out[4]) {
 // over rows, their multiply-adds per gradient (forward only), longest dot, number of distinct dots in the emitted code]
 int rn_model_dot_structure(rn_model* m, const rn_config* cfg, double out[4]) {
   if (!m || !out) return fail(RN_E_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   KernelKey key = key_for(m, cfg);
   const Program* P = nullptr;
   int rc = get_program(m, key.adjoint, key.fast, &P);
@@ -826,6 +834,7 @@ int rn_model_separable_structure(rn_model* m, double out[4]) {
 
 int rn_density_batch(rn_model* m, const double* q, int chains, double* out) {
   if (!m || !q || !out || chains <= 0) return fail(RN_E_INVALID, "bad argument");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   if (m->device < 0) return fail(RN_E_CUDA, "model was created without a device (no CPU fallback)");
   std::string why;
   const Api* A = api(&why);
@@ -1081,6 +1090,7 @@ extern "C" {
 
 int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, rn_sampler** out) {
   if (!m || !out) return fail(RN_E_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   int rc = check_config(m, cfg, chains);
   if (rc) return rc;
   if (!seeds && !cfg->rng_states) return fail(RN_E_INVALID, "need seeds or rng_states");
@@ -1518,6 +1528,7 @@ int rn_sampler_stats(rn_sampler* s, rn_chain_stats* stats, double* mass, double*
 // rn_sampler_run writes), 1: [chains][iterations][n] (the caller-facing order).  out: host [n][2] = rHat, ess.
 int rn_sampler_diagnostics(rn_sampler* s, const double* d_samples, int iterations, int layout, double* out) {
   if (!s || !d_samples || !out) return fail(RN_E_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> model_lock_(s->m->mu);
   if (s->chains < 2) return fail(RN_E_INVALID, "requirement failed: diagnostics requires multiple chains (Trace.scala:12)");
   if (iterations < 2) return fail(RN_E_INVALID, "diagnostics needs at least 2 iterations");
   std::string why;
@@ -1628,6 +1639,7 @@ int rn_sampler_set_comm(rn_sampler* s, rn_comm* comm) {
 
 void rn_sampler_destroy(rn_sampler* s) {
   if (!s) return;
+  std::unique_lock<std::recursive_mutex> model_lock_(s->m->mu);
   std::string why;
   const Api* A = api(&why);
   if (A) {
@@ -1832,7 +1844,14 @@ int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, siz
     std::lock_guard<std::mutex> lk(g_ring.mu);
     if (g_ring.bytes < slice) {
       NumaScope numa(gpu_numa_node(A));  // staging buffers on the GPU's socket
-      for (int r = 0; r < PinnedRing::R; r++) CU(A->cuMemAllocHost(&g_ring.buf[r], slice));
+      for (int r = 0; r < PinnedRing::R; r++) {
+        if (g_ring.buf[r]) continue;  // (kept from an earlier, partly failed attempt)
+        const CUresult a = A->cuMemAllocHost(&g_ring.buf[r], slice);
+        if (a != 0) {
+          g_ring.buf[r] = nullptr;
+          return cufail(A, a, "drain: cuMemAllocHost");  // the slots allocated so far stay in g_ring and are reused next time
+        }
+      }
       g_ring.bytes = slice;
     }
   }
@@ -1840,8 +1859,14 @@ int drain_to_host(const Api* A, CUstream copy, CUdeviceptr src, double* dst, siz
   Workers& pool = drain_workers();
   const int T = pool.size();
   constexpr int R = PinnedRing::R;
-  CUevent ev[R];
-  for (int r = 0; r < R; r++) CU(A->cuEventCreate(&ev[r], 2));
+  CUevent ev[R] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int r = 0; r < R; r++) {
+    const CUresult e = A->cuEventCreate(&ev[r], 2);
+    if (e != 0) {
+      for (int q = 0; q < r; q++) A->cuEventDestroy(ev[q]);
+      return cufail(A, e, "drain: cuEventCreate");
+    }
+  }
   const size_t n_slices = (bytes + slice - 1) / slice;
   // Each worker owns one stripe of every slice: it waits until slice k has landed in the ring (`ready`), copies its
   // stripe into the caller's pages and counts itself in done[k]; the DMA of slices k+1.. runs meanwhile.
@@ -1898,6 +1923,7 @@ extern "C" {
 
 int rn_sample(rn_model* m, const rn_config* cfg, const int64_t* seeds, int chains, double* samples, double* mass,
               rn_chain_stats* stats) {
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   const bool timing = getenv("RN_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t0 = now();
@@ -2592,6 +2618,7 @@ void rn_optimize_config_default(rn_optimize_config* c) {  // Optimizer.scala:12-
 
 int rn_optimize_emit_source(rn_model* m, const rn_optimize_config* oc, char* buf, size_t cap, size_t* needed) {
   if (!m) return fail(RN_E_INVALID, "null model");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   rn_model::OptKernel* K = nullptr;
   int rc = get_opt_kernel(m, oc, &K);
   if (rc) return rc;
@@ -2606,6 +2633,7 @@ int rn_optimize_emit_source(rn_model* m, const rn_optimize_config* oc, char* buf
 
 int rn_optimize_emit_cubin(rn_model* m, const rn_optimize_config* oc, void* buf, size_t cap, size_t* needed) {
   if (!m) return fail(RN_E_INVALID, "null model");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   rn_model::OptKernel* K = nullptr;
   int rc = get_opt_kernel(m, oc, &K);
   if (rc) return rc;
@@ -2617,6 +2645,7 @@ int rn_optimize_emit_cubin(rn_model* m, const rn_optimize_config* oc, void* buf,
 int rn_optimize(rn_model* m, const rn_optimize_config* oc, const double* x0, int starts, double* x, double* f, int32_t* info,
                 int32_t* evaluations) {
   if (!m || !x || starts <= 0) return fail(RN_E_INVALID, "bad argument");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   if (m->device < 0) return fail(RN_E_CUDA, "model was created without a device (no CPU fallback)");
   std::string why;
   const Api* A = api(&why);
@@ -2696,6 +2725,8 @@ int rn_optimize(rn_model* m, const rn_optimize_config* oc, const double* x0, int
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int rn_sample_predict(rn_model* m, const rn_config* cfg, rn_function* f, const int64_t* seeds, int chains,
                                  double* predictions, double* mass, rn_chain_stats* stats) {
+  if (!m) return fail(RN_E_INVALID, "null model");
+  std::lock_guard<std::recursive_mutex> model_lock_(m->mu);
   if (!m || !cfg || !f || chains <= 0 || cfg->iterations < 0) return fail(RN_E_INVALID, "bad argument");
   if (!predictions && cfg->iterations > 0) return fail(RN_E_INVALID, "null predictions buffer");
   if (m->device < 0 || f->device < 0) return fail(RN_E_CUDA, "model/function was created without a device (no CPU fallback)");
