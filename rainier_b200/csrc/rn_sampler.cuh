@@ -252,6 +252,8 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
   }
 #if RN_X_NORMALS == 1
 #pragma unroll 1
+#elif RN_X_NORMALS == 3
+#pragma unroll 2
 #endif
   for (int k = 0; k < npairs; k++) {
     const int i = i0 + 2 * k;
