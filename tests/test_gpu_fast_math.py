@@ -19,7 +19,8 @@ CASES = {
     "cfg2_linreg_inlined": (lambda: configs.linreg(2000), api.HMCSampler(5), 0.002, None),
     "cfg3_logreg_streamed": (lambda: configs.logreg(1500, 6), api.HMCSampler(3), 0.01, abi.RN_BACKEND_WARP),
     "cfg4_eight_schools": (lambda: configs.eight_schools(), api.HMCSampler(5), 0.05, None),
-    "cfg5_poisson_glm": (lambda: configs.poisson_glm(20, 2000), api.HMCSampler(3), 0.002, abi.RN_BACKEND_WARP),
+    # (a random start of this model needs the step size findReasonableStepSize / DualAvg pick: a fixed guess is rejected every time)
+    "cfg5_poisson_glm": (lambda: configs.poisson_glm(20, 2000), api.HMCSampler(3), None, abi.RN_BACKEND_WARP),
 }
 
 
@@ -32,15 +33,20 @@ def test_fast_math_sampler_within_tolerance(name):
     gpu_rir, gpu_cols = (rir, cols)
     if backend is not None:
         gpu_rir, gpu_cols = model.compile(False)  # streamed shapes take the primal container (adjoint gradient)
-    cfg = api.make_config(iterations=12, warmupIterations=0, sampler=sampler, stepSizeTuner=api.StaticStepSize(eps),
+    adaptive = eps is None
+    cfg = api.make_config(iterations=6 if adaptive else 12, warmupIterations=14 if adaptive else 0, sampler=sampler,
+                          stepSizeTuner=api.DualAvgTuner(0.8) if adaptive else api.StaticStepSize(eps),
                           massMatrixTuner=api.IdentityMassMatrixTuner(), mathMode=abi.RN_MATH_FAST, **kw)
     r = parity.run_both(rir, cols, cfg, seeds=np.arange(64) + 21, rir_gpu=gpu_rir, cols_gpu=gpu_cols)
     gt, rt = r["gpu_trace"], r["ref_trace"]
     assert np.array_equal(gt[:, :, 1], rt[:, :, 1]), "accept decisions differ"
     assert np.array_equal(gt[:, :, 3], rt[:, :, 3])
     fin = np.isfinite(rt[:, :, 0])
-    assert np.max(np.abs(gt[:, :, 0][fin] - rt[:, :, 0][fin])) < 1e-9 * max(1.0, float(np.max(np.abs(rt[:, :, 0][fin]))))
-    assert parity.rel_err(r["gpu"], r["ref"], 1e-9) < 1e-9
+    assert fin.mean() > 0.5 and rt[:, :, 1].mean() > 0.3, "the run must be in the regime where proposals are accepted"
+    assert np.array_equal(np.isfinite(gt[:, :, 0]), fin)
+    tol = 1e-6 if adaptive else 1e-9  # (20 adaptive iterations amplify last-bit differences, cf. tests/test_zz_gpu_wpc_dense.py)
+    assert np.max(np.abs(gt[:, :, 0][fin] - rt[:, :, 0][fin])) < tol * max(1.0, float(np.max(np.abs(rt[:, :, 0][fin]))))
+    assert parity.rel_err(r["gpu"], r["ref"], 1e-9) < tol
 
 
 def test_fast_math_with_adaptation_early_horizon():
