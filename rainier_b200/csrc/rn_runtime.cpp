@@ -1330,10 +1330,19 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.n_iter = k;
     a.adaptation = s->cfg.adaptation == RN_ADAPT_POOLED ? 1 : 0;
     a.tma = s->K->tma_stages > 0 ? 1 : 0;
-    if (s->K->mma && ((chain_begin % s->K->mma_chains) != 0 || ((chain_end - chain_begin) % s->K->mma_chains) != 0))
-      a.tma = 0;  // the DMMA path wants full CTAs (8 or 16 chains); a ragged batch runs the per-warp path of the same kernel
+    // the DMMA path wants full CTAs (8 or 16 chains): the whole groups of a batch run it, a ragged tail (and a batch that
+    // does not start on a group boundary) runs the per-warp path of the same kernel in a second launch
+    int tail_begin = chain_end;
+    if (s->K->mma) {
+      const int nc = s->K->mma_chains;
+      if (chain_begin % nc != 0)
+        a.tma = 0;
+      else
+        tail_begin = chain_begin + ((chain_end - chain_begin) / nc) * nc;
+      if (tail_begin == chain_begin) a.tma = 0, tail_begin = chain_end;
+    }
     a.chain_begin = chain_begin;
-    a.chain_end = chain_end;
+    a.chain_end = tail_begin;
     a.mass_kind = s->mass_kind;
     a.win_size = s->win_size;
     a.win_i = s->win_i;
@@ -1341,8 +1350,15 @@ static int run_phase(const Api* A, rn_sampler* s, int phase, int iterations, dou
     a.est_samples = s->est_samples;
     a.samples = (phase == 1 && d_samples) ? d_samples + (size_t)done * s->m->n_params * (size_t)s->chains : nullptr;
     a.trace = s->d_trace ? (double*)(uintptr_t)(s->d_trace + s->trace_pos * 4 * (size_t)s->chains * 8) : nullptr;
-    int rc = launch(A, s, phase == 0 ? s->K->k_warmup : s->K->k_iter, chain_end - chain_begin);
+    int rc = launch(A, s, phase == 0 ? s->K->k_warmup : s->K->k_iter, tail_begin - chain_begin);
     if (rc) return rc;
+    if (tail_begin < chain_end) {
+      a.tma = 0;
+      a.chain_begin = tail_begin;
+      a.chain_end = chain_end;
+      rc = launch(A, s, phase == 0 ? s->K->k_warmup : s->K->k_iter, chain_end - tail_begin);
+      if (rc) return rc;
+    }
     if (phase == 0) {
       const int closed = advance_window(s, k);
       if (pooled && closed > 0) {

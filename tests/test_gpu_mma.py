@@ -54,6 +54,10 @@ def test_dmma_and_rows_across_lanes_agree_and_ragged_chain_counts_fall_back():
     assert parity.rel_err(a.chains, b.chains) < 1e-9
     c = api.CudaModel(prir, pcols).sample(cfg, seeds=seeds[:13])
     assert parity.rel_err(c.chains, b.chains[:13]) < 1e-9
+    # 40 chains = two full groups of 16 on the DMMA path + a tail of 8 on the per-warp path (second launch): the first 32 are
+    # bit-identical to the same chains run as a batch of 32
+    d = api.CudaModel(prir, pcols).sample(cfg, seeds=seeds[:32])
+    assert np.array_equal(a.chains[:32], d.chains)
 
 
 def test_dmma_with_adaptation_short_horizon():
