@@ -138,17 +138,22 @@ struct Emitter {
         if (!lists.count(c)) comp_order.push_back(c);
         lists[c].push_back(id);
       }
+      // round-robin over at most `interleave` components at a time: every component in flight keeps its temporaries in
+      // registers (8 observations of a Poisson row x ~16 registers did not fit the 128 of a 16-warp CTA: 1.4e9 spill
+      // accesses and 244 GB of DRAM traffic per launch, profiles/r2_ncu_cfg5_v1.csv)
+      const size_t W = (size_t)std::max(1, opt.interleave);
       std::vector<size_t> pos(comp_order.size(), 0);
-      for (bool any = true; any;) {
-        any = false;
-        for (size_t k = 0; k < comp_order.size(); k++) {
-          const std::vector<int>& l = lists[comp_order[k]];
-          if (pos[k] < l.size()) {
-            out.push_back(l[pos[k]++]);
-            any = true;
+      for (size_t g0 = 0; g0 < comp_order.size(); g0 += W)
+        for (bool any = true; any;) {
+          any = false;
+          for (size_t k = g0; k < std::min(comp_order.size(), g0 + W); k++) {
+            const std::vector<int>& l = lists[comp_order[k]];
+            if (pos[k] < l.size()) {
+              out.push_back(l[pos[k]++]);
+              any = true;
+            }
           }
         }
-      }
       out.insert(out.end(), tails.begin(), tails.end());
     };
     schedule(fwd, order_fwd);
@@ -190,12 +195,17 @@ struct Emitter {
     };
     auto emit_acc = [&](const AccStmt& a) { os << ind << accref(a.slot) << " += " << val(a.node) << ";\n"; };
     auto emit_scatter = [&](const ScatterStmt& sc) {
+      if (atomic_scatter) {
+        // branch-free (an index outside the table raises the flag and adds 0 to entry 0) and in the shared state space: the
+        // generic atomicAdd carries one code path per address space behind a run-time test, 16 times per row body on cfg 5
+        os << ind << "{ const int k = rn_d2i(" << val(sc.index_node) << ") - (" << sc.low << "); const bool bad = (unsigned)k >= " << sc.len
+           << "u; err |= (int)bad; rn_scatter_add(&scr[" << (scatter_base_off + smem_slot[sc.slot_base]) << " + (bad ? 0 : k)], bad ? 0.0 : "
+           << val(sc.node) << "); }\n";
+        return;
+      }
       os << ind << "{ const int k = rn_d2i(" << val(sc.index_node) << ") - (" << sc.low << "); if (k < 0 || k >= " << sc.len
          << ") err |= 1; else ";
-      if (atomic_scatter)
-        os << "atomicAdd(&scr[" << (scatter_base_off + smem_slot[sc.slot_base]) << " + k], " << val(sc.node) << "); }\n";
-      else
-        os << "acc[" << sc.slot_base << " + k] += " << val(sc.node) << "; }\n";
+      os << "acc[" << sc.slot_base << " + k] += " << val(sc.node) << "; }\n";
     };
     auto one = [&](int id) {
       if (!body.count(id)) return;
@@ -251,6 +261,10 @@ struct Emitter {
   }
 
   std::string val(int id) const {
+    if (!name_override.empty()) {
+      auto it = name_override.find(id);
+      if (it != name_override.end()) return it->second;
+    }
     const Node& n = P.nodes[id];
     if (n.kind == K_CONST) return lit(n.value);
     if (n.kind == K_INPUT) {
@@ -920,6 +934,465 @@ struct Emitter {
        << "    }\n";
   }
 
+  // ---- re-rolling of the invariant sections (warp-per-chain) ----------------------------------------------------------
+  // The reference unrolls everything: a vector of 1000 latent group effects is 1000 copies of the same prior term, 1000 table
+  // entries mu + sd * z_k, 1000 gradient expressions.  On the thread-per-chain shape that is one copy per chain.  On this shape
+  // every thread of the chain's group would run the same ~20 000 straight-line statements with ~2000 values live across the row
+  // loops (cfg 5: 19 KB of stack per thread, 1.4e9 local-memory accesses and 244 GB of DRAM traffic per launch, a fifth of the
+  // stall samples; profiles/r2_ncu_cfg5_v1.csv).  So families of isomorphic statements are found again by anti-unification
+  // from three kinds of seeds -- the entries of a Lookup table, the gradient outputs of consecutive parameters, the terms of a
+  // long left fold of additions -- and emitted as ONE loop over the members with the members across the group's threads:
+  //   for (k = lane; k < L; k += RN_G) { w0 = q[i0 + k]; w1 = (vU * w0); ...; scr[tab + k] = w5; }
+  // Leaves are either uniform (the same scalar node for every member), parameters q[a + b k], or shared accumulators
+  // scr[a + b k].  Interior values other sections need are recomputed by the family that needs them.  Sums over a family are
+  // accumulated per thread and reduced across the group in a fixed order (the per-element values are bit-identical to the
+  // unrolled statements; only the association of those sums changes, like the row sums of this shape).
+  struct VNode {
+    std::vector<int> mem;
+    int leaf = 0;  // 0 interior, 1 parameter gather, 2 shared-accumulator gather
+    long long base = 0, stride = 0;
+  };
+  struct FamOut {
+    int kind = 0;  // 0 table store, 1 gradient store, 2 sum
+    int vn = -1;   // vnode index, or -1 - node id when the value is uniform... (not produced: uniform seeds are refused)
+    long long base = 0, stride = 0;  // table offset in scratch / first parameter index
+    int sum = -1;                    // index into rr_sums
+  };
+  struct Family {
+    int L = 0;
+    std::vector<VNode> vn;
+    std::map<std::vector<int>, int> memo;  // member vector -> vnode index (-2 failed)
+    std::set<int> uniforms;      // scalar statements the loop reads
+    std::set<int> uniform_all;   // ... plus constants and parameters used uniformly
+    std::vector<FamOut> outs;
+    bool bwd = false;
+    bool done = false;
+  };
+  struct Spine {
+    int end = -1;                    // node holding the complete sum
+    std::vector<int> chain;          // interior fold nodes (eliminated)
+    std::vector<int> scalar_terms;   // terms left to the scalar code, fold order
+    std::vector<int> sums;           // rr_sums indices added after them
+    bool bwd = false;
+  };
+  std::vector<Family> fams;
+  std::vector<Spine> spines;
+  int rr_n_sums = 0;
+  std::set<int> rr_elim;               // scalar statements not emitted
+  std::map<int, int> rr_spine_of;      // end node -> spine index
+  std::set<int> rr_family_tables;      // tab_fill ids stored by a family
+  std::vector<char> rr_family_grad;    // parameter i: gradient stored by a family
+  std::map<int, std::string> name_override;
+  int rr_max_round_sums = 0;
+
+  static bool inv_region(const Node& n) { return n.region == R_INV_FWD || n.region == R_INV_BWD; }
+
+  // anti-unification of L nodes; returns the vnode index, -1 - id for a uniform node, or INT_MIN on failure
+  static constexpr int RR_FAIL = -2147483647;
+  int rr_pack(Family& F, const std::vector<int>& V) {
+    bool same = true;
+    for (int id : V) same = same && id == V[0];
+    if (same) {
+      const Node& u = P.nodes[V[0]];
+      if (u.kind != K_CONST && u.kind != K_INPUT) {
+        if (!inv_region(u)) return RR_FAIL;
+        F.uniforms.insert(V[0]);
+      } else if (u.kind == K_INPUT && (uint32_t)u.a >= P.n_params) {
+        return RR_FAIL;
+      }
+      F.uniform_all.insert(V[0]);
+      return -1 - V[0];
+    }
+    auto it = F.memo.find(V);
+    if (it != F.memo.end()) return it->second == -2 ? RR_FAIL : it->second;
+    F.memo[V] = -2;
+    const Node& n0 = P.nodes[V[0]];
+    for (int id : V) {
+      const Node& n = P.nodes[id];
+      if (n.kind != n0.kind || n.op != n0.op) return RR_FAIL;
+      if (n.kind != K_CONST && n.kind != K_INPUT && !inv_region(n)) return RR_FAIL;
+    }
+    VNode vn;
+    vn.mem = V;
+    auto affine = [&](const std::function<long long(int)>& get) {
+      vn.base = get(0);
+      vn.stride = V.size() > 1 ? get(1) - get(0) : 0;
+      for (size_t k = 0; k < V.size(); k++)
+        if (get((int)k) != vn.base + vn.stride * (long long)k) return false;
+      return vn.stride != 0;
+    };
+    switch (n0.kind) {
+      case K_CONST: {
+        for (int id : V)
+          if (std::memcmp(&P.nodes[id].value, &n0.value, sizeof(double)) != 0) return RR_FAIL;
+        F.uniform_all.insert(V[0]);
+        return -1 - V[0];
+      }
+      case K_INPUT: {
+        for (int id : V)
+          if ((uint32_t)P.nodes[id].a >= P.n_params) return RR_FAIL;
+        if (!affine([&](int k) { return (long long)P.nodes[V[k]].a; })) return RR_FAIL;
+        vn.leaf = 1;
+        break;
+      }
+      case K_ACC: {
+        for (int id : V)
+          if (smem_slot[P.nodes[id].a] < 0) return RR_FAIL;
+        if (!affine([&](int k) { return (long long)smem_slot[P.nodes[V[k]].a]; })) return RR_FAIL;
+        vn.base += tab_doubles;
+        vn.leaf = 2;
+        break;
+      }
+      case K_UNARY:
+      case K_BINARY: {
+        std::vector<int> A(V.size()), B(V.size());
+        for (size_t k = 0; k < V.size(); k++) {
+          A[k] = P.nodes[V[k]].a;
+          B[k] = P.nodes[V[k]].b;
+        }
+        if (rr_pack(F, A) == RR_FAIL) return RR_FAIL;
+        if (n0.kind == K_BINARY && rr_pack(F, B) == RR_FAIL) return RR_FAIL;
+        break;
+      }
+      default: return RR_FAIL;
+    }
+    F.vn.push_back(vn);
+    return F.memo[V] = (int)F.vn.size() - 1;
+  }
+
+  // structural hash with holes for parameters and shared accumulators: equal hashes are necessary for rr_pack to succeed
+  std::vector<uint64_t> rr_hash_memo;
+  uint64_t rr_hash(int id) {
+    if (rr_hash_memo[id]) return rr_hash_memo[id];
+    const Node& n = P.nodes[id];
+    auto mix = [](uint64_t h, uint64_t v) { return (h ^ (v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2))) * 0xff51afd7ed558ccdull; };
+    uint64_t h = mix(0x1234567ull, n.kind * 64 + n.op);
+    switch (n.kind) {
+      case K_CONST: {
+        uint64_t b;
+        std::memcpy(&b, &n.value, 8);
+        h = mix(h, b);
+        break;
+      }
+      case K_INPUT: h = mix(h, (uint32_t)n.a < P.n_params ? 1 : 1000 + n.a); break;
+      case K_ACC: h = mix(h, smem_slot[n.a] >= 0 ? 2 : 2000 + n.a); break;
+      case K_UNARY: h = mix(h, rr_hash(n.a)); break;
+      case K_BINARY: h = mix(mix(h, rr_hash(n.a)), rr_hash(n.b)); break;
+      default: h = mix(h, 7777 + (uint64_t)id); break;
+    }
+    if (!h) h = 1;
+    return rr_hash_memo[id] = h;
+  }
+
+  void rr_plan() {
+    const int MINL = 32;
+    if (P.symbolic || getenv("RN_NO_REROLL")) return;
+    const size_t nn = P.nodes.size();
+    rr_hash_memo.assign(nn, 0);
+    rr_family_grad.assign(P.n_params, 0);
+    // use counts over everything that is emitted
+    std::vector<int> uses(nn, 0);
+    std::vector<int> ops;
+    auto count_list = [&](const std::vector<int>& l) {
+      for (int id : l) {
+        operands(id, ops);
+        for (int o : ops) uses[o]++;
+      }
+    };
+    count_list(P.inv_fwd);
+    count_list(P.inv_bwd);
+    for (const TargetInfo& T : P.targets) {
+      count_list(T.row_fwd);
+      count_list(T.row_bwd);
+      for (const AccStmt& a : T.row_acc) uses[a.node]++;
+      for (const ScatterStmt& sc : T.row_scatter) uses[sc.node]++, uses[sc.index_node]++;
+    }
+    for (const AccStmt& a : P.inv_acc) uses[a.node]++;
+    for (int g : P.grad_nodes) uses[g]++;
+
+    auto try_family = [&](const std::vector<int>& V, FamOut out) -> bool {
+      Family F;
+      F.L = (int)V.size();
+      const int r = rr_pack(F, V);
+      if (r == RR_FAIL || r < 0) return false;
+      // one representative per vnode names it during emission: they must be distinct
+      std::set<int> reps;
+      for (const VNode& v : F.vn)
+        if (!reps.insert(v.mem[0]).second || F.uniform_all.count(v.mem[0])) return false;
+      out.vn = r;
+      F.outs.push_back(out);
+      for (const VNode& v : F.vn)
+        for (int id : v.mem) F.bwd = F.bwd || P.nodes[id].region == R_INV_BWD;
+      for (int u : F.uniforms) F.bwd = F.bwd || P.nodes[u].region == R_INV_BWD;
+      fams.push_back(std::move(F));
+      return true;
+    };
+
+    // (A) Lookup tables
+    for (int id : tab_fill) {
+      const Node& n = P.nodes[id];
+      if (n.c < MINL) continue;
+      std::vector<int> V(P.lookup_refs.begin() + n.b, P.lookup_refs.begin() + n.b + n.c);
+      FamOut o;
+      o.kind = 0;
+      o.base = tab_off.at(id);
+      if (try_family(V, o)) rr_family_tables.insert(id);
+    }
+    // (C) gradient outputs of runs of consecutive parameters with the same shape
+    for (uint32_t i = 0; i < P.n_params;) {
+      uint32_t j = i + 1;
+      const uint64_t h = rr_hash(P.grad_nodes[i]);
+      while (j < P.n_params && rr_hash(P.grad_nodes[j]) == h) j++;
+      if ((int)(j - i) >= MINL) {
+        std::vector<int> V(P.grad_nodes.begin() + i, P.grad_nodes.begin() + j);
+        FamOut o;
+        o.kind = 1;
+        o.base = i;
+        if (try_family(V, o))
+          for (uint32_t k = i; k < j; k++) rr_family_grad[k] = 1;
+      }
+      i = j;
+    }
+    // (B) long left folds of additions whose interior sums have no other reader
+    std::vector<char> in_chain(nn, 0);
+    auto scan_spines = [&](const std::vector<int>& list) {
+      for (size_t pos = list.size(); pos-- > 0;) {
+        const int end = list[pos];
+        const Node& e = P.nodes[end];
+        if (in_chain[end] || e.kind != K_BINARY || e.op != RIR_B_ADD) continue;
+        std::vector<int> chain, terms;  // terms collected last-to-first
+        int cur = end;
+        for (;;) {
+          const Node& c = P.nodes[cur];
+          terms.push_back(c.b);
+          const Node& l = P.nodes[c.a];
+          if (l.kind == K_BINARY && l.op == RIR_B_ADD && uses[c.a] == 1 && inv_region(l) && !in_chain[c.a]) {
+            chain.push_back(c.a);
+            cur = c.a;
+          } else {
+            terms.push_back(c.a);
+            break;
+          }
+        }
+        if ((int)terms.size() < MINL) continue;
+        std::reverse(terms.begin(), terms.end());
+        Spine S;
+        S.end = end;
+        S.chain = chain;
+        S.bwd = e.region == R_INV_BWD;
+        bool any = false;
+        for (size_t i = 0; i < terms.size();) {
+          size_t j = i + 1;
+          const uint64_t h = rr_hash(terms[i]);
+          while (j < terms.size() && rr_hash(terms[j]) == h) j++;
+          bool ok = false;
+          if ((int)(j - i) >= MINL) {
+            std::vector<int> V(terms.begin() + i, terms.begin() + j);
+            FamOut o;
+            o.kind = 2;
+            o.sum = rr_n_sums;
+            if (try_family(V, o)) {
+              S.sums.push_back(rr_n_sums++);
+              ok = any = true;
+            }
+          }
+          if (!ok)
+            for (size_t k = i; k < j; k++) S.scalar_terms.push_back(terms[k]);
+          i = j;
+        }
+        if (!any) continue;
+        for (int c : chain) in_chain[c] = 1;
+        rr_spine_of[end] = (int)spines.size();
+        spines.push_back(std::move(S));
+      }
+    };
+    scan_spines(P.inv_fwd);
+    scan_spines(P.inv_bwd);
+    if (fams.empty()) return;
+
+    // which absorbed statements can go: the members of the families and the interior fold nodes, unless something that is
+    // still emitted as a scalar statement (or a row body, an accumulation, an unrolled table / gradient store) reads them
+    std::set<int> absorbed;
+    for (const Family& F : fams)
+      for (const VNode& v : F.vn)
+        if (v.leaf != 1)
+          for (int id : v.mem) absorbed.insert(id);
+    for (const Spine& S : spines)
+      for (int c : S.chain) absorbed.insert(c);
+    std::vector<char> needed(nn, 0);
+    std::vector<int> work;
+    auto need = [&](int id) {
+      if (!needed[id]) {
+        needed[id] = 1;
+        work.push_back(id);
+      }
+    };
+    auto scalar_reads = [&](int id) {  // operands the scalar form of statement `id` reads
+      auto sp = rr_spine_of.find(id);
+      if (sp != rr_spine_of.end()) {
+        for (int t : spines[sp->second].scalar_terms) need(t);
+        return;
+      }
+      const Node& n = P.nodes[id];
+      if (n.kind == K_LOOKUP && tab_off.count(id)) {
+        need(n.a);
+        return;  // its table is filled separately
+      }
+      operands(id, ops);
+      for (int o : ops) need(o);
+    };
+    for (const std::vector<int>* l : {&P.inv_fwd, &P.inv_bwd})
+      for (int id : *l)
+        if (!absorbed.count(id)) scalar_reads(id);
+    for (const TargetInfo& T : P.targets) {
+      for (int id : T.row_fwd) scalar_reads(id);
+      for (int id : T.row_bwd) scalar_reads(id);
+      for (const AccStmt& a : T.row_acc) need(a.node);
+      for (const ScatterStmt& sc : T.row_scatter) need(sc.node), need(sc.index_node);
+    }
+    for (const AccStmt& a : P.inv_acc) need(a.node);
+    for (uint32_t i = 0; i < P.n_params; i++)
+      if (!rr_family_grad[i]) need(P.grad_nodes[i]);
+    for (int id : tab_fill)
+      if (!rr_family_tables.count(id)) {
+        const Node& n = P.nodes[id];
+        for (int k = 0; k < n.c; k++) need(P.lookup_refs[n.b + k]);
+      }
+    for (const Family& F : fams)
+      for (int u : F.uniforms) need(u);
+    while (!work.empty()) {
+      const int id = work.back();
+      work.pop_back();
+      if (absorbed.count(id)) scalar_reads(id);  // an absorbed statement that has to stay: so do its operands
+    }
+    for (int id : absorbed)
+      if (!needed[id]) rr_elim.insert(id);
+    // a fold whose interior sums have to stay is not re-rolled after all (its families still are: they then only feed dead sums,
+    // so drop them too)
+    for (size_t si = 0; si < spines.size(); si++) {
+      bool broken = false;
+      for (int c : spines[si].chain) broken = broken || needed[c];
+      if (broken) {
+        fams.clear();
+        spines.clear();
+        rr_elim.clear();
+        rr_spine_of.clear();
+        rr_family_tables.clear();
+        rr_family_grad.assign(P.n_params, 0);
+        rr_n_sums = 0;
+        return;
+      }
+    }
+    rr_max_round_sums = rr_n_sums;
+  }
+
+  // one family = one loop; uniform operands keep their scalar names, vnodes are named after their first member
+  void rr_emit_family(const Family& F, const char* ind) {
+    os << ind << "for (int k = lane; k < " << F.L << "; k += RN_G) {\n";
+    const std::string in2 = std::string(ind) + "  ";
+    name_override.clear();
+    for (size_t i = 0; i < F.vn.size(); i++) {
+      const VNode& v = F.vn[i];
+      if (v.leaf) {
+        name_override[v.mem[0]] = std::string(v.leaf == 1 ? "q[" : "scr[") + std::to_string(v.base) + " + " + std::to_string(v.stride) + " * k]";
+      } else {
+        name_override[v.mem[0]] = "w" + std::to_string(i);
+        stmt(v.mem[0], in2.c_str());
+      }
+    }
+    for (const FamOut& o : F.outs) {
+      const std::string x = val(F.vn[o.vn].mem[0]);
+      if (o.kind == 0) os << in2 << "scr[" << o.base << " + k] = " << x << ";\n";
+      if (o.kind == 1) os << in2 << "grad[" << o.base << " + k] = " << x << ";\n";
+      if (o.kind == 2) os << in2 << "s" << o.sum << " += " << x << ";\n";
+    }
+    name_override.clear();
+    os << ind << "}\n";
+  }
+
+  // the invariant statements of one section with the families in their place: scalar statements as soon as their operands
+  // exist, then every family whose uniform operands exist, then the group-wide reduction of that round's sums; repeat
+  void rr_emit_section(const std::vector<int>& list, bool bwd, std::set<int>& avail, std::set<int>& sums_ready) {
+    const int K = std::max(1, opt.wpc_k);
+    std::vector<int> pending;
+    for (int id : list)
+      if (!rr_elim.count(id)) pending.push_back(id);
+    std::vector<int> ops;
+    auto ready = [&](int id) {
+      const Node& n = P.nodes[id];
+      return n.kind == K_CONST || n.kind == K_INPUT || avail.count(id) > 0;
+    };
+    for (int guard = 0; guard < 64; guard++) {
+      std::vector<int> blocked;
+      for (int id : pending) {
+        bool ok = true;
+        auto sp = rr_spine_of.find(id);
+        if (sp != rr_spine_of.end()) {
+          const Spine& S = spines[sp->second];
+          for (int t : S.scalar_terms) ok = ok && ready(t);
+          for (int sidx : S.sums) ok = ok && sums_ready.count(sidx) > 0;
+          if (ok) {
+            os << "  const double " << val(id) << " = ";
+            std::string e;
+            for (int t : S.scalar_terms) e = e.empty() ? val(t) : "(" + e + " + " + val(t) + ")";
+            for (int sidx : S.sums) e = e.empty() ? "s" + std::to_string(sidx) : "(" + e + " + s" + std::to_string(sidx) + ")";
+            os << e << ";\n";
+          }
+        } else {
+          operands(id, ops);
+          if (P.nodes[id].kind == K_LOOKUP && tab_off.count(id)) ops.resize(1);
+          for (int o : ops) ok = ok && ready(o);
+          if (ok) stmt(id, "  ");
+        }
+        if (ok)
+          avail.insert(id);
+        else
+          blocked.push_back(id);
+      }
+      pending.swap(blocked);
+      std::vector<int> round_sums;
+      bool any_family = false;
+      for (Family& F : fams) {
+        if (F.done || F.bwd != bwd) continue;
+        bool ok = true;
+        for (int u : F.uniforms) ok = ok && ready(u);
+        if (!ok) continue;
+        for (const FamOut& o : F.outs)
+          if (o.kind == 2) {
+            os << "  double s" << o.sum << " = 0.0;\n";
+            round_sums.push_back(o.sum);
+          }
+        rr_emit_family(F, "  ");
+        F.done = true;
+        any_family = true;
+      }
+      if (!round_sums.empty()) {
+        const int m = (int)round_sums.size();
+        for (int sidx : round_sums) os << "  s" << sidx << " = rn_warp_sum(s" << sidx << ");\n";
+        if (K > 1) {
+          os << "  {\n    double* red = scr + " << red_off << ";\n    const int wg = lane >> 5;\n    RN_SYNC();\n    if ((lane & 31) == 0) {\n";
+          for (int j = 0; j < m; j++) os << "      red[wg * " << m << " + " << j << "] = s" << round_sums[j] << ";\n";
+          os << "    }\n    RN_SYNC();\n";
+          for (int j = 0; j < m; j++) {
+            os << "    s" << round_sums[j] << " = red[" << j << "]";
+            for (int k = 1; k < K; k++) os << " + red[" << k * m + j << "]";
+            os << ";\n";
+          }
+          os << "  }\n";
+        }
+        for (int sidx : round_sums) sums_ready.insert(sidx);
+      }
+      if (pending.empty() && !any_family) break;
+      if (!any_family && round_sums.empty() && !pending.empty()) {
+        // nothing moved: should not happen (the fixpoint in rr_plan keeps every operand of a scalar statement); emit the rest
+        // in order so that a compile error, not a wrong value, is the symptom
+        for (int id : pending) stmt(id, "  ");
+        pending.clear();
+        break;
+      }
+    }
+  }
+
   void density_wpc() {
     wpc = true;
     // which accumulator slots live in shared memory (targets of a scatter) and which in registers
@@ -963,15 +1436,18 @@ struct Emitter {
     int n_reg_acc = 0;
     for (int sl = 0; sl < P.n_slots; sl++)
       if (smem_slot[sl] < 0) n_reg_acc++;
-    // cross-warp reduction scratch of the chain's group (K warps): [warp][register accumulators..., err]
+    rr_plan();
+    // cross-warp reduction scratch of the chain's group (K warps): [warp][register accumulators..., err]; the sums of the
+    // re-rolled families go through it too, before and after the row loops
     red_off = tab_doubles + n_smem_acc;
-    red_doubles = K > 1 ? K * (n_reg_acc + 1) : 0;
+    red_doubles = K > 1 ? K * std::max(n_reg_acc + 1, rr_max_round_sums) : 0;
     mma_inv_off = tab_doubles + n_smem_acc + red_doubles;
     os << "#define RN_WPC_SCRATCH " << (tab_doubles + n_smem_acc + red_doubles + (use_mma ? (int)mma_inv.size() : 0)) << "\n";
     os << "#define RN_MMA_BARS " << (use_mma ? MMA_WARPS : 0) << "\n";
     os << "#define RN_WPC_RED_OFF " << red_off << "\n";
     os << "RN_DEVICE double rn_tab_lookup(const double* tab, int len, int low, double idx, int& err) {\n"
-          "  const int k = rn_d2i(idx) - low;\n  if (k < 0 || k >= len) { err |= 1; return RN_NAN; }\n  return tab[k];\n}\n";
+          "  const int k = rn_d2i(idx) - low;\n  const bool bad = (unsigned)k >= (unsigned)len;\n  err |= (int)bad;\n"
+          "  const double v = tab[bad ? 0 : k];\n  return bad ? RN_NAN : v;\n}\n";
     os << "RN_DEVICE double rn_warp_sum(double x) {\n  RN_UNROLL\n  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);\n  return x;\n}\n";
     lookup_helpers();
     if (use_mma)
@@ -982,8 +1458,13 @@ struct Emitter {
           "const double* RN_RESTRICT data, int& err, RnTma& tma) {\n";
     os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x % RN_G);  // thread of the chain's group\n  (void)lane;\n";
     if (n_smem_acc) os << "  for (int k = lane; k < " << n_smem_acc << "; k += RN_G) scr[" << tab_doubles << " + k] = 0.0;\n";
-    for (int id : P.inv_fwd) stmt(id, "  ");
+    std::set<int> rr_avail, rr_sums_ready;
+    if (fams.empty())
+      for (int id : P.inv_fwd) stmt(id, "  ");
+    else
+      rr_emit_section(P.inv_fwd, false, rr_avail, rr_sums_ready);
     for (int id : tab_fill) {
+      if (rr_family_tables.count(id)) continue;
       const Node& n = P.nodes[id];
       for (int k = 0; k < n.c; k++) os << "  scr[" << (tab_off.at(id) + k) << "] = " << val(P.lookup_refs[n.b + k]) << ";\n";
     }
@@ -1065,14 +1546,22 @@ struct Emitter {
     if (P.symbolic) {
       for (uint32_t i = 0; i < P.n_params; i++) os << "  if (lane == 0) grad[" << i << "] = " << acc_ref(1 + (int)i) << ";\n";
     } else {
-      for (int id : P.inv_bwd) stmt(id, "  ");
-      for (uint32_t i = 0; i < P.n_params; i++) os << "  if (lane == 0) grad[" << i << "] = " << val(P.grad_nodes[i]) << ";\n";
+      if (fams.empty())
+        for (int id : P.inv_bwd) stmt(id, "  ");
+      else
+        rr_emit_section(P.inv_bwd, true, rr_avail, rr_sums_ready);
+      for (uint32_t i = 0; i < P.n_params; i++)
+        if (fams.empty() || !rr_family_grad[i]) os << "  if (lane == 0) grad[" << i << "] = " << val(P.grad_nodes[i]) << ";\n";
     }
     os << "  RN_SYNC();\n}\n";
   }
 };
 
 }  // namespace
+
+// vectors of n doubles in a chain's shared-memory slice (rn_sampler_wpc.cuh: rn_w_setup): q, p, gradient, [diagonal mass],
+// [3 EHMC snapshots], [2 dense-mass work vectors]
+static int wpc_vectors(const EmitOptions& opt) { return 3 + (opt.mass_max >= 1 ? 1 : 0) + (opt.enable_ehmc ? 3 : 0) + (opt.mass_max == 2 ? 2 : 0); }
 
 std::string emit_density(const Program& P, const EmitOptions& opt) {
   Emitter E(P, opt);
@@ -1088,7 +1577,7 @@ WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
   Emitter E(P, opt);
   E.density_wpc();
   // chain vectors (q, p, gradient, mass [+ EHMC snapshot]) [+ 2 scratch vectors of the dense mass matrix code] + density scratch
-  z.per_warp_doubles = ((opt.enable_ehmc ? 7 : 4) + (opt.mass_max == 2 ? 2 : 0)) * (int)P.n_params + E.tab_doubles + E.n_smem_acc + E.red_doubles +
+  z.per_warp_doubles = wpc_vectors(opt) * (int)P.n_params + E.tab_doubles + E.n_smem_acc + E.red_doubles +
                        ((opt.mma && E.mma_all_ok) ? (int)E.mma_inv.size() : 0);
   for (const TargetInfo& T : P.targets)
     if (T.streamed() && T.n_rows >= 32ull * (uint64_t)std::max(1, opt.wpc_k))
@@ -1161,7 +1650,7 @@ std::string emit_source(const Program& P, const EmitOptions& opt) {
   }
   os << kPreludeSource << "\n";
   if (opt.backend == 1)  // (RN_WPC_SCRATCH is defined by the emitted density; macros expand where they are used)
-    os << "#define RN_WPC_SMEM_DOUBLES (" << ((opt.enable_ehmc ? 7 : 4) + (opt.mass_max == 2 ? 2 : 0)) << " * RN_N + RN_WPC_SCRATCH)\n";
+    os << "#define RN_WPC_SMEM_DOUBLES (" << wpc_vectors(opt) << " * RN_N + RN_WPC_SCRATCH)\n";
   os << emit_density(P, opt) << "\n";
   if (opt.backend == 1) {
     os << kSamplerWpcSource << "\n";

@@ -308,7 +308,8 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
       return fail(RN_E_UNSUPPORTED, "thread-per-chain shape: the chain's shared-memory state does not fit; use RN_BACKEND_WARP");
   }
   if (eo.backend == 1) {
-    const size_t cap = 227 * 1024 - 2048;  // opt-in dynamic shared memory per CTA on sm_100, minus static/reserved
+    const size_t cap = 227 * 1024 - 128;  // opt-in dynamic shared memory per CTA on sm_100 (232448 B; the sampler kernels have no static
+                                         // shared memory and the 1 KB the system reserves per CTA is outside that figure)
     int wmax = 8;
     if (const char* e = getenv("RN_WPC_WARPS")) wmax = std::max(1, std::min(32, atoi(e)));
     // warps per chain: one, unless the chain's shared-memory state is so large that fewer than 16 chains fit an SM
@@ -372,6 +373,12 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
         }
       }
     }
+  }
+  if (eo.backend == 1) {  // registers per thread the CTA leaves (see the cap below): fewer components in flight when it is tight
+    const int warps = K->warps_per_cta * K->wpc_k;
+    const int regs = warps * 32 * 255 > 65536 ? ((65536 / warps) / 512) * 512 / 32 : 255;
+    eo.interleave = regs <= 128 ? 4 : 8;
+    if (const char* e = getenv("RN_INTERLEAVE")) eo.interleave = std::max(1, atoi(e));
   }
   K->source = emit_source(*P, eo);
   if (source_only) {

@@ -71,15 +71,23 @@ RN_DEVICE void rn_w_setup(RnW& w, double* base) {
   w.q = base;
   w.p = base + RN_N;
   w.g = base + 2 * RN_N;
+  // RN_W_VECS (rn_emit.cpp: wpc_vectors()) = 3 with the identity mass compiled in alone -- no mass vector: on cfg 5 those 8 KB
+  // per chain are what lets a second data-tile stage fit beside 4 chains
+#if RN_MASS_MAX >= 1
   w.m = base + 3 * RN_N;
+  double* const rest = base + 4 * RN_N;
+#else
+  w.m = base;  // never read: mass_kind stays 0
+  double* const rest = base + 3 * RN_N;
+#endif
 #if RN_ENABLE_EHMC
-  w.sq = base + 4 * RN_N;
-  w.sp = base + 5 * RN_N;
-  w.sg = base + 6 * RN_N;
-  w.scr = base + 7 * RN_N;
+  w.sq = rest;
+  w.sp = rest + RN_N;
+  w.sg = rest + 2 * RN_N;
+  w.scr = rest + 3 * RN_N;
 #else
   w.sq = w.sp = w.sg = base;
-  w.scr = base + 4 * RN_N;
+  w.scr = rest;
 #endif
 #if RN_MASS_MAX >= 2
   w.v = w.scr;  // the slice is [vectors | v | v2 | density scratch] when dense mass is compiled in

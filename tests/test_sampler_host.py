@@ -194,3 +194,33 @@ def test_wpc_several_chains_per_cta_share_the_data_tiles_on_host():
     cfg = api.make_config(iterations=3, warmupIterations=0, sampler=api.HMCSampler(2), stepSizeTuner=api.StaticStepSize(0.02),
                           massMatrixTuner=api.IdentityMassMatrixTuner())
     _run_wpc(model, cfg, np.arange(3) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2", k="2", chains_per_cta=2)
+
+
+def test_wpc_rerolled_invariant_sections_on_host():
+    """A vector of 48 latent group effects (cfg 5's shape, small): the warp-per-chain density re-rolls the 48 table entries,
+    prior terms and gradient outputs into loops across the group's threads (rn_emit.cpp: rr_plan).  Same values as the
+    unrolled statements (RN_NO_REROLL) to rounding of the re-associated sums, same accept decisions as the oracle."""
+    import os
+    model = configs.poisson_glm(48, 768)
+    prir, pcols = model.compile(False)
+    cfg = api.make_config(iterations=4, warmupIterations=0, sampler=api.HMCSampler(3), stepSizeTuner=api.StaticStepSize(0.004),
+                          massMatrixTuner=api.IdentityMassMatrixTuner())
+    cfg.backend = abi.RN_BACKEND_WARP
+    cm = api.CudaModel(prir, pcols, device=-1)
+    src = cm.emit_source(cfg)
+    dens = src[src.index("// ---- emitted"):src.index("// rn_sampler_wpc.cuh --")]
+    assert "for (int k = lane; k < 48; k += RN_G) {" in dens and "grad[2 + k] = " in dens and "scr[0 + k] = " in dens
+    assert dens.count("\n") < 700, "the invariant sections are loops, not 48 copies"
+    os.environ["RN_NO_REROLL"] = "1"
+    try:
+        src0 = api.CudaModel(prir, pcols, device=-1).emit_source(cfg)
+    finally:
+        del os.environ["RN_NO_REROLL"]
+    assert "grad[2 + k] = " not in src0[src0.index("// ---- emitted"):src0.index("// rn_sampler_wpc.cuh --")]
+    q = np.random.default_rng(4).normal(size=(3, cm.nVars)) * 0.3
+    d1, e1 = he.density(src, q, None, cm)
+    d0, e0 = he.density(src0, q, None, cm)
+    assert e0 == 0 and e1 == 0
+    assert np.max(np.abs(d1 - d0) / np.maximum(np.abs(d0), 1e-9)) < 1e-12
+    _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2")
+    _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2", k="2", chains_per_cta=2)
