@@ -3,11 +3,12 @@
   profiles/<tag>.csv              key metrics (one per line)
   profiles/<tag>_by_opcode.csv    instruction mix and stall attribution from the source page
   profiles/ncu_funnel_<math>.json what bench.py quotes (roofline.traffic, fp64 pipe)
-Usage: python scripts/ncu_summary.py gpurun_out/x.ncu-rep <tag> [parity|fast]"""
+Usage: python scripts/ncu_summary.py gpurun_out/x.ncu-rep <tag> [parity|fast|<name>] [workload description]"""
 import collections, csv, io, json, os, re, subprocess, sys
 
 rep, tag = sys.argv[1], sys.argv[2]
 math = sys.argv[3] if len(sys.argv) > 3 else "parity"
+WHAT = sys.argv[4] if len(sys.argv) > 4 else "151552 chains x 100 iterations"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -38,7 +39,7 @@ out = {"dram_bytes": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
        "fp64_pipe_active_pct": float(m["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"][0]),
        "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
        "registers_per_thread": int(float(m["launch__registers_per_thread"][0])), "warp_instructions": float(m["smsp__inst_executed.sum"][0]),
-       "source": "profiles/%s.csv (ncu --set full --clock-control none, one rn_k_iter launch, 151552 chains x 100 iterations)" % tag}
+       "source": "profiles/%s.csv (ncu --set full --clock-control none, one rn_k_iter launch, %s)" % (tag, WHAT)}
 json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_funnel_%s.json" % math), "w"), indent=1)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))

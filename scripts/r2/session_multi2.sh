@@ -1,0 +1,2 @@
+#!/bin/bash
+exec bash "$(dirname "$0")/session_multi.sh" 2
