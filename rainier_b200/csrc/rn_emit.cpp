@@ -343,7 +343,18 @@ struct Emitter {
           case RIR_B_ADD: os << "(" << x << " + " << y << ")"; break;
           case RIR_B_MUL: os << "(" << x << " * " << y << ")"; break;
           case RIR_B_SUB: os << "(" << x << " - " << y << ")"; break;
-          case RIR_B_DIV: os << "(" << x << " / " << y << ")"; break;
+          case RIR_B_DIV:
+            // Reverse-sweep quotients of the warp-per-chain row bodies (adj / x, the adjoint of log): their numerators are
+            // exactly 0 for half the observations of a 0/1-valued column, and a zero numerator fails the range test of
+            // CUDA's inline IEEE division, whose out-of-line completion then ran for 94 % of the warps: a quarter of all
+            // instructions of cfg 3 (profiles/r2_ncu_cfg3_mma_v1_regions.txt).  adj * (1 / x) keeps the inline path (the
+            // numerator is 1); one more rounding, in a region that agrees with the oracle to 1e-13 by construction
+            // (tree sums), not bit for bit.  Everything that is compared bit for bit keeps the exact quotient.
+            if (wpc && n.region == R_ROW_BWD && !getenv("RN_EXACT_ROW_DIV"))
+              os << "(" << x << " * (1.0 / " << y << "))";
+            else
+              os << "(" << x << " / " << y << ")";
+            break;
           case RIR_B_POW: os << pow_expr(n.a, n.b, n.region == R_ROW_BWD || n.region == R_INV_BWD, row_libm(n)); break;
           case RIR_B_COMPARE: os << "rn_compare(" << x << ", " << y << ")"; break;
         }
@@ -1455,8 +1466,10 @@ struct Emitter {
         if (plans[t].ok)
           for (size_t di = 0; di < (plans[t].uniform ? 1 : plans[t].dots.size()); di++) mma_helper(P.targets[t], t, plans[t], di);
     os << "RN_DEVICE void rn_density(const double* q, double& dens, double* grad, double* scr, "
-          "const double* RN_RESTRICT data, int& err, RnTma& tma) {\n";
-    os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x % RN_G);  // thread of the chain's group\n  (void)lane;\n";
+          "const double* RN_RESTRICT data, int& err_io, RnTma& tma) {\n";
+    // the error flag in a register: through the reference it lived in local memory, one LDL / LOP3 / STL chain per lookup
+    os << "  (void)data; (void)scr; (void)tma;\n  const int lane = (int)(threadIdx.x % RN_G);  // thread of the chain's group\n  (void)lane;\n"
+       << "  int err = 0;\n";
     if (n_smem_acc) os << "  for (int k = lane; k < " << n_smem_acc << "; k += RN_G) scr[" << tab_doubles << " + k] = 0.0;\n";
     std::set<int> rr_avail, rr_sums_ready;
     if (fams.empty())
@@ -1496,10 +1509,10 @@ struct Emitter {
              << "          rn_tma_load(tma, seq + (RN_TMA_STAGES - 1), src + (size_t)(tile + (RN_TMA_STAGES - 1)) * " << td * K << "ULL, "
              << td * K * 8 << "u);\n"
              << "        rn_mbar_wait(tma.full + (seq % RN_TMA_STAGES), (seq / RN_TMA_STAGES) & 1u);\n"
-             << "        const double* rp = tma.stage + (size_t)(seq % RN_TMA_STAGES) * RN_TMA_TILE_DOUBLES + (size_t)(lane >> 5) * " << td
-             << " + (lane & 31);\n";
+             << "        const RnSA rp = rn_sa(tma.stage + (size_t)(seq % RN_TMA_STAGES) * RN_TMA_TILE_DOUBLES + (size_t)(lane >> 5) * " << td
+             << " + (lane & 31));\n";
           row_body(
-              T, "        ", [&](int k) { return "rp[" + std::to_string(local_col(T, k) * pitch) + "]"; },
+              T, "        ", [&](int k) { return "rn_lds_tile(rp, " + std::to_string(local_col(T, k) * pitch) + ")"; },
               [&](int slot) { return acc_ref(slot); }, true, tab_doubles);
           os << "        rn_cta_bar(tma.nthreads);\n"
              << "      }\n"
@@ -1553,7 +1566,7 @@ struct Emitter {
       for (uint32_t i = 0; i < P.n_params; i++)
         if (fams.empty() || !rr_family_grad[i]) os << "  if (lane == 0) grad[" << i << "] = " << val(P.grad_nodes[i]) << ";\n";
     }
-    os << "  RN_SYNC();\n}\n";
+    os << "  err_io |= err;\n  RN_SYNC();\n}\n";
   }
 };
 
