@@ -1590,8 +1590,8 @@ WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
   Emitter E(P, opt);
   E.density_wpc();
   // chain vectors (q, p, gradient, mass [+ EHMC snapshot]) [+ 2 scratch vectors of the dense mass matrix code] + density scratch
-  z.per_warp_doubles = wpc_vectors(opt) * (int)P.n_params + E.tab_doubles + E.n_smem_acc + E.red_doubles +
-                       ((opt.mma && E.mma_all_ok) ? (int)E.mma_inv.size() : 0);
+  z.scratch_doubles = E.tab_doubles + E.n_smem_acc + E.red_doubles + ((opt.mma && E.mma_all_ok) ? (int)E.mma_inv.size() : 0);
+  z.per_warp_doubles = wpc_vectors(opt) * (int)P.n_params + z.scratch_doubles;
   for (const TargetInfo& T : P.targets)
     if (T.streamed() && T.n_rows >= 32ull * (uint64_t)std::max(1, opt.wpc_k))
       z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * opt.pitch((size_t)(&T - &P.targets[0])) * std::max(1, opt.wpc_k));

@@ -41,7 +41,8 @@ std::string emit_optimizer_source(const Program& P, const EmitOptions& opt, int 
 // shared-memory needs of the warp-per-chain kernels: doubles per warp (chain vectors + density scratch) and doubles of
 // the largest data tile (n_cols * 32 over the streamed targets; 0 when nothing is streamed)
 struct WpcSizes {
-  int per_warp_doubles = 0;  // per CHAIN (its wpc_k warps share the slice)
+  int per_warp_doubles = 0;  // per CHAIN (its wpc_k warps share the slice): the sampler's vectors + scratch_doubles
+  int scratch_doubles = 0;   // the emitted density's part of it (RN_WPC_SCRATCH): tables, scatter slots, reduction scratch
   int tile_doubles = 0;
   bool mma_ok = false;       // every streamed target with full tiles can take the chain-batched DMMA path
   int mma_shared_doubles = 0;  // CTA-shared doubles of that path: 8 per-warp column-block regions + the reduction scratch

@@ -2602,7 +2602,7 @@ static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::O
     int k = 1;
     {
       eo.wpc_k = 1;
-      const uint64_t one = (uint64_t)wpc_sizes(*P, eo).per_warp_doubles + lb_w + 1;
+      const uint64_t one = 4ull * P->n_params + (uint64_t)wpc_sizes(*P, eo).scratch_doubles + lb_w + 1;
       if (one > cap) return fail(RN_E_UNSUPPORTED, "rn_optimize: the L-BFGS history of one start does not fit shared memory");
       const uint64_t fit = std::max<uint64_t>(1, cap / one);
       while (k < 8 && fit * (uint64_t)k < 16) k *= 2;
@@ -2610,8 +2610,8 @@ static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::O
       if (k != 1 && k != 2 && k != 4 && k != 8) k = 1;
     }
     eo.wpc_k = k;
-    const WpcSizes z = wpc_sizes(*P, eo);  // 4n (x, gradient, g, diag take the sampler's q/p/g/m slots) + density scratch
-    const uint64_t per_start = (uint64_t)z.per_warp_doubles + lb_w + (uint64_t)k;
+    const WpcSizes z = wpc_sizes(*P, eo);  // RN_OPT_SMEM_DOUBLES (rn_optimizer.cuh): 4n (x, gradient, g, diag) + history + density scratch + k
+    const uint64_t per_start = 4ull * P->n_params + (uint64_t)z.scratch_doubles + lb_w + (uint64_t)k;
     if (per_start > cap) return fail(RN_E_UNSUPPORTED, "rn_optimize: the L-BFGS history of one start does not fit shared memory");
     K->wpc_k = k;
     K->smem_doubles = (int)per_start;
