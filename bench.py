@@ -264,6 +264,12 @@ def extra_configs(args, torch, dist, api, abi, rank, local_rank, world):
         seeds = np.arange(total, dtype=np.int64)[rank * per:(rank + 1) * per] + 1
         comm = api.Comm.from_torch_distributed(local_rank) if world > 1 else None
         res = {}
+        if comm is not None:  # NCCL sets its channels up inside the first collective (~0.2 s): not a warmup's cost
+            w = api.CudaSampler(model, api.SamplerConfig(iterations=1, warmupIterations=500, adaptation=abi.RN_ADAPT_POOLED), seeds=seeds)
+            w.set_comm(comm)
+            w.warmup(-1)
+            w.sync()
+            w.close()
         for mode in ("pooled", "per_chain"):
             cfg = api.SamplerConfig(iterations=500, warmupIterations=500, adaptation=abi.RN_ADAPT_POOLED if mode == "pooled" else 0)
             s = api.CudaSampler(model, cfg, seeds=seeds)
