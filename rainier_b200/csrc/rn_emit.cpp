@@ -1614,6 +1614,7 @@ std::string emit_optimizer_source(const Program& P, const EmitOptions& opt, int 
   os << "#define RN_NSLOTS " << P.n_slots << "\n";
   os << "#define RN_BACKEND " << (opt.backend == 1 ? 1 : 0) << "\n";
   os << "#define RN_LBFGS_M " << history << "\n";
+  if (opt.expect_slice_doubles > 0) os << "#define RN_OPT_EXPECT_SMEM " << opt.expect_slice_doubles << "\n";
   if (opt.fast_math) os << "#define RN_FAST_MATH 1\n";
   EmitOptions eo = opt;
   if (opt.backend == 1) {  // K warps per start, independent per-warp row loads (no CTA-shared tiles: starts diverge)

@@ -20,6 +20,7 @@ struct EmitOptions {
                                       // 36 where the chain-batched DMMA path may run: X^T fragments are then bank-conflict free
   bool mma = false;       // warp per chain: chain-batched fp64 tensor-core contraction of the row bodies' dot products (see
                           // Emitter::mma_block); needs full CTAs of mma_chains chains (= warps, wpc_k == 1)
+  int expect_slice_doubles = 0;  // optimizer: the launcher's shared-memory doubles per start (checked against the kernel's own layout at compile time)
   int interleave = 8;     // independent dataflow components of a row body (unrolled observations) emitted round-robin at a time
   int mma_chains = 8;     // 8 or 16: chains (warps) per CTA on that path -- 16 = two groups of 8 chains whose warps pair up on
                           // a dot's column block (twice the warps per SM for the same shared memory)

@@ -373,6 +373,9 @@ RN_DEVICE int rn_lb_apply(RnLbfgs& S, const double f, const double* g) {
 #if RN_BACKEND == 1
 // shared-memory slice of one start: x | gradient | g = -gradient | diag | w | scratch of the emitted density | K reduction slots
 #define RN_OPT_SMEM_DOUBLES (4 * RN_N + RN_LB_W + RN_WPC_SCRATCH + RN_WPC_K)
+#ifdef RN_OPT_EXPECT_SMEM  // what rn_runtime.cpp:get_opt_kernel allocates per start; a mismatch is a slice overrun on the device
+static_assert(RN_OPT_SMEM_DOUBLES == RN_OPT_EXPECT_SMEM, "rn_optimize: launcher and kernel disagree on the shared-memory slice of a start");
+#endif
 #ifdef RN_HOST_EMULATION
 static double rn_smem[1 << 17];  // one emulated start at a time
 #else

@@ -2615,6 +2615,7 @@ static int get_opt_kernel(rn_model* m, const rn_optimize_config* oc, rn_model::O
     if (per_start > cap) return fail(RN_E_UNSUPPORTED, "rn_optimize: the L-BFGS history of one start does not fit shared memory");
     K->wpc_k = k;
     K->smem_doubles = (int)per_start;
+    eo.expect_slice_doubles = (int)per_start;
     // at most 256 threads per CTA (255 registers each fit the register file); named barriers 2..15 when K > 1
     K->starts_per_cta = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)(8 / k), cap / per_start));
   }
