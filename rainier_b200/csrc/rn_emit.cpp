@@ -278,6 +278,16 @@ struct Emitter {
   // `derived`: the node was created by the emitter's own reverse sweep (there is no reference operation to mirror), so
   // constant powers are strength-reduced in parity mode as well -- d/dx x^-1 = -x^-2 would otherwise cost one fdlibm
   // pow() per observation of a logistic regression
+  // Row bodies of the warp-per-chain shape: total, branch-free exp / log / reciprocal (rn_prelude.cuh: rn_row_*) instead of CUDA's
+  // exp(), log() and 1.0 / x, each of which ends a basic block with its range test -- and the statements of 4 or 8 observations
+  // are interleaved precisely so that ptxas can overlap their chains.  RN_ROW_LIBM=0 keeps CUDA's functions (A/B).
+  static bool row_libm_on() {
+    const char* e = getenv("RN_ROW_LIBM");
+    return !e || atoi(e) != 0;
+  }
+  std::string recip(const std::string& x, bool row_variant) const {
+    return (row_variant && row_libm_on()) ? "rn_row_rcp(" + x + ")" : "(1.0 / " + x + ")";
+  }
   std::string pow_expr(int a, int b, bool derived, bool row_variant = false) const {
     const Node& e = P.nodes[b];
     const std::string x = val(a);
@@ -285,21 +295,21 @@ struct Emitter {
       const double c = e.value;
       if (c == 1.0) return x;
       if (c == 2.0) return "(" + x + " * " + x + ")";
-      if (c == -1.0) return "(1.0 / " + x + ")";
+      if (c == -1.0) return recip(x, row_variant);
       if (derived && !opt.fast_math) {
         if (c == 3.0) return "(" + x + " * " + x + " * " + x + ")";
         if (c == 4.0) return "((" + x + " * " + x + ") * (" + x + " * " + x + "))";
-        if (c == -2.0) return "(1.0 / (" + x + " * " + x + "))";
-        if (c == -3.0) return "(1.0 / (" + x + " * " + x + " * " + x + "))";
+        if (c == -2.0) return recip("(" + x + " * " + x + ")", row_variant);
+        if (c == -3.0) return recip("(" + x + " * " + x + " * " + x + ")", row_variant);
         if (c == 0.5) return "sqrt(" + x + ")";
-        if (c == -0.5) return "(1.0 / sqrt(" + x + "))";
+        if (c == -0.5) return recip("sqrt(" + x + ")", row_variant);
         if (c == 1.5) return "(" + x + " * sqrt(" + x + "))";
-        if (c == -1.5) return "(1.0 / (" + x + " * sqrt(" + x + ")))";
+        if (c == -1.5) return recip("(" + x + " * sqrt(" + x + "))", row_variant);
       }
       if (opt.fast_math) {
         if (c == 3.0) return "(" + x + " * " + x + " * " + x + ")";
         if (c == 4.0) return "((" + x + " * " + x + ") * (" + x + " * " + x + "))";
-        if (c == -2.0) return "(1.0 / (" + x + " * " + x + "))";
+        if (c == -2.0) return recip("(" + x + " * " + x + ")", row_variant);
         if (c == 0.5) return "sqrt(" + x + ")";
         if (c == -0.5) return "rsqrt(" + x + ")";
         if (c == 1.5) return "(" + x + " * sqrt(" + x + "))";
@@ -321,8 +331,8 @@ struct Emitter {
           // Math.exp/log intrinsics): rows are summed in tree order there, so those results are not bit-comparable with
           // the oracle anyway (1e-13 agreement), and fdlibm costs twice the instructions.  Everything that stays
           // bit-exact -- invariant parts, data-free targets, the thread-per-chain kernels -- keeps fdlibm.
-          case RIR_U_EXP: os << (row_libm(n) && !getenv("RN_ROW_EXP_FDLIBM") ? "exp(" : "rn_exp(") << x << ")"; break;
-          case RIR_U_LOG: os << (row_libm(n) ? "log(" : "rn_log(") << x << ")"; break;
+          case RIR_U_EXP: os << (row_libm(n) && !getenv("RN_ROW_EXP_FDLIBM") ? (row_libm_on() ? "rn_row_exp(" : "exp(") : "rn_exp(") << x << ")"; break;
+          case RIR_U_LOG: os << (row_libm(n) ? (row_libm_on() ? "rn_row_log(" : "log(") : "rn_log(") << x << ")"; break;
           case RIR_U_ABS: os << "fabs(" << x << ")"; break;
           case RIR_U_NOOP: os << x; break;
           case RIR_U_SIN: os << "sin(" << x << ")"; break;
@@ -332,7 +342,7 @@ struct Emitter {
           case RIR_U_ACOS: os << "acos(" << x << ")"; break;
           case RIR_U_ATAN: os << "atan(" << x << ")"; break;
           case U_NEG: os << "(-" << x << ")"; break;
-          case U_RECIP: os << "(1.0 / " << x << ")"; break;
+          case U_RECIP: os << recip(x, row_libm(n)); break;
           case U_SQRT: os << "sqrt(" << x << ")"; break;
         }
         break;
@@ -351,7 +361,7 @@ struct Emitter {
             // numerator is 1); one more rounding, in a region that agrees with the oracle to 1e-13 by construction
             // (tree sums), not bit for bit.  Everything that is compared bit for bit keeps the exact quotient.
             if (wpc && n.region == R_ROW_BWD && !getenv("RN_EXACT_ROW_DIV"))
-              os << "(" << x << " * (1.0 / " << y << "))";
+              os << "(" << x << " * " << recip(y, true) << ")";
             else
               os << "(" << x << " / " << y << ")";
             break;
@@ -760,8 +770,14 @@ struct Emitter {
         os << "  const double c" << k << sfx(e) << " = rn_lds(" << (e & 1 ? "rp1" : "rp0") << ", roff + " << (e >> 1) * 8 + (local_col(T, k) - d.cmin) * pitch << ");\n";
     };
     std::vector<int> o;
+    // elements in flight per statement (RN_MMA_ELEMS, experiment switch; default 4): with the branch-free row functions all four
+    // chains sit in one basic block and ptxas overlaps them completely -- at 128 registers that can cost more in spills than it
+    // gains; 2 runs the helper's body twice over two elements
+    int EW = 4;
+    if (const char* ev = getenv("RN_MMA_ELEMS")) EW = std::max(1, std::min(4, atoi(ev)));
+    int e_lo = 0, e_hi = 4;
     auto one = [&](int id) {
-      for (int e = 0; e < 4; e++) {
+      for (int e = e_lo; e < e_hi; e++) {
         node_suffix = col_suffix = sfx(e);
         if (id == d.z) {  // the dot itself: the tensor core's sum, plus the fold's first operand
           if (d.base >= 0) {
@@ -777,26 +793,30 @@ struct Emitter {
         stmt(id, "  ");
       }
     };
-    bool z_done = false;
-    for (int id : d.fwd) {
-      one(id);
-      if (id == d.z) z_done = true;
-    }
-    if (!z_done) one(d.z);
-    for (int l : d.leaves)
-      for (int e = 0; e < 4; e++) {
-        node_suffix = col_suffix = sfx(e);
-        need_col(l, e);
-        os << "  dens += " << val(l) << ";\n";
+    for (e_lo = 0; e_lo < 4; e_lo += EW) {
+      e_hi = std::min(4, e_lo + EW);
+      if (e_lo > 0) os << "  RN_FENCE();\n";
+      bool z_done = false;
+      for (int id : d.fwd) {
+        one(id);
+        if (id == d.z) z_done = true;
       }
-    for (int id : d.bwd) one(id);
-    for (int e = 0; e < 4; e++) {
-      node_suffix = col_suffix = sfx(e);
-      need_col(d.w, e);
-      os << "  wout[" << e << "] = " << val(d.w) << ";\n";
-      for (const AccStmt& a : d.acc) {
-        need_col(a.node, e);
-        os << "  osum[" << a.slot << "] += " << val(a.node) << ";\n";
+      if (!z_done) one(d.z);
+      for (int l : d.leaves)
+        for (int e = e_lo; e < e_hi; e++) {
+          node_suffix = col_suffix = sfx(e);
+          need_col(l, e);
+          os << "  dens += " << val(l) << ";\n";
+        }
+      for (int id : d.bwd) one(id);
+      for (int e = e_lo; e < e_hi; e++) {
+        node_suffix = col_suffix = sfx(e);
+        need_col(d.w, e);
+        os << "  wout[" << e << "] = " << val(d.w) << ";\n";
+        for (const AccStmt& a : d.acc) {
+          need_col(a.node, e);
+          os << "  osum[" << a.slot << "] += " << val(a.node) << ";\n";
+        }
       }
     }
     node_suffix.clear();

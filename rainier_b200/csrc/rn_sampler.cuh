@@ -80,7 +80,10 @@ RN_DEVICE RnTs rn_ts_get() {
 #define RN_X_P_REGS 1 /* momentum in registers: 3.25 ms vs 3.41 ms per launch at the headline size with it in shared memory */
 #endif
 #ifndef RN_X_NORMALS
-#define RN_X_NORMALS 1 /* flat rejection loop + second pass kept as a LOOP: the kernel is sensitive to code size (3.41 vs 3.68 ms unrolled) */
+/* flat rejection loop + second pass kept as a LOOP (the kernel is sensitive to code size: 3.41 vs 3.68 ms fully unrolled, round 2),
+   two pairs per trip since round 3: with the check-free division / square root and the one-branch log the two chains of a trip
+   overlap (2.505 -> 2.482 ms; the hand-paired form, RN_X_NORMALS == 4, is slower: 2.554 -- profiles/r2_sweep_iter_v4_*.jsonl) */
+#define RN_X_NORMALS 3
 #endif
 #define RN_Z(i) RN_TSD(RN_TS_P + (i)) /* scratch of the normal draws (aliases the shared-memory momentum) */
 #if RN_X_P_REGS
@@ -250,6 +253,39 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
       k += 1;
     }
   }
+#if RN_X_NORMALS == 4 && RN_X_SPEC && !defined(RN_FAST_MATH) && !(defined(RN_X_LIBM_PLAIN) && RN_X_LIBM_PLAIN)
+  // two pairs per trip: their log -> division -> square root chains are independent, and with the `_try` form of the log (one
+  // shared fallback branch) they sit in ONE basic block, so ptxas interleaves them.  An odd number of pairs repeats the last
+  // pair (same inputs, same outputs, written twice).
+#pragma unroll 1
+  for (int k = 0; k < npairs; k += 2) {
+    const int ia = i0 + 2 * k, ib = i0 + 2 * (k + 1 < npairs ? k + 1 : k);
+    const double a1 = RN_Z(ia), a2 = RN_Z(ia + 1), b1 = RN_Z(ib), b2 = RN_Z(ib + 1);
+    const double sa = a1 * a1 + a2 * a2, sb = b1 * b1 + b2 * b2;
+    bool oka, okb;
+    double la = rn_strict_log_try(sa, oka), lb = rn_strict_log_try(sb, okb);
+    if (!(oka && okb)) {
+      la = rn_strict_log_full(sa);
+      lb = rn_strict_log_full(sb);
+    }
+    const double ma = rn_sqrt_nc(rn_div_nc(-2 * la, sa)), mb = rn_sqrt_nc(rn_div_nc(-2 * lb, sb));  // ranges: rn_polar_multiplier
+    RN_Z(ia) = a1 * ma;
+    if (ia + 1 < RN_N) {
+      RN_Z(ia + 1) = a2 * ma;
+    } else {
+      rng.nng = a2 * ma;
+      rng.have = 1;
+    }
+    RN_Z(ib) = b1 * mb;
+    if (ib + 1 < RN_N) {
+      RN_Z(ib + 1) = b2 * mb;
+    } else {
+      rng.nng = b2 * mb;
+      rng.have = 1;
+    }
+  }
+  return;
+#endif
 #if RN_X_NORMALS == 1
 #pragma unroll 1
 #elif RN_X_NORMALS == 3
@@ -259,7 +295,7 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
     const int i = i0 + 2 * k;
     const double v1 = RN_Z(i), v2 = RN_Z(i + 1);
     const double s = v1 * v1 + v2 * v2;
-    const double multiplier = sqrt(-2 * rn_strict_log(s) / s);
+    const double multiplier = rn_polar_multiplier(s);
     RN_Z(i) = v1 * multiplier;
     if (i + 1 < RN_N) {
       RN_Z(i + 1) = v2 * multiplier;

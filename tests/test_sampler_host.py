@@ -12,13 +12,13 @@ from rainier_b200 import abi, api
 import host_emulation as he
 
 
-def _run(model, config, seeds, dense=False):
+def _run(model, config, seeds, dense=False, defs=""):
     rir, cols = model.compile(True)
     cfg, keep = api.lower_config(config)
     cfg.backend = abi.RN_BACKEND_THREAD
     cm = api.CudaModel(rir, cols, device=-1)
     config.backend = abi.RN_BACKEND_THREAD
-    got = he.sample(cm.emit_source(config), cfg, seeds, cm)
+    got = he.sample(defs + cm.emit_source(config), cfg, seeds, cm)
     ref = OracleModel(rir, cols).sample(cfg, seeds=seeds, trace=True, dense_mass=dense)
     assert np.array_equal(got["trace"][:, :, 1], ref["trace"][:, :, 1]), "accept decisions differ"
     assert np.array_equal(got["trace"][:, :, 3], ref["trace"][:, :, 3]), "leapfrog step counts differ"
@@ -36,6 +36,18 @@ def _cfg(it, warm, sampler, step, mass, **kw):
 
 def test_hmc_dualavg_funnel_on_host():
     _run(configs.funnel(), _cfg(30, 120, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(6) + 7)
+
+
+@pytest.mark.parametrize("defs", ["#define RN_X_NORMALS 4\n", "#define RN_X_SPEC 0\n", "#define RN_X_KCONST 0\n#define RN_X_NORMALS 1\n"])
+def test_round3_source_variants_on_host(defs):
+    """the experiment switches of round 3 (two polar pairs per trip through the `_try` form of the log; the branching forms of
+    the fdlibm common paths; coefficients as literals) leave every bit where it was -- even and odd numbers of parameters
+    (odd: the cached second variate alternates, the last pair of a draw is repeated by the two-at-a-time pass)"""
+    _run(configs.funnel(), _cfg(12, 40, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(4) + 7, defs=defs)
+    _run(configs.funnel(7), _cfg(12, 30, api.HMCSampler(4), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(3) + 3, defs=defs)
+    model = sbc_models.build("SBCGamma")[0]
+    _run(model, _cfg(10, 30, api.HMCSampler(3), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(3) + 2, defs=defs)
+    _run(configs.eight_schools(), api.SamplerConfig(iterations=10, warmupIterations=60), np.arange(2) + 11, defs=defs)
 
 
 def test_default_config_eight_schools_on_host():
