@@ -283,7 +283,7 @@ struct Emitter {
   // are interleaved precisely so that ptxas can overlap their chains.  RN_ROW_LIBM=0 keeps CUDA's functions (A/B).
   static bool row_libm_on() {
     const char* e = getenv("RN_ROW_LIBM");
-    return !e || atoi(e) != 0;
+    return e && atoi(e) != 0;  // off until the B200 A/B is in (profiles/)
   }
   std::string recip(const std::string& x, bool row_variant) const {
     return (row_variant && row_libm_on()) ? "rn_row_rcp(" + x + ")" : "(1.0 / " + x + ")";
