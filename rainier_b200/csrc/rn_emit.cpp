@@ -196,6 +196,13 @@ struct Emitter {
     auto emit_acc = [&](const AccStmt& a) { os << ind << accref(a.slot) << " += " << val(a.node) << ";\n"; };
     auto emit_scatter = [&](const ScatterStmt& sc) {
       if (atomic_scatter) {
+        auto ri = row_index.find(sc.index_node);
+        if (ri != row_index.end() && ri->second.low == sc.low && ri->second.len == sc.len) {
+          // the forward Lookup's index (-1: outside the table, flag already raised there)
+          os << ind << "{ const int k = " << ri->second.var << "; const bool bad = k < 0; rn_scatter_add(&scr["
+             << (scatter_base_off + smem_slot[sc.slot_base]) << " + (bad ? 0 : k)], bad ? 0.0 : " << val(sc.node) << "); }\n";
+          return;
+        }
         // branch-free (an index outside the table raises the flag and adds 0 to entry 0) and in the shared state space: the
         // generic atomicAdd carries one code path per address space behind a run-time test, 16 times per row body on cfg 5
         os << ind << "{ const int k = rn_d2i(" << val(sc.index_node) << ") - (" << sc.low << "); const bool bad = (unsigned)k >= " << sc.len
@@ -217,7 +224,8 @@ struct Emitter {
       auto is = sc_at.find(id);
       if (is != sc_at.end())
         for (const ScatterStmt* sc : is->second) {
-          need_col(sc->index_node);
+          auto ri = row_index.find(sc->index_node);
+          if (!(atomic_scatter && ri != row_index.end() && ri->second.low == sc->low && ri->second.len == sc->len)) need_col(sc->index_node);
           emit_scatter(*sc);
         }
     };
@@ -229,6 +237,8 @@ struct Emitter {
     std::vector<int> order_fwd, order_bwd;
     interleave_components(T, body, order_fwd, order_bwd);
     col_suffix.clear();
+    row_index.clear();
+    capture_row_index = atomic_scatter && !(getenv("RN_SCATTER_REUSE_INDEX") && atoi(getenv("RN_SCATTER_REUSE_INDEX")) == 0);
     for (int id : order_fwd) one(id);
     if (!order_bwd.empty()) {
       os << ind << "RN_FENCE();\n";
@@ -241,11 +251,14 @@ struct Emitter {
       emit_acc(*a);
     }
     for (const ScatterStmt* sc : sc_tail) {
-      need_col(sc->index_node);
+      auto ri = row_index.find(sc->index_node);
+      if (!(atomic_scatter && ri != row_index.end() && ri->second.low == sc->low && ri->second.len == sc->len)) need_col(sc->index_node);
       need_col(sc->node);
       emit_scatter(*sc);
     }
     col_suffix.clear();
+    capture_row_index = false;
+    row_index.clear();
   }
 
   std::string acc_ref(int slot) const {
@@ -281,9 +294,14 @@ struct Emitter {
   // Row bodies of the warp-per-chain shape: total, branch-free exp / log / reciprocal (rn_prelude.cuh: rn_row_*) instead of CUDA's
   // exp(), log() and 1.0 / x, each of which ends a basic block with its range test -- and the statements of 4 or 8 observations
   // are interleaved precisely so that ptxas can overlap their chains.  RN_ROW_LIBM=0 keeps CUDA's functions (A/B).
-  static bool row_libm_on() {
-    const char* e = getenv("RN_ROW_LIBM");
-    return e && atoi(e) != 0;  // off until the B200 A/B is in (profiles/)
+  // Measured on B200 (profiles/r2_bench_row_libm_ab_v1.txt): the rows-across-lanes body gains (cfg 5: 2.22e5 -> 2.41e5, 2.46e5 with
+  // two observations in flight), the chain-batched DMMA kernel loses (cfg 3: 5.25e5 -> 4.66e5; at 128 registers the four elements
+  // of its helper in one basic block spill: stack 976 -> 4776 bytes) -- so the default is on for kernels without the DMMA path
+  // and off for those with it (helper and its rows-across-lanes tail alike: that kernel stays exactly what round 2 validated).
+  bool in_mma_helper = false, kernel_uses_mma = false;
+  bool row_libm_on() const {
+    if (const char* e = getenv("RN_ROW_LIBM")) return atoi(e) != 0;
+    return !kernel_uses_mma;
   }
   std::string recip(const std::string& x, bool row_variant) const {
     return (row_variant && row_libm_on()) ? "rn_row_rcp(" + x + ")" : "(1.0 / " + x + ")";
@@ -315,13 +333,26 @@ struct Emitter {
         if (c == 1.5) return "(" + x + " * sqrt(" + x + "))";
       }
     }
+    if (merged && !row_variant) return "rn_pow_m<SLOW>(" + x + ", " + val(b) + ", bad)";
     return std::string(row_variant ? "rn_pow_libm(" : "rn_pow(") + x + ", " + val(b) + ")";
   }
   bool row_libm(const Node& n) const { return wpc && (n.region == R_ROW_FWD || n.region == R_ROW_BWD); }
+  // density_tpc() of a data-free model in parity mode: the fdlibm calls of the whole density share ONE fallback branch -- the
+  // common paths accumulate a flag (rn_exp_m<0> ...), and only if it is set the density is evaluated again, out of line, by the
+  // complete functions (rn_exp_m<1> ...).  See density_tpc().
+  bool merged = false;
+  // warp-per-chain row bodies: a Lookup's table index (D2I, range test) is kept in an int and reused by the scatter-add of its
+  // adjoint in the reverse sweep, instead of re-loading the index column from the tile and converting it again (ncu, cfg 5:
+  // the F2I behind that second LDS was 9.5 % of the row loop's stall samples, all short_scoreboard).  key: index node.
+  struct RowIndex { int low, len; std::string var; };
+  std::map<int, RowIndex> row_index;
+  bool capture_row_index = false;
 
   void stmt(int id, const char* indent) {
     const Node& n = P.nodes[id];
     if (n.kind == K_CONST || n.kind == K_INPUT) return;
+    if (n.kind == K_LOOKUP && wpc && tab_off.count(id) && capture_row_index && !row_index.count(n.a))
+      os << indent << "int ki" << id << node_suffix << ";\n";
     os << indent << "const double " << val(id) << " = ";
     switch (n.kind) {
       case K_UNARY: {
@@ -331,8 +362,14 @@ struct Emitter {
           // Math.exp/log intrinsics): rows are summed in tree order there, so those results are not bit-comparable with
           // the oracle anyway (1e-13 agreement), and fdlibm costs twice the instructions.  Everything that stays
           // bit-exact -- invariant parts, data-free targets, the thread-per-chain kernels -- keeps fdlibm.
-          case RIR_U_EXP: os << (row_libm(n) && !getenv("RN_ROW_EXP_FDLIBM") ? (row_libm_on() ? "rn_row_exp(" : "exp(") : "rn_exp(") << x << ")"; break;
-          case RIR_U_LOG: os << (row_libm(n) ? (row_libm_on() ? "rn_row_log(" : "log(") : "rn_log(") << x << ")"; break;
+          case RIR_U_EXP:
+            if (merged) { os << "rn_exp_m<SLOW>(" << x << ", bad)"; break; }
+            os << (row_libm(n) && !getenv("RN_ROW_EXP_FDLIBM") ? (row_libm_on() ? "rn_row_exp(" : "exp(") : "rn_exp(") << x << ")";
+            break;
+          case RIR_U_LOG:
+            if (merged) { os << "rn_log_m<SLOW>(" << x << ", bad)"; break; }
+            os << (row_libm(n) ? (row_libm_on() ? "rn_row_log(" : "log(") : "rn_log(") << x << ")";
+            break;
           case RIR_U_ABS: os << "fabs(" << x << ")"; break;
           case RIR_U_NOOP: os << x; break;
           case RIR_U_SIN: os << "sin(" << x << ")"; break;
@@ -373,6 +410,12 @@ struct Emitter {
       case K_LOOKUP: {
         // D2I ; tableswitch ; default -> throw (ir/ExprMethodGenerator.scala:50-56): flag + NaN instead of a fault
         if (wpc && tab_off.count(id)) {
+          if (capture_row_index && !row_index.count(n.a)) {
+            const std::string var = "ki" + std::to_string(id) + node_suffix;
+            row_index[n.a] = RowIndex{n.d, n.c, var};
+            os << "rn_tab_lookup_k(scr + " << tab_off.at(id) << ", " << n.c << ", " << n.d << ", " << val(n.a) << ", err, " << var << ")";
+            break;
+          }
           os << "rn_tab_lookup(scr + " << tab_off.at(id) << ", " << n.c << ", " << n.d << ", " << val(n.a) << ", err)";
           break;
         }
@@ -405,8 +448,15 @@ struct Emitter {
     os << "// ---- emitted: log-density and gradient of the frozen DAG (" << (P.symbolic ? "symbolic" : "adjoint")
        << " gradient) ----\n";
     lookup_helpers();
-    os << "RN_DEVICE void rn_density(const double (&q)[RN_N], double& dens, double (&grad)[RN_N], "
-          "const double* RN_RESTRICT data, int& err) {\n";
+    bool data_free = true;
+    for (const TargetInfo& T : P.targets) data_free = data_free && !T.streamed();
+    merged = data_free && !opt.fast_math && getenv("RN_MERGED_FALLBACK") && atoi(getenv("RN_MERGED_FALLBACK")) != 0;  // opt-in (A/B)
+    if (merged)
+      os << "template <int SLOW>\nRN_DEVICE void rn_density_t(const double (&q)[RN_N], double& dens, double (&grad)[RN_N], "
+            "const double* RN_RESTRICT data, int& err, bool& bad) {\n";
+    else
+      os << "RN_DEVICE void rn_density(const double (&q)[RN_N], double& dens, double (&grad)[RN_N], "
+            "const double* RN_RESTRICT data, int& err) {\n";
     os << "  (void)data; (void)err;\n";
     os << "  double acc[RN_NSLOTS];\n  for (int s = 0; s < RN_NSLOTS; s++) acc[s] = 0.0;\n";
     for (int id : P.inv_fwd) stmt(id, "  ");
@@ -434,6 +484,16 @@ struct Emitter {
       for (uint32_t i = 0; i < P.n_params; i++) os << "  grad[" << i << "] = " << val(P.grad_nodes[i]) << ";\n";
     }
     os << "}\n";
+    if (merged) {
+      // one straight-line instance of the common paths; the complete functions re-evaluate the density out of line when any
+      // argument left a common path (NaN / inf / subnormal / overflow candidates, |f| < 2^-20 in log, special exponents of pow)
+      // (the second instance is inlined too: an out-of-line function taking q / grad by reference would pin those arrays to
+      // local memory on the hot path -- measured in SASS: 30 STL.64 + 30 LDL.64 per leapfrog step; its libm calls are out of line)
+      os << "RN_DEVICE void rn_density(const double (&q)[RN_N], double& dens, double (&grad)[RN_N], "
+            "const double* RN_RESTRICT data, int& err) {\n  bool bad = false;\n  rn_density_t<0>(q, dens, grad, data, err, bad);\n"
+            "  if (bad) rn_density_t<1>(q, dens, grad, data, err, bad);\n}\n";
+      merged = false;
+    }
   }
 
   // Function flavour: forward evaluation of the m outputs of Compiler.compile(inputs, outputs).  An output is stored as
@@ -754,6 +814,7 @@ struct Emitter {
   // rows-across-lanes body (one element at a time left a warp with a single serial chain of exp / log / divisions; eight at
   // a time spilled at 128 registers)
   void mma_helper(const TargetInfo& T, size_t t, const MmaPlan& pl, size_t di) {
+    in_mma_helper = true;
     const MmaDot& d = pl.dots[di];
     const int pitch = opt.pitch(t);
     os << "RN_DEVICE void rn_mma_e" << t << "_" << di << "(const double* zz, const RnSA rp0, const RnSA rp1, const int roff, const double* RN_RESTRICT q, "
@@ -822,6 +883,7 @@ struct Emitter {
     node_suffix.clear();
     col_suffix.clear();
     os << "}\n";
+    in_mma_helper = false;
   }
 
   void mma_block(const TargetInfo& T, size_t t, const MmaPlan& pl, unsigned long long n_full) {
@@ -1464,6 +1526,7 @@ struct Emitter {
     if (!any_full) mma_all_ok = false;
     if (!mma_all_ok) mma_shared_doubles = 0;
     const bool use_mma = opt.mma && mma_all_ok;
+    kernel_uses_mma = use_mma;
     int n_reg_acc = 0;
     for (int sl = 0; sl < P.n_slots; sl++)
       if (smem_slot[sl] < 0) n_reg_acc++;
@@ -1478,6 +1541,9 @@ struct Emitter {
     os << "#define RN_WPC_RED_OFF " << red_off << "\n";
     os << "RN_DEVICE double rn_tab_lookup(const double* tab, int len, int low, double idx, int& err) {\n"
           "  const int k = rn_d2i(idx) - low;\n  const bool bad = (unsigned)k >= (unsigned)len;\n  err |= (int)bad;\n"
+          "  const double v = tab[bad ? 0 : k];\n  return bad ? RN_NAN : v;\n}\n";
+    os << "RN_DEVICE double rn_tab_lookup_k(const double* tab, int len, int low, double idx, int& err, int& kout) {\n"
+          "  const int k = rn_d2i(idx) - low;\n  const bool bad = (unsigned)k >= (unsigned)len;\n  err |= (int)bad;\n  kout = bad ? -1 : k;\n"
           "  const double v = tab[bad ? 0 : k];\n  return bad ? RN_NAN : v;\n}\n";
     os << "RN_DEVICE double rn_warp_sum(double x) {\n  RN_UNROLL\n  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);\n  return x;\n}\n";
     lookup_helpers();

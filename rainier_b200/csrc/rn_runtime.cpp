@@ -377,7 +377,11 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
   if (eo.backend == 1) {  // registers per thread the CTA leaves (see the cap below): fewer components in flight when it is tight
     const int warps = K->warps_per_cta * K->wpc_k;
     const int regs = warps * 32 * 255 > 65536 ? ((65536 / warps) / 512) * 512 / 32 : 255;
-    eo.interleave = regs <= 128 ? 4 : 8;
+    // (with the branch-free row functions the components in flight share ONE basic block and ptxas overlaps them completely:
+    // two at 128 registers -- cfg 5: 2.46e5 against 2.41e5 with four, profiles/r2_bench_row_libm_ab_v1.txt; the DMMA kernels
+    // keep CUDA's libm and four)
+    const bool row_libm = getenv("RN_ROW_LIBM") ? atoi(getenv("RN_ROW_LIBM")) != 0 : !eo.mma;
+    eo.interleave = regs <= 128 ? (row_libm ? 2 : 4) : 8;
     if (const char* e = getenv("RN_INTERLEAVE")) eo.interleave = std::max(1, atoi(e));
   }
   K->source = emit_source(*P, eo);

@@ -81,7 +81,7 @@ RN_DEVICE RnTs rn_ts_get() {
 #endif
 #ifndef RN_X_NORMALS
 /* flat rejection loop + second pass kept as a LOOP (the kernel is sensitive to code size: 3.41 vs 3.68 ms fully unrolled, round 2),
-   two pairs per trip since round 3: with the check-free division / square root and the one-branch log the two chains of a trip
+   two pairs per trip since the second session of round 2: with the check-free division / square root and the one-branch log the two chains of a trip
    overlap (2.505 -> 2.482 ms; the hand-paired form, RN_X_NORMALS == 4, is slower: 2.554 -- profiles/r2_sweep_iter_v4_*.jsonl) */
 #define RN_X_NORMALS 3
 #endif
@@ -243,6 +243,29 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
     i0 = 1;
   }
   const int npairs = (RN_N - i0 + 1) / 2;  // the last pair's second variate may be left over (-> rng.nng); slot RN_N is scratch
+#if defined(RN_X_POLAR2) && RN_X_POLAR2
+  // experiment switch: two attempts per trip (see rn_polar_attempt2); the second one is consumed only if it is needed
+  for (int k = 0; k < npairs;) {
+    double a1, a2, b1, b2;
+    rn_i64 seed4, seed8;
+    rn_polar_attempt2(rng, a1, a2, b1, b2, seed4, seed8);
+    const double sa = a1 * a1 + a2 * a2, sb = b1 * b1 + b2 * b2;
+    const bool oka = !(sa >= 1 || sa == 0);
+    const int kb = k + (oka ? 1 : 0);
+    const bool needb = kb < npairs;
+    const bool okb = needb && !(sb >= 1 || sb == 0);
+    if (oka) {
+      RN_Z(i0 + 2 * k) = a1;
+      RN_Z(i0 + 2 * k + 1) = a2;
+    }
+    if (okb) {
+      RN_Z(i0 + 2 * kb) = b1;
+      RN_Z(i0 + 2 * kb + 1) = b2;
+    }
+    rng.seed = needb ? seed8 : seed4;
+    k = kb + (okb ? 1 : 0);
+  }
+#else
   for (int k = 0; k < npairs;) {
     double v1, v2;
     rn_polar_attempt(rng, v1, v2);
@@ -253,6 +276,7 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
       k += 1;
     }
   }
+#endif
 #if RN_X_NORMALS == 4 && RN_X_SPEC && !defined(RN_FAST_MATH) && !(defined(RN_X_LIBM_PLAIN) && RN_X_LIBM_PLAIN)
   // two pairs per trip: their log -> division -> square root chains are independent, and with the `_try` form of the log (one
   // shared fallback branch) they sit in ONE basic block, so ptxas interleaves them.  An odd number of pairs repeats the last

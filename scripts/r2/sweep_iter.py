@@ -17,7 +17,11 @@ ref = None
 for defs in defsets:
   for cap in caps:
     for block in blocks:
-        os.environ["RN_NVRTC_DEFS"] = defs
+        # tokens ENV:NAME=VALUE set an environment switch of the runtime / emitter for this variant instead of a -D
+        for tok in defs.split():
+            if tok.startswith("ENV:"):
+                os.environ[tok[4:].split("=")[0]] = tok.split("=", 1)[1]
+        os.environ["RN_NVRTC_DEFS"] = " ".join(t for t in defs.split() if not t.startswith("ENV:"))
         os.environ["RN_MAXRREGCOUNT"] = str(cap)
         os.environ["RN_BLOCK"] = str(block)
         model = api.CudaModel(rir, [], device=0)
@@ -41,3 +45,6 @@ for defs in defsets:
         print(json.dumps({"defs": defs, "cap": cap, "block": block, "ms_min": ms[0], "ms_med": ms[2], "rate": C_ * I_ * 5 / (ms[2] * 1e-3),
                           "same_bits": h == ref, "hash": h}), flush=True)
         smp.close(); model.close()
+        for tok in defs.split():
+            if tok.startswith("ENV:"):
+                os.environ.pop(tok[4:].split("=")[0], None)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Static SASS of rn_k_iter for cfg3 / cfg5 (no device): instruction count, control flow, registers, per environment setting.
-Usage: RN_ROW_LIBM=0|1 python scripts/r3/sass_cfg.py cfg3 cfg5"""
+Usage: RN_ROW_LIBM=0|1 python scripts/r2b/sass_cfg.py cfg3 cfg5"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)

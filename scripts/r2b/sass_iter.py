@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Static SASS of the funnel's rn_k_iter for a set of RN_X_* switches (no device): instruction count, opcode mix, branches,
 registers, of the whole kernel and of the leapfrog loop (between the two backward branches with the largest span).
-Usage: python scripts/r3/sass_iter.py "<defs A>" "<defs B>" ...   (RN_MAXRREGCOUNT from the environment)"""
+Usage: python scripts/r2b/sass_iter.py "<defs A>" "<defs B>" ...   (RN_MAXRREGCOUNT from the environment)"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)

@@ -65,6 +65,7 @@ def test_warp_per_chain_source_shape():
     # logistic regression = dot products + elementwise code: the chain-batched DMMA path (per-warp TMA column blocks) ...
     assert "rn_dmma(" in dens and "rn_tma_load_raw(" in dens and "rn_mbar_wait_warp(" in dens and "rn_cta_bar(" in dens
     assert "#define RN_MMA_BARS 8" in src and dens.count("RN_DEVICE void rn_mma_e") == 1  # one copy serves the 8 unrolled observations
+    dens_mma = dens
     import os
     os.environ["RN_MMA"] = "0"  # ... and, switched off, the CTA-shared tile pipeline of the rows-across-lanes body
     try:
@@ -77,7 +78,10 @@ def test_warp_per_chain_source_shape():
     assert "RN_LDG(rp +" in dens                                                          # independent per-warp path
     assert "rn_pow(" not in dens and "rn_pow_libm(" not in dens                           # d/dx x^-1 strength-reduced
     rows = dens[dens.index("// target 1"):]
-    assert " exp(" in rows and " log(" in rows and "rn_exp(" not in rows                  # libm in row regions only
+    # row regions: the branch-free row functions (kernels without the DMMA path), never fdlibm; with the DMMA path: CUDA's libm
+    assert "rn_row_exp(" in rows and "rn_row_log(" in rows and "rn_row_rcp(" in rows and "rn_exp(" not in rows and " exp(" not in rows
+    mma_rows = dens_mma[dens_mma.index("RN_DEVICE void rn_mma_e"):]
+    assert " exp(" in mma_rows and " log(" in mma_rows and "rn_row_exp(" not in mma_rows and "rn_exp(" not in mma_rows
     assert "RN_FENCE();" in rows                                                          # reverse sweep reloads columns
     assert "#define RN_TMA_STAGES" in src and "#define RN_WPC_K 1" in src
     assert m.emit_source(cfg) == api.CudaModel(rir, cols, device=-1).emit_source(cfg)

@@ -1,5 +1,5 @@
 """
-Device-side bit-for-bit checks of the arithmetic helpers the parity kernels rest on (round 3):
+Device-side bit-for-bit checks of the arithmetic helpers the parity kernels rest on (round 2, second session):
   * rn_div_nc / rn_sqrt_nc -- CUDA's inline division / square-root sequences without the range test and the conditional
     call of the complete routine -- against the `/` and sqrt() operators, over the whole domain the sequences are stated
     for (rn_prelude.cuh) and, densely, over the operand ranges of every call site;

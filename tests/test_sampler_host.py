@@ -38,9 +38,9 @@ def test_hmc_dualavg_funnel_on_host():
     _run(configs.funnel(), _cfg(30, 120, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(6) + 7)
 
 
-@pytest.mark.parametrize("defs", ["#define RN_X_NORMALS 4\n", "#define RN_X_SPEC 0\n", "#define RN_X_KCONST 0\n#define RN_X_NORMALS 1\n"])
-def test_round3_source_variants_on_host(defs):
-    """the experiment switches of round 3 (two polar pairs per trip through the `_try` form of the log; the branching forms of
+@pytest.mark.parametrize("defs", ["#define RN_X_NORMALS 4\n", "#define RN_X_SPEC 0\n", "#define RN_X_KCONST 0\n#define RN_X_NORMALS 1\n", "#define RN_X_POLAR2 1\n"])
+def test_round2b_source_variants_on_host(defs):
+    """the experiment switches of round 2b (two polar pairs per trip through the `_try` form of the log; the branching forms of
     the fdlibm common paths; coefficients as literals) leave every bit where it was -- even and odd numbers of parameters
     (odd: the cached second variate alternates, the last pair of a draw is repeated by the two-at-a-time pass)"""
     _run(configs.funnel(), _cfg(12, 40, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(4) + 7, defs=defs)
