@@ -238,7 +238,9 @@ struct Emitter {
     interleave_components(T, body, order_fwd, order_bwd);
     col_suffix.clear();
     row_index.clear();
-    capture_row_index = atomic_scatter && !(getenv("RN_SCATTER_REUSE_INDEX") && atoi(getenv("RN_SCATTER_REUSE_INDEX")) == 0);
+    // opt-in: measured on B200 it LOSES 3 % on cfg 5 (2.455e5 -> 2.374e5, profiles/r2_bench_row_libm_ab_v2.txt) -- eight more values
+    // live across the reverse sweep's fence at 128 registers cost more than the second LDS + F2I they replace
+    capture_row_index = atomic_scatter && getenv("RN_SCATTER_REUSE_INDEX") && atoi(getenv("RN_SCATTER_REUSE_INDEX")) != 0;
     for (int id : order_fwd) one(id);
     if (!order_bwd.empty()) {
       os << ind << "RN_FENCE();\n";
@@ -294,8 +296,9 @@ struct Emitter {
   // Row bodies of the warp-per-chain shape: total, branch-free exp / log / reciprocal (rn_prelude.cuh: rn_row_*) instead of CUDA's
   // exp(), log() and 1.0 / x, each of which ends a basic block with its range test -- and the statements of 4 or 8 observations
   // are interleaved precisely so that ptxas can overlap their chains.  RN_ROW_LIBM=0 keeps CUDA's functions (A/B).
-  // Measured on B200 (profiles/r2_bench_row_libm_ab_v1.txt): the rows-across-lanes body gains (cfg 5: 2.22e5 -> 2.41e5, 2.46e5 with
-  // two observations in flight), the chain-batched DMMA kernel loses (cfg 3: 5.25e5 -> 4.66e5; at 128 registers the four elements
+  // Measured on B200 (profiles/r2_bench_row_libm_ab_v1.txt, ..._v2.txt): the rows-across-lanes body gains -- cfg 5: 2.22e5 -> 2.46e5
+  // with two observations in flight where the arguments of exp are wild (every proposal rejected far from the mode: CUDA's exp
+  // takes its out-of-line completion there), 2.41e5 -> 2.46e5 after an adaptive warmup --, the chain-batched DMMA kernel loses (cfg 3: 5.25e5 -> 4.66e5; at 128 registers the four elements
   // of its helper in one basic block spill: stack 976 -> 4776 bytes) -- so the default is on for kernels without the DMMA path
   // and off for those with it (helper and its rows-across-lanes tail alike: that kernel stays exactly what round 2 validated).
   bool in_mma_helper = false, kernel_uses_mma = false;

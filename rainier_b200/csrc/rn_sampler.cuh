@@ -243,8 +243,11 @@ RN_DEVICE void rn_draw_normals(const RnTs& T, RnRng& rng) {
     i0 = 1;
   }
   const int npairs = (RN_N - i0 + 1) / 2;  // the last pair's second variate may be left over (-> rng.nng); slot RN_N is scratch
-#if defined(RN_X_POLAR2) && RN_X_POLAR2
-  // experiment switch: two attempts per trip (see rn_polar_attempt2); the second one is consumed only if it is needed
+#ifndef RN_X_POLAR2
+#define RN_X_POLAR2 1 /* 2.488 -> 2.467 ms per launch at the headline size (profiles/r2_sweep_iter_v6_polar2_merged.jsonl) */
+#endif
+#if RN_X_POLAR2
+  // two attempts per trip (see rn_polar_attempt2); the second one is consumed only if it is needed
   for (int k = 0; k < npairs;) {
     double a1, a2, b1, b2;
     rn_i64 seed4, seed8;

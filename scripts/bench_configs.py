@@ -121,25 +121,33 @@ for name in which:
         chains, iters, eps, label = 4096, 1, 0.001, "poisson GLM %d groups, %d obs, 4096 chains (primal RIR, adjoint gradient)" % (g, n_obs)
     build_s = time.perf_counter() - t0
     res = {"config": name, "label": label, "model_build_s": round(build_s, 1)}
+    mk = static
+    if name == "cfg5" and "--static-step" not in sys.argv:
+        # a fixed step from a random start is rejected every time on a posterior this narrow (accept_rate 0.0 in round 1's
+        # numbers): like bench.py, take the step from 30 warmup iterations of DualAvg(0.8) and time the sampling phase
+        def mk(eps, iters, **kw):
+            return api.make_config(iterations=iters, warmupIterations=30, sampler=api.HMCSampler(5), stepSizeTuner=api.DualAvgTuner(0.8),
+                                   massMatrixTuner=api.IdentityMassMatrixTuner(), launchIterations=iters, **kw)
+        res["step_size"] = "DualAvg(0.8), 30 warmup iterations"
     if precompile:
         model = api.CudaModel(prir, pcols, device=-1)
         for mm in (abi.RN_MATH_PARITY, abi.RN_MATH_FAST):
             t1 = time.perf_counter()
-            model.emit_cubin(static(eps, iters, mathMode=mm))
+            model.emit_cubin(mk(eps, iters, mathMode=mm))
             print(name, "math", mm, "compiled in %.1f s" % (time.perf_counter() - t1), flush=True)
         continue
     model = api.CudaModel(prir, pcols)
     for math_mode, mm in (("parity", abi.RN_MATH_PARITY), ("fast", abi.RN_MATH_FAST)):
         if only_math and math_mode not in only_math:
             continue
-        cfg = static(eps, iters, mathMode=mm)
+        cfg = mk(eps, iters, mathMode=mm)
         try:
             rate, secs, acc = timed_run(model, cfg, chains, iters)
             res[math_mode] = {"steps_x_chains_per_s": rate, "seconds_per_launch": secs, "accept_rate": acc}
         except api.RainierCudaError as e:
             res[math_mode] = {"error": str(e)[:300]}
-    res["backend"] = "warp-per-chain" if "warp-per-chain" in model.emit_source(static(eps, iters)) else "thread-per-chain"
-    res["op_counts"] = model.op_counts(static(eps, iters))
+    res["backend"] = "warp-per-chain" if "#define RN_BACKEND 1" in model.emit_source(mk(eps, iters)) else "thread-per-chain"
+    res["op_counts"] = model.op_counts(mk(eps, iters))
     if rir is not None and not no_cpu:
         cpu_iters = {"cfg2": 2000, "cfg2s": 20, "cfg3": 1, "cfg4": 2000}[name]
         r, cores, dt = cpu_rate(rir, cols, static(eps, cpu_iters), cpu_iters)
