@@ -154,10 +154,21 @@ static int cufail(const Api* A, CUresult r, const char* what) {
 struct KernelKey {
   bool adjoint, fast, ehmc;
   int mass_max, backend;
+  int block = 0;  // thread-per-chain: CTA size the module was compiled for (RN_BLOCK_DIM), 0 = any (emit / density-only uses)
   bool operator<(const KernelKey& o) const {
-    return std::tie(adjoint, fast, ehmc, mass_max, backend) < std::tie(o.adjoint, o.fast, o.ehmc, o.mass_max, o.backend);
+    return std::tie(adjoint, fast, ehmc, mass_max, backend, block) < std::tie(o.adjoint, o.fast, o.ehmc, o.mass_max, o.backend, o.block);
   }
 };
+// CTA size of the thread-per-chain kernels: 128 threads when there are chains to fill the chip twice over; a few thousand chains
+// (cfg 2 / cfg 4: 4096-8192) are spread over all 148 SMs with smaller CTAs instead of packing 64 SMs and idling the rest.
+// The sampler's module is COMPILED for this size (slot offsets of the per-thread shared-memory state become immediates:
+// 2.469 -> 2.446 ms per launch at the headline size, profiles/r2_sweep_iter_v7_keep_state_block_dim.jsonl).
+static unsigned tpc_block_for(size_t chains) {
+  unsigned block = 128u;
+  while (block > 32u && chains < (size_t)block * 148 * 2) block >>= 1;
+  if (const char* e = getenv("RN_BLOCK")) block = std::max(32u, std::min(128u, (unsigned)atoi(e) & ~31u));
+  return block;
+}
 struct Kernel {
   std::string source;
   std::vector<char> cubin;
@@ -166,6 +177,7 @@ struct Kernel {
              k_pool_apply = nullptr, k_diag_chain = nullptr, k_diag_reduce = nullptr;
   const Program* prog = nullptr;
   int backend = 0;            // 0 thread per chain, 1 warp per chain
+  unsigned tpc_block = 0;     // backend 0: the CTA size this module was compiled for (0: reads blockDim.x)
   int wpc_smem_doubles = 0;   // per-warp dynamic shared memory (backend 1)
   int warps_per_cta = 4;      // backend 1: CHAINS per CTA (each owned by wpc_k warps)
   int wpc_k = 1;
@@ -275,8 +287,9 @@ static KernelKey key_for(const rn_model* m, const rn_config* cfg) {
 extern "C" const char* rn_version(void);
 // emit + NVRTC (no device needed)
 // source_only: just emit (rn_emit_source, the analogue of rainier-decompile) -- no NVRTC run, nothing cached
-static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::string* source_only = nullptr) {
+static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::string* source_only = nullptr, size_t chains_hint = 0) {
   KernelKey key = key_for(m, cfg);
+  if (key.backend == 0 && chains_hint > 0 && !(getenv("RN_GENERIC_BLOCK") && atoi(getenv("RN_GENERIC_BLOCK")) != 0)) key.block = (int)tpc_block_for(chains_hint);
   auto it = m->kernels.find(key);
   if (it != m->kernels.end()) {
     if (source_only)
@@ -300,6 +313,7 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
   if (eo.backend == 1 && P->symbolic && P->n_params > 96)
     return fail(RN_E_UNSUPPORTED, "warp-per-chain with a symbolic gradient keeps n+1 accumulators in registers; use RN_GRAD_ADJOINT for n > 96");
   K->backend = eo.backend;
+  K->tpc_block = (unsigned)key.block;
   if (eo.backend == 0) {  // rn_sampler.cuh: RN_TS_DOUBLES * 8 + RN_TS_INTS * 4
     const unsigned n = P->n_params;
     const unsigned doubles = (n + 1) + (key.mass_max >= 1 ? n : 0) + (key.ehmc ? n : 0) + 5 + 4;
@@ -393,6 +407,8 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   opts.push_back(key.fast ? "--fmad=true" : "--fmad=false");
   if (getenv("RN_LIBM_NOINLINE")) opts.push_back("-DRN_LIBM_NOINLINE=1");
+  const std::string block_def = "-DRN_BLOCK_DIM=" + std::to_string(key.block);
+  if (key.block > 0) opts.push_back(block_def.c_str());
   std::vector<std::string> extra_defs;  // experiment switches of the device sources (RN_X_*): RN_NVRTC_DEFS="-DRN_X_P_REGS=1 ..."
   if (const char* e = getenv("RN_NVRTC_DEFS")) {
     std::istringstream is(e);
@@ -1001,11 +1017,7 @@ int launch(const Api* A, rn_sampler* s, CUfunction f, int count = -1) {
     s->launches++;
     return RN_OK;
   }
-  // 128 threads per CTA when there are chains to fill the chip twice over; a few thousand chains (cfg 2 / cfg 4: 4096-8192)
-  // are spread over all 148 SMs with smaller CTAs instead of packing 64 SMs and idling the rest
-  unsigned block = 128u;
-  while (block > 32u && chains < (size_t)block * 148 * 2) block >>= 1;
-  if (const char* e = getenv("RN_BLOCK")) block = std::max(32u, std::min(128u, (unsigned)atoi(e) & ~31u));
+  const unsigned block = s->K->tpc_block ? s->K->tpc_block : tpc_block_for(chains);  // (the module may be compiled for its CTA size)
   const unsigned grid = (unsigned)((chains + block - 1) / block);
   CU(A->cuLaunchKernel(f, grid, 1, 1, block, 1, 1, s->K->tpc_smem_per_thread * block, s->stream, params, nullptr));
   s->launches++;
@@ -1116,7 +1128,7 @@ int rn_sampler_create(rn_model* m, const rn_config* cfg, const int64_t* seeds, i
   s->m = m;
   s->cfg = *cfg;
   s->chains = chains;
-  rc = get_kernel(m, cfg, &s->K);
+  rc = get_kernel(m, cfg, &s->K, nullptr, (size_t)chains);
   if (rc) return rc;
   rc = load_kernel(A, m, s->K);
   if (rc) return rc;

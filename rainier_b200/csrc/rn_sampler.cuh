@@ -67,7 +67,11 @@ RN_DEVICE RnTs rn_ts_get() { return RnTs{rn_ts_mem_d, rn_ts_mem_i, 1u}; }
 extern __shared__ double rn_ts_mem[];
 RN_DEVICE RnTs rn_ts_get() {
   RnTs T;
+#ifdef RN_BLOCK_DIM
+  T.bs = RN_BLOCK_DIM;  // the runtime compiled this module for the block size it launches with: slot offsets become immediates
+#else
   T.bs = blockDim.x;
+#endif
   T.d = rn_ts_mem + threadIdx.x;
   T.i = (int*)(rn_ts_mem + (size_t)RN_TS_DOUBLES * blockDim.x) + threadIdx.x;
   return T;
@@ -548,10 +552,32 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
   // was replaced in between.  It is carried in a register and recomputed only then (and at the start of a launch).
   bool havePrevH = false;
 
+  // RN_X_KEEP_STATE: the current position, its gradient and potential stay in registers from one iteration to the next -- after an
+  // accepted proposal they ARE the state the next iteration starts from, so only a rejection re-reads them from `params` (which is
+  // written on accept exactly as before: it is what a rejection restores, what isUTurn measures against, and the state the launch
+  // leaves behind).  The drawn momentum reaches `params` only where the reference's copy survives the iteration: on rejection
+  // (from the scratch of the normal draws, intact while the momentum lives in registers under the identity mass).
+#ifndef RN_X_KEEP_STATE
+#define RN_X_KEEP_STATE 1 /* with the compile-time CTA size: 2.446 -> 2.400 ms per launch (profiles/r2_sweep_iter_v7_keep_state_block_dim.jsonl) */
+#endif
+#define RN_KEEP_P_LATE (RN_X_KEEP_STATE && RN_X_P_REGS)
+  RnPQ s;
+#if RN_X_KEEP_STATE
+  RN_UNROLL
+  for (int i = 0; i < RN_N; i++) {
+    s.q[i] = RN_AT(A.params, RN_N + i, c);
+    s.g[i] = RN_AT(A.grad, i, c);
+  }
+  s.U = RN_AT(A.params, 2 * RN_N, c);
+#endif
+
   for (int it = 0; it < A.n_iter; it++) {
     // ---------------- lf.startIteration, LeapFrog.scala:52-59 ----------------
-    RnPQ s;
+#if RN_X_KEEP_STATE
+    const double cU = s.U;
+#else
     const double cU = RN_AT(A.params, 2 * RN_N, c);
+#endif
     if (!havePrevH) {
       RN_UNROLL
       for (int i = 0; i < RN_N; i++) RN_P(i) = RN_AT(A.params, i, c);  // old momentum
@@ -562,12 +588,19 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
       rn_initialize_ps(A, c, T, s, kind, rng);
       rn_rng_park(T, rng);
     }
+#if RN_X_KEEP_STATE
+    if (!(RN_KEEP_P_LATE && kind == 0)) {
+      RN_UNROLL
+      for (int i = 0; i < RN_N; i++) RN_AT(A.params, i, c) = RN_P(i);
+    }
+#else
     RN_UNROLL
     for (int i = 0; i < RN_N; i++) {
       RN_AT(A.params, i, c) = RN_P(i);  // initializePs writes into params (LeapFrog.scala:55); kept on reject
       s.q[i] = RN_AT(A.params, RN_N + i, c);
       s.g[i] = RN_AT(A.grad, i, c);
     }
+#endif
     s.U = cU;
     RN_TS_START_H = rn_energy(A, c, T, s, kind, cU);  // finishIteration's energy(params), :62
     const double usedStep = stepSize;
@@ -653,6 +686,15 @@ RN_DEVICE void rn_iterate(const RnArgs& A) {
     } else {
       RN_UNROLL
       for (int i = 0; i < RN_N; i++) s.q[i] = RN_AT(A.params, RN_N + i, c);  // s.q := current position either way
+#if RN_X_KEEP_STATE
+      RN_UNROLL
+      for (int i = 0; i < RN_N; i++) s.g[i] = RN_AT(A.grad, i, c);
+      s.U = RN_AT(A.params, 2 * RN_N, c);
+      if (RN_KEEP_P_LATE && kind == 0) {  // the momentum drawn at startIteration stays in params (LeapFrog.scala:55)
+        RN_UNROLL
+        for (int i = 0; i < RN_N; i++) RN_AT(A.params, i, c) = RN_Z(i);
+      }
+#endif
       eH = startH;
     }
     {  // stats.energyVariance.update(eH); energyTransitions2 += pow(eH - prevH, 2)

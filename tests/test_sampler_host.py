@@ -38,7 +38,7 @@ def test_hmc_dualavg_funnel_on_host():
     _run(configs.funnel(), _cfg(30, 120, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(6) + 7)
 
 
-@pytest.mark.parametrize("defs", ["#define RN_X_NORMALS 4\n", "#define RN_X_SPEC 0\n", "#define RN_X_KCONST 0\n#define RN_X_NORMALS 1\n", "#define RN_X_POLAR2 0\n"])
+@pytest.mark.parametrize("defs", ["#define RN_X_NORMALS 4\n", "#define RN_X_SPEC 0\n", "#define RN_X_KCONST 0\n#define RN_X_NORMALS 1\n", "#define RN_X_POLAR2 0\n", "#define RN_X_KEEP_STATE 0\n"])
 def test_round2b_source_variants_on_host(defs):
     """the experiment switches of round 2b (two polar pairs per trip through the `_try` form of the log; the branching forms of
     the fdlibm common paths; coefficients as literals) leave every bit where it was -- even and odd numbers of parameters
