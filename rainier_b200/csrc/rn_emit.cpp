@@ -70,8 +70,10 @@ struct Emitter {
   }
 
   // see row_body(): splits the row statements into independent dataflow components and merges them round-robin
+  // `fused` (optional): ONE order in which every group of components runs its forward statements and then, at once, its reverse
+  // statements -- see row_body()
   void interleave_components(const TargetInfo& T, const std::set<int>& body, std::vector<int>& order_fwd,
-                             std::vector<int>& order_bwd) const {
+                             std::vector<int>& order_bwd, std::vector<int>* fused = nullptr) const {
     const int BIG = 4;  // two components of at least this many statements meeting in one statement = a joiner
     std::map<int, int> parent, size;  // union-find over statement ids
     std::set<int> tail;
@@ -83,11 +85,43 @@ struct Emitter {
       return x;
     };
     std::vector<int> ops;
+    // fused mode: the additions that only fold the row's terms into the accumulated value (reachable from an accumulate statement
+    // through single-use ADD nodes) are joiners by definition -- otherwise the running sum swallows every observation it meets
+    // while that observation's component is still small, and the whole row becomes one chain
+    std::set<int> fold;
+    if (fused) {
+      std::map<int, int> uses;
+      auto count_ops = [&](int s) {
+        operands(s, ops);
+        for (int o : ops) uses[o]++;
+      };
+      for (int id : T.row_fwd)
+        if (body.count(id)) count_ops(id);
+      for (int id : T.row_bwd)
+        if (body.count(id)) count_ops(id);
+      for (const AccStmt& a : T.row_acc) uses[a.node] += 2;  // (roots: entered below whatever their count)
+      for (const ScatterStmt& sc : T.row_scatter) uses[sc.node] += 2, uses[sc.index_node] += 2;
+      std::vector<int> stack;
+      for (const AccStmt& a : T.row_acc)
+        if (body.count(a.node)) stack.push_back(a.node);
+      std::set<int> roots(stack.begin(), stack.end());
+      while (!stack.empty()) {
+        const int id = stack.back();
+        stack.pop_back();
+        const Node& n = P.nodes[id];
+        if (n.kind != K_BINARY || n.op != RIR_B_ADD) continue;
+        if (!roots.count(id) && uses[id] != 1) continue;
+        if (!fold.insert(id).second) continue;
+        if (body.count(n.a)) stack.push_back(n.a);
+        if (body.count(n.b)) stack.push_back(n.b);
+      }
+    }
     auto classify = [&](int s) {
       operands(s, ops);
-      bool is_tail = false;
+      bool is_tail = fold.count(s) > 0;
       std::set<int> comps;
       for (int o : ops) {
+        if (is_tail) break;
         if (!body.count(o)) continue;
         if (tail.count(o)) {
           is_tail = true;
@@ -156,6 +190,77 @@ struct Emitter {
         }
       out.insert(out.end(), tails.begin(), tails.end());
     };
+    if (fused) {
+      std::vector<int> comp_order, tails_f, tails_b;
+      std::map<int, std::vector<int>> lf, lb;
+      for (int id : fwd) {
+        if (tail.count(id)) {
+          tails_f.push_back(id);
+          continue;
+        }
+        const int c = find(id);
+        if (!lf.count(c) && !lb.count(c)) comp_order.push_back(c);
+        lf[c].push_back(id);
+      }
+      for (int id : bwd) {
+        if (tail.count(id)) {
+          tails_b.push_back(id);
+          continue;
+        }
+        const int c = find(id);
+        if (!lf.count(c) && !lb.count(c)) comp_order.push_back(c);
+        lb[c].push_back(id);
+      }
+      const size_t W = (size_t)std::max(1, opt.interleave);
+      auto rr = [&](std::map<int, std::vector<int>>& lists, size_t g0) {
+        std::vector<size_t> pos(W, 0);
+        for (bool any = true; any;) {
+          any = false;
+          for (size_t k = g0; k < std::min(comp_order.size(), g0 + W); k++) {
+            const std::vector<int>& l = lists[comp_order[k]];
+            if (pos[k - g0] < l.size()) {
+              fused->push_back(l[pos[k - g0]++]);
+              any = true;
+            }
+          }
+        }
+      };
+      // joiners are issued as soon as their operands exist (a fold addition right after the term it adds), not at the end
+      std::vector<int> pending(tails_f);
+      pending.insert(pending.end(), tails_b.begin(), tails_b.end());
+      std::set<int> done;
+      size_t flushed = 0;
+      auto flush = [&]() {
+        for (size_t i = flushed; i < fused->size(); i++) done.insert((*fused)[i]);
+        for (bool any = true; any;) {
+          any = false;
+          for (size_t i = 0; i < pending.size(); i++) {
+            const int t = pending[i];
+            if (t < 0) continue;
+            operands(t, ops);
+            bool ready = true;
+            for (int o : ops)
+              if (body.count(o) && !done.count(o)) ready = false;
+            if (!ready) continue;
+            fused->push_back(t);
+            done.insert(t);
+            pending[i] = -1;
+            any = true;
+          }
+        }
+        flushed = fused->size();
+      };
+      for (size_t g0 = 0; g0 < comp_order.size(); g0 += W) {
+        rr(lf, g0);
+        flush();
+        rr(lb, g0);
+        flush();
+      }
+      flush();
+      for (int t : pending)
+        if (t >= 0) fused->push_back(t);  // (cannot happen for an acyclic body; keeps the order total)
+      return;
+    }
     schedule(fwd, order_fwd);
     schedule(bwd, order_bwd);
   }
@@ -235,6 +340,31 @@ struct Emitter {
     // statements of the components are interleaved round-robin; "joiner" statements (and everything downstream of
     // them) follow in their original order.  Values are unchanged (SSA); only the issue order moves.
     std::vector<int> order_fwd, order_bwd;
+    // RN_ROW_FUSED_SWEEPS (warp-per-chain, experiment switch): the reverse statements of a group of observations follow its forward
+    // statements directly instead of after the forward sweep of the whole row.  A component's reverse statements read only its own
+    // forward values (anything that reads a joiner is a joiner itself and stays at the end), so this is the same dataflow; the
+    // columns a group loaded are still in registers for its reverse sweep: no fence, no second read of the tile (ncu, cfg 5:
+    // shared-memory wavefronts are 53 % of the pipe's capacity and `short_scoreboard` the first stall reason; each column is read
+    // twice per observation today).
+    const bool fused_sweeps = wpc && getenv("RN_ROW_FUSED_SWEEPS") && atoi(getenv("RN_ROW_FUSED_SWEEPS")) != 0;
+    if (fused_sweeps) {
+      std::vector<int> order;
+      interleave_components(T, body, order_fwd, order_bwd, &order);
+      col_suffix.clear();
+      row_index.clear();
+      capture_row_index = false;
+      for (int id : order) one(id);
+      for (const AccStmt* a : acc_tail) {
+        need_col(a->node);
+        emit_acc(*a);
+      }
+      for (const ScatterStmt* sc : sc_tail) {
+        need_col(sc->index_node);
+        need_col(sc->node);
+        emit_scatter(*sc);
+      }
+      return;
+    }
     interleave_components(T, body, order_fwd, order_bwd);
     col_suffix.clear();
     row_index.clear();
@@ -301,10 +431,16 @@ struct Emitter {
   // takes its out-of-line completion there), 2.41e5 -> 2.46e5 after an adaptive warmup --, the chain-batched DMMA kernel loses (cfg 3: 5.25e5 -> 4.66e5; at 128 registers the four elements
   // of its helper in one basic block spill: stack 976 -> 4776 bytes) -- so the default is on for kernels without the DMMA path
   // and off for those with it (helper and its rows-across-lanes tail alike: that kernel stays exactly what round 2 validated).
+  // ... and neither do row bodies that keep many accumulators in registers: the rows-across-lanes form of cfg 3 (RN_MMA=0: 51
+  // accumulators) runs 5.4e4 with the row functions against 2.1e5 with CUDA's libm, the merged block spills.  The default is on
+  // only where the registers have room: no DMMA path and at most RN_ROW_LIBM_MAX_ACC (8) register accumulators (cfg 5: 2).
   bool in_mma_helper = false, kernel_uses_mma = false;
+  int kernel_reg_accumulators = 0;
   bool row_libm_on() const {
     if (const char* e = getenv("RN_ROW_LIBM")) return atoi(e) != 0;
-    return !kernel_uses_mma;
+    int max_acc = 8;
+    if (const char* e = getenv("RN_ROW_LIBM_MAX_ACC")) max_acc = atoi(e);
+    return !kernel_uses_mma && kernel_reg_accumulators <= max_acc;
   }
   std::string recip(const std::string& x, bool row_variant) const {
     return (row_variant && row_libm_on()) ? "rn_row_rcp(" + x + ")" : "(1.0 / " + x + ")";
@@ -1533,6 +1669,7 @@ struct Emitter {
     int n_reg_acc = 0;
     for (int sl = 0; sl < P.n_slots; sl++)
       if (smem_slot[sl] < 0) n_reg_acc++;
+    kernel_reg_accumulators = n_reg_acc;
     rr_plan();
     // cross-warp reduction scratch of the chain's group (K warps): [warp][register accumulators..., err]; the sums of the
     // re-rolled families go through it too, before and after the row loops
@@ -1686,6 +1823,7 @@ WpcSizes wpc_sizes(const Program& P, const EmitOptions& opt) {
       z.tile_doubles = std::max(z.tile_doubles, (int)T.n_cols * opt.pitch((size_t)(&T - &P.targets[0])) * std::max(1, opt.wpc_k));
   z.mma_ok = E.mma_all_ok;
   z.mma_shared_doubles = E.mma_shared_doubles;
+  z.reg_accumulators = E.kernel_reg_accumulators;
   return z;
 }
 

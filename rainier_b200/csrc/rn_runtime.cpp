@@ -394,7 +394,9 @@ static int get_kernel(rn_model* m, const rn_config* cfg, Kernel** out, std::stri
     // (with the branch-free row functions the components in flight share ONE basic block and ptxas overlaps them completely:
     // two at 128 registers -- cfg 5: 2.46e5 against 2.41e5 with four, profiles/r2_bench_row_libm_ab_v1.txt; the DMMA kernels
     // keep CUDA's libm and four)
-    const bool row_libm = getenv("RN_ROW_LIBM") ? atoi(getenv("RN_ROW_LIBM")) != 0 : !eo.mma;
+    int max_acc = 8;  // (the emitter's own rule: Emitter::row_libm_on)
+    if (const char* e = getenv("RN_ROW_LIBM_MAX_ACC")) max_acc = atoi(e);
+    const bool row_libm = getenv("RN_ROW_LIBM") ? atoi(getenv("RN_ROW_LIBM")) != 0 : (!eo.mma && wpc_sizes(*P, eo).reg_accumulators <= max_acc);
     eo.interleave = regs <= 128 ? (row_libm ? 2 : 4) : 8;
     if (const char* e = getenv("RN_INTERLEAVE")) eo.interleave = std::max(1, atoi(e));
   }
