@@ -236,3 +236,42 @@ def test_wpc_rerolled_invariant_sections_on_host():
     assert np.max(np.abs(d1 - d0) / np.maximum(np.abs(d0), 1e-9)) < 1e-12
     _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2")
     _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2", k="2", chains_per_cta=2)
+
+
+@pytest.mark.parametrize("switch", ["RN_ROW_FUSED_SWEEPS", "RN_SCATTER_REUSE_INDEX", "RN_ROW_LIBM"])
+def test_wpc_opt_in_emitter_switches_on_host(switch, monkeypatch):
+    """the measured-and-rejected variants of the warp-per-chain row bodies stay correct while they stay in the tree: a group's
+    reverse statements right after its forward statements (the row's fold additions recognised as joiners, no second read of the
+    tile), the forward Lookup's index reused by the scatter-add, CUDA's libm instead of the row functions -- same accept decisions
+    as the oracle, densities to the tolerance of this shape, on a Lookup / scatter model and on a regression with dot products"""
+    monkeypatch.setenv(switch, "0" if switch == "RN_ROW_LIBM" else "1")
+    model = configs.poisson_glm(48, 768)
+    prir, pcols = model.compile(False)
+    cfg = api.make_config(iterations=4, warmupIterations=0, sampler=api.HMCSampler(3), stepSizeTuner=api.StaticStepSize(0.004),
+                          massMatrixTuner=api.IdentityMassMatrixTuner())
+    cfg.backend = abi.RN_BACKEND_WARP
+    src = api.CudaModel(prir, pcols, device=-1).emit_source(cfg)
+    dens = src[src.index("// ---- emitted"):src.index("// rn_sampler_wpc.cuh --")]
+    if switch == "RN_ROW_FUSED_SWEEPS":
+        assert "RN_FENCE();" not in dens[dens.index("// target 1"):]
+    if switch == "RN_SCATTER_REUSE_INDEX":
+        assert "rn_tab_lookup_k(" in dens[dens.index("// target 1"):]
+    if switch == "RN_ROW_LIBM":
+        assert "rn_row_exp(" not in dens and " exp(" in dens
+    _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2")
+    _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2", k="2", chains_per_cta=2)
+    model = configs.logreg(300, 3)
+    prir, pcols = model.compile(False)
+    cfg = api.make_config(iterations=5, warmupIterations=0, sampler=api.HMCSampler(3), stepSizeTuner=api.StaticStepSize(0.02),
+                          massMatrixTuner=api.IdentityMassMatrixTuner())
+    monkeypatch.setenv("RN_MMA", "0")
+    _run_wpc(model, cfg, np.arange(2) + 9, tol=1e-9, rir_gpu=prir, cols_gpu=pcols, tma="2")
+
+
+def test_merged_fallback_density_on_host(monkeypatch):
+    """RN_MERGED_FALLBACK (opt-in, measured slower): the fdlibm calls of a data-free density share one fallback branch; the
+    complete functions re-evaluate the density when any argument left a common path -- bit-identical to the oracle through an
+    adaptive warmup (whose step-size search doubles the step until the trajectory leaves the common paths' domain)"""
+    monkeypatch.setenv("RN_MERGED_FALLBACK", "1")
+    _run(configs.funnel(), _cfg(12, 40, api.HMCSampler(5), api.DualAvgTuner(0.8), api.IdentityMassMatrixTuner()), np.arange(4) + 7)
+    _run(configs.eight_schools(), api.SamplerConfig(iterations=10, warmupIterations=60), np.arange(2) + 11)
